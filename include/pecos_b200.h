@@ -1,0 +1,144 @@
+/*
+ * pecos_b200 C ABI  --  libpecos_b200_float32.so
+ *
+ * Drop-in replacement, on one NVIDIA B200 (sm_100a), for the two inference hot paths that the reference exports
+ * from pecos/core/libpecos.cpp and binds through ctypes in pecos/core/base.py:
+ *
+ *   XR-Linear beam-search prediction   (libpecos.cpp:116-176,  base.py:799-976, :990-1095)
+ *   HNSW dense search                  (libpecos.cpp:449-564,  base.py:1865-1964)
+ *
+ * The `c_*` entry points below have byte-identical signatures, argument meaning and ownership rules to the reference
+ * symbols of the same name, so `pecos.core.base.corelib` can bind them unchanged.
+ * The `pb200_*` entry points are additions (device selection, device-resident batches for benchmarking, profiling
+ * counters, host-only model inspection for tests).
+ *
+ * Conventions (same as the reference): no error codes.  The reference lets C++ exceptions escape `extern "C"`
+ * (=> std::terminate); this library prints the message to stderr and calls abort().  There is NO CPU fallback:
+ * every compute entry point requires a CUDA device and fails loudly without one.
+ * `threads` arguments are accepted and ignored (the GPU schedules the work).
+ */
+#ifndef PECOS_B200_H_
+#define PECOS_B200_H_
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- plain-C views of scipy/numpy buffers: pecos/core/utils/matrix.hpp:43-73, ctypes mirrors base.py:177-310 ---- */
+typedef struct {
+    uint32_t rows, cols;
+    uint64_t* col_ptr;
+    uint32_t* row_idx;
+    float* val;
+} ScipyCscF32;
+
+typedef struct {
+    uint32_t rows, cols;
+    uint64_t* row_ptr;
+    uint32_t* col_idx;
+    float* val;
+} ScipyCsrF32;
+
+typedef struct {
+    uint32_t rows, cols;
+    float* val; /* row-major */
+} ScipyDrmF32;
+
+/* Result allocator callback (matrix.hpp:47; Python side base.py:407-478):
+ *   pred_alloc(is_col_major=false, rows, cols, nnz, &indices /u32[nnz]/, &indptr /u64[rows+1]/, &data /f32[nnz]/)
+ * Called exactly once per predict call, from the calling thread. */
+typedef void (*py_sparse_allocator_t)(bool, uint64_t, uint64_t, uint64_t, void*, void*, void*);
+
+/* ======================================= XR-Linear (reference-compatible) ======================================= */
+
+/* libpecos.cpp:116  model_path = the `ranker/` folder of an XLinearModel; default layer type. */
+void* c_xlinear_load_model_from_disk(const char* model_path);
+/* libpecos.cpp:121  weight_matrix_type in {0 CSC, 1 HASH_CHUNKED, 2 BINARY_SEARCH_CHUNKED} (base.py:49).
+ * All three are served by the one HBM chunk layout; the requested type is remembered and reported back by
+ * c_xlinear_get_layer_type (pecos/xmc/base.py:1736-1743 gates features on it).  Rejects mmap folders. */
+void* c_xlinear_load_model_from_disk_ext(const char* model_path, int weight_matrix_type);
+/* libpecos.cpp:128  folder written by c_xlinear_compile_mmap_model (W/C/perm.mmap_store per layer). */
+void* c_xlinear_load_mmap_model_from_disk(const char* model_path, const bool lazy_load);
+/* libpecos.cpp:140 */
+void c_xlinear_destruct_model(void* ptr);
+/* libpecos.cpp:147  attr in {"depth","nr_features","nr_labels","nr_codes"} (inference.hpp:2367-2379). */
+uint32_t c_xlinear_get_int_attr(void* ptr, const char* attr);
+/* libpecos.cpp:152 */
+int c_xlinear_get_layer_type(void* ptr, int layer_depth);
+/* libpecos.cpp:158-175  0 / NULL overrides mean "use the value stored with each layer". */
+void c_xlinear_predict_csr_f32(void* ptr, const ScipyCsrF32* input_x, const uint32_t overridden_beam_size,
+                               const char* overridden_post_processor_str, const uint32_t overridden_only_topk,
+                               const int threads, py_sparse_allocator_t pred_alloc);
+/* libpecos.cpp:176 */
+void c_xlinear_predict_drm_f32(void* ptr, const ScipyDrmF32* input_x, const uint32_t overridden_beam_size,
+                               const char* overridden_post_processor_str, const uint32_t overridden_only_topk,
+                               const int threads, py_sparse_allocator_t pred_alloc);
+
+/* ========================================= HNSW (reference-compatible) ========================================== */
+
+/* libpecos.cpp:471-480  model_dir = ".../c_model" holding config.json + index.mmap_store (hnsw.hpp:534-552). */
+void* c_ann_hnsw_load_drm_ip_f32(const char* model_dir, const bool lazy_load);
+void* c_ann_hnsw_load_drm_l2_f32(const char* model_dir, const bool lazy_load);
+/* libpecos.cpp:492-499 */
+void c_ann_hnsw_destruct_drm_ip_f32(void* model_ptr);
+void c_ann_hnsw_destruct_drm_l2_f32(void* model_ptr);
+/* libpecos.cpp:501-524  opaque scratch pool; here: pre-allocated per-query device scratch. */
+void* c_ann_hnsw_searchers_create_drm_ip_f32(void* model_ptr, uint32_t num_searcher);
+void* c_ann_hnsw_searchers_create_drm_l2_f32(void* model_ptr, uint32_t num_searcher);
+void c_ann_hnsw_searchers_destruct_drm_ip_f32(void* searchers_ptr);
+void c_ann_hnsw_searchers_destruct_drm_l2_f32(void* searchers_ptr);
+/* libpecos.cpp:527-564  caller passes zeroed Q x topk arrays; row q gets its neighbours in ascending distance. */
+void c_ann_hnsw_predict_drm_ip_f32(void* model_ptr, const ScipyDrmF32* pX, uint32_t* ret_idx, float* ret_val,
+                                   uint32_t efS, uint32_t topk, int32_t threads, void* searchers_ptr);
+void c_ann_hnsw_predict_drm_l2_f32(void* model_ptr, const ScipyDrmF32* pX, uint32_t* ret_idx, float* ret_val,
+                                   uint32_t efS, uint32_t topk, int32_t threads, void* searchers_ptr);
+
+/* ============================================ pecos_b200 additions ============================================== */
+
+const char* pb200_version(void);
+/* Number of visible CUDA devices (0 when there is none; never aborts). */
+int pb200_device_count(void);
+/* Device used by subsequently created model handles (default 0). Returns 0 on success. */
+int pb200_set_device(int device);
+int pb200_get_device(void);
+/* Pinned host memory for end-to-end runs (cudaMallocHost / cudaFreeHost). */
+void* pb200_host_alloc(size_t bytes);
+void pb200_host_free(void* ptr);
+/* Overwrite a scratch buffer larger than L2 (126 MB) so the next timed iteration starts cold. */
+void pb200_l2_flush(void);
+
+/* Device-resident query batch: upload once, run the layers with inputs already in HBM, fetch when wanted. */
+void pb200_xlinear_resident_upload_csr(void* ptr, const ScipyCsrF32* input_x);
+/* Returns the device time (ms, CUDA events on the engine's stream) of one pass over the resident batch. */
+double pb200_xlinear_resident_predict(void* ptr, uint32_t overridden_beam_size, const char* overridden_post_processor_str,
+                                      uint32_t overridden_only_topk, int collect_stats);
+void pb200_xlinear_resident_fetch(void* ptr, py_sparse_allocator_t pred_alloc);
+
+/* Per-layer kernel timing (CUDA events) and algorithmic-byte counters.
+ *   profile: out[2*d] = chunk-score kernel ms, out[2*d+1] = top-k kernel ms   (accumulated since reset)
+ *   stats:   out[7*d + {0..6}] = chunks, sum R, sum m, sum e, sum c, sum nnz(x), sum beam-out   (last stats pass) */
+void pb200_xlinear_set_profile(void* ptr, int on);
+void pb200_xlinear_reset_profile(void* ptr);
+void pb200_xlinear_get_profile(void* ptr, double* out);
+void pb200_xlinear_get_stats(void* ptr, uint64_t* out);
+uint64_t pb200_xlinear_launches(void* ptr);
+uint64_t pb200_xlinear_model_bytes(void* ptr);
+
+/* Host-only model ingest (no GPU needed): loads + builds the chunk layout, for layout tests.
+ *   kind: 0 = npz folder, 1 = mmap folder.  dims out[8] = {w_rows, n_cols, out_cols, n_chunks, c_max, meta_len,
+ *   n_entries, label_of_col_len}.  export copies the arrays into caller buffers (any may be NULL). */
+void* pb200_xlinear_host_load(const char* model_path, int kind);
+void pb200_xlinear_host_free(void* hptr);
+uint32_t pb200_xlinear_host_depth(void* hptr);
+void pb200_xlinear_host_layer_dims(void* hptr, uint32_t layer, uint64_t* out);
+void pb200_xlinear_host_layer_export(void* hptr, uint32_t layer, void* chunks32, uint32_t* meta, void* entries8,
+                                     uint32_t* label_of_col);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PECOS_B200_H_ */

@@ -1,0 +1,156 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes driver for ``oracle/_ref/libpecos_float32.so`` (the unmodified reference library).
+
+Binds the same symbols, with the same prototypes, that ``pecos/core/base.py`` binds (:799-976 XR-Linear,
+:1865-1949 HNSW), without importing the reference's Python package (which does not exist on the GPU box).
+"""
+import ctypes
+import os
+from ctypes import POINTER, byref, c_bool, c_char_p, c_float, c_int, c_int32, c_uint32, c_void_p
+
+import numpy as np
+import scipy.sparse as smat
+
+from pecos_b200.core import (
+    XLINEAR_INFERENCE_MODEL_TYPES,
+    ScipyCompressedSparseAllocator,
+    ScipyCsrF32,
+    ScipyDrmF32,
+)
+
+from . import REF_LIB
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(REF_LIB):
+            raise RuntimeError(f"{REF_LIB} missing: run `make -C oracle` where /root/reference is available")
+        L = ctypes.CDLL(REF_LIB)
+        L.c_xlinear_load_model_from_disk_ext.restype = c_void_p
+        L.c_xlinear_load_model_from_disk_ext.argtypes = [c_char_p, c_int]
+        L.c_xlinear_load_mmap_model_from_disk.restype = c_void_p
+        L.c_xlinear_load_mmap_model_from_disk.argtypes = [c_char_p, c_bool]
+        L.c_xlinear_compile_mmap_model.restype = None
+        L.c_xlinear_compile_mmap_model.argtypes = [c_char_p, c_char_p]
+        L.c_xlinear_destruct_model.restype = None
+        L.c_xlinear_destruct_model.argtypes = [c_void_p]
+        L.c_xlinear_get_int_attr.restype = c_uint32
+        L.c_xlinear_get_int_attr.argtypes = [c_void_p, c_char_p]
+        pred = [c_uint32, c_char_p, c_uint32, c_int, ScipyCompressedSparseAllocator.CFUNCTYPE]
+        L.c_xlinear_predict_csr_f32.restype = None
+        L.c_xlinear_predict_csr_f32.argtypes = [c_void_p, POINTER(ScipyCsrF32)] + pred
+        L.c_xlinear_predict_drm_f32.restype = None
+        L.c_xlinear_predict_drm_f32.argtypes = [c_void_p, POINTER(ScipyDrmF32)] + pred
+        for metric in ("ip", "l2"):
+            sfx = f"drm_{metric}_f32"
+            f = getattr(L, "c_ann_hnsw_train_" + sfx)
+            f.restype = c_void_p
+            f.argtypes = [POINTER(ScipyDrmF32), c_uint32, c_uint32, c_int, c_int]
+            f = getattr(L, "c_ann_hnsw_load_" + sfx)
+            f.restype = c_void_p
+            f.argtypes = [c_char_p, c_bool]
+            f = getattr(L, "c_ann_hnsw_save_" + sfx)
+            f.restype = None
+            f.argtypes = [c_void_p, c_char_p]
+            f = getattr(L, "c_ann_hnsw_destruct_" + sfx)
+            f.restype = None
+            f.argtypes = [c_void_p]
+            f = getattr(L, "c_ann_hnsw_searchers_create_" + sfx)
+            f.restype = c_void_p
+            f.argtypes = [c_void_p, c_uint32]
+            f = getattr(L, "c_ann_hnsw_searchers_destruct_" + sfx)
+            f.restype = None
+            f.argtypes = [c_void_p]
+            f = getattr(L, "c_ann_hnsw_predict_" + sfx)
+            f.restype = None
+            f.argtypes = [c_void_p, POINTER(ScipyDrmF32), POINTER(c_uint32), POINTER(c_float), c_uint32, c_uint32,
+                          c_int32, c_void_p]
+        _lib = L
+    return _lib
+
+
+class RefXLinear(object):
+    """Reference XR-Linear model handle (predict-only)."""
+
+    def __init__(self, ranker_folder, weight_matrix_type="BINARY_SEARCH_CHUNKED", is_mmap=False):
+        L = lib()
+        if is_mmap:
+            self.h = c_void_p(L.c_xlinear_load_mmap_model_from_disk(ranker_folder.encode(), False))
+        else:
+            self.h = c_void_p(L.c_xlinear_load_model_from_disk_ext(ranker_folder.encode(),
+                                                                   XLINEAR_INFERENCE_MODEL_TYPES[weight_matrix_type]))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().c_xlinear_destruct_model(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def attr(self, name):
+        return lib().c_xlinear_get_int_attr(self.h, name.encode())
+
+    def predict(self, X, beam_size=0, post_processor=None, only_topk=0, threads=-1):
+        L = lib()
+        alloc = ScipyCompressedSparseAllocator()
+        pp = post_processor.encode() if post_processor else None
+        if isinstance(X, smat.csr_matrix):
+            assert X.has_sorted_indices
+            cx = ScipyCsrF32.init_from(X)
+            L.c_xlinear_predict_csr_f32(self.h, byref(cx), beam_size or 0, pp, only_topk or 0, threads, alloc.cfunc)
+        else:
+            cx = ScipyDrmF32.init_from(np.ascontiguousarray(X, dtype=np.float32))
+            L.c_xlinear_predict_drm_f32(self.h, byref(cx), beam_size or 0, pp, only_topk or 0, threads, alloc.cfunc)
+        return alloc.get()
+
+
+def compile_mmap_model(npz_ranker_folder, mmap_folder):
+    lib().c_xlinear_compile_mmap_model(npz_ranker_folder.encode(), mmap_folder.encode())
+
+
+class RefHNSW(object):
+    """Reference HNSW index handle (dense float32, ip or l2)."""
+
+    def __init__(self, handle, metric):
+        self.h, self.metric = handle, metric
+
+    @classmethod
+    def train(cls, X, M=32, efC=100, metric="ip", threads=-1, max_level_upper_bound=-1):
+        L = lib()
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        cx = ScipyDrmF32.init_from(X)
+        h = getattr(L, f"c_ann_hnsw_train_drm_{metric}_f32")(byref(cx), M, efC, threads, max_level_upper_bound)
+        return cls(c_void_p(h), metric)
+
+    @classmethod
+    def load(cls, c_model_dir, metric="ip", lazy_load=False):
+        h = getattr(lib(), f"c_ann_hnsw_load_drm_{metric}_f32")(c_model_dir.encode(), lazy_load)
+        return cls(c_void_p(h), metric)
+
+    def save(self, c_model_dir):
+        os.makedirs(c_model_dir, exist_ok=True)
+        getattr(lib(), f"c_ann_hnsw_save_drm_{self.metric}_f32")(self.h, c_model_dir.encode())
+
+    def predict(self, X, efS, topk, threads=1):
+        L = lib()
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        cx = ScipyDrmF32.init_from(X)
+        idx = np.zeros((X.shape[0], topk), dtype=np.uint32)
+        val = np.zeros((X.shape[0], topk), dtype=np.float32)
+        searchers = c_void_p(getattr(L, f"c_ann_hnsw_searchers_create_drm_{self.metric}_f32")(self.h, max(1, threads)))
+        getattr(L, f"c_ann_hnsw_predict_drm_{self.metric}_f32")(
+            self.h, byref(cx), idx.ctypes.data_as(POINTER(c_uint32)), val.ctypes.data_as(POINTER(c_float)), efS, topk,
+            threads, searchers)
+        getattr(L, f"c_ann_hnsw_searchers_destruct_drm_{self.metric}_f32")(searchers)
+        return idx, val
+
+    def __del__(self):
+        try:
+            if self.h:
+                getattr(lib(), f"c_ann_hnsw_destruct_drm_{self.metric}_f32")(self.h)
+                self.h = None
+        except Exception:
+            pass

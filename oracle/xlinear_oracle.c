@@ -1,0 +1,223 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- CPU restatement ("oracle") of the reference's XR-Linear beam-search prediction.
+ *
+ * Nothing under pecos_b200/ may link, import or call this file; it is used by tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline leg as the checker.  Parity status: PINNED -- tests/test_oracle_cpu.py checks this
+ * restatement bit-for-bit against oracle/_ref (the reference's own libpecos.cpp compiled unmodified) on the reference's
+ * toy fixture (tests/golden) and on random trees (contiguous, permuted and pruned), for every post-processor.
+ *
+ * Plain C, single thread, works directly on the CSC weight / code matrices of each layer (no chunk layout), with the
+ * arithmetic order of the reference's default BINARY_SEARCH_CHUNKED path.  Each function cites the code it restates
+ * (paths relative to the reference checkout):
+ *
+ *   xlo_predict ................ HierarchicalMLModel::predict       pecos/core/xmc/inference.hpp:2446-2488
+ *   layer_predict .............. MLModel::predict_internal          pecos/core/xmc/inference.hpp:2029-2080
+ *   candidates (prolongation) .. prolongate_predictions             pecos/core/xmc/inference.hpp:1155-1219
+ *   score_sparse ............... chunk_ops<csr, bin_search>         pecos/core/xmc/inference.hpp:769-813 (+ :506-518)
+ *   score_dense ................ chunk_ops<drm, bin_search>         pecos/core/xmc/inference.hpp:815-839
+ *   transform / combine ........ PostProcessor<T>::get              pecos/core/xmc/inference.hpp:192-240, :1360-1384
+ *   cmp_desc_then_pos .......... sorted_csr comparator              pecos/core/xmc/inference.hpp:1265-1273
+ *   label mapping .............. rearrangement_t (perm_inv)         pecos/core/xmc/inference.hpp:1745-1784
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+    uint32_t rows, cols;
+    const uint64_t* col_ptr;
+    const uint32_t* row_idx;
+    const float* val;
+} xlo_csc_t;
+
+typedef struct {
+    uint32_t rows, cols;
+    const uint64_t* row_ptr; /* NULL => dense */
+    const uint32_t* col_idx;
+    const float* val;        /* csr values or row-major dense matrix */
+} xlo_query_t;
+
+enum { XLO_NOOP = 0, XLO_SIGMOID = 1, XLO_LOG_SIGMOID = 2, XLO_LP_HINGE = 3, XLO_LOG_LP_HINGE = 4 };
+
+typedef struct {
+    uint64_t* indptr;  /* rows + 1 */
+    uint32_t* indices;
+    float* data;
+    uint64_t nnz;
+    uint32_t rows, cols;
+    /* algorithmic-byte counters of SURVEY.md 8(d), summed over layers: chunks, sum R (needs chunk view: not counted
+       here), matched rows, entries, out cols, query nnz, beam out */
+} xlo_result_t;
+
+static float xlo_transform(float v, int kind, int p) {
+    /* float/double promotion pattern of the reference lambdas (inference.hpp:208-238) */
+    switch (kind) {
+        case XLO_SIGMOID: return (float)(1.0 / (1.0 + expf(-v)));
+        case XLO_LOG_SIGMOID: return (float)(-log(1.0 + expf(-v)));
+        case XLO_LP_HINGE: {
+            float z = (float)fmax(0.0, 1.0 - v);
+            return (float)exp(-pow((double)z, (double)(size_t)p));
+        }
+        case XLO_LOG_LP_HINGE: {
+            float z = (float)fmax(0.0, 1.0 - v);
+            return (float)(-pow((double)z, (double)(size_t)p));
+        }
+        default: return v;
+    }
+}
+
+static float xlo_combine(float x, float parent, int kind) {
+    switch (kind) {
+        case XLO_SIGMOID:
+        case XLO_LP_HINGE: return x * parent;
+        case XLO_LOG_SIGMOID:
+        case XLO_LOG_LP_HINGE: return x + parent;
+        default: return x;
+    }
+}
+
+/* first position t in sorted idx[0..n) with idx[t] >= key (std::lower_bound) */
+static uint32_t lower_bound_u32(const uint32_t* idx, uint32_t n, uint32_t key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (idx[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+/* One output column of a chunk against a sparse query: matched features in ascending index order, un-fused
+ * multiply then add, bias row (feature index rows-1, only when bias > 0) last. */
+static float score_sparse(const xlo_csc_t* W, uint32_t col, const uint32_t* qidx, const float* qval, uint32_t qn, float bias) {
+    const uint64_t b = W->col_ptr[col], e = W->col_ptr[col + 1];
+    const int use_bias = bias > 0.0f;
+    volatile float acc = 0.0f; /* volatile: forbid any re-association / contraction by the compiler */
+    for (uint64_t i = b; i < e; ++i) {
+        const uint32_t r = W->row_idx[i];
+        if (use_bias && r == W->rows - 1) continue; /* handled below */
+        const uint32_t t = lower_bound_u32(qidx, qn, r);
+        if (t < qn && qidx[t] == r) {
+            volatile float prod = qval[t] * W->val[i];
+            acc = acc + prod;
+        }
+    }
+    if (use_bias) {
+        for (uint64_t i = b; i < e; ++i) {
+            if (W->row_idx[i] == W->rows - 1) {
+                volatile float prod = bias * W->val[i];
+                acc = acc + prod;
+            }
+        }
+    }
+    return acc;
+}
+
+/* Dense query: bias row first, then every stored row of the column in ascending order (zeros included). */
+static float score_dense(const xlo_csc_t* W, uint32_t col, const float* x, float bias) {
+    const uint64_t b = W->col_ptr[col], e = W->col_ptr[col + 1];
+    const int use_bias = bias > 0.0f;
+    volatile float acc = 0.0f;
+    if (use_bias) {
+        for (uint64_t i = b; i < e; ++i) {
+            if (W->row_idx[i] == W->rows - 1) {
+                volatile float prod = bias * W->val[i];
+                acc = acc + prod;
+            }
+        }
+    }
+    for (uint64_t i = b; i < e; ++i) {
+        const uint32_t r = W->row_idx[i];
+        if (use_bias && r == W->rows - 1) continue;
+        volatile float prod = x[r] * W->val[i];
+        acc = acc + prod;
+    }
+    return acc;
+}
+
+typedef struct {
+    float val;
+    uint32_t pos;
+    uint32_t label;
+} xlo_cand_t;
+
+static int cmp_desc_then_pos(const void* pa, const void* pb) {
+    const xlo_cand_t* a = (const xlo_cand_t*)pa;
+    const xlo_cand_t* b = (const xlo_cand_t*)pb;
+    if (a->val == b->val) return (a->pos > b->pos) - (a->pos < b->pos);
+    return (a->val > b->val) ? -1 : 1;
+}
+
+/* Sorted-by-row copy of a CSC column is assumed (scipy writes sorted indices; the reference would stable-sort). */
+
+int xlo_predict(int depth, const xlo_csc_t* W, const xlo_csc_t* C, const float* bias, const int* pp_kind,
+                const int* pp_p, const uint32_t* only_topk, const xlo_query_t* X, xlo_result_t* out) {
+    const uint32_t Q = X->rows;
+    /* beam per query: ids / vals, ragged */
+    uint64_t* beam_ptr = (uint64_t*)malloc(sizeof(uint64_t) * ((size_t)Q + 1));
+    uint32_t* beam_id = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(Q ? Q : 1));
+    float* beam_val = (float*)malloc(sizeof(float) * (size_t)(Q ? Q : 1));
+    for (uint32_t q = 0; q < Q; ++q) { beam_ptr[q] = q; beam_id[q] = 0; beam_val[q] = 1.0f; } /* ones(Q x 1) */
+    beam_ptr[Q] = Q;
+    uint32_t out_cols = 1;
+
+    for (int d = 0; d < depth; ++d) {
+        const xlo_csc_t* Wd = &W[d];
+        const xlo_csc_t* Cd = &C[d];
+        const uint32_t k = only_topk[d];
+        /* pass 1: sizes */
+        uint64_t* new_ptr = (uint64_t*)malloc(sizeof(uint64_t) * ((size_t)Q + 1));
+        new_ptr[0] = 0;
+        uint64_t max_cand = 0;
+        for (uint32_t q = 0; q < Q; ++q) {
+            uint64_t n = 0;
+            for (uint64_t j = beam_ptr[q]; j < beam_ptr[q + 1]; ++j) n += Cd->col_ptr[beam_id[j] + 1] - Cd->col_ptr[beam_id[j]];
+            if (n > max_cand) max_cand = n;
+            new_ptr[q + 1] = new_ptr[q] + (n < k ? n : k);
+        }
+        uint32_t* new_id = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(new_ptr[Q] ? new_ptr[Q] : 1));
+        float* new_val = (float*)malloc(sizeof(float) * (size_t)(new_ptr[Q] ? new_ptr[Q] : 1));
+        xlo_cand_t* cand = (xlo_cand_t*)malloc(sizeof(xlo_cand_t) * (size_t)(max_cand ? max_cand : 1));
+        for (uint32_t q = 0; q < Q; ++q) {
+            uint32_t n = 0;
+            const uint32_t* qidx = NULL; const float* qval = NULL; uint32_t qn = 0;
+            const float* xd = NULL;
+            if (X->row_ptr) {
+                qidx = X->col_idx + X->row_ptr[q]; qval = X->val + X->row_ptr[q];
+                qn = (uint32_t)(X->row_ptr[q + 1] - X->row_ptr[q]);
+            } else {
+                xd = X->val + (size_t)q * X->cols;
+            }
+            for (uint64_t j = beam_ptr[q]; j < beam_ptr[q + 1]; ++j) {
+                const uint32_t parent = beam_id[j];
+                for (uint64_t c = Cd->col_ptr[parent]; c < Cd->col_ptr[parent + 1]; ++c) {
+                    const uint32_t label = Cd->row_idx[c]; /* == c when the tree is contiguously ordered */
+                    float raw = X->row_ptr ? score_sparse(Wd, label, qidx, qval, qn, bias[d]) : score_dense(Wd, label, xd, bias[d]);
+                    float v = xlo_transform(raw, pp_kind[d], pp_p[d]);
+                    if (d > 0) v = xlo_combine(v, beam_val[j], pp_kind[d]);
+                    cand[n].val = v; cand[n].pos = n; cand[n].label = label;
+                    ++n;
+                }
+            }
+            qsort(cand, n, sizeof(xlo_cand_t), cmp_desc_then_pos);
+            const uint32_t keep = (uint32_t)(new_ptr[q + 1] - new_ptr[q]);
+            for (uint32_t i = 0; i < keep; ++i) { new_id[new_ptr[q] + i] = cand[i].label; new_val[new_ptr[q] + i] = cand[i].val; }
+        }
+        free(cand);
+        free(beam_ptr); free(beam_id); free(beam_val);
+        beam_ptr = new_ptr; beam_id = new_id; beam_val = new_val;
+        out_cols = Cd->rows; /* W.cols when contiguous, perm.size() when rearranged: both == C.rows */
+    }
+    out->indptr = beam_ptr;
+    out->indices = beam_id;
+    out->data = beam_val;
+    out->nnz = beam_ptr[Q];
+    out->rows = Q;
+    out->cols = out_cols;
+    return 0;
+}
+
+void xlo_free_result(xlo_result_t* r) {
+    free(r->indptr); free(r->indices); free(r->data);
+    r->indptr = NULL; r->indices = NULL; r->data = NULL;
+}

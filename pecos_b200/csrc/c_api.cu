@@ -1,0 +1,287 @@
+// extern "C" boundary of libpecos_b200_float32.so: XR-Linear entry points + pb200_* additions.
+// Signatures mirror pecos/core/libpecos.cpp:116-176 (see include/pecos_b200.h for the per-symbol citations).
+#include "../../include/pecos_b200.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "xlinear_engine.h"
+
+namespace {
+
+std::atomic<int> g_device{0};
+
+[[noreturn]] void die(const char* where, const char* what) {
+    std::fprintf(stderr, "pecos_b200 fatal error in %s: %s\n", where, what);
+    std::fflush(stderr);
+    std::abort();
+}
+
+#define PB200_API_BEGIN try {
+#define PB200_API_END(name)                                  \
+    }                                                        \
+    catch (const std::exception& e) { die(name, e.what()); } \
+    catch (...) { die(name, "unknown exception"); }
+
+struct XLinearHandle {
+    std::unique_ptr<pb200::XLinearEngine> engine;
+};
+
+pb200::XLinearEngine& engine_of(void* ptr) {
+    if (!ptr) throw std::runtime_error("null model handle");
+    return *static_cast<XLinearHandle*>(ptr)->engine;
+}
+
+void emit_result(const pb200::XLinearEngine::Result& r, py_sparse_allocator_t pred_alloc) {
+    // create_pycsr contract (pecos/core/utils/matrix.hpp:300-316): one allocator call, then fill the three arrays.
+    uint64_t nnz = 0;
+    for (uint32_t i = 0; i < r.rows; ++i) nnz += r.cnt[i];
+    uint32_t* indices = nullptr;
+    uint64_t* indptr = nullptr;
+    float* data = nullptr;
+    pred_alloc(false, r.rows, r.out_cols, nnz, &indices, &indptr, &data);
+    if (!indptr || (nnz && (!indices || !data))) throw std::runtime_error("result allocator returned null buffers");
+    uint64_t w = 0;
+    indptr[0] = 0;
+    if (nnz == static_cast<uint64_t>(r.rows) * r.stride) {
+        // every row is full: the fixed-stride device layout already is the CSR payload
+        std::memcpy(indices, r.ids, nnz * sizeof(uint32_t));
+        std::memcpy(data, r.vals, nnz * sizeof(float));
+        for (uint32_t i = 0; i < r.rows; ++i) indptr[i + 1] = static_cast<uint64_t>(i + 1) * r.stride;
+        return;
+    }
+    for (uint32_t i = 0; i < r.rows; ++i) {
+        const uint32_t c = r.cnt[i];
+        std::memcpy(indices + w, r.ids + static_cast<uint64_t>(i) * r.stride, c * sizeof(uint32_t));
+        std::memcpy(data + w, r.vals + static_cast<uint64_t>(i) * r.stride, c * sizeof(float));
+        w += c;
+        indptr[i + 1] = w;
+    }
+}
+
+void* make_engine(std::unique_ptr<pb200::XLinearHostModel> host) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0)
+        throw std::runtime_error("no CUDA device visible: pecos_b200 has no CPU fallback");
+    auto h = new XLinearHandle();
+    h->engine = std::make_unique<pb200::XLinearEngine>(std::move(host), g_device.load());
+    return h;
+}
+
+pb200::DeviceBuffer<unsigned char>* g_flush_buf = nullptr;
+std::mutex g_flush_mutex;
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------ XR-Linear ------------------------------------------------------
+void* c_xlinear_load_model_from_disk(const char* model_path) {
+    PB200_API_BEGIN
+    return make_engine(pb200::load_xlinear_npz_model(model_path, pb200::LT_BINARY_SEARCH_CHUNKED));
+    PB200_API_END("c_xlinear_load_model_from_disk")
+}
+
+void* c_xlinear_load_model_from_disk_ext(const char* model_path, int weight_matrix_type) {
+    PB200_API_BEGIN
+    return make_engine(pb200::load_xlinear_npz_model(model_path, weight_matrix_type));
+    PB200_API_END("c_xlinear_load_model_from_disk_ext")
+}
+
+void* c_xlinear_load_mmap_model_from_disk(const char* model_path, const bool lazy_load) {
+    PB200_API_BEGIN
+    return make_engine(pb200::load_xlinear_mmap_model(model_path, lazy_load));
+    PB200_API_END("c_xlinear_load_mmap_model_from_disk")
+}
+
+void c_xlinear_destruct_model(void* ptr) {
+    PB200_API_BEGIN
+    delete static_cast<XLinearHandle*>(ptr);
+    PB200_API_END("c_xlinear_destruct_model")
+}
+
+uint32_t c_xlinear_get_int_attr(void* ptr, const char* attr) {
+    PB200_API_BEGIN
+    const auto& m = engine_of(ptr).host();
+    if (std::strcmp(attr, "depth") == 0) return m.depth();
+    if (std::strcmp(attr, "nr_features") == 0) return m.nr_features();
+    if (std::strcmp(attr, "nr_labels") == 0) return m.nr_labels();
+    if (std::strcmp(attr, "nr_codes") == 0) return m.nr_codes();
+    throw std::runtime_error(std::string(attr) + " is not implemented in get_int_attr.");
+    PB200_API_END("c_xlinear_get_int_attr")
+}
+
+int c_xlinear_get_layer_type(void* ptr, int layer_depth) {
+    PB200_API_BEGIN
+    const auto& m = engine_of(ptr).host();
+    if (layer_depth < 0 || static_cast<uint32_t>(layer_depth) >= m.depth()) throw std::runtime_error("layer_depth out of range");
+    return m.layer_type;
+    PB200_API_END("c_xlinear_get_layer_type")
+}
+
+void c_xlinear_predict_csr_f32(void* ptr, const ScipyCsrF32* X, const uint32_t overridden_beam_size,
+                               const char* overridden_post_processor_str, const uint32_t overridden_only_topk,
+                               const int threads, py_sparse_allocator_t pred_alloc) {
+    (void)threads;
+    PB200_API_BEGIN
+    auto& eng = engine_of(ptr);
+    auto r = eng.predict_csr(X->row_ptr, X->col_idx, X->val, X->rows, X->cols, overridden_beam_size,
+                             overridden_post_processor_str, overridden_only_topk);
+    emit_result(r, pred_alloc);
+    PB200_API_END("c_xlinear_predict_csr_f32")
+}
+
+void c_xlinear_predict_drm_f32(void* ptr, const ScipyDrmF32* X, const uint32_t overridden_beam_size,
+                               const char* overridden_post_processor_str, const uint32_t overridden_only_topk,
+                               const int threads, py_sparse_allocator_t pred_alloc) {
+    (void)threads;
+    PB200_API_BEGIN
+    auto& eng = engine_of(ptr);
+    if (X->cols != eng.host().nr_features()) throw std::runtime_error("dense query width != nr_features");
+    auto r = eng.predict_drm(X->val, X->rows, X->cols, overridden_beam_size, overridden_post_processor_str,
+                             overridden_only_topk);
+    emit_result(r, pred_alloc);
+    PB200_API_END("c_xlinear_predict_drm_f32")
+}
+
+// ------------------------------------------------ additions ------------------------------------------------------
+const char* pb200_version(void) { return "pecos_b200 0.1 (sm_100a)"; }
+
+int pb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int pb200_set_device(int device) {
+    int n = pb200_device_count();
+    if (device < 0 || device >= n) return 1;
+    g_device.store(device);
+    return cudaSetDevice(device) == cudaSuccess ? 0 : 1;
+}
+
+int pb200_get_device(void) { return g_device.load(); }
+
+void* pb200_host_alloc(size_t bytes) {
+    PB200_API_BEGIN
+    void* p = nullptr;
+    PB200_CUDA(cudaSetDevice(g_device.load()));
+    PB200_CUDA(cudaMallocHost(&p, bytes ? bytes : 1));
+    return p;
+    PB200_API_END("pb200_host_alloc")
+}
+
+void pb200_host_free(void* ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
+void pb200_l2_flush(void) {
+    PB200_API_BEGIN
+    std::lock_guard<std::mutex> lock(g_flush_mutex);
+    PB200_CUDA(cudaSetDevice(g_device.load()));
+    if (!g_flush_buf) g_flush_buf = new pb200::DeviceBuffer<unsigned char>();
+    const uint64_t bytes = 512ull << 20;  // 4x the 126 MB L2
+    g_flush_buf->reserve(bytes);
+    static int tick = 0;
+    PB200_CUDA(cudaMemset(g_flush_buf->get(), (++tick) & 0xFF, bytes));
+    PB200_CUDA(cudaDeviceSynchronize());
+    PB200_API_END("pb200_l2_flush")
+}
+
+void pb200_xlinear_resident_upload_csr(void* ptr, const ScipyCsrF32* X) {
+    PB200_API_BEGIN
+    engine_of(ptr).resident_upload_csr(X->row_ptr, X->col_idx, X->val, X->rows, X->cols);
+    PB200_API_END("pb200_xlinear_resident_upload_csr")
+}
+
+double pb200_xlinear_resident_predict(void* ptr, uint32_t beam, const char* pp, uint32_t topk, int collect_stats) {
+    PB200_API_BEGIN
+    return engine_of(ptr).resident_predict(beam, pp, topk, collect_stats != 0);
+    PB200_API_END("pb200_xlinear_resident_predict")
+}
+
+void pb200_xlinear_resident_fetch(void* ptr, py_sparse_allocator_t pred_alloc) {
+    PB200_API_BEGIN
+    emit_result(engine_of(ptr).resident_fetch(), pred_alloc);
+    PB200_API_END("pb200_xlinear_resident_fetch")
+}
+
+void pb200_xlinear_set_profile(void* ptr, int on) {
+    PB200_API_BEGIN
+    engine_of(ptr).set_profile(on != 0);
+    PB200_API_END("pb200_xlinear_set_profile")
+}
+
+void pb200_xlinear_reset_profile(void* ptr) {
+    PB200_API_BEGIN
+    engine_of(ptr).reset_profile();
+    PB200_API_END("pb200_xlinear_reset_profile")
+}
+
+void pb200_xlinear_get_profile(void* ptr, double* out) {
+    PB200_API_BEGIN
+    const auto& p = engine_of(ptr).layer_profile();
+    for (size_t d = 0; d < p.size(); ++d) { out[2 * d] = p[d].scores_ms; out[2 * d + 1] = p[d].topk_ms; }
+    PB200_API_END("pb200_xlinear_get_profile")
+}
+
+void pb200_xlinear_get_stats(void* ptr, uint64_t* out) {
+    PB200_API_BEGIN
+    const auto& s = engine_of(ptr).layer_stats();
+    for (size_t d = 0; d < s.size(); ++d) {
+        out[7 * d + 0] = s[d].chunks; out[7 * d + 1] = s[d].chunk_rows; out[7 * d + 2] = s[d].matched;
+        out[7 * d + 3] = s[d].entries; out[7 * d + 4] = s[d].out_cols; out[7 * d + 5] = s[d].query_nnz;
+        out[7 * d + 6] = s[d].beam_out;
+    }
+    PB200_API_END("pb200_xlinear_get_stats")
+}
+
+uint64_t pb200_xlinear_launches(void* ptr) {
+    PB200_API_BEGIN
+    return engine_of(ptr).launches();
+    PB200_API_END("pb200_xlinear_launches")
+}
+
+uint64_t pb200_xlinear_model_bytes(void* ptr) {
+    PB200_API_BEGIN
+    return engine_of(ptr).model_bytes();
+    PB200_API_END("pb200_xlinear_model_bytes")
+}
+
+// host-only inspection (no CUDA calls)
+void* pb200_xlinear_host_load(const char* model_path, int kind) {
+    PB200_API_BEGIN
+    std::unique_ptr<pb200::XLinearHostModel> m =
+        kind == 1 ? pb200::load_xlinear_mmap_model(model_path, false)
+                  : pb200::load_xlinear_npz_model(model_path, pb200::LT_BINARY_SEARCH_CHUNKED);
+    return m.release();
+    PB200_API_END("pb200_xlinear_host_load")
+}
+
+void pb200_xlinear_host_free(void* hptr) { delete static_cast<pb200::XLinearHostModel*>(hptr); }
+
+uint32_t pb200_xlinear_host_depth(void* hptr) { return static_cast<pb200::XLinearHostModel*>(hptr)->depth(); }
+
+void pb200_xlinear_host_layer_dims(void* hptr, uint32_t layer, uint64_t* out) {
+    PB200_API_BEGIN
+    const auto& L = static_cast<pb200::XLinearHostModel*>(hptr)->layers.at(layer);
+    out[0] = L.w_rows; out[1] = L.n_cols; out[2] = L.out_cols; out[3] = L.n_chunks; out[4] = L.c_max;
+    out[5] = L.meta.size(); out[6] = L.entries.size(); out[7] = L.label_of_col.size();
+    PB200_API_END("pb200_xlinear_host_layer_dims")
+}
+
+void pb200_xlinear_host_layer_export(void* hptr, uint32_t layer, void* chunks32, uint32_t* meta, void* entries8,
+                                     uint32_t* label_of_col) {
+    PB200_API_BEGIN
+    const auto& L = static_cast<pb200::XLinearHostModel*>(hptr)->layers.at(layer);
+    if (chunks32) std::memcpy(chunks32, L.chunks.data(), L.chunks.size() * sizeof(pb200::ChunkHeader));
+    if (meta) std::memcpy(meta, L.meta.data(), L.meta.size() * 4);
+    if (entries8) std::memcpy(entries8, L.entries.data(), L.entries.size() * 8);
+    if (label_of_col) std::memcpy(label_of_col, L.label_of_col.data(), L.label_of_col.size() * 4);
+    PB200_API_END("pb200_xlinear_host_layer_export")
+}
+
+}  // extern "C"

@@ -1,0 +1,793 @@
+// XR-Linear beam search on B200 (sm_100a): kernels + engine.  See xlinear_engine.h for the reference map.
+//
+// Per tree layer two kernels run over a tile of queries:
+//
+//   xl_chunk_scores_kernel   one CTA per query, one warp per beam slot (= one weight chunk).  The warp streams the
+//                            chunk's sorted row-index list from HBM with 128-bit loads, intersects it with the query's
+//                            sorted feature list held in shared memory, gathers the matched rows' {col,val} entries and
+//                            accumulates them into the chunk's dense output block IN THE REFERENCE'S ORDER:
+//                            ascending feature index, separate round-to-nearest multiply and add, bias row last
+//                            (inference.hpp:788-811; dense queries: bias first, inference.hpp:823-837).
+//                            HBM-bound; algorithmic bytes per (query, chunk) = 32 + 4R + 16m + 8e + 4c  (SURVEY 8d).
+//
+//   xl_topk_kernel           one CTA per query: post-processor transform in double precision (inference.hpp:208-238),
+//                            combine with the parent's path score, then exact top-k on the composite key
+//                            (score desc, position-in-prolongated-row asc) == sorted_csr's comparator
+//                            (inference.hpp:1265-1273).  Bitonic sort of 64-bit keys in shared memory.
+//
+// No FMA contraction anywhere on the score path: products use __fmul_rn, sums use __fadd_rn (the reference build has
+// no -march flag, so its XR-Linear loops are scalar mulss/addss).
+#include "xlinear_engine.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace pb200 {
+
+namespace {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr int kWarpsMax = 8;     // warps per CTA of the chunk kernel
+constexpr int kMCap = 256;       // match list capacity per warp
+constexpr int kMFlush = 128;     // flush the match list once it holds this many rows (kMCap - 128 new per pass)
+constexpr int kECap = 256;       // staged entries per accumulate pass
+constexpr int kCSmem = 128;      // chunk widths up to this accumulate in shared memory, wider ones in the HBM block
+constexpr int kQCap = 1024;      // query non-zeros staged in shared memory (longer queries are read through L1/L2)
+constexpr int kSortCap = 2048;   // keys sorted in shared memory per pass of the top-k kernel
+constexpr int kTopkThreads = 256;
+
+struct __align__(16) WarpScratch {
+    uint32_t ms[kMCap];        // chunk-row index of each match; becomes the row's first entry offset during flush
+    float mx[kMCap];           // multiplier of the row: query value, or the bias
+    uint32_t off[kMCap + 4];   // exclusive prefix of the matched rows' entry counts
+    uint2 stage[kECap];        // staged {col_offset, bits of x*w}
+    float out[kCSmem];         // dense output block of the chunk
+};
+
+__device__ __forceinline__ uint4 ld_stream_u4(const uint32_t* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ int lower_bound_u32(const uint32_t* a, int n, uint32_t key) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// largest i in [0, n) with a[i] <= key, given a[0] <= key
+__device__ __forceinline__ int last_le_u32(const uint32_t* a, int n, uint32_t key) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (a[mid] <= key) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(kFull, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// Apply the matched rows collected in ws (in ascending feature order) to the output block.
+__device__ __noinline__ void xl_flush(WarpScratch& ws, int m, const uint32_t* __restrict__ rp,
+                                      const uint2* __restrict__ ent, float* out, int has_dup, int lane,
+                                      unsigned long long& e_total) {
+    if (m == 0) return;
+    __syncwarp();
+    constexpr int PER = kMCap / 32;
+    uint32_t a[PER], c[PER];
+    uint32_t local = 0;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int i = lane * PER + u;
+        a[u] = 0; c[u] = 0;
+        if (i < m) {
+            const uint32_t s = ws.ms[i];
+            const uint32_t lo = __ldg(rp + s);
+            const uint32_t hi = __ldg(rp + s + 1);
+            a[u] = lo; c[u] = hi - lo;
+        }
+        local += c[u];
+    }
+    const uint32_t incl = warp_incl_scan(local, lane);
+    uint32_t run = incl - local;
+    const uint32_t total = __shfl_sync(kFull, incl, 31);
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int i = lane * PER + u;
+        if (i < m) { ws.ms[i] = a[u]; ws.off[i] = run; run += c[u]; }
+    }
+    if (lane == 0) ws.off[m] = total;
+    __syncwarp();
+    e_total += total;
+
+    for (uint32_t t0 = 0; t0 < total; t0 += kECap) {
+        const uint32_t tn = min(static_cast<uint32_t>(kECap), total - t0);
+        for (uint32_t g = lane; g < tn; g += 32) {
+            const uint32_t G = t0 + g;
+            const int i = last_le_u32(ws.off, m, G);
+            const uint2 en = __ldg(ent + ws.ms[i] + (G - ws.off[i]));
+            const float prod = __fmul_rn(ws.mx[i], __uint_as_float(en.y));
+            ws.stage[g] = make_uint2(en.x, __float_as_uint(prod));
+        }
+        __syncwarp();
+        const int i_lo = last_le_u32(ws.off, m, t0);
+        const int i_hi = last_le_u32(ws.off, m, t0 + tn - 1);
+        for (int i = i_lo; i <= i_hi; ++i) {
+            const uint32_t lo = max(ws.off[i], t0) - t0;
+            const uint32_t hi = min(ws.off[i + 1], t0 + tn) - t0;
+            if (!has_dup) {
+                // entries of one chunk row carry distinct columns: lanes never collide
+                for (uint32_t g = lo + lane; g < hi; g += 32) {
+                    const uint2 s = ws.stage[g];
+                    out[s.x] = __fadd_rn(out[s.x], __uint_as_float(s.y));
+                }
+            } else if (lane == 0) {
+                for (uint32_t g = lo; g < hi; ++g) {
+                    const uint2 s = ws.stage[g];
+                    out[s.x] = __fadd_rn(out[s.x], __uint_as_float(s.y));
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+template <bool DENSE, bool STATS>
+__global__ void __launch_bounds__(kWarpsMax * 32)
+xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __restrict__ beam_id,
+                       const uint32_t* __restrict__ beam_cnt, const uint32_t beam_stride, float* __restrict__ cand,
+                       const uint64_t cand_stride_q, const uint32_t c_stride, unsigned long long* stats) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* q_idx_s = reinterpret_cast<uint32_t*>(smem_raw);
+    float* q_val_s = reinterpret_cast<float*>(smem_raw + kQCap * 4);
+    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem_raw + kQCap * 8);
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const uint32_t q = blockIdx.x;
+
+    const uint32_t* qidx = nullptr;
+    const float* qval = nullptr;
+    int qn = 0;
+    if (!DENSE) {
+        const uint64_t b = X.row_ptr[q] - X.nnz_base;
+        const uint64_t e = X.row_ptr[q + 1] - X.nnz_base;
+        qn = static_cast<int>(e - b);
+        const uint32_t* gi = X.col_idx + b;
+        const float* gv = X.val + b;
+        if (qn <= kQCap) {
+            for (int i = threadIdx.x; i < qn; i += blockDim.x) { q_idx_s[i] = gi[i]; q_val_s[i] = gv[i]; }
+            qidx = q_idx_s; qval = q_val_s;
+        } else {
+            qidx = gi; qval = gv;
+        }
+        __syncthreads();
+    } else {
+        qval = X.val + static_cast<uint64_t>(q) * X.cols;
+    }
+
+    const uint32_t cnt = beam_cnt[q];
+    WarpScratch& ws = scratch[warp];
+    unsigned long long st_chunks = 0, st_rows = 0, st_match = 0, st_ent = 0, st_cols = 0;
+
+    for (uint32_t j = warp; j < cnt; j += nwarps) {
+        const uint32_t p = beam_id[static_cast<uint64_t>(q) * beam_stride + j];
+        const ChunkHeader h = L.chunks[p];
+        const uint32_t R = h.nnz_rows;
+        const uint32_t R4 = (R + 3u) & ~3u;
+        const uint32_t* ridx = L.meta + h.meta_off;
+        const uint32_t* rp = ridx + R4;
+        const uint2* ent = L.entries + h.ent_off;
+        float* blk = cand + static_cast<uint64_t>(q) * cand_stride_q + static_cast<uint64_t>(j) * c_stride;
+        const bool in_smem = h.n_cols <= static_cast<uint32_t>(kCSmem);
+        float* out = in_smem ? ws.out : blk;
+        for (uint32_t c = lane; c < h.n_cols; c += 32) out[c] = 0.0f;
+        __syncwarp();
+
+        int m = 0;
+        unsigned long long e_total = 0, m_total = 0;
+
+        if (DENSE) {
+            // chunk_ops<drm, bin_search>: bias row first, then every chunk row (inference.hpp:823-837)
+            const uint32_t r_lim = h.has_bias ? R - 1u : R;
+            if (h.has_bias) {
+                if (lane == 0) { ws.ms[0] = R - 1u; ws.mx[0] = L.bias; }
+                m = 1;
+                __syncwarp();
+            }
+            for (uint32_t base = 0; base < r_lim; base += 128u) {
+                const uint32_t i = base + lane * 4u;
+                const uint32_t n_here = (i < r_lim) ? min(4u, r_lim - i) : 0u;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (n_here) v = ld_stream_u4(ridx + i);
+                const uint32_t incl = warp_incl_scan(n_here, lane);
+                const uint32_t tot = __shfl_sync(kFull, incl, 31);
+                uint32_t pos = m + incl - n_here;
+                if (n_here > 0) { ws.ms[pos] = i; ws.mx[pos] = qval[v.x]; }
+                if (n_here > 1) { ws.ms[pos + 1] = i + 1; ws.mx[pos + 1] = qval[v.y]; }
+                if (n_here > 2) { ws.ms[pos + 2] = i + 2; ws.mx[pos + 2] = qval[v.z]; }
+                if (n_here > 3) { ws.ms[pos + 3] = i + 3; ws.mx[pos + 3] = qval[v.w]; }
+                m += static_cast<int>(tot);
+                if (m >= kMFlush) {
+                    m_total += m;
+                    xl_flush(ws, m, rp, ent, out, L.has_dup_cols, lane, e_total);
+                    m = 0;
+                }
+            }
+        } else {
+            // chunk_ops<csr, bin_search>: matched rows in ascending feature order, bias row last (inference.hpp:788-811)
+            if (qn > 0 && R > 0) {
+                const uint32_t qmin = qidx[0];
+                const uint32_t qmax = qidx[qn - 1];
+                const uint4 sentinel = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                uint32_t i = lane * 4u;
+                uint4 v_next = (i < R4) ? ld_stream_u4(ridx + i) : sentinel;
+                for (uint32_t base = 0; base < R4; base += 128u) {
+                    const uint4 v = v_next;
+                    i = base + lane * 4u;
+                    const uint32_t i_n = i + 128u;
+                    v_next = (i_n < R4) ? ld_stream_u4(ridx + i_n) : sentinel;
+                    const uint32_t first = __shfl_sync(kFull, v.x, 0);
+                    if (first > qmax) break;  // the remaining (sorted) chunk rows lie beyond the query's last feature
+                    int t0 = -1, t1 = -1, t2 = -1, t3 = -1;
+                    if (v.x >= qmin && v.x <= qmax) { int t = lower_bound_u32(qidx, qn, v.x); if (t < qn && qidx[t] == v.x) t0 = t; }
+                    if (v.y >= qmin && v.y <= qmax) { int t = lower_bound_u32(qidx, qn, v.y); if (t < qn && qidx[t] == v.y) t1 = t; }
+                    if (v.z >= qmin && v.z <= qmax) { int t = lower_bound_u32(qidx, qn, v.z); if (t < qn && qidx[t] == v.z) t2 = t; }
+                    if (v.w >= qmin && v.w <= qmax) { int t = lower_bound_u32(qidx, qn, v.w); if (t < qn && qidx[t] == v.w) t3 = t; }
+                    const uint32_t n_here = (t0 >= 0) + (t1 >= 0) + (t2 >= 0) + (t3 >= 0);
+                    if (__ballot_sync(kFull, n_here > 0) == 0u) continue;
+                    const uint32_t incl = warp_incl_scan(n_here, lane);
+                    const uint32_t tot = __shfl_sync(kFull, incl, 31);
+                    uint32_t pos = m + incl - n_here;
+                    if (t0 >= 0) { ws.ms[pos] = i; ws.mx[pos] = qval[t0]; ++pos; }
+                    if (t1 >= 0) { ws.ms[pos] = i + 1; ws.mx[pos] = qval[t1]; ++pos; }
+                    if (t2 >= 0) { ws.ms[pos] = i + 2; ws.mx[pos] = qval[t2]; ++pos; }
+                    if (t3 >= 0) { ws.ms[pos] = i + 3; ws.mx[pos] = qval[t3]; ++pos; }
+                    m += static_cast<int>(tot);
+                    if (m >= kMFlush) {
+                        m_total += m;
+                        xl_flush(ws, m, rp, ent, out, L.has_dup_cols, lane, e_total);
+                        m = 0;
+                    }
+                }
+            }
+            if (h.has_bias) {
+                __syncwarp();
+                if (lane == 0) { ws.ms[m] = R - 1u; ws.mx[m] = L.bias; }
+                ++m;
+            }
+        }
+        m_total += m;
+        xl_flush(ws, m, rp, ent, out, L.has_dup_cols, lane, e_total);
+        __syncwarp();
+        if (in_smem) {
+            for (uint32_t c = lane; c < h.n_cols; c += 32) blk[c] = ws.out[c];
+        }
+        __syncwarp();
+        if (STATS) { st_chunks += 1; st_rows += R; st_match += m_total; st_ent += e_total; st_cols += h.n_cols; }
+    }
+    if (STATS) {
+        if (lane == 0 && st_chunks) {
+            atomicAdd(&stats[0], st_chunks);
+            atomicAdd(&stats[1], st_rows);
+            atomicAdd(&stats[2], st_match);
+            atomicAdd(&stats[3], st_ent);
+            atomicAdd(&stats[4], st_cols);
+        }
+        if (threadIdx.x == 0 && cnt > 0) atomicAdd(&stats[5], static_cast<unsigned long long>(DENSE ? X.cols : qn));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// post-processor (inference.hpp:208-238).  The reference evaluates these through double precision libm calls and
+// narrows to float; we do the same arithmetic with CUDA's double routines.  exp/log may differ from glibc in the last
+// ulp of the DOUBLE result, which survives the narrowing to float only with probability ~2^-29 per element.
+// Integer powers p <= 4 are formed by exact/singly-rounded multiplications (== correctly rounded pow).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double xl_hinge_pow(float v, int p) {
+    const double zd = fmax(0.0, 1.0 - static_cast<double>(v));
+    const float z = static_cast<float>(zd);
+    const double x = static_cast<double>(z);
+    switch (p) {
+        case 0: return 1.0;
+        case 1: return x;
+        case 2: return x * x;
+        case 3: return (x * x) * x;
+        case 4: { const double x2 = x * x; return x2 * x2; }
+        default: return pow(x, static_cast<double>(static_cast<size_t>(static_cast<long long>(p))));
+    }
+}
+
+__device__ __forceinline__ float xl_transform(float v, int kind, int p) {
+    switch (kind) {
+        case PP_SIGMOID: {
+            const float e = static_cast<float>(exp(static_cast<double>(-v)));  // expf(-v), correctly rounded
+            return static_cast<float>(1.0 / (1.0 + static_cast<double>(e)));
+        }
+        case PP_LOG_SIGMOID: {
+            const float e = static_cast<float>(exp(static_cast<double>(-v)));
+            return static_cast<float>(-log(1.0 + static_cast<double>(e)));
+        }
+        case PP_LP_HINGE: return static_cast<float>(exp(-xl_hinge_pow(v, p)));
+        case PP_LOG_LP_HINGE: return static_cast<float>(-xl_hinge_pow(v, p));
+        default: return v;
+    }
+}
+
+__device__ __forceinline__ float xl_combine(float x, float parent, int kind) {
+    switch (kind) {
+        case PP_SIGMOID:
+        case PP_LP_HINGE: return __fmul_rn(x, parent);
+        case PP_LOG_SIGMOID:
+        case PP_LOG_LP_HINGE: return __fadd_rn(x, parent);
+        default: return x;
+    }
+}
+
+__device__ __forceinline__ unsigned long long xl_make_key(float v, uint32_t pos) {
+    uint32_t u = __float_as_uint(v);
+    if ((u & 0x7FFFFFFFu) == 0u) u = 0u;  // -0.0 and +0.0 compare equal in the reference comparator
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return (static_cast<unsigned long long>(u) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - pos);
+}
+
+// descending bitonic sort of n (power of two) keys; a may live in shared or global memory
+__device__ void xl_bitonic_desc(unsigned long long* a, uint32_t n) {
+    for (uint32_t k = 2; k <= n; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                const uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long x = a[i], y = a[ixj];
+                    const bool desc_block = ((i & k) == 0);
+                    if (desc_block ? (x < y) : (x > y)) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t next_pow2_u32(uint32_t v) {
+    if (v <= 2) return 2;
+    return 1u << (32 - __clz(v - 1));
+}
+
+__global__ void __launch_bounds__(kTopkThreads)
+xl_topk_kernel(const LayerDev L, const int pp_kind, const int pp_p, const int combine, const uint32_t k,
+               const uint32_t* __restrict__ beam_id, const float* __restrict__ beam_val,
+               const uint32_t* __restrict__ beam_cnt, const uint32_t beam_stride, const float* __restrict__ cand,
+               const uint64_t cand_stride_q, const uint32_t c_stride, uint32_t* __restrict__ out_id,
+               float* __restrict__ out_val, uint32_t* __restrict__ out_cnt, const uint32_t out_stride,
+               unsigned long long* sortbuf, const uint64_t sortbuf_stride, const uint32_t b_prev,
+               unsigned long long* stats) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+    uint32_t* s_base = reinterpret_cast<uint32_t*>(smem_raw + kSortCap * 8);  // [b_prev + 1]
+    uint32_t* s_colbeg = s_base + (b_prev + 1);                               // [b_prev]
+    float* s_pval = reinterpret_cast<float*>(s_colbeg + b_prev);              // [b_prev]
+
+    const uint32_t q = blockIdx.x;
+    const uint32_t cnt = beam_cnt[q];
+    for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
+        const uint32_t p = beam_id[static_cast<uint64_t>(q) * beam_stride + j];
+        const ChunkHeader h = L.chunks[p];
+        s_base[j + 1] = h.n_cols;
+        s_colbeg[j] = h.col_begin;
+        s_pval[j] = beam_val[static_cast<uint64_t>(q) * beam_stride + j];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        s_base[0] = 0;
+        for (uint32_t j = 0; j < cnt; ++j) { run += s_base[j + 1]; s_base[j + 1] = run; }
+    }
+    __syncthreads();
+    const uint32_t n_valid = s_base[cnt];
+    const uint32_t kk = min(k, n_valid);
+    if (threadIdx.x == 0) {
+        out_cnt[q] = kk;
+        if (stats) atomicAdd(&stats[6], static_cast<unsigned long long>(kk));
+    }
+    if (n_valid == 0) return;
+
+    const float* cq = cand + static_cast<uint64_t>(q) * cand_stride_q;
+    auto score_at = [&](uint32_t cpos, uint32_t& label) -> float {
+        const uint32_t j = static_cast<uint32_t>(last_le_u32(s_base, static_cast<int>(cnt), cpos));
+        const uint32_t off = cpos - s_base[j];
+        float v = xl_transform(cq[static_cast<uint64_t>(j) * c_stride + off], pp_kind, pp_p);
+        if (combine) v = xl_combine(v, s_pval[j], pp_kind);
+        label = s_colbeg[j] + off;
+        return v;
+    };
+
+    unsigned long long* sorted = keys;
+    if (n_valid <= static_cast<uint32_t>(kSortCap)) {
+        const uint32_t P = next_pow2_u32(n_valid);
+        for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+            unsigned long long key = 0ull;
+            if (i < n_valid) { uint32_t lab; key = xl_make_key(score_at(i, lab), i); }
+            keys[i] = key;
+        }
+        __syncthreads();
+        xl_bitonic_desc(keys, P);
+    } else if (k <= static_cast<uint32_t>(kSortCap / 2)) {
+        // streaming: keys[0, KP) hold the best so far, keys[KP, kSortCap) the next tile of candidates
+        const uint32_t KP = next_pow2_u32(k);
+        const uint32_t tile = kSortCap - KP;
+        for (uint32_t i = threadIdx.x; i < KP; i += blockDim.x) keys[i] = 0ull;
+        for (uint32_t t0 = 0; t0 < n_valid; t0 += tile) {
+            for (uint32_t i = threadIdx.x; i < tile; i += blockDim.x) {
+                const uint32_t cpos = t0 + i;
+                unsigned long long key = 0ull;
+                if (cpos < n_valid) { uint32_t lab; key = xl_make_key(score_at(cpos, lab), cpos); }
+                keys[KP + i] = key;
+            }
+            __syncthreads();
+            xl_bitonic_desc(keys, kSortCap);
+        }
+    } else {
+        // wide beam AND large k: sort the whole candidate list in the HBM scratch
+        sorted = sortbuf + static_cast<uint64_t>(q) * sortbuf_stride;
+        const uint32_t P = next_pow2_u32(n_valid);
+        for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+            unsigned long long key = 0ull;
+            if (i < n_valid) { uint32_t lab; key = xl_make_key(score_at(i, lab), i); }
+            sorted[i] = key;
+        }
+        __syncthreads();
+        xl_bitonic_desc(sorted, P);
+    }
+
+    for (uint32_t r = threadIdx.x; r < kk; r += blockDim.x) {
+        const uint32_t cpos = 0xFFFFFFFFu - static_cast<uint32_t>(sorted[r] & 0xFFFFFFFFull);
+        uint32_t label;
+        const float v = score_at(cpos, label);  // recomputed so that the stored value keeps its exact bits (-0.0)
+        if (L.label_of_col) label = L.label_of_col[label];
+        out_id[static_cast<uint64_t>(q) * out_stride + r] = label;
+        out_val[static_cast<uint64_t>(q) * out_stride + r] = v;
+    }
+}
+
+__global__ void xl_init_beam_kernel(uint32_t* beam_id, float* beam_val, uint32_t* beam_cnt, uint32_t beam_stride,
+                                    uint32_t rows) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < rows) {
+        beam_id[static_cast<uint64_t>(q) * beam_stride] = 0u;   // prev_layer_pred = ones(Q x 1) (inference.hpp:2462-2463)
+        beam_val[static_cast<uint64_t>(q) * beam_stride] = 1.0f;
+        beam_cnt[q] = 1u;
+    }
+}
+
+uint32_t next_pow2_host(uint64_t v) {
+    uint64_t p = 2;
+    while (p < v) p <<= 1;
+    return static_cast<uint32_t>(p);
+}
+
+size_t chunk_kernel_smem(int warps) { return static_cast<size_t>(kQCap) * 8 + static_cast<size_t>(warps) * sizeof(WarpScratch); }
+size_t topk_kernel_smem(uint32_t b_prev) { return static_cast<size_t>(kSortCap) * 8 + (static_cast<size_t>(b_prev) * 3 + 1) * 4; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------------------------------------
+XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device) : host_(std::move(host)), device_(device) {
+    PB200_CUDA(cudaSetDevice(device_));
+    PB200_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    for (auto& e : ev_) PB200_CUDA(cudaEventCreate(&e));
+    layers_.resize(host_->layers.size());
+    for (size_t d = 0; d < layers_.size(); ++d) {
+        auto& src = host_->layers[d];
+        auto& dst = layers_[d];
+        dst.chunks.upload(src.chunks.data(), src.chunks.size(), stream_);
+        dst.meta.upload(src.meta.data(), src.meta.size(), stream_);
+        dst.entries.upload(reinterpret_cast<const uint2*>(src.entries.data()), src.entries.size(), stream_);
+        if (src.reordered) dst.label_of_col.upload(src.label_of_col.data(), src.label_of_col.size(), stream_);
+        dst.view.chunks = dst.chunks.get();
+        dst.view.meta = dst.meta.get();
+        dst.view.entries = dst.entries.get();
+        dst.view.label_of_col = src.reordered ? dst.label_of_col.get() : nullptr;
+        dst.view.n_cols = src.n_cols;
+        dst.view.n_chunks = src.n_chunks;
+        dst.view.c_max = src.c_max;
+        dst.view.w_rows = src.w_rows;
+        dst.view.bias = src.bias;
+        dst.view.has_dup_cols = src.has_dup_cols ? 1 : 0;
+        model_bytes_ += src.chunks.size() * sizeof(ChunkHeader) + src.meta.size() * 4 + src.entries.size() * 8 +
+                        src.label_of_col.size() * 4;
+    }
+    PB200_CUDA(cudaStreamSynchronize(stream_));
+    // host copies of the big arrays are no longer needed
+    for (auto& l : host_->layers) {
+        std::vector<uint32_t>().swap(l.meta);
+        std::vector<ChunkEntry>().swap(l.entries);
+    }
+    const int max_smem = 200 * 1024;
+    PB200_CUDA(cudaFuncSetAttribute(xl_chunk_scores_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(xl_chunk_scores_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(xl_chunk_scores_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(xl_chunk_scores_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(xl_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    stats_dev_.reserve(8 * layers_.size());
+    layer_profile_.assign(layers_.size(), XLinearLayerProfile{});
+    layer_stats_.assign(layers_.size(), XLinearStats{});
+}
+
+XLinearEngine::~XLinearEngine() {
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    for (auto& e : ev_) if (e) cudaEventDestroy(e);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+void XLinearEngine::reset_profile() {
+    layer_profile_.assign(layers_.size(), XLinearLayerProfile{});
+    launches_ = 0;
+}
+
+std::vector<XLinearEngine::LayerPlan> XLinearEngine::make_plan_(uint32_t beam_size, const char* post_processor,
+                                                                 uint32_t only_topk) const {
+    const size_t depth = layers_.size();
+    std::vector<LayerPlan> plan(depth);
+    uint32_t b_prev = 1;
+    for (size_t d = 0; d < depth; ++d) {
+        const auto& L = host_->layers[d];
+        // local_only_topk (inference.hpp:2471) then only_topk_to_use (inference.hpp:2055)
+        const uint32_t local = (d + 1 == depth) ? only_topk : beam_size;
+        const uint32_t k = local > 0 ? local : static_cast<uint32_t>(L.only_topk);
+        plan[d].k = k;
+        plan[d].pp = post_processor ? parse_post_processor(post_processor) : L.post_processor;
+        plan[d].b_prev = b_prev;
+        const uint64_t cand_max = static_cast<uint64_t>(b_prev) * std::max<uint32_t>(L.c_max, 1u);
+        plan[d].k_cap = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(k, cand_max)));
+        if (topk_kernel_smem(b_prev) > 200u * 1024u)
+            throw std::runtime_error("pecos_b200: beam of " + std::to_string(b_prev) + " nodes exceeds the supported maximum");
+        b_prev = plan[d].k_cap;
+    }
+    return plan;
+}
+
+uint32_t XLinearEngine::pick_tile_rows_(const std::vector<LayerPlan>& plan, uint32_t rows) const {
+    uint64_t budget = 8ull << 30;
+    if (const char* env = std::getenv("PB200_WORKSPACE_MB")) budget = std::max<uint64_t>(64, std::strtoull(env, nullptr, 10)) << 20;
+    uint64_t per_query = 16;
+    uint64_t beam_stride = 1, cand_max = 1, sort_max = 0;
+    for (size_t d = 0; d < plan.size(); ++d) {
+        const uint64_t c = static_cast<uint64_t>(plan[d].b_prev) * std::max<uint32_t>(host_->layers[d].c_max, 1u);
+        cand_max = std::max(cand_max, c);
+        beam_stride = std::max<uint64_t>(beam_stride, plan[d].k_cap);
+        if (c > static_cast<uint64_t>(kSortCap) && plan[d].k > static_cast<uint32_t>(kSortCap / 2)) sort_max = std::max<uint64_t>(sort_max, next_pow2_host(c));
+    }
+    per_query += 2 * beam_stride * 8 + cand_max * 4 + sort_max * 8;
+    uint64_t tile = std::max<uint64_t>(1, budget / per_query);
+    return static_cast<uint32_t>(std::min<uint64_t>(tile, std::max<uint32_t>(rows, 1u)));
+}
+
+void XLinearEngine::ensure_workspace_(const std::vector<LayerPlan>& plan, uint32_t tile_rows) {
+    uint64_t beam_stride = 1, cand_max = 1, sort_max = 0;
+    for (size_t d = 0; d < plan.size(); ++d) {
+        const uint64_t c = static_cast<uint64_t>(plan[d].b_prev) * std::max<uint32_t>(host_->layers[d].c_max, 1u);
+        cand_max = std::max(cand_max, c);
+        beam_stride = std::max<uint64_t>(beam_stride, plan[d].k_cap);
+        if (c > static_cast<uint64_t>(kSortCap) && plan[d].k > static_cast<uint32_t>(kSortCap / 2)) sort_max = std::max<uint64_t>(sort_max, next_pow2_host(c));
+    }
+    beam_stride_ = static_cast<uint32_t>(beam_stride);
+    for (int b = 0; b < 2; ++b) {
+        beam_id_[b].reserve(static_cast<uint64_t>(tile_rows) * beam_stride);
+        beam_val_[b].reserve(static_cast<uint64_t>(tile_rows) * beam_stride);
+        beam_cnt_[b].reserve(tile_rows);
+    }
+    cand_.reserve(static_cast<uint64_t>(tile_rows) * cand_max);
+    if (sort_max) sortbuf_.reserve(static_cast<uint64_t>(tile_rows) * sort_max);
+}
+
+// Runs every layer over one tile of queries.  The last layer writes into res_*_dev_ at row offset res_row0_.
+void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& plan, bool collect_stats) {
+    const uint32_t rows = q.rows;
+    if (rows == 0) return;
+    const bool dense = (q.row_ptr == nullptr);
+    int cur = 0;
+    xl_init_beam_kernel<<<(rows + 255) / 256, 256, 0, stream_>>>(beam_id_[cur].get(), beam_val_[cur].get(),
+                                                                 beam_cnt_[cur].get(), beam_stride_, rows);
+    ++launches_;
+    const size_t depth = plan.size();
+    for (size_t d = 0; d < depth; ++d) {
+        const LayerDev& L = layers_[d].view;
+        const LayerPlan& lp = plan[d];
+        const uint32_t c_stride = std::max<uint32_t>(L.c_max, 1u);
+        const uint64_t cand_stride_q = static_cast<uint64_t>(lp.b_prev) * c_stride;
+        const int warps = static_cast<int>(std::max<uint32_t>(1, std::min<uint32_t>(lp.b_prev, kWarpsMax)));
+        unsigned long long* stats = collect_stats ? stats_dev_.get() + 8 * d : nullptr;
+        if (profile_) PB200_CUDA(cudaEventRecord(ev_[0], stream_));
+        const dim3 grid(rows), block(warps * 32);
+        const size_t smem1 = chunk_kernel_smem(warps);
+        if (dense) {
+            if (collect_stats) xl_chunk_scores_kernel<true, true><<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(), cand_stride_q, c_stride, stats);
+            else xl_chunk_scores_kernel<true, false><<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(), cand_stride_q, c_stride, stats);
+        } else {
+            if (collect_stats) xl_chunk_scores_kernel<false, true><<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(), cand_stride_q, c_stride, stats);
+            else xl_chunk_scores_kernel<false, false><<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(), cand_stride_q, c_stride, stats);
+        }
+        PB200_CUDA(cudaGetLastError());
+        ++launches_;
+        if (profile_) PB200_CUDA(cudaEventRecord(ev_[1], stream_));
+
+        const bool last = (d + 1 == depth);
+        uint32_t* o_id; float* o_val; uint32_t* o_cnt; uint32_t o_stride;
+        if (last) {
+            o_id = res_ids_dev_.get() + static_cast<uint64_t>(res_rows_) * res_stride_;
+            o_val = res_vals_dev_.get() + static_cast<uint64_t>(res_rows_) * res_stride_;
+            o_cnt = res_cnt_dev_.get() + res_rows_;
+            o_stride = res_stride_;
+        } else {
+            o_id = beam_id_[cur ^ 1].get(); o_val = beam_val_[cur ^ 1].get(); o_cnt = beam_cnt_[cur ^ 1].get();
+            o_stride = beam_stride_;
+        }
+        const uint64_t sort_stride = next_pow2_host(cand_stride_q);
+        xl_topk_kernel<<<grid, kTopkThreads, topk_kernel_smem(lp.b_prev), stream_>>>(
+            L, lp.pp.kind, lp.pp.p, d == 0 ? 0 : 1, lp.k, beam_id_[cur].get(), beam_val_[cur].get(), beam_cnt_[cur].get(),
+            beam_stride_, cand_.get(), cand_stride_q, c_stride, o_id, o_val, o_cnt, o_stride, sortbuf_.get(), sort_stride,
+            lp.b_prev, stats);
+        PB200_CUDA(cudaGetLastError());
+        ++launches_;
+        if (profile_) {
+            PB200_CUDA(cudaEventRecord(ev_[2], stream_));
+            PB200_CUDA(cudaEventSynchronize(ev_[2]));
+            float a = 0.f, b = 0.f;
+            PB200_CUDA(cudaEventElapsedTime(&a, ev_[0], ev_[1]));
+            PB200_CUDA(cudaEventElapsedTime(&b, ev_[1], ev_[2]));
+            layer_profile_[d].scores_ms += a;
+            layer_profile_[d].topk_ms += b;
+            layer_profile_[d].launches += 2;
+        }
+        cur ^= 1;
+    }
+}
+
+XLinearEngine::Result XLinearEngine::finish_result_(uint32_t rows, uint32_t stride) {
+    out_ids_.reserve(static_cast<uint64_t>(rows) * stride + 1);
+    out_vals_.reserve(static_cast<uint64_t>(rows) * stride + 1);
+    out_cnt_.reserve(static_cast<uint64_t>(rows) + 1);
+    if (rows) {
+        PB200_CUDA(cudaMemcpyAsync(out_ids_.get(), res_ids_dev_.get(), static_cast<uint64_t>(rows) * stride * 4, cudaMemcpyDeviceToHost, stream_));
+        PB200_CUDA(cudaMemcpyAsync(out_vals_.get(), res_vals_dev_.get(), static_cast<uint64_t>(rows) * stride * 4, cudaMemcpyDeviceToHost, stream_));
+        PB200_CUDA(cudaMemcpyAsync(out_cnt_.get(), res_cnt_dev_.get(), static_cast<uint64_t>(rows) * 4, cudaMemcpyDeviceToHost, stream_));
+    }
+    PB200_CUDA(cudaStreamSynchronize(stream_));
+    Result r;
+    r.rows = rows;
+    r.stride = stride;
+    r.out_cols = host_->layers.back().out_cols;
+    r.ids = out_ids_.get();
+    r.vals = out_vals_.get();
+    r.cnt = out_cnt_.get();
+    return r;
+}
+
+XLinearEngine::Result XLinearEngine::predict_csr(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val,
+                                                 uint32_t rows, uint32_t cols, uint32_t beam_size,
+                                                 const char* post_processor, uint32_t only_topk) {
+    PB200_CUDA(cudaSetDevice(device_));
+    const auto plan = make_plan_(beam_size, post_processor, only_topk);
+    const uint32_t tile = pick_tile_rows_(plan, rows);
+    ensure_workspace_(plan, tile);
+    const uint32_t stride = plan.back().k_cap;
+    res_stride_ = stride;
+    res_ids_dev_.reserve(static_cast<uint64_t>(rows) * stride + 1);
+    res_vals_dev_.reserve(static_cast<uint64_t>(rows) * stride + 1);
+    res_cnt_dev_.reserve(static_cast<uint64_t>(rows) + 1);
+    for (uint32_t r0 = 0; r0 < rows; r0 += tile) {
+        const uint32_t tr = std::min(tile, rows - r0);
+        const uint64_t base = row_ptr[r0], end = row_ptr[r0 + tr];
+        x_row_ptr_.upload(row_ptr + r0, static_cast<uint64_t>(tr) + 1, stream_);
+        x_col_idx_.upload(col_idx + base, end - base, stream_);
+        x_val_.upload(val + base, end - base, stream_);
+        QueryDev q{x_row_ptr_.get(), x_col_idx_.get(), x_val_.get(), base, tr, cols};
+        res_rows_ = r0;
+        run_tile_(q, plan, false);
+        if (r0 + tr < rows) PB200_CUDA(cudaStreamSynchronize(stream_));  // staging buffers are reused by the next tile
+    }
+    return finish_result_(rows, stride);
+}
+
+XLinearEngine::Result XLinearEngine::predict_drm(const float* dense, uint32_t rows, uint32_t cols, uint32_t beam_size,
+                                                 const char* post_processor, uint32_t only_topk) {
+    PB200_CUDA(cudaSetDevice(device_));
+    const auto plan = make_plan_(beam_size, post_processor, only_topk);
+    uint32_t tile = pick_tile_rows_(plan, rows);
+    const uint64_t max_dense_rows = std::max<uint64_t>(1, (4ull << 30) / (static_cast<uint64_t>(std::max<uint32_t>(cols, 1u)) * 4));
+    tile = static_cast<uint32_t>(std::min<uint64_t>(tile, max_dense_rows));
+    ensure_workspace_(plan, tile);
+    const uint32_t stride = plan.back().k_cap;
+    res_stride_ = stride;
+    res_ids_dev_.reserve(static_cast<uint64_t>(rows) * stride + 1);
+    res_vals_dev_.reserve(static_cast<uint64_t>(rows) * stride + 1);
+    res_cnt_dev_.reserve(static_cast<uint64_t>(rows) + 1);
+    for (uint32_t r0 = 0; r0 < rows; r0 += tile) {
+        const uint32_t tr = std::min(tile, rows - r0);
+        x_val_.upload(dense + static_cast<uint64_t>(r0) * cols, static_cast<uint64_t>(tr) * cols, stream_);
+        QueryDev q{nullptr, nullptr, x_val_.get(), 0, tr, cols};
+        res_rows_ = r0;
+        run_tile_(q, plan, false);
+        if (r0 + tr < rows) PB200_CUDA(cudaStreamSynchronize(stream_));
+    }
+    return finish_result_(rows, stride);
+}
+
+void XLinearEngine::resident_upload_csr(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, uint32_t rows,
+                                        uint32_t cols) {
+    PB200_CUDA(cudaSetDevice(device_));
+    const uint64_t nnz = row_ptr[rows];
+    x_row_ptr_.upload(row_ptr, static_cast<uint64_t>(rows) + 1, stream_);
+    x_col_idx_.upload(col_idx, nnz, stream_);
+    x_val_.upload(val, nnz, stream_);
+    PB200_CUDA(cudaStreamSynchronize(stream_));
+    resident_ = QueryDev{x_row_ptr_.get(), x_col_idx_.get(), x_val_.get(), 0, rows, cols};
+    has_resident_ = true;
+}
+
+double XLinearEngine::resident_predict(uint32_t beam_size, const char* post_processor, uint32_t only_topk, bool collect_stats) {
+    if (!has_resident_) throw std::runtime_error("pecos_b200: no resident query batch uploaded");
+    PB200_CUDA(cudaSetDevice(device_));
+    const auto plan = make_plan_(beam_size, post_processor, only_topk);
+    const uint32_t rows = resident_.rows;
+    const uint32_t tile = pick_tile_rows_(plan, rows);
+    ensure_workspace_(plan, tile);
+    const uint32_t stride = plan.back().k_cap;
+    res_stride_ = stride;
+    res_ids_dev_.reserve(static_cast<uint64_t>(rows) * stride + 1);
+    res_vals_dev_.reserve(static_cast<uint64_t>(rows) * stride + 1);
+    res_cnt_dev_.reserve(static_cast<uint64_t>(rows) + 1);
+    if (collect_stats) PB200_CUDA(cudaMemsetAsync(stats_dev_.get(), 0, stats_dev_.bytes(), stream_));
+    PB200_CUDA(cudaEventRecord(ev_[3], stream_));
+    cudaEvent_t stop;
+    PB200_CUDA(cudaEventCreate(&stop));
+    for (uint32_t r0 = 0; r0 < rows; r0 += tile) {
+        const uint32_t tr = std::min(tile, rows - r0);
+        QueryDev q = resident_;
+        q.row_ptr = resident_.row_ptr + r0;
+        q.rows = tr;
+        res_rows_ = r0;
+        run_tile_(q, plan, collect_stats);
+    }
+    PB200_CUDA(cudaEventRecord(stop, stream_));
+    PB200_CUDA(cudaEventSynchronize(stop));
+    float ms = 0.f;
+    PB200_CUDA(cudaEventElapsedTime(&ms, ev_[3], stop));
+    cudaEventDestroy(stop);
+    res_rows_ = rows;
+    if (collect_stats) {
+        std::vector<unsigned long long> h(8 * layers_.size());
+        PB200_CUDA(cudaMemcpy(h.data(), stats_dev_.get(), h.size() * 8, cudaMemcpyDeviceToHost));
+        for (size_t d = 0; d < layers_.size(); ++d) {
+            XLinearStats s{};
+            s.chunks = h[8 * d + 0]; s.chunk_rows = h[8 * d + 1]; s.matched = h[8 * d + 2]; s.entries = h[8 * d + 3];
+            s.out_cols = h[8 * d + 4]; s.query_nnz = h[8 * d + 5]; s.beam_out = h[8 * d + 6];
+            layer_stats_[d] = s;
+        }
+    }
+    return static_cast<double>(ms);
+}
+
+XLinearEngine::Result XLinearEngine::resident_fetch() {
+    PB200_CUDA(cudaSetDevice(device_));
+    return finish_result_(resident_.rows, res_stride_);
+}
+
+}  // namespace pb200

@@ -1,0 +1,157 @@
+// XR-Linear beam-search engine on one B200: device-resident model + the two kernels per tree layer.
+//
+// Replaces (reference, CPU/OpenMP):
+//   HierarchicalMLModel::predict ........ pecos/core/xmc/inference.hpp:2446-2488
+//   MLModel::predict_internal ........... pecos/core/xmc/inference.hpp:2029-2080
+//     prolongate_predictions ............ :1155-1219   (implicit here: beam slot j -> chunk j, no materialised pattern)
+//     w_ops::compute_sparse_predictions . :925-1007    -> xl_chunk_scores_kernel
+//       chunk_ops<csr|drm, bin_search> .. :769-839
+//     transform / combine / sorted_csr .. :1360-1384, :1223-1298 -> xl_topk_kernel
+//     reorder_prediction ................ :1919-1923   (label_of_col lookup in xl_topk_kernel)
+#pragma once
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "cuda_util.h"
+#include "xlinear_host.h"
+
+namespace pb200 {
+
+struct LayerDev {
+    const ChunkHeader* chunks;
+    const uint32_t* meta;
+    const uint2* entries;
+    const uint32_t* label_of_col;  // nullptr when the layer is contiguously ordered
+    uint32_t n_cols;
+    uint32_t n_chunks;
+    uint32_t c_max;
+    uint32_t w_rows;
+    float bias;
+    int has_dup_cols;
+};
+
+// Device view of a batch of queries (either CSR or row-major dense).
+struct QueryDev {
+    const uint64_t* row_ptr;  // CSR: absolute offsets (row_ptr[r] - nnz_base indexes col_idx/val); nullptr for dense
+    const uint32_t* col_idx;
+    const float* val;         // CSR values, or the dense matrix
+    uint64_t nnz_base;
+    uint32_t rows;
+    uint32_t cols;
+};
+
+struct XLinearStats {  // algorithmic-byte counters of SURVEY.md section 8(d), accumulated by the STATS kernel variant
+    unsigned long long chunks;      // (query, chunk) products evaluated
+    unsigned long long chunk_rows;  // sum R_p
+    unsigned long long matched;     // sum m(q,p)   (bias row included when applied)
+    unsigned long long entries;     // sum e(q,p)
+    unsigned long long out_cols;    // sum c_p
+    unsigned long long query_nnz;   // sum nnz(x_q) (once per query per layer)
+    unsigned long long beam_out;    // sum min(k, candidates)
+};
+
+struct XLinearLayerProfile {
+    double scores_ms = 0.0;  // xl_chunk_scores_kernel
+    double topk_ms = 0.0;    // xl_topk_kernel
+    uint64_t launches = 0;
+};
+
+class XLinearEngine {
+public:
+    XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device);
+    ~XLinearEngine();
+
+    const XLinearHostModel& host() const { return *host_; }
+    int device() const { return device_; }
+
+    struct Result {  // fixed-stride top-k per query, host side (pinned)
+        uint32_t rows = 0;
+        uint32_t stride = 0;
+        uint32_t out_cols = 0;
+        const uint32_t* ids = nullptr;
+        const float* vals = nullptr;
+        const uint32_t* cnt = nullptr;
+    };
+
+    // Host-buffer entry points (H2D + kernels + D2H inside). Exactly one of (row_ptr/col_idx/val) or dense is used.
+    Result predict_csr(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, uint32_t rows, uint32_t cols,
+                       uint32_t beam_size, const char* post_processor, uint32_t only_topk);
+    Result predict_drm(const float* dense, uint32_t rows, uint32_t cols, uint32_t beam_size, const char* post_processor,
+                       uint32_t only_topk);
+
+    // Device-resident queries (bench "value" leg: inputs already in HBM when the timed region starts).
+    void resident_upload_csr(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, uint32_t rows, uint32_t cols);
+    // Runs all layers over the resident batch; results stay in HBM (fetch with resident_fetch). Returns device ms.
+    double resident_predict(uint32_t beam_size, const char* post_processor, uint32_t only_topk, bool collect_stats);
+    Result resident_fetch();
+
+    void set_profile(bool on) { profile_ = on; }
+    const std::vector<XLinearLayerProfile>& layer_profile() const { return layer_profile_; }
+    void reset_profile();
+    const std::vector<XLinearStats>& layer_stats() const { return layer_stats_; }
+    uint64_t launches() const { return launches_; }
+    uint64_t model_bytes() const { return model_bytes_; }
+
+private:
+    struct LayerPlan {
+        uint32_t k = 0;       // only_topk used for this layer
+        uint32_t b_prev = 0;  // beam capacity entering the layer
+        uint32_t k_cap = 0;   // beam capacity leaving the layer
+        PostProc pp;
+    };
+    struct LayerStore {
+        DeviceBuffer<ChunkHeader> chunks;
+        DeviceBuffer<uint32_t> meta;
+        DeviceBuffer<uint2> entries;
+        DeviceBuffer<uint32_t> label_of_col;
+        LayerDev view{};
+    };
+
+    std::vector<LayerPlan> make_plan_(uint32_t beam_size, const char* post_processor, uint32_t only_topk) const;
+    void ensure_workspace_(const std::vector<LayerPlan>& plan, uint32_t tile_rows);
+    uint32_t pick_tile_rows_(const std::vector<LayerPlan>& plan, uint32_t rows) const;
+    void run_tile_(const QueryDev& q, const std::vector<LayerPlan>& plan, bool collect_stats);
+    Result finish_result_(uint32_t rows, uint32_t stride);
+
+    std::unique_ptr<XLinearHostModel> host_;
+    int device_ = 0;
+    cudaStream_t stream_ = nullptr;
+    std::vector<LayerStore> layers_;
+    uint64_t model_bytes_ = 0;
+
+    // per-tile workspace
+    DeviceBuffer<uint32_t> beam_id_[2];
+    DeviceBuffer<float> beam_val_[2];
+    DeviceBuffer<uint32_t> beam_cnt_[2];
+    DeviceBuffer<float> cand_;
+    DeviceBuffer<unsigned long long> sortbuf_;
+    DeviceBuffer<unsigned long long> stats_dev_;
+    int final_buf_ = 0;  // which ping-pong buffer holds the last layer's output
+    uint32_t beam_stride_ = 0;
+
+    // staged inputs (host-buffer path) and resident batch
+    DeviceBuffer<uint64_t> x_row_ptr_;
+    DeviceBuffer<uint32_t> x_col_idx_;
+    DeviceBuffer<float> x_val_;
+    QueryDev resident_{};
+    bool has_resident_ = false;
+    DeviceBuffer<uint32_t> res_ids_dev_;
+    DeviceBuffer<float> res_vals_dev_;
+    DeviceBuffer<uint32_t> res_cnt_dev_;
+    uint32_t res_rows_ = 0, res_stride_ = 0;
+
+    // host result staging (pinned)
+    PinnedBuffer<uint32_t> out_ids_;
+    PinnedBuffer<float> out_vals_;
+    PinnedBuffer<uint32_t> out_cnt_;
+
+    bool profile_ = false;
+    std::vector<XLinearLayerProfile> layer_profile_;
+    std::vector<XLinearStats> layer_stats_;
+    uint64_t launches_ = 0;
+    cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+}  // namespace pb200
