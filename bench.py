@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py -- XR-Linear beam-search prediction throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload eurlex-4k|synthetic-small|synthetic-3m]
+
+A "step" is one pass of the hot path (all tree layers: chunk-score kernel + top-k kernel per layer) over one batch of
+synthetic queries.  At N=1 the workload is BASELINE.json configs[1] ("eurlex-4k": N=15,449 queries, D=5,000,
+L=3,956, beam 10, top-10).  For N>1 (launched by torchrun, one rank per GPU) every rank holds a replica of the model
+and processes its own batch of the same shape: query-sharded, no data-path collective, weak scaling.
+
+Printed JSON line (rank 0): `value` = queries/s with the batch already resident in HBM (CUDA-event time of the K
+steps, max over ranks); `e2e` = queries/s through the reference-facing C-ABI call `c_xlinear_predict_csr_f32` with
+pinned HOST buffers (H2D + kernels + D2H + result marshalling inside the timed region); `roofline` = achieved
+algorithmic HBM GB/s of the dominant kernel vs the measured peak; `cpu_baseline` = the reference's own OpenMP C++
+library (oracle/_ref) timed on this box's host cores.  `--impl reference` times that reference library alone.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "XR-Linear top-10 queries/sec"
+UNIT = "queries/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="eurlex-4k")
+    ap.add_argument("--cache-dir", default=os.environ.get("PB200_BENCH_CACHE", os.path.join(tempfile.gettempdir(), "pecos_b200_bench")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler(object):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def prepare_workload(args, rank, world, barrier):
+    """Rank 0 writes the synthetic model folder once; every rank generates its own query batch from a seed."""
+    from pecos_b200 import synth
+
+    folder = os.path.join(args.cache_dir, args.workload)
+    if rank == 0:
+        os.makedirs(args.cache_dir, exist_ok=True)
+        synth.build_workload(args.workload, folder, scale_queries=8)  # writes the model if absent
+    barrier()
+    cfg = dict(synth.WORKLOADS[args.workload])
+    cdf = synth.zipf_cdf(cfg["D"]) if cfg["zipf"] else None
+    X = synth.make_queries(cfg["query_seed"] + 1000 * rank, cfg["Q"], cfg["D"], cfg["nnz_per_row"], cdf)
+    return folder, X, cfg
+
+
+def time_reference(folder, X, cfg, steps, warmup, threads=-1, budget_s=120.0):
+    """Times the reference's own OpenMP C++ library (oracle/_ref) -- or the scalar C port when _ref is absent."""
+    import oracle
+
+    n_cores = os.cpu_count() or 1
+    if oracle.have_ref():
+        from oracle import ref
+
+        model = ref.RefXLinear(os.path.join(folder, "ranker"))
+        kind, cores = "reference", n_cores
+        sample = X
+
+        def run():
+            return model.predict(sample, cfg["beam_size"], None, cfg["only_topk"], threads)
+    else:
+        from oracle import restatement
+
+        model = restatement.OracleXLinear(os.path.join(folder, "ranker"))
+        kind, cores = "port", 1
+        sample = X[: min(X.shape[0], 256)]
+
+        def run():
+            return model.predict(sample, cfg["beam_size"], None, cfg["only_topk"])
+
+    # bound the sample so that warmup + steps stays within the budget
+    t0 = time.perf_counter()
+    run()
+    first = time.perf_counter() - t0
+    max_rows = sample.shape[0]
+    est_total = first * (steps + warmup)
+    if est_total > budget_s and max_rows > 64:
+        rows = max(64, int(max_rows * budget_s / est_total))
+        sample = sample[:rows]
+    for _ in range(max(0, warmup - 1)):
+        run()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        run()
+        times.append(time.perf_counter() - t0)
+    mean_t = sum(times) / len(times)
+    return {
+        "value": sample.shape[0] / mean_t,
+        "best": sample.shape[0] / min(times),
+        "ms_per_step": 1e3 * mean_t,
+        "kind": kind,
+        "cores": cores,
+        "sample": f"{sample.shape[0]} of {X.shape[0]} queries of the workload per step, {steps} steps, threads={threads} (all host threads)",
+    }
+
+
+def run_reference_arm(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return 0
+    import oracle
+
+    oracle.build()
+    folder, X, cfg = prepare_workload(args, 0, 1, lambda: None)
+    r = time_reference(folder, X, cfg, args.steps, args.warmup)
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, cfg, X, extra={"l2": "n/a (host cores)"}),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(name, cfg, X, extra=None):
+    c = {
+        "workload": name,
+        "queries_per_step_per_gpu": int(X.shape[0]),
+        "nnz_per_query": int(X.nnz // max(1, X.shape[0])),
+        "features": int(cfg["D"]),
+        "labels": int(cfg["layer_sizes"][-1]),
+        "tree_layers": list(cfg["layer_sizes"]),
+        "nnz_per_weight_col": int(cfg["nnz_per_col"]) + 1,
+        "beam_size": int(cfg["beam_size"]),
+        "only_topk": int(cfg["only_topk"]),
+        "post_processor": "l3-hinge",
+        "parallelism": "query-sharded replicas (no collective)",
+    }
+    if extra:
+        c.update(extra)
+    return c
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        print(f"warning: WORLD_SIZE={world} != --gpus {args.gpus}", file=sys.stderr)
+    n_gpus = max(world, 1)
+
+    import __graft_entry__ as entry
+    from ctypes import byref, c_double, c_uint64
+
+    from pecos_b200 import core
+    from pecos_b200.core import ScipyCompressedSparseAllocator, ScipyCsrF32
+    from pecos_b200.xlinear import XLinearModel
+
+    if rank == 0 and not os.path.exists(core.LIB_PATH):
+        entry.build()
+
+    dist = None
+    if n_gpus > 1:
+        import torch
+        import torch.distributed as dist_mod
+
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    barrier()
+    lib = core.get_clib()
+    lib.require_gpu()
+    lib.set_device(local)
+    c = lib.clib_float32
+
+    folder, X, cfg = prepare_workload(args, rank, n_gpus, barrier)
+    model = XLinearModel.load(folder, is_predict_only=True)
+    h = model.model.model_chain
+    depth = model.depth
+    beam, topk = cfg["beam_size"], cfg["only_topk"]
+    Q = X.shape[0]
+
+    # ------------------------------------------------------------ resident batch + algorithmic-byte counters
+    cx = ScipyCsrF32.init_from(X)
+    c.pb200_xlinear_resident_upload_csr(h, byref(cx))
+    c.pb200_xlinear_resident_predict(h, beam, None, topk, 1)
+    stats = (c_uint64 * (7 * depth))()
+    c.pb200_xlinear_get_stats(h, stats)
+    st = np.array(list(stats), dtype=np.float64).reshape(depth, 7)
+    # per (query, chunk) 32 + 4R + 16m + 8e + 4c ; per query and layer 8 nnz(x) + 8 min(k, sum c)
+    scores_bytes = 32 * st[:, 0] + 4 * st[:, 1] + 16 * st[:, 2] + 8 * st[:, 3] + 4 * st[:, 4] + 8 * st[:, 5]
+    topk_bytes = 4 * st[:, 4] + 8 * st[:, 6]
+    bytes_per_step = float(scores_bytes.sum() + 8 * st[:, 6].sum())
+
+    def one_step():
+        c.pb200_l2_flush()  # outside the event-timed region: every step starts with a cold L2
+        return c.pb200_xlinear_resident_predict(h, beam, None, topk, 0)
+
+    for _ in range(max(3, args.warmup)):
+        one_step()
+
+    # ------------------------------------------------------------ timed region: K steps, device time, max over ranks
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    c.pb200_xlinear_reset_profile(h)
+    barrier()
+    wall0 = time.perf_counter()
+    step_ms = [one_step() for _ in range(args.steps)]
+    wall1 = time.perf_counter()
+    launches = int(c.pb200_xlinear_launches(h))
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = float(sum(step_ms))
+    if dist is not None:
+        import torch
+
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = n_gpus * Q / (ms_per_step * 1e-3)
+
+    # ------------------------------------------------------------ per-kernel timing (CUDA events on the launch stream)
+    c.pb200_xlinear_set_profile(h, 1)
+    c.pb200_xlinear_reset_profile(h)
+    prof_steps = max(3, min(args.steps, 10))
+    for _ in range(prof_steps):
+        one_step()
+    prof = (c_double * (2 * depth))()
+    c.pb200_xlinear_get_profile(h, prof)
+    c.pb200_xlinear_set_profile(h, 0)
+    pm = np.array(list(prof), dtype=np.float64).reshape(depth, 2) / prof_steps
+    peak, peak_src = measured_peak_gbs()
+    kernels = []
+    for d in range(depth):
+        kernels.append({"kernel": f"xl_chunk_scores_kernel[layer {d}]", "ms": pm[d, 0], "algorithmic_bytes": float(scores_bytes[d])})
+        kernels.append({"kernel": f"xl_topk_kernel[layer {d}]", "ms": pm[d, 1], "algorithmic_bytes": float(topk_bytes[d])})
+    dom = max(kernels, key=lambda k: k["ms"])
+    achieved = dom["algorithmic_bytes"] / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
+    ncu_traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            ncu_traffic = json.load(f).get(args.workload, {}).get(dom["kernel"].split("[")[0])
+    except Exception:
+        pass
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+        "traffic": ncu_traffic, "kernel": dom["kernel"], "kernel_ms": dom["ms"], "algorithmic_bytes_per_launch": dom["algorithmic_bytes"],
+        "peak_source": peak_src,
+        "whole_step": {"algorithmic_bytes": bytes_per_step, "achieved": bytes_per_step / (ms_per_step * 1e-3) / 1e9,
+                       "bytes_per_query": bytes_per_step / Q},
+        "kernels": kernels,
+    }
+
+    # ------------------------------------------------------------ end to end through the C ABI with pinned host buffers
+    ip = lib.pinned_empty(Q + 1, np.uint64)
+    ix = lib.pinned_empty(X.nnz, np.uint32)
+    dv = lib.pinned_empty(X.nnz, np.float32)
+    ip.array[:] = X.indptr
+    ix.array[:] = X.indices
+    dv.array[:] = X.data
+    cx_pinned = ScipyCsrF32.init_from_arrays(X.shape[0], X.shape[1], ip.array, ix.array, dv.array)
+
+    def e2e_step():
+        alloc = ScipyCompressedSparseAllocator()
+        c.c_xlinear_predict_csr_f32(h, byref(cx_pinned), beam, None, topk, -1, alloc.cfunc)
+        return alloc
+
+    for _ in range(max(3, args.warmup)):
+        e2e_step()
+    barrier()
+    e2e_times = []
+    for _ in range(args.steps):
+        c.pb200_l2_flush()
+        t0 = time.perf_counter()
+        out = e2e_step()
+        e2e_times.append(time.perf_counter() - t0)
+    barrier()
+    e2e_total = float(sum(e2e_times))
+    if dist is not None:
+        import torch
+
+        t = torch.tensor([e2e_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_total = float(t.item())
+    e2e_value = n_gpus * Q * args.steps / e2e_total
+    h2d = int(ip.array.nbytes + ix.array.nbytes + dv.array.nbytes)
+    d2h = int(out.indices.nbytes + out.data.nbytes + 4 * Q)
+
+    # ------------------------------------------------------------ CPU baseline beside it (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        r = time_reference(folder, X, cfg, steps=5, warmup=2, budget_s=30.0)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+               "best": r["best"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, cfg, X, extra={
+                "l2": "flushed between timed iterations (512 MiB memset outside the event-timed region)",
+                "timing": "CUDA events on the engine stream per step, summed over steps, max over ranks",
+            }),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_total / args.steps, "api": "c_xlinear_predict_csr_f32 (pinned host CSR in, scipy CSR out)"},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "wall_s_timed_region": wall1 - wall0,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
