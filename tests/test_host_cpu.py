@@ -1,0 +1,171 @@
+"""CPU tests of the host-side logic: C-ABI surface, model ingest (npz / mmap readers, chunk layout), Python mirror."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.sparse as smat
+
+from pecos_b200 import synth
+
+from .util import random_tree
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "xlinear_toy")
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pecos_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:c_xlinear|c_ann_hnsw|pb200)_[A-Za-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(clib):
+    names = _declared_symbols()
+    assert len(names) >= 30
+    out = subprocess.run(["nm", "-D", "--defined-only", clib.path], stdout=subprocess.PIPE, text=True, check=True).stdout
+    exported = set(line.split()[-1] for line in out.splitlines() if line.strip())
+    missing = [n for n in names if n not in exported]
+    assert not missing, f"declared in include/pecos_b200.h but not exported: {missing}"
+    for n in names:
+        assert hasattr(clib.clib_float32, n)
+
+
+def test_no_gpu_means_loud_failure_not_fallback(clib, tmp_path):
+    if clib.device_count() > 0:
+        pytest.skip("a GPU is visible here")
+    from pecos_b200.xlinear import XLinearModel
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        XLinearModel.load(os.path.join(GOLD, "model"), is_predict_only=True)
+    with pytest.raises(NotImplementedError):
+        XLinearModel.load(os.path.join(GOLD, "model"), is_predict_only=False)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pecos_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp", ".cuh")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"
+                assert "liboracle" not in text and "oracle/_ref" not in text, f"{f} references the oracle"
+
+
+def _check_layout(layers, Ws, Cs, bias):
+    """Structural properties of the HBM chunk layout + exact content vs the source CSC matrices."""
+    for d, L in enumerate(layers):
+        W, C = smat.csc_matrix(Ws[d]), smat.csc_matrix(Cs[d])
+        chunks, meta, ent = L["chunks"], L["meta"], L["entries"]
+        assert L["n_chunks"] == C.shape[1]
+        assert L["n_cols"] == C.nnz
+        assert L["out_cols"] == C.shape[0]
+        contiguous = C.nnz >= C.shape[0] and np.array_equal(C.indices, np.arange(C.nnz))
+        assert (len(L["label_of_col"]) == 0) == contiguous
+        col_cursor = 0
+        dense_W = W.toarray()
+        for p in range(L["n_chunks"]):
+            h = chunks[p]
+            R, nc = int(h["nnz_rows"]), int(h["n_cols"])
+            assert int(h["col_begin"]) == col_cursor
+            col_cursor += nc
+            assert int(h["meta_off"]) % 4 == 0  # 16-byte aligned row-index list for 128-bit loads
+            rows = meta[int(h["meta_off"]): int(h["meta_off"]) + R].astype(np.int64)
+            R4 = (R + 3) // 4 * 4
+            assert (meta[int(h["meta_off"]) + R: int(h["meta_off"]) + R4] == 0xFFFFFFFF).all()
+            rp = meta[int(h["meta_off"]) + R4: int(h["meta_off"]) + R4 + R + 1].astype(np.int64)
+            assert (np.diff(rows) > 0).all()           # sorted, distinct
+            assert rp[0] == 0 and (np.diff(rp) > 0).all()
+            cols = (np.arange(nc) + int(h["col_begin"]))
+            labels = L["label_of_col"][cols] if len(L["label_of_col"]) else cols
+            sub = dense_W[:, labels]                    # (w_rows, nc) block of the source matrix
+            want_rows = np.nonzero((sub != 0).any(axis=1))[0]
+            assert np.array_equal(rows, want_rows)
+            e = ent[int(h["ent_off"]): int(h["ent_off"]) + rp[-1]]
+            rebuilt = np.zeros_like(sub)
+            for i, r in enumerate(rows):
+                seg = e[rp[i]: rp[i + 1]]
+                assert (np.diff(seg["col_offset"].astype(np.int64)) > 0).all()
+                rebuilt[r, seg["col_offset"]] = seg["val"]
+            assert np.array_equal(rebuilt, sub)
+            has_bias = bias > 0 and R > 0 and rows[-1] == W.shape[0] - 1
+            assert bool(h["has_bias"]) == bool(has_bias)
+        assert col_cursor == L["n_cols"]
+
+
+@pytest.mark.parametrize("permute,prune,bias", [(False, 0.0, 1.0), (True, 0.0, 1.0), (True, 0.3, 1.0), (False, 0.0, -1.0)])
+def test_chunk_layout_from_npz(clib, tmp_path, permute, prune, bias):
+    folder = str(tmp_path / "m")
+    layers = random_tree(3, [3, 14, 90], 120, 12, bias=bias, permute=permute, prune=prune)
+    synth.save_xlinear_model(folder, layers, bias=bias, only_topk=4)
+    got = clib.host_model_layout(os.path.join(folder, "ranker"), is_mmap=False)
+    _check_layout(got, [w for w, _ in layers], [c for _, c in layers], bias)
+
+
+def test_root_layer_without_C_file(clib, tmp_path):
+    folder = str(tmp_path / "m")
+    layers = random_tree(4, [5, 40], 64, 8, bias=1.0)
+    synth.save_xlinear_model(folder, layers, bias=1.0, only_topk=4, skip_root_C=True)
+    assert not os.path.exists(os.path.join(folder, "ranker", "0.model", "C.npz"))
+    got = clib.host_model_layout(os.path.join(folder, "ranker"))
+    assert got[0]["n_chunks"] == 1 and got[0]["n_cols"] == 5
+
+
+def test_mmap_reader_repacks_to_the_same_layout_as_the_npz_builder(clib):
+    """tests/golden/xlinear_toy/model_mmap was written by the reference's c_xlinear_compile_mmap_model."""
+    a = clib.host_model_layout(os.path.join(GOLD, "model", "ranker"), is_mmap=False)
+    b = clib.host_model_layout(os.path.join(GOLD, "model_mmap", "ranker"), is_mmap=True)
+    assert len(a) == len(b) >= 2
+    for la, lb in zip(a, b):
+        for k in ("w_rows", "n_cols", "out_cols", "n_chunks", "c_max"):
+            assert la[k] == lb[k]
+        for k in ("chunks", "meta", "entries", "label_of_col"):
+            assert np.array_equal(la[k], lb[k]), k
+
+
+def test_npz_reader_dtype_conversion_and_compressed_rejection(clib, tmp_path):
+    # int64 indices / float64 data are converted (scipy_loader.hpp:153-184); compressed archives are rejected (:247-249)
+    folder = str(tmp_path / "m")
+    layers = random_tree(8, [4, 30], 50, 6, bias=1.0)
+    synth.save_xlinear_model(folder, layers, bias=1.0, only_topk=4)
+    base = clib.host_model_layout(os.path.join(folder, "ranker"))
+    wpath = os.path.join(folder, "ranker", "1.model", "W.npz")
+    W = smat.load_npz(wpath).tocsc()
+    W64 = smat.csc_matrix((W.data.astype(np.float64), W.indices.astype(np.int64), W.indptr.astype(np.int64)), shape=W.shape)
+    with open(wpath, "wb") as f:
+        smat.save_npz(f, W64, compressed=False)
+    again = clib.host_model_layout(os.path.join(folder, "ranker"))
+    assert np.array_equal(base[1]["entries"], again[1]["entries"]) and np.array_equal(base[1]["meta"], again[1]["meta"])
+    # a compressed archive must be refused loudly: run in a child process because the C ABI aborts
+    with open(wpath, "wb") as f:
+        smat.save_npz(f, W, compressed=True)
+    code = ("import sys; sys.path.insert(0, %r); from pecos_b200 import core; "
+            "core.get_clib().host_model_layout(%r)" % (ROOT, os.path.join(folder, "ranker")))
+    r = subprocess.run(["python", "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode != 0 and "compressed" in r.stderr
+
+
+def test_pred_params_override_semantics():
+    """beam_size -> only_topk of all non-final layers, only_topk -> final layer (pecos/xmc/base.py:1158-1166)."""
+    from pecos_b200.xlinear import HierarchicalPredParams, MLModelPredParams
+
+    p = HierarchicalPredParams(model_chain=[MLModelPredParams(20, "l3-hinge") for _ in range(3)])
+    p.override_with_kwargs({"beam_size": 7, "only_topk": 3, "post_processor": "sigmoid"})
+    assert [m.only_topk for m in p.model_chain] == [7, 7, 3]
+    assert all(m.post_processor == "sigmoid" for m in p.model_chain)
+    with pytest.raises(TypeError):
+        p.override_with_kwargs([1, 2])
+
+
+def test_ctypes_views_keep_reference_struct_layout():
+    import ctypes
+
+    from pecos_b200.core import ScipyCsrF32, ScipyDrmF32
+
+    assert ctypes.sizeof(ScipyCsrF32) == 32 and ctypes.sizeof(ScipyDrmF32) == 16  # matrix.hpp:49-71
+    X = synth.make_queries(1, 5, 20, 4)
+    v = ScipyCsrF32.init_from(X)
+    assert (v.rows, v.cols) == (5, 20) and v.indptr[5] == X.nnz
+    with pytest.raises(ValueError):
+        ScipyCsrF32.init_from(X.astype(np.float64))
