@@ -128,6 +128,15 @@ void pb200_xlinear_get_stats(void* ptr, uint64_t* out);
 uint64_t pb200_xlinear_launches(void* ptr);
 uint64_t pb200_xlinear_model_bytes(void* ptr);
 
+/* HNSW: device-resident query batch, search-kernel time (ms, CUDA events), algorithmic counters of the last search
+ *   counters out[4] = {distance evaluations, level-0 expansions, upper-level neighbourhood reads, queries}
+ *   info     out[8] = {num_node, feat_dim, maxM, maxM0, max_level, init_node, index bytes in HBM, kernel launches} */
+void pb200_hnsw_resident_upload(void* model_ptr, const ScipyDrmF32* pX);
+double pb200_hnsw_resident_predict(void* model_ptr, uint32_t efS, uint32_t topk);
+void pb200_hnsw_resident_fetch(void* model_ptr, uint32_t* ret_idx, float* ret_val);
+void pb200_hnsw_get_counters(void* model_ptr, uint64_t* out);
+void pb200_hnsw_get_info(void* model_ptr, uint64_t* out);
+
 /* Host-only model ingest (no GPU needed): loads + builds the chunk layout, for layout tests.
  *   kind: 0 = npz folder, 1 = mmap folder.  dims out[8] = {w_rows, n_cols, out_cols, n_chunks, c_max, meta_len,
  *   n_entries, label_of_col_len}.  export copies the arrays into caller buffers (any may be NULL). */

@@ -133,3 +133,109 @@ class OracleXLinear(object):
         out = smat.csr_matrix((data, indices, indptr), shape=(res.rows, res.cols))
         L.xlo_free_result(byref(res))
         return out
+
+
+# ------------------------------------------------------------------------------------------------------ HNSW
+class _HnswIndex(Structure):
+    _fields_ = [("num_node", c_uint32), ("maxM", c_uint32), ("maxM0", c_uint32), ("efC", c_uint32),
+                ("max_level", c_uint32), ("init_node", c_uint32),
+                ("feat_dim", c_uint32), ("l0_max_degree", c_uint32), ("l0_node_mem_size", c_uint32),
+                ("l0_buffer", ctypes.c_void_p),
+                ("l1_max_level", c_uint32), ("l1_max_degree", c_uint32), ("l1_node_mem_size", c_uint32),
+                ("l1_level_mem_size", c_uint32), ("l1_buffer", ctypes.c_void_p),
+                ("metric", c_int), ("isa", c_int)]
+
+
+def _hnsw_lib():
+    L = lib()
+    if not hasattr(L, "_hnsw_ready"):
+        L.hno_search.restype = c_int
+        L.hno_search.argtypes = [POINTER(_HnswIndex), POINTER(c_float), c_uint32, c_uint32, c_uint32, POINTER(c_uint32),
+                                 POINTER(c_float), POINTER(c_uint64)]
+        L.hno_distance.restype = c_float
+        L.hno_distance.argtypes = [POINTER(c_float), POINTER(c_float), c_uint32, c_int, c_int]
+        L._hnsw_ready = True
+    return L
+
+
+def read_mmap_store(path):
+    """Blocks of a PECOS ``*.mmap_store`` file as a list of uint8 arrays (pecos/core/utils/mmap_util.hpp:54-184)."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    sig = raw[-16:]
+    assert bytes(sig[:6]) == b"\x93PECOS" and sig[6] == ord("<") and sig[7] == 1, "not a PECOS mmap_store"
+    meta_off = int(sig[8:16].view(np.uint64)[0])
+    n_blocks = int(raw[meta_off:meta_off + 8].view(np.uint64)[0])
+    info = raw[meta_off + 8: meta_off + 8 + 16 * n_blocks].view(np.uint64).reshape(n_blocks, 2)
+    return [raw[int(o): int(o) + int(s)] for o, s in info]
+
+
+def host_isa():
+    """Which SIMD clone the reference's ifunc resolver picks on this CPU (distance_impl/x86.hpp:37-42, :84-85, :121-122)."""
+    try:
+        flags = [ln for ln in open("/proc/cpuinfo") if ln.startswith("flags")][0].split()
+    except Exception:
+        return 0
+    if "avx512f" in flags:
+        return 0
+    if "avx" in flags:
+        return 1
+    if "sse" in flags:
+        return 2
+    return 3
+
+
+class OracleHNSW(object):
+    """Parses ``<model>/c_model/index.mmap_store`` with numpy and searches with the C restatement."""
+
+    def __init__(self, model_dir, isa=0):
+        param = json.load(open(os.path.join(model_dir, "param.json")))
+        assert param["data_type"] == "drm", "only dense indices are restated"
+        self.metric = {"ip": 0, "l2": 1}[param["metric_type"]]
+        blocks = read_mmap_store(os.path.join(model_dir, "c_model", "index.mmap_store"))
+        u32 = lambda b: int(b.view(np.uint32)[0])  # noqa: E731
+        it = iter(blocks)
+        self.num_node, self.maxM, self.maxM0, self.efC, self.max_level, self.init_node = [u32(next(it)) for _ in range(6)]
+        l0_num, self.feat_dim, self.l0_max_degree, self.l0_node_mem = [u32(next(it)) for _ in range(4)]
+        next(it); next(it)  # mem_start_of_node: size + data
+        next(it)            # buffer size
+        self.l0 = np.ascontiguousarray(next(it))
+        l1_num, self.l1_max_level, self.l1_max_degree, self.l1_node_mem, self.l1_level_mem = [u32(next(it)) for _ in range(5)]
+        next(it)
+        self.l1 = np.ascontiguousarray(next(it))
+        if self.l1.size == 0:
+            self.l1 = np.zeros(4, dtype=np.uint8)
+        self.isa = isa
+        assert self.l0_node_mem == (1 + self.l0_max_degree) * 4 + 4 + 4 * self.feat_dim
+
+    def _struct(self):
+        s = _HnswIndex()
+        s.num_node, s.maxM, s.maxM0, s.efC, s.max_level, s.init_node = (self.num_node, self.maxM, self.maxM0, self.efC,
+                                                                            self.max_level, self.init_node)
+        s.feat_dim, s.l0_max_degree, s.l0_node_mem_size = self.feat_dim, self.l0_max_degree, self.l0_node_mem
+        s.l0_buffer = self.l0.ctypes.data
+        s.l1_max_level, s.l1_max_degree, s.l1_node_mem_size, s.l1_level_mem_size = (self.l1_max_level, self.l1_max_degree,
+                                                                                      self.l1_node_mem, self.l1_level_mem)
+        s.l1_buffer = self.l1.ctypes.data
+        s.metric, s.isa = self.metric, self.isa
+        return s
+
+    def vectors(self):
+        rec = self.l0.reshape(self.num_node, self.l0_node_mem)
+        off = (1 + self.l0_max_degree) * 4 + 4
+        return np.ascontiguousarray(rec[:, off:]).view(np.float32).reshape(self.num_node, self.feat_dim)
+
+    def predict(self, X, efS, topk, return_counters=False):
+        L = _hnsw_lib()
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        assert X.shape[1] == self.feat_dim
+        nq = X.shape[0]
+        idx = np.zeros((nq, topk), dtype=np.uint32)
+        val = np.zeros((nq, topk), dtype=np.float32)
+        cnt = np.zeros((nq, 3), dtype=np.uint64)
+        s = self._struct()
+        rc = L.hno_search(byref(s), X.ctypes.data_as(POINTER(c_float)), nq, efS, topk, idx.ctypes.data_as(POINTER(c_uint32)),
+                          val.ctypes.data_as(POINTER(c_float)), cnt.ctypes.data_as(POINTER(c_uint64)))
+        assert rc == 0
+        if return_counters:
+            return idx, val, cnt
+        return idx, val

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "hnsw_engine.h"
 #include "xlinear_engine.h"
 
 namespace {
@@ -282,6 +283,110 @@ void pb200_xlinear_host_layer_export(void* hptr, uint32_t layer, void* chunks32,
     if (entries8) std::memcpy(entries8, L.entries.data(), L.entries.size() * 8);
     if (label_of_col) std::memcpy(label_of_col, L.label_of_col.data(), L.label_of_col.size() * 4);
     PB200_API_END("pb200_xlinear_host_layer_export")
+}
+
+}  // extern "C"
+
+// ------------------------------------------------ HNSW ----------------------------------------------------------
+namespace {
+
+struct HnswHandle {
+    std::unique_ptr<pb200::HnswEngine> engine;
+};
+
+struct HnswSearchers {  // the reference hands out a vector<Searcher>; our scratch lives with the engine (per warp)
+    HnswHandle* owner;
+    uint32_t num_searcher;
+};
+
+pb200::HnswEngine& hnsw_of(void* ptr) {
+    if (!ptr) throw std::runtime_error("null HNSW handle");
+    return *static_cast<HnswHandle*>(ptr)->engine;
+}
+
+void* hnsw_load(const char* model_dir, bool lazy_load, int metric) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0)
+        throw std::runtime_error("no CUDA device visible: pecos_b200 has no CPU fallback");
+    auto host = pb200::load_hnsw_index(model_dir, metric, lazy_load);
+    auto h = new HnswHandle();
+    h->engine = std::make_unique<pb200::HnswEngine>(std::move(host), g_device.load());
+    return h;
+}
+
+void hnsw_predict(void* model_ptr, const ScipyDrmF32* pX, uint32_t* ret_idx, float* ret_val, uint32_t efS, uint32_t topk,
+                  int metric) {
+    auto& eng = hnsw_of(model_ptr);
+    if (eng.metric() != metric) throw std::runtime_error("HNSW handle was loaded with a different metric");
+    eng.predict(pX->val, pX->rows, pX->cols, efS, topk, ret_idx, ret_val);
+}
+
+}  // namespace
+
+extern "C" {
+
+#define PB200_HNSW_API(SUFFIX, METRIC)                                                                                  \
+    void* c_ann_hnsw_load##SUFFIX(const char* model_dir, const bool lazy_load) {                                        \
+        PB200_API_BEGIN                                                                                                 \
+        return hnsw_load(model_dir, lazy_load, METRIC);                                                                 \
+        PB200_API_END("c_ann_hnsw_load" #SUFFIX)                                                                        \
+    }                                                                                                                   \
+    void c_ann_hnsw_destruct##SUFFIX(void* model_ptr) {                                                                 \
+        PB200_API_BEGIN                                                                                                 \
+        delete static_cast<HnswHandle*>(model_ptr);                                                                     \
+        PB200_API_END("c_ann_hnsw_destruct" #SUFFIX)                                                                    \
+    }                                                                                                                   \
+    void* c_ann_hnsw_searchers_create##SUFFIX(void* model_ptr, uint32_t num_searcher) {                                 \
+        PB200_API_BEGIN                                                                                                 \
+        (void)hnsw_of(model_ptr);                                                                                       \
+        return new HnswSearchers{static_cast<HnswHandle*>(model_ptr), num_searcher};                                    \
+        PB200_API_END("c_ann_hnsw_searchers_create" #SUFFIX)                                                            \
+    }                                                                                                                   \
+    void c_ann_hnsw_searchers_destruct##SUFFIX(void* searchers_ptr) { delete static_cast<HnswSearchers*>(searchers_ptr); } \
+    void c_ann_hnsw_predict##SUFFIX(void* model_ptr, const ScipyDrmF32* pX, uint32_t* ret_idx, float* ret_val,          \
+                                    uint32_t efS, uint32_t topk, int32_t threads, void* searchers_ptr) {                \
+        (void)threads;                                                                                                  \
+        (void)searchers_ptr;                                                                                            \
+        PB200_API_BEGIN                                                                                                 \
+        hnsw_predict(model_ptr, pX, ret_idx, ret_val, efS, topk, METRIC);                                               \
+        PB200_API_END("c_ann_hnsw_predict" #SUFFIX)                                                                     \
+    }
+
+PB200_HNSW_API(_drm_ip_f32, pb200::HNSW_IP)
+PB200_HNSW_API(_drm_l2_f32, pb200::HNSW_L2)
+
+void pb200_hnsw_resident_upload(void* model_ptr, const ScipyDrmF32* pX) {
+    PB200_API_BEGIN
+    hnsw_of(model_ptr).resident_upload(pX->val, pX->rows, pX->cols);
+    PB200_API_END("pb200_hnsw_resident_upload")
+}
+
+double pb200_hnsw_resident_predict(void* model_ptr, uint32_t efS, uint32_t topk) {
+    PB200_API_BEGIN
+    return hnsw_of(model_ptr).resident_predict(efS, topk);
+    PB200_API_END("pb200_hnsw_resident_predict")
+}
+
+void pb200_hnsw_resident_fetch(void* model_ptr, uint32_t* ret_idx, float* ret_val) {
+    PB200_API_BEGIN
+    hnsw_of(model_ptr).resident_fetch(ret_idx, ret_val);
+    PB200_API_END("pb200_hnsw_resident_fetch")
+}
+
+void pb200_hnsw_get_counters(void* model_ptr, uint64_t* out) {
+    PB200_API_BEGIN
+    auto c = hnsw_of(model_ptr).counters();
+    out[0] = c.n_dist; out[1] = c.n_expand; out[2] = c.n_hops; out[3] = c.n_queries;
+    PB200_API_END("pb200_hnsw_get_counters")
+}
+
+void pb200_hnsw_get_info(void* model_ptr, uint64_t* out) {
+    PB200_API_BEGIN
+    auto& e = hnsw_of(model_ptr);
+    const auto& h = e.host();
+    out[0] = h.num_node; out[1] = h.feat_dim; out[2] = h.maxM; out[3] = h.maxM0; out[4] = h.max_level; out[5] = h.init_node;
+    out[6] = e.index_bytes(); out[7] = e.launches();
+    PB200_API_END("pb200_hnsw_get_info")
 }
 
 }  // extern "C"

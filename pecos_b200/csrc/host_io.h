@@ -13,6 +13,7 @@
 // which mirrors the reference (C++ exceptions escaping extern "C" => std::terminate).
 #pragma once
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +22,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <fcntl.h>
@@ -510,5 +512,35 @@ private:
     std::vector<std::pair<uint64_t, uint64_t>> blocks_;  // (offset, size)
     uint64_t next_ = 0;
 };
+
+// ----------------------------------------------------------------------------------------------
+// tiny host thread pool for load-time work
+// ----------------------------------------------------------------------------------------------
+template <typename F>
+inline void parallel_for_chunks(uint64_t n, F&& fn) {
+    unsigned hw = std::thread::hardware_concurrency();
+    unsigned nt = std::max(1u, std::min(hw ? hw : 1u, 64u));
+    if (n < 64 || nt == 1) { for (uint64_t i = 0; i < n; ++i) fn(i); return; }
+    std::atomic<uint64_t> next{0};
+    std::vector<std::thread> pool;
+    std::exception_ptr err = nullptr;
+    std::atomic<bool> failed{false};
+    for (unsigned t = 0; t < nt; ++t) {
+        pool.emplace_back([&]() {
+            try {
+                for (;;) {
+                    uint64_t i0 = next.fetch_add(16);
+                    if (i0 >= n || failed.load()) break;
+                    uint64_t i1 = std::min(n, i0 + 16);
+                    for (uint64_t i = i0; i < i1; ++i) fn(i);
+                }
+            } catch (...) {
+                if (!failed.exchange(true)) err = std::current_exception();
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
+    if (err) std::rethrow_exception(err);
+}
 
 }  // namespace pb200

@@ -179,33 +179,6 @@ inline CscHost csc_ones_column(uint32_t rows) {  // C of the root layer when C.n
     return m;
 }
 
-template <typename F>
-inline void parallel_for_chunks(uint64_t n, F&& fn) {
-    unsigned hw = std::thread::hardware_concurrency();
-    unsigned nt = std::max(1u, std::min(hw ? hw : 1u, 64u));
-    if (n < 64 || nt == 1) { for (uint64_t i = 0; i < n; ++i) fn(i); return; }
-    std::atomic<uint64_t> next{0};
-    std::vector<std::thread> pool;
-    std::exception_ptr err = nullptr;
-    std::atomic<bool> failed{false};
-    for (unsigned t = 0; t < nt; ++t) {
-        pool.emplace_back([&]() {
-            try {
-                for (;;) {
-                    uint64_t i0 = next.fetch_add(16);
-                    if (i0 >= n || failed.load()) break;
-                    uint64_t i1 = std::min(n, i0 + 16);
-                    for (uint64_t i = i0; i < i1; ++i) fn(i);
-                }
-            } catch (...) {
-                if (!failed.exchange(true)) err = std::current_exception();
-            }
-        });
-    }
-    for (auto& th : pool) th.join();
-    if (err) std::rethrow_exception(err);
-}
-
 // ---------------------------------------------------------------------------------------------
 // (W, C) -> chunked layer
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,161 @@
+"""GPU parity tests for the HNSW hot path: CUDA engine (through the C ABI / Python mirror) vs the CPU oracles.
+
+Bar: bit-exact neighbour ids and ranks; distances bit-exact when the oracle ran the avx512f summation order the kernel
+restates (the reference picks its SIMD clone at run time), else within 1e-5 relative.
+
+Mirrors test/pecos/ann/test_hnsw.py: load -> predict identity incl. lazy_load (:20-56), recall vs brute force on the
+prebuilt fixture index for efS in {50, 75, 100} (:58-124).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hnsw_toy")
+
+
+def _load(folder, **kw):
+    from pecos_b200.hnsw import HNSW
+
+    return HNSW.load(folder, **kw)
+
+
+def _pp(efS, topk):
+    from pecos_b200.hnsw import HNSW
+
+    return HNSW.PredParams(efS=efS, topk=topk, threads=1)
+
+
+@pytest.fixture(scope="module")
+def golden(gpu_clib):
+    E = np.load(os.path.join(GOLD, "expected.npz"))
+    index = json.load(open(os.path.join(GOLD, "expected_index.json")))
+    return E, index, np.load(os.path.join(GOLD, "X.tst.npy")), np.load(os.path.join(GOLD, "X.trn.npy"))
+
+
+def test_golden_vectors_from_the_reference(golden):
+    """Every recorded (model, efS, topk): ids, order and distance BITS (goldens were produced by the avx512f clone)."""
+    E, index, Xt, _ = golden
+    models = {}
+    for it in index:
+        m = models.get(it["model"]) or models.setdefault(it["model"], _load(os.path.join(GOLD, it["model"])))
+        idx, dist = m.predict(Xt, pred_params=_pp(it["efS"], it["topk"]), ret_csr=False)
+        assert np.array_equal(idx, E[it["key"] + "|idx"]), it["key"]
+        assert np.array_equal(dist.view(np.uint32), E[it["key"] + "|dist"].view(np.uint32)), it["key"]
+
+
+def test_load_predict_identity_lazy_and_searchers(golden):
+    E, index, Xt, _ = golden
+    a = _load(os.path.join(GOLD, "model_ip"))
+    b = _load(os.path.join(GOLD, "model_ip"), lazy_load=True)
+    s = a.searchers_create(2)
+    ia, da = a.predict(Xt, pred_params=_pp(50, 10), searchers=s, ret_csr=False)
+    ib, db = b.predict(Xt, pred_params=_pp(50, 10), ret_csr=False)
+    assert np.array_equal(ia, ib) and np.array_equal(da, db)
+    Y = a.predict(Xt, pred_params=_pp(50, 10), ret_csr=True)
+    assert Y.shape == (Xt.shape[0], 90) and Y.nnz == Xt.shape[0] * 10
+    with pytest.raises(ValueError):
+        a.searchers_create(0)
+    with pytest.raises(ValueError):
+        a.predict(np.zeros((2, 5), dtype=np.float32))
+
+
+def test_recall_against_brute_force(golden):
+    E, index, Xt, Xtrn = golden
+    m = _load(os.path.join(GOLD, "model_ip"))
+    exact = np.argsort(1.0 - Xt @ Xtrn.T, axis=1, kind="stable")[:, :10]
+    for efS in (50, 75, 100):
+        idx, _ = m.predict(Xt, pred_params=_pp(efS, 10), ret_csr=False)
+        recall = np.mean([len(set(idx[i]) & set(exact[i])) / 10.0 for i in range(Xt.shape[0])])
+        assert recall == pytest.approx(1.0, abs=1e-2)
+
+
+def _save_index(tmp, X, M, efC, metric, threads=8):
+    from oracle import ref
+
+    r = ref.RefHNSW.train(X, M=M, efC=efC, metric=metric, threads=threads)
+    os.makedirs(tmp, exist_ok=True)
+    r.save(os.path.join(tmp, "c_model"))
+    json.dump({"model": "HNSW", "data_type": "drm", "metric_type": metric, "num_item": int(X.shape[0]),
+               "feat_dim": int(X.shape[1]), "pred_kwargs": {"efS": 50, "topk": 10, "threads": 1}},
+              open(os.path.join(tmp, "param.json"), "w"))
+    return r
+
+
+@pytest.mark.parametrize("N,d,M,metric", [(4000, 64, 8, "ip"), (3000, 70, 12, "l2"), (2500, 128, 16, "ip"),
+                                          (1200, 3, 4, "l2"), (6000, 768, 16, "ip"), (2000, 100, 6, "l2")])
+def test_random_indices_match_reference_library(tmp_path, gpu_clib, have_ref, N, d, M, metric):
+    """Indices built by the reference on this box; same saved index searched by the reference, the restatement and us."""
+    if not have_ref:
+        pytest.skip("building an index needs oracle/_ref (c_ann_hnsw_train stays on the reference)")
+    from oracle import restatement
+
+    rng = np.random.default_rng(N + d)
+    X = rng.standard_normal((N, d)).astype(np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    Q = rng.standard_normal((257, d)).astype(np.float32)
+    Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+    folder = str(tmp_path / "idx")
+    r = _save_index(folder, X, M, 60, metric)
+    m = _load(folder)
+    o = restatement.OracleHNSW(folder, isa=0)  # avx512f order == what the kernel restates
+    isa = restatement.host_isa()
+    for efS, topk in [(10, 10), (64, 10), (200, 10), (5, 40), (600, 100)]:
+        idx, dist = m.predict(Q, pred_params=_pp(efS, topk), ret_csr=False)
+        oi, od = o.predict(Q, efS, topk)
+        assert np.array_equal(idx, oi), f"ids vs restatement efS={efS} topk={topk}"
+        assert np.array_equal(dist.view(np.uint32), od.view(np.uint32)), f"distance bits vs restatement efS={efS}"
+        ri, rd = r.predict(Q, efS, topk, threads=8)
+        if isa == 0:
+            assert np.array_equal(idx, ri) and np.array_equal(dist.view(np.uint32), rd.view(np.uint32)), "vs reference"
+        else:  # the reference ran another SIMD clone: summation order differs in the last bits
+            assert np.mean(idx == ri) > 0.99 and np.allclose(dist, rd, rtol=1e-5, atol=1e-6)
+
+
+def test_duplicate_points_and_ties(tmp_path, gpu_clib, have_ref):
+    """Many exactly equal distances: the restated libstdc++ heap algorithms decide which duplicates survive."""
+    if not have_ref:
+        pytest.skip("needs oracle/_ref to build the index")
+    from oracle import restatement
+
+    rng = np.random.default_rng(7)
+    base = rng.standard_normal((300, 32)).astype(np.float32)
+    base /= np.linalg.norm(base, axis=1, keepdims=True)
+    X = np.concatenate([base] * 6, axis=0)  # every point six times
+    Q = base[:64] + 0.0
+    folder = str(tmp_path / "idx")
+    r = _save_index(folder, X, 8, 50, "l2", threads=1)
+    m = _load(folder)
+    for efS, topk in [(30, 12), (100, 20)]:
+        idx, dist = m.predict(Q, pred_params=_pp(efS, topk), ret_csr=False)
+        ri, rd = r.predict(Q, efS, topk, threads=1)
+        oi, od = restatement.OracleHNSW(folder, isa=0).predict(Q, efS, topk)
+        assert np.array_equal(idx, oi) and np.array_equal(dist.view(np.uint32), od.view(np.uint32))
+        if restatement.host_isa() == 0:
+            assert np.array_equal(idx, ri) and np.array_equal(dist.view(np.uint32), rd.view(np.uint32))
+
+
+def test_resident_batch_and_counters(golden, gpu_clib):
+    from ctypes import POINTER, byref, c_float, c_uint32, c_uint64
+
+    from oracle import restatement
+    from pecos_b200.core import ScipyDrmF32
+
+    E, index, Xt, _ = golden
+    m = _load(os.path.join(GOLD, "model_l2"))
+    c = gpu_clib.clib_float32
+    px = ScipyDrmF32.init_from(np.ascontiguousarray(Xt))
+    c.pb200_hnsw_resident_upload(m.model_ptr, byref(px))
+    ms = c.pb200_hnsw_resident_predict(m.model_ptr, 50, 10)
+    assert ms > 0
+    idx = np.zeros((Xt.shape[0], 10), dtype=np.uint32)
+    val = np.zeros((Xt.shape[0], 10), dtype=np.float32)
+    c.pb200_hnsw_resident_fetch(m.model_ptr, idx.ctypes.data_as(POINTER(c_uint32)), val.ctypes.data_as(POINTER(c_float)))
+    assert np.array_equal(idx, E["model_l2|50|10|idx"])
+    cnt = (c_uint64 * 4)()
+    c.pb200_hnsw_get_counters(m.model_ptr, cnt)
+    oi, od, oc = restatement.OracleHNSW(os.path.join(GOLD, "model_l2"), isa=0).predict(Xt, 50, 10, return_counters=True)
+    assert [int(x) for x in cnt] == [int(oc[:, 0].sum()), int(oc[:, 1].sum()), int(oc[:, 2].sum()), Xt.shape[0]]
