@@ -185,7 +185,7 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const uint32_t
     float* qs = reinterpret_cast<float*>(base);
     uint32_t* nb_ids = reinterpret_cast<uint32_t*>(qs + ix.vstride);
     float* nb_dist = reinterpret_cast<float*>(nb_ids + nbmax);
-    uint2* topq = topk_all ? topk_all + static_cast<uint64_t>(gw) * ef : reinterpret_cast<uint2*>(nb_dist + nbmax);
+    uint2* topq = topk_all ? topk_all + static_cast<uint64_t>(gw) * (ef + 1) : reinterpret_cast<uint2*>(nb_dist + nbmax);
     uint32_t* bitmap = bitmap_all + static_cast<uint64_t>(gw) * bitmap_words;
     uint32_t* vlist = vlist_all + static_cast<uint64_t>(gw) * vcap;
     uint2* cand = cand_all + static_cast<uint64_t>(gw) * vcap;
@@ -430,7 +430,7 @@ void HnswEngine::ensure_scratch_(uint32_t ef) {
     const HnswHostIndex& H = *host_;
     const uint32_t nbmax = ((std::max(H.l0_max_degree, H.l1_max_degree) + 31u) / 32u) * 32u;
     const bool top_in_smem = ef <= kEfSmemMax;
-    const uint32_t per_warp = (H.vstride() * 4 + nbmax * 8 + (top_in_smem ? ef * 8 : 0) + 15u) & ~15u;
+    const uint32_t per_warp = (H.vstride() * 4 + nbmax * 8 + (top_in_smem ? (ef + 1) * 8 : 0) + 15u) & ~15u;
     uint32_t warps = 8;
     while (warps > 1 && static_cast<uint64_t>(warps) * per_warp > 96u * 1024u) warps >>= 1;
     if (static_cast<uint64_t>(warps) * per_warp > 200u * 1024u)
@@ -444,7 +444,7 @@ void HnswEngine::ensure_scratch_(uint32_t ef) {
     uint32_t vcap = 32768;
     if (const char* env = std::getenv("PB200_HNSW_VCAP")) vcap = static_cast<uint32_t>(std::max<uint64_t>(1024, std::strtoull(env, nullptr, 10)));
     vcap = static_cast<uint32_t>(std::min<uint64_t>(vcap, static_cast<uint64_t>(H.num_node) + 1));
-    const uint64_t per_warp_scratch = words * 4 + static_cast<uint64_t>(vcap) * 12 + (top_in_smem ? 0 : static_cast<uint64_t>(ef) * 8);
+    const uint64_t per_warp_scratch = words * 4 + static_cast<uint64_t>(vcap) * 12 + (top_in_smem ? 0 : static_cast<uint64_t>(ef + 1) * 8);
     while (n_ctas > static_cast<uint32_t>(sms) && static_cast<uint64_t>(n_ctas) * warps * per_warp_scratch > (24ull << 30)) n_ctas -= sms;
     const uint32_t n_warps = n_ctas * warps;
     if (n_warps != n_warps_ || vcap != vcap_ || (!top_in_smem && ef > scratch_ef_) || warps != warps_per_cta_) {
@@ -452,7 +452,7 @@ void HnswEngine::ensure_scratch_(uint32_t ef) {
         PB200_CUDA(cudaMemsetAsync(bitmap_.get(), 0, static_cast<uint64_t>(n_warps) * words * 4, stream_));
         vlist_.reserve(static_cast<uint64_t>(n_warps) * vcap);
         cand_.reserve(static_cast<uint64_t>(n_warps) * vcap);
-        if (!top_in_smem) { topk_heap_.reserve(static_cast<uint64_t>(n_warps) * ef); scratch_ef_ = ef; }
+        if (!top_in_smem) { topk_heap_.reserve(static_cast<uint64_t>(n_warps) * (ef + 1)); scratch_ef_ = ef; }
         n_warps_ = n_warps; warps_per_cta_ = warps; n_ctas_ = n_ctas; vcap_ = vcap;
     }
 }
@@ -464,7 +464,7 @@ double HnswEngine::launch_(const float* q_dev, uint32_t nq, uint32_t efS, uint32
     ensure_scratch_(ef);
     const uint32_t nbmax = ((std::max(H.l0_max_degree, H.l1_max_degree) + 31u) / 32u) * 32u;
     const bool top_in_smem = ef <= kEfSmemMax;
-    const uint32_t per_warp = (H.vstride() * 4 + nbmax * 8 + (top_in_smem ? ef * 8 : 0) + 15u) & ~15u;
+    const uint32_t per_warp = (H.vstride() * 4 + nbmax * 8 + (top_in_smem ? (ef + 1) * 8 : 0) + 15u) & ~15u;
     const uint32_t words = static_cast<uint32_t>((static_cast<uint64_t>(H.num_node) + 31) / 32);
     PB200_CUDA(cudaMemsetAsync(ctrl_.get(), 0, 8 * sizeof(unsigned long long), stream_));
     PB200_CUDA(cudaMemsetAsync(out_idx_.get(), 0, static_cast<uint64_t>(nq) * topk * 4, stream_));
