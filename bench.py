@@ -78,6 +78,10 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Samples taken before this call (warm-up) are dropped if enough samples follow."""
+        self.mark_at = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -87,9 +91,12 @@ class ClockSampler(object):
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        lines = self.lines[getattr(self, "mark_at", 0):]
+        if len(lines) < 3:
+            lines = self.lines
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in lines:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 9:
                 continue
@@ -222,8 +229,224 @@ def workload_config(name, cfg, X, extra=None):
     return c
 
 
+HNSW_WORKLOADS = {
+    # BASELINE.json configs[3] shape (dense d=768, ip, M=32, efS=200, top-10) at sizes the reference trainer can build
+    # inside a GPU lease; the index is built once per box by the reference's own HNSW.train (oracle/_ref), all host threads
+    "hnsw-100k": dict(N=100_000, d=768, M=32, efC=100, Q=10_000, efS=200, topk=10, metric="ip"),
+    "hnsw-1m": dict(N=1_000_000, d=768, M=32, efC=100, Q=50_000, efS=200, topk=10, metric="ip"),
+    "hnsw-10m": dict(N=10_000_000, d=768, M=32, efC=200, Q=100_000, efS=200, topk=10, metric="ip"),
+}
+
+
+def hnsw_prepare(args, rank, barrier):
+    cfg = dict(HNSW_WORKLOADS[args.workload])
+    folder = os.path.join(args.cache_dir, args.workload)
+    if rank == 0 and not os.path.exists(os.path.join(folder, "c_model", "index.mmap_store")):
+        import oracle
+        from oracle import ref
+
+        oracle.build()
+        os.makedirs(folder, exist_ok=True)
+        rng = np.random.default_rng(30)
+        X = rng.standard_normal((cfg["N"], cfg["d"]), dtype=np.float32)
+        X /= np.linalg.norm(X, axis=1, keepdims=True)
+        t0 = time.perf_counter()
+        r = ref.RefHNSW.train(X, M=cfg["M"], efC=cfg["efC"], metric=cfg["metric"], threads=-1)
+        r.save(os.path.join(folder, "c_model"))
+        with open(os.path.join(folder, "param.json"), "w") as f:
+            json.dump({"model": "HNSW", "data_type": "drm", "metric_type": cfg["metric"], "num_item": cfg["N"],
+                       "feat_dim": cfg["d"], "pred_kwargs": {"efS": cfg["efS"], "topk": cfg["topk"], "threads": 1},
+                       "build_seconds": time.perf_counter() - t0}, f)
+        del r, X
+    barrier()
+    rng = np.random.default_rng(31 + 1000 * rank)
+    Q = rng.standard_normal((cfg["Q"], cfg["d"]), dtype=np.float32)
+    Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+    return folder, np.ascontiguousarray(Q), cfg
+
+
+def hnsw_config(name, cfg, extra=None):
+    c = {"workload": name, "base_vectors": cfg["N"], "dim": cfg["d"], "M": cfg["M"], "efC": cfg["efC"], "efS": cfg["efS"],
+         "topk": cfg["topk"], "metric": cfg["metric"], "queries_per_step_per_gpu": cfg["Q"],
+         "parallelism": "query-sharded replicas (no collective)"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def hnsw_time_reference(folder, Q, cfg, steps, warmup, budget_s=60.0):
+    from oracle import ref
+
+    n_cores = os.cpu_count() or 1
+    m = ref.RefHNSW.load(os.path.join(folder, "c_model"), cfg["metric"])
+    sample = Q
+    t0 = time.perf_counter()
+    m.predict(sample[:2048], cfg["efS"], cfg["topk"], threads=n_cores)
+    first = (time.perf_counter() - t0) * sample.shape[0] / 2048.0
+    if first * (steps + warmup) > budget_s:
+        sample = sample[: max(2048, int(sample.shape[0] * budget_s / (first * (steps + warmup))))]
+    for _ in range(max(0, warmup - 1)):
+        m.predict(sample, cfg["efS"], cfg["topk"], threads=n_cores)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        m.predict(sample, cfg["efS"], cfg["topk"], threads=n_cores)
+        times.append(time.perf_counter() - t0)
+    mean_t = sum(times) / len(times)
+    return {"value": sample.shape[0] / mean_t, "ms_per_step": 1e3 * mean_t, "kind": "reference", "cores": n_cores,
+            "sample": f"{sample.shape[0]} of {Q.shape[0]} queries per step, {steps} steps, {n_cores} searchers (all host threads)"}
+
+
+def main_hnsw(args):
+    rank, world, local = dist_env()
+    n_gpus = max(world, 1)
+    metric_name, unit = "HNSW top-10 queries/sec (efS=200)", UNIT
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        folder, Q, cfg = hnsw_prepare(args, 0, lambda: None)
+        r = hnsw_time_reference(folder, Q, cfg, args.steps, args.warmup)
+        print(json.dumps({"impl": "reference", "metric": metric_name, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": hnsw_config(args.workload, cfg),
+                          "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+                          "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return 0
+
+    from ctypes import POINTER, byref, c_float, c_uint32, c_uint64
+
+    from pecos_b200 import core
+    from pecos_b200.core import ScipyDrmF32
+    from pecos_b200.hnsw import HNSW
+
+    dist = None
+    if n_gpus > 1:
+        import torch
+        import torch.distributed as dist_mod
+
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    barrier()
+    lib = core.get_clib()
+    lib.require_gpu()
+    lib.set_device(local)
+    c = lib.clib_float32
+    folder, Q, cfg = hnsw_prepare(args, rank, barrier)
+    model = HNSW.load(folder)
+    h = model.model_ptr
+    nq, d, efS, topk = Q.shape[0], Q.shape[1], cfg["efS"], cfg["topk"]
+    qv = ScipyDrmF32.init_from(Q)
+    c.pb200_hnsw_resident_upload(h, byref(qv))
+
+    def one_step():
+        c.pb200_l2_flush()
+        return c.pb200_hnsw_resident_predict(h, efS, topk)
+
+    for _ in range(max(3, args.warmup)):
+        one_step()
+    cnt = (c_uint64 * 4)()
+    c.pb200_hnsw_get_counters(h, cnt)
+    n_dist, n_expand, n_hops, _ = [int(x) for x in cnt]
+    info = (c_uint64 * 8)()
+    c.pb200_hnsw_get_info(h, info)
+    maxM, maxM0 = int(info[2]), int(info[3])
+    # n_dist * 4d + n_expand * 4(1+maxM0) + hops * 4(1+maxM) + 4d + 8k per query
+    bytes_per_step = n_dist * 4.0 * d + n_expand * 4.0 * (1 + maxM0) + n_hops * 4.0 * (1 + maxM) + nq * (4.0 * d + 8.0 * topk)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = int(info[7])
+    barrier()
+    step_ms = [one_step() for _ in range(args.steps)]
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    c.pb200_hnsw_get_info(h, info)
+    launches = int(info[7]) - launches0
+    total_ms = float(sum(step_ms))
+    if dist is not None:
+        import torch
+
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = n_gpus * nq / (ms_per_step * 1e-3)
+    peak, peak_src = measured_peak_gbs()
+    achieved = bytes_per_step / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "hnsw_search_kernel", "kernel_ms": ms_per_step, "algorithmic_bytes_per_launch": bytes_per_step,
+                "peak_source": peak_src, "per_query": {"distance_evals": n_dist / nq, "expansions": n_expand / nq,
+                                                       "upper_level_reads": n_hops / nq, "bytes": bytes_per_step / nq}}
+
+    # end to end through the C ABI with pinned host buffers
+    qp = lib.pinned_empty(Q.size, np.float32)
+    qp.array[:] = Q.ravel()
+    qpin = qp.array.reshape(Q.shape)
+    ip = lib.pinned_empty(nq * topk, np.uint32)
+    dp = lib.pinned_empty(nq * topk, np.float32)
+    qv_p = ScipyDrmF32.init_from(qpin)
+    predict = model.fn_dict["predict"]
+
+    def e2e_step():
+        ip.array[:] = 0
+        dp.array[:] = 0
+        predict(h, byref(qv_p), ip.array.ctypes.data_as(POINTER(c_uint32)), dp.array.ctypes.data_as(POINTER(c_float)), efS, topk, 1, None)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_times = []
+    for _ in range(args.steps):
+        c.pb200_l2_flush()
+        t0 = time.perf_counter()
+        e2e_step()
+        e2e_times.append(time.perf_counter() - t0)
+    barrier()
+    e2e_total = float(sum(e2e_times))
+    if dist is not None:
+        import torch
+
+        t = torch.tensor([e2e_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_total = float(t.item())
+    cpu = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        import oracle
+
+        if oracle.have_ref():
+            r = hnsw_time_reference(folder, Q, cfg, steps=3, warmup=1, budget_s=30.0)
+            cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+    if rank == 0:
+        print(json.dumps({
+            "metric": metric_name, "value": value, "unit": unit, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": hnsw_config(args.workload, cfg, {"l2": "flushed between timed iterations; index (%.1f GB) >> L2" % (int(info[6]) / 1e9),
+                                                       "timing": "CUDA events around the search kernel per step, summed, max over ranks"}),
+            "clocks": clocks,
+            "e2e": {"value": n_gpus * nq * args.steps / e2e_total, "unit": unit, "h2d_bytes_per_step": int(Q.nbytes),
+                    "d2h_bytes_per_step": int(nq * topk * 8), "ms_per_step": 1e3 * e2e_total / args.steps,
+                    "api": "c_ann_hnsw_predict_drm_ip_f32 (pinned host queries in, host id/distance arrays out)"},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse_args()
+    if args.workload.startswith("hnsw"):
+        return main_hnsw(args)
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -284,13 +507,15 @@ def main():
         c.pb200_l2_flush()  # outside the event-timed region: every step starts with a cold L2
         return c.pb200_xlinear_resident_predict(h, beam, None, topk, 0)
 
-    for _ in range(max(3, args.warmup)):
-        one_step()
-
-    # ------------------------------------------------------------ timed region: K steps, device time, max over ranks
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # started before the warm-up: nvidia-smi needs ~0.3 s before its first sample
+    for _ in range(max(3, args.warmup)):
+        one_step()
+    if rank == 0:
+        sampler.mark()
+
+    # ------------------------------------------------------------ timed region: K steps, device time, max over ranks
     c.pb200_xlinear_reset_profile(h)
     barrier()
     wall0 = time.perf_counter()

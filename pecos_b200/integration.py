@@ -1,0 +1,49 @@
+"""Overlay the B200 hot-path symbols onto a live ``pecos.core.clib``.
+
+``overlay(clib)`` re-points the XR-Linear predict-only and dense-HNSW function pointers of the reference's
+``corelib`` instance (pecos/core/base.py:481-539, :1951-1964) at ``libpecos_b200_float32.so``; every other symbol keeps
+using the reference CPU library.  The reference package itself is not imported here: pass its ``clib`` object in.
+"""
+import ctypes
+
+from .core import LIB_PATH
+
+XLINEAR_SYMBOLS = (
+    "c_xlinear_load_model_from_disk",
+    "c_xlinear_load_model_from_disk_ext",
+    "c_xlinear_load_mmap_model_from_disk",
+    "c_xlinear_destruct_model",
+    "c_xlinear_get_int_attr",
+    "c_xlinear_get_layer_type",
+    "c_xlinear_predict_csr_f32",
+    "c_xlinear_predict_drm_f32",
+)
+HNSW_SLOTS = ("load", "destruct", "searchers_create", "searchers_destruct", "predict")
+
+
+def overlay(clib, lib_path=LIB_PATH):
+    """Returns the list of symbols that were re-pointed."""
+    b200 = ctypes.CDLL(lib_path)
+    if b200.pb200_device_count() <= 0:
+        raise RuntimeError("pecos_b200: no CUDA device visible and there is no CPU fallback")
+    swapped = []
+    for name in XLINEAR_SYMBOLS:
+        ref = getattr(clib.clib_float32, name)
+        fn = getattr(b200, name)
+        fn.restype, fn.argtypes = ref.restype, ref.argtypes
+        setattr(clib.clib_float32, name, fn)
+        swapped.append(name)
+    fn_dict = getattr(clib, "ann_hnsw_fn_dict", {})
+    for metric in ("ip", "l2"):
+        key = ("drm", metric)
+        if key not in fn_dict:
+            continue
+        for slot in HNSW_SLOTS:
+            name = "c_ann_hnsw_{}_drm_{}_f32".format(slot, metric)
+            ref = fn_dict[key][slot]
+            fn = getattr(b200, name)
+            fn.restype, fn.argtypes = ref.restype, ref.argtypes
+            fn_dict[key][slot] = fn
+            swapped.append(name)
+    clib.clib_b200 = b200
+    return swapped
