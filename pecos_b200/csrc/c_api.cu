@@ -216,6 +216,13 @@ void pb200_xlinear_set_profile(void* ptr, int on) {
     PB200_API_END("pb200_xlinear_set_profile")
 }
 
+int pb200_xlinear_set_lookup(void* ptr, int on) {
+    PB200_API_BEGIN
+    engine_of(ptr).set_lookup(on != 0);
+    return engine_of(ptr).has_feature_maps() ? 1 : 0;
+    PB200_API_END("pb200_xlinear_set_lookup")
+}
+
 void pb200_xlinear_reset_profile(void* ptr) {
     PB200_API_BEGIN
     engine_of(ptr).reset_profile();

@@ -27,7 +27,7 @@ namespace pb200 {
 namespace {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
-constexpr int kWarpsMax = 8;     // warps per CTA of the chunk kernel
+constexpr int kWarpsMax = 16;    // warps per CTA of the chunk kernel
 constexpr int kMCap = 256;       // match list capacity per warp
 constexpr int kMFlush = 128;     // flush the match list once it holds this many rows (kMCap - 128 new per pass)
 constexpr int kECap = 256;       // staged entries per accumulate pass
@@ -145,7 +145,9 @@ __device__ __noinline__ void xl_flush(WarpScratch& ws, int m, const uint32_t* __
     }
 }
 
-template <bool DENSE, bool STATS>
+// DENSE: row-major dense queries.  LOOKUP: sparse queries probe the chunk's feature map (one 8-byte cell per query
+// feature) instead of streaming the chunk's row list -- same matches in the same order, far fewer bytes/instructions.
+template <bool DENSE, bool STATS, bool LOOKUP>
 __global__ void __launch_bounds__(kWarpsMax * 32)
 xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __restrict__ beam_id,
                        const uint32_t* __restrict__ beam_cnt, const uint32_t beam_stride, float* __restrict__ cand,
@@ -230,7 +232,40 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
             }
         } else {
             // chunk_ops<csr, bin_search>: matched rows in ascending feature order, bias row last (inference.hpp:788-811)
-            if (qn > 0 && R > 0) {
+            if (LOOKUP) {
+                if (R > 0) {
+                    const uint2* fm = L.featmap + static_cast<uint64_t>(p) * L.fm_words;
+                    for (int tb = 0; tb < qn; tb += 32) {
+                        const int t = tb + lane;
+                        bool hit = false;
+                        uint32_t slot = 0;
+                        if (t < qn) {
+                            const uint32_t f = qidx[t];
+                            // a repeated column index only counts once: the reference's marching loop consumes the first
+                            const bool dup = (t > 0) && (qidx[t - 1] == f);
+                            if (!dup && f < L.w_rows) {
+                                const uint2 cell = __ldg(fm + (f >> 5));
+                                const uint32_t bit = f & 31u;
+                                hit = (cell.x >> bit) & 1u;
+                                slot = cell.y + __popc(cell.x & ((1u << bit) - 1u));
+                            }
+                        }
+                        const unsigned mask = __ballot_sync(kFull, hit);
+                        if (mask == 0u) continue;
+                        if (hit) {
+                            const uint32_t pos = m + __popc(mask & ((1u << lane) - 1u));
+                            ws.ms[pos] = slot;
+                            ws.mx[pos] = qval[t];
+                        }
+                        m += __popc(mask);
+                        if (m > kMCap - 33) {  // keep room for the next 32 matches and the bias row
+                            m_total += m;
+                            xl_flush(ws, m, rp, ent, out, L.has_dup_cols, lane, e_total);
+                            m = 0;
+                        }
+                    }
+                }
+            } else if (qn > 0 && R > 0) {
                 const uint32_t qmin = qidx[0];
                 const uint32_t qmax = qidx[qn - 1];
                 const uint4 sentinel = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
@@ -492,6 +527,8 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
     PB200_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     for (auto& e : ev_) PB200_CUDA(cudaEventCreate(&e));
     layers_.resize(host_->layers.size());
+    uint64_t featmap_budget = 32ull << 30;  // bytes of HBM the feature maps may take in total
+    if (const char* env = std::getenv("PB200_FEATMAP_MB")) featmap_budget = std::strtoull(env, nullptr, 10) << 20;
     for (size_t d = 0; d < layers_.size(); ++d) {
         auto& src = host_->layers[d];
         auto& dst = layers_[d];
@@ -499,6 +536,19 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
         dst.meta.upload(src.meta.data(), src.meta.size(), stream_);
         dst.entries.upload(reinterpret_cast<const uint2*>(src.entries.data()), src.entries.size(), stream_);
         if (src.reordered) dst.label_of_col.upload(src.label_of_col.data(), src.label_of_col.size(), stream_);
+        // query-driven lookup structure, unless it would blow the memory budget (then the kernel streams the row lists)
+        dst.view.featmap = nullptr;
+        dst.view.fm_words = 0;
+        if (featmap_budget >= feature_map_bytes(src)) {
+            featmap_budget -= feature_map_bytes(src);
+            build_feature_map(src);
+            dst.featmap.upload(reinterpret_cast<const uint2*>(src.featmap.data()), src.featmap.size(), stream_);
+            PB200_CUDA(cudaStreamSynchronize(stream_));
+            dst.view.featmap = dst.featmap.get();
+            dst.view.fm_words = src.fm_words;
+            model_bytes_ += src.featmap.size() * 8;
+            std::vector<uint2_host>().swap(src.featmap);
+        }
         dst.view.chunks = dst.chunks.get();
         dst.view.meta = dst.meta.get();
         dst.view.entries = dst.entries.get();
@@ -519,10 +569,12 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
         std::vector<ChunkEntry>().swap(l.entries);
     }
     const int max_smem = 200 * 1024;
-    PB200_CUDA(cudaFuncSetAttribute(xl_chunk_scores_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PB200_CUDA(cudaFuncSetAttribute(xl_chunk_scores_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PB200_CUDA(cudaFuncSetAttribute(xl_chunk_scores_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PB200_CUDA(cudaFuncSetAttribute(xl_chunk_scores_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(xl_chunk_scores_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(xl_chunk_scores_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(xl_chunk_scores_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(xl_chunk_scores_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(xl_chunk_scores_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(xl_chunk_scores_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     stats_dev_.reserve(8 * layers_.size());
     layer_profile_.assign(layers_.size(), XLinearLayerProfile{});
@@ -534,6 +586,15 @@ XLinearEngine::~XLinearEngine() {
     if (stream_) cudaStreamSynchronize(stream_);
     for (auto& e : ev_) if (e) cudaEventDestroy(e);
     if (stream_) cudaStreamDestroy(stream_);
+}
+
+void XLinearEngine::set_lookup(bool on) {
+    for (auto& l : layers_) l.view.featmap = (on && l.featmap.capacity()) ? l.featmap.get() : nullptr;
+}
+
+bool XLinearEngine::has_feature_maps() const {
+    for (auto& l : layers_) if (!l.featmap.capacity()) return false;
+    return true;
 }
 
 void XLinearEngine::reset_profile() {
@@ -612,17 +673,27 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
         const LayerPlan& lp = plan[d];
         const uint32_t c_stride = std::max<uint32_t>(L.c_max, 1u);
         const uint64_t cand_stride_q = static_cast<uint64_t>(lp.b_prev) * c_stride;
-        const int warps = static_cast<int>(std::max<uint32_t>(1, std::min<uint32_t>(lp.b_prev, kWarpsMax)));
+        // spread the beam slots evenly: b = 10 -> 10 warps x 1 slot, b = 20 -> 10 warps x 2 slots
+        const uint32_t rounds = (lp.b_prev + kWarpsMax - 1) / kWarpsMax;
+        const int warps = static_cast<int>(std::max<uint32_t>(1, (lp.b_prev + rounds - 1) / std::max<uint32_t>(rounds, 1)));
         unsigned long long* stats = collect_stats ? stats_dev_.get() + 8 * d : nullptr;
         if (profile_) PB200_CUDA(cudaEventRecord(ev_[0], stream_));
         const dim3 grid(rows), block(warps * 32);
         const size_t smem1 = chunk_kernel_smem(warps);
+        auto launch = [&](auto kernel) {
+            kernel<<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(),
+                                                   cand_stride_q, c_stride, stats);
+        };
+        const bool lookup = !dense && L.featmap != nullptr;
         if (dense) {
-            if (collect_stats) xl_chunk_scores_kernel<true, true><<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(), cand_stride_q, c_stride, stats);
-            else xl_chunk_scores_kernel<true, false><<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(), cand_stride_q, c_stride, stats);
+            if (collect_stats) launch(xl_chunk_scores_kernel<true, true, false>);
+            else launch(xl_chunk_scores_kernel<true, false, false>);
+        } else if (lookup) {
+            if (collect_stats) launch(xl_chunk_scores_kernel<false, true, true>);
+            else launch(xl_chunk_scores_kernel<false, false, true>);
         } else {
-            if (collect_stats) xl_chunk_scores_kernel<false, true><<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(), cand_stride_q, c_stride, stats);
-            else xl_chunk_scores_kernel<false, false><<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(), cand_stride_q, c_stride, stats);
+            if (collect_stats) launch(xl_chunk_scores_kernel<false, true, false>);
+            else launch(xl_chunk_scores_kernel<false, false, false>);
         }
         PB200_CUDA(cudaGetLastError());
         ++launches_;

@@ -24,6 +24,8 @@ struct LayerDev {
     const uint32_t* meta;
     const uint2* entries;
     const uint32_t* label_of_col;  // nullptr when the layer is contiguously ordered
+    const uint2* featmap;          // per-chunk {bits, prefix} cells for query-driven lookups; nullptr = stream row lists
+    uint32_t fm_words;
     uint32_t n_cols;
     uint32_t n_chunks;
     uint32_t c_max;
@@ -88,6 +90,9 @@ public:
     Result resident_fetch();
 
     void set_profile(bool on) { profile_ = on; }
+    // false = stream the chunk row lists (first-generation kernel) even when feature maps exist; for A/B tests
+    void set_lookup(bool on);
+    bool has_feature_maps() const;
     const std::vector<XLinearLayerProfile>& layer_profile() const { return layer_profile_; }
     void reset_profile();
     const std::vector<XLinearStats>& layer_stats() const { return layer_stats_; }
@@ -106,6 +111,7 @@ private:
         DeviceBuffer<uint32_t> meta;
         DeviceBuffer<uint2> entries;
         DeviceBuffer<uint32_t> label_of_col;
+        DeviceBuffer<uint2> featmap;
         LayerDev view{};
     };
 

@@ -83,6 +83,10 @@ static_assert(sizeof(ChunkEntry) == 8, "chunk entry must stay 8 bytes");
 
 inline uint64_t round_up4(uint64_t x) { return (x + 3) & ~uint64_t(3); }
 
+struct uint2_host {
+    uint32_t x, y;
+};
+
 struct ChunkedLayerHost {
     uint32_t w_rows = 0;     // W.rows (nr_features + 1 when bias > 0)
     uint32_t n_cols = 0;     // columns scored by this layer (after rearrangement: nnz(C))
@@ -100,6 +104,11 @@ struct ChunkedLayerHost {
     std::vector<uint32_t> meta;
     std::vector<ChunkEntry> entries;
     std::vector<uint32_t> label_of_col;
+    // Optional per-chunk feature map for query-driven lookups: fm_words = ceil(w_rows / 32) cells per chunk, cell w =
+    // {bits: which of the features [32w, 32w+32) own a row in the chunk, prefix: number of chunk rows below 32w}.
+    // slot(f) = prefix + popc(bits & ((1 << (f & 31)) - 1)) when bit f is set.  Built on request (build_feature_map).
+    uint32_t fm_words = 0;
+    std::vector<uint2_host> featmap;
 };
 
 struct XLinearHostModel {
@@ -288,6 +297,28 @@ inline void build_chunked_layer(const CscHost& W, const CscHost& C, float bias, 
         std::copy(chunk_rows[p].begin(), chunk_rows[p].end(), m);
         uint32_t* rp = m + round_up4(h.nnz_rows);
         std::copy(chunk_rptr[p].begin(), chunk_rptr[p].end(), rp);
+    });
+}
+
+// Bytes the feature map of a layer would occupy.
+inline uint64_t feature_map_bytes(const ChunkedLayerHost& L) {
+    return static_cast<uint64_t>(L.n_chunks) * ((static_cast<uint64_t>(L.w_rows) + 31) / 32) * 8;
+}
+
+// Builds the per-chunk {bits, prefix} cells from the chunk row lists (must run before meta[] is released).
+inline void build_feature_map(ChunkedLayerHost& L) {
+    L.fm_words = static_cast<uint32_t>((static_cast<uint64_t>(L.w_rows) + 31) / 32);
+    L.featmap.assign(static_cast<uint64_t>(L.n_chunks) * L.fm_words, uint2_host{0u, 0u});
+    parallel_for_chunks(L.n_chunks, [&](uint64_t p) {
+        const ChunkHeader& h = L.chunks[p];
+        const uint32_t* rows = L.meta.data() + h.meta_off;
+        uint2_host* cells = L.featmap.data() + p * L.fm_words;
+        for (uint32_t r = 0; r < h.nnz_rows; ++r) cells[rows[r] >> 5].x |= 1u << (rows[r] & 31u);
+        uint32_t run = 0;
+        for (uint32_t w = 0; w < L.fm_words; ++w) {
+            cells[w].y = run;
+            run += static_cast<uint32_t>(__builtin_popcount(cells[w].x));
+        }
     });
 }
 

@@ -189,6 +189,33 @@ def test_mmap_model_equals_npz_model(tmp_path, gpu_clib, have_ref, small_model):
     assert_csr_parity(mm_lazy.predict(X, beam_size=5, only_topk=5), a, rtol=0.0, what="lazy mmap vs npz")
 
 
+def test_streaming_and_lookup_kernels_agree(tmp_path, gpu_clib, have_ref):
+    """The query-driven feature-map kernel and the row-list streaming kernel must return identical bits."""
+    folder = str(tmp_path / "m")
+    layers = random_tree(71, [6, 50, 700], 900, 35, bias=1.0, permute=True, prune=0.1)
+    synth.save_xlinear_model(folder, layers, bias=1.0, only_topk=8)
+    X = synth.make_queries(72, 150, 900, 300)
+    # non-canonical CSR: repeat some column indices (only the first occurrence may count, inference.hpp:788-803)
+    Xd = X.copy()
+    per_row = Xd.indices.reshape(X.shape[0], -1)  # every synthetic row has the same nnz
+    per_row[:, 1::7] = per_row[:, 0:-1:7][:, : per_row[:, 1::7].shape[1]]  # duplicates stay adjacent => rows stay sorted
+    Xd.indices = per_row.reshape(-1)
+    Xd.has_sorted_indices = True
+    m, oracles = _load(folder), _oracles(folder, have_ref)
+    c = gpu_clib.clib_float32
+    assert c.pb200_xlinear_set_lookup(m.model.model_chain, 1) == 1
+    a = _check(m, oracles, X, "lookup", beam_size=8, only_topk=10)
+    a_dup = m.predict(Xd, beam_size=8, only_topk=10)
+    c.pb200_xlinear_set_lookup(m.model.model_chain, 0)
+    b = _check(m, oracles, X, "streaming", beam_size=8, only_topk=10)
+    b_dup = m.predict(Xd, beam_size=8, only_topk=10)
+    c.pb200_xlinear_set_lookup(m.model.model_chain, 1)
+    assert_csr_parity(a, b, rtol=0.0, what="lookup vs streaming")
+    assert_csr_parity(a_dup, b_dup, rtol=0.0, what="lookup vs streaming, duplicated column indices")
+    if "reference" in oracles:
+        assert_csr_parity(a_dup, oracles["reference"].predict(Xd, 8, None, 10), what="duplicated column indices vs reference")
+
+
 def test_resident_batch_and_counters(small_model, gpu_clib):
     """Device-resident path used by bench.py: same answers, plus algorithmic-byte counters and launch counts."""
     from ctypes import byref, c_double, c_uint64
