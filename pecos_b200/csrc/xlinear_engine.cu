@@ -113,35 +113,60 @@ __device__ __noinline__ void xl_flush(WarpScratch& ws, int m, const uint32_t* __
     __syncwarp();
     e_total += total;
 
-    for (uint32_t t0 = 0; t0 < total; t0 += kECap) {
-        const uint32_t tn = min(static_cast<uint32_t>(kECap), total - t0);
-        for (uint32_t g = lane; g < tn; g += 32) {
-            const uint32_t G = t0 + g;
-            const int i = last_le_u32(ws.off, m, G);
-            const uint2 en = __ldg(ent + ws.ms[i] + (G - ws.off[i]));
-            const float prod = __fmul_rn(ws.mx[i], __uint_as_float(en.y));
-            ws.stage[g] = make_uint2(en.x, __float_as_uint(prod));
-        }
-        __syncwarp();
-        const int i_lo = last_le_u32(ws.off, m, t0);
-        const int i_hi = last_le_u32(ws.off, m, t0 + tn - 1);
-        for (int i = i_lo; i <= i_hi; ++i) {
-            const uint32_t lo = max(ws.off[i], t0) - t0;
-            const uint32_t hi = min(ws.off[i + 1], t0 + tn) - t0;
-            if (!has_dup) {
-                // entries of one chunk row carry distinct columns: lanes never collide
-                for (uint32_t g = lo + lane; g < hi; g += 32) {
-                    const uint2 s = ws.stage[g];
-                    out[s.x] = __fadd_rn(out[s.x], __uint_as_float(s.y));
-                }
-            } else if (lane == 0) {
-                for (uint32_t g = lo; g < hi; ++g) {
-                    const uint2 s = ws.stage[g];
-                    out[s.x] = __fadd_rn(out[s.x], __uint_as_float(s.y));
+    // Stage tiles of whole matched rows (one lane per row: rows are short), then apply the staged entries to the
+    // output block 32 at a time.  Entries of one 32-group that hit the same column (they come from different rows, or
+    // from a row that repeats a column) are applied in staged order = ascending feature order; __match_any_sync finds
+    // the collisions, so the common collision-free group costs a single round.
+    (void)has_dup;
+    int i0 = 0;
+    uint32_t part = 0;  // entries of row i0 already applied (only rows longer than the staging area are split)
+    while (i0 < m) {
+        const uint32_t row_begin = ws.off[i0];
+        const uint32_t base = row_begin + part;
+        int i_next;
+        uint32_t part_next = 0, ne;
+        if (part == 0 && ws.off[i0 + 1] - row_begin <= static_cast<uint32_t>(kECap)) {
+            const int i1 = last_le_u32(ws.off, m + 1, base + kECap);  // rows [i0, i1) fit entirely; i1 > i0
+            for (int i = i0 + lane; i < i1; i += 32) {
+                const uint32_t a = ws.ms[i];
+                const uint32_t n = ws.off[i + 1] - ws.off[i];
+                const uint32_t o = ws.off[i] - base;
+                const float x = ws.mx[i];
+                for (uint32_t j = 0; j < n; ++j) {
+                    const uint2 en = __ldg(ent + a + j);
+                    ws.stage[o + j] = make_uint2(en.x, __float_as_uint(__fmul_rn(x, __uint_as_float(en.y))));
                 }
             }
-            __syncwarp();
+            ne = ws.off[i1] - base;
+            i_next = i1;
+        } else {
+            const uint32_t n_left = ws.off[i0 + 1] - base;
+            ne = min(static_cast<uint32_t>(kECap), n_left);
+            const uint32_t a = ws.ms[i0] + part;
+            const float x = ws.mx[i0];
+            for (uint32_t g = lane; g < ne; g += 32) {
+                const uint2 en = __ldg(ent + a + g);
+                ws.stage[g] = make_uint2(en.x, __float_as_uint(__fmul_rn(x, __uint_as_float(en.y))));
+            }
+            if (ne == n_left) { i_next = i0 + 1; } else { i_next = i0; part_next = part + ne; }
         }
+        __syncwarp();
+        for (uint32_t g0 = 0; g0 < ne; g0 += 32) {
+            const uint32_t g = g0 + lane;
+            const bool valid = g < ne;
+            const uint2 s = valid ? ws.stage[g] : make_uint2(0xFFFFFFFFu - lane, 0u);
+            const unsigned peers = __match_any_sync(kFull, s.x);
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            unsigned pending = __ballot_sync(kFull, valid);
+            for (int r = 0; pending; ++r) {
+                if (valid && rank == r) out[s.x] = __fadd_rn(out[s.x], __uint_as_float(s.y));
+                __syncwarp();
+                pending = __ballot_sync(kFull, valid && rank > r);
+            }
+        }
+        __syncwarp();
+        i0 = i_next;
+        part = part_next;
     }
 }
 
@@ -498,6 +523,96 @@ xl_topk_kernel(const LayerDev L, const int pp_kind, const int pp_p, const int co
     }
 }
 
+// Narrow-beam variant: one WARP per query (kSelWarps queries per CTA).  The keys of the <= kSelKeys candidates sit in the
+// warp's shared-memory slice; the top-k is extracted by k rounds of warp arg-max on the 64-bit composite key (keys are
+// unique because they embed the candidate position), the winning lane rescanning only its own stride-32 subset.
+// Same keys, same order, same values as xl_topk_kernel.
+constexpr int kSelWarps = 4;
+constexpr int kSelKeys = 1024;
+constexpr int kSelSlots = 64;
+constexpr int kSelK = 64;
+
+struct __align__(16) SelScratch {
+    unsigned long long keys[kSelKeys];
+    uint32_t base[kSelSlots + 1];
+    uint32_t colbeg[kSelSlots];
+    float pval[kSelSlots];
+};
+
+__global__ void __launch_bounds__(kSelWarps * 32)
+xl_topk_warp_kernel(const LayerDev L, const int pp_kind, const int pp_p, const int combine, const uint32_t k,
+                    const uint32_t* __restrict__ beam_id, const float* __restrict__ beam_val,
+                    const uint32_t* __restrict__ beam_cnt, const uint32_t beam_stride, const float* __restrict__ cand,
+                    const uint64_t cand_stride_q, const uint32_t c_stride, uint32_t* __restrict__ out_id,
+                    float* __restrict__ out_val, uint32_t* __restrict__ out_cnt, const uint32_t out_stride,
+                    const uint32_t rows, unsigned long long* stats) {
+    __shared__ SelScratch scratch[kSelWarps];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * kSelWarps + warp;
+    if (q >= rows) return;
+    SelScratch& S = scratch[warp];
+    const uint32_t cnt = beam_cnt[q];
+    for (uint32_t j = lane; j < cnt; j += 32) {
+        const uint32_t p = beam_id[static_cast<uint64_t>(q) * beam_stride + j];
+        const ChunkHeader h = L.chunks[p];
+        S.base[j + 1] = h.n_cols;
+        S.colbeg[j] = h.col_begin;
+        S.pval[j] = beam_val[static_cast<uint64_t>(q) * beam_stride + j];
+    }
+    __syncwarp();
+    if (lane == 0) {
+        uint32_t run = 0;
+        S.base[0] = 0;
+        for (uint32_t j = 0; j < cnt; ++j) { run += S.base[j + 1]; S.base[j + 1] = run; }
+    }
+    __syncwarp();
+    const uint32_t n_valid = S.base[cnt];
+    const uint32_t kk = min(k, n_valid);
+    if (lane == 0) {
+        out_cnt[q] = kk;
+        if (stats) atomicAdd(&stats[6], static_cast<unsigned long long>(kk));
+    }
+    if (n_valid == 0) return;
+    const float* cq = cand + static_cast<uint64_t>(q) * cand_stride_q;
+    auto score_at = [&](uint32_t cpos, uint32_t& label) -> float {
+        const uint32_t j = static_cast<uint32_t>(last_le_u32(S.base, static_cast<int>(cnt), cpos));
+        const uint32_t off = cpos - S.base[j];
+        float v = xl_transform(cq[static_cast<uint64_t>(j) * c_stride + off], pp_kind, pp_p);
+        if (combine) v = xl_combine(v, S.pval[j], pp_kind);
+        label = S.colbeg[j] + off;
+        return v;
+    };
+    unsigned long long best = 0ull;  // lane-local maximum over positions lane, lane+32, ...
+    for (uint32_t i = lane; i < n_valid; i += 32) {
+        uint32_t lab;
+        const unsigned long long key = xl_make_key(score_at(i, lab), i);
+        S.keys[i] = key;
+        best = key > best ? key : best;
+    }
+    __syncwarp();
+    for (uint32_t r = 0; r < kk; ++r) {
+        unsigned long long top = best;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(kFull, top, d);
+            top = o > top ? o : top;
+        }
+        const uint32_t cpos = 0xFFFFFFFFu - static_cast<uint32_t>(top & 0xFFFFFFFFull);
+        if ((cpos & 31u) == static_cast<uint32_t>(lane)) {
+            uint32_t label;
+            const float v = score_at(cpos, label);  // recomputed: keeps the exact bits (-0.0) of the stored value
+            if (L.label_of_col) label = L.label_of_col[label];
+            out_id[static_cast<uint64_t>(q) * out_stride + r] = label;
+            out_val[static_cast<uint64_t>(q) * out_stride + r] = v;
+            S.keys[cpos] = 0ull;
+            best = 0ull;
+            for (uint32_t i = lane; i < n_valid; i += 32) { const unsigned long long key = S.keys[i]; best = key > best ? key : best; }
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void xl_init_beam_kernel(uint32_t* beam_id, float* beam_val, uint32_t* beam_cnt, uint32_t beam_stride,
                                     uint32_t rows) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -590,6 +705,7 @@ XLinearEngine::~XLinearEngine() {
 
 void XLinearEngine::set_lookup(bool on) {
     for (auto& l : layers_) l.view.featmap = (on && l.featmap.capacity()) ? l.featmap.get() : nullptr;
+    force_block_topk_ = !on;
 }
 
 bool XLinearEngine::has_feature_maps() const {
@@ -711,10 +827,18 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
             o_stride = beam_stride_;
         }
         const uint64_t sort_stride = next_pow2_host(cand_stride_q);
-        xl_topk_kernel<<<grid, kTopkThreads, topk_kernel_smem(lp.b_prev), stream_>>>(
-            L, lp.pp.kind, lp.pp.p, d == 0 ? 0 : 1, lp.k, beam_id_[cur].get(), beam_val_[cur].get(), beam_cnt_[cur].get(),
-            beam_stride_, cand_.get(), cand_stride_q, c_stride, o_id, o_val, o_cnt, o_stride, sortbuf_.get(), sort_stride,
-            lp.b_prev, stats);
+        const bool warp_select = !force_block_topk_ && lp.b_prev <= static_cast<uint32_t>(kSelSlots) &&
+                                 cand_stride_q <= static_cast<uint64_t>(kSelKeys) && lp.k <= static_cast<uint32_t>(kSelK);
+        if (warp_select) {
+            xl_topk_warp_kernel<<<(rows + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream_>>>(
+                L, lp.pp.kind, lp.pp.p, d == 0 ? 0 : 1, lp.k, beam_id_[cur].get(), beam_val_[cur].get(), beam_cnt_[cur].get(),
+                beam_stride_, cand_.get(), cand_stride_q, c_stride, o_id, o_val, o_cnt, o_stride, rows, stats);
+        } else {
+            xl_topk_kernel<<<grid, kTopkThreads, topk_kernel_smem(lp.b_prev), stream_>>>(
+                L, lp.pp.kind, lp.pp.p, d == 0 ? 0 : 1, lp.k, beam_id_[cur].get(), beam_val_[cur].get(), beam_cnt_[cur].get(),
+                beam_stride_, cand_.get(), cand_stride_q, c_stride, o_id, o_val, o_cnt, o_stride, sortbuf_.get(), sort_stride,
+                lp.b_prev, stats);
+        }
         PB200_CUDA(cudaGetLastError());
         ++launches_;
         if (profile_) {

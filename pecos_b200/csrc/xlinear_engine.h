@@ -154,6 +154,7 @@ private:
     PinnedBuffer<uint32_t> out_cnt_;
 
     bool profile_ = false;
+    bool force_block_topk_ = false;  // A/B switch: first-generation kernels (row-list streaming + block-wide sort)
     std::vector<XLinearLayerProfile> layer_profile_;
     std::vector<XLinearStats> layer_stats_;
     uint64_t launches_ = 0;
