@@ -36,10 +36,13 @@ constexpr int kQCap = 1024;      // query non-zeros staged in shared memory (lon
 constexpr int kSortCap = 2048;   // keys sorted in shared memory per pass of the top-k kernel
 constexpr int kTopkThreads = 256;
 
+constexpr int kMCapLookup = 128; // the lookup kernel adds at most 32 matches per pass: a shorter list => higher occupancy
+
+template <int MCAP>
 struct __align__(16) WarpScratch {
-    uint32_t ms[kMCap];        // chunk-row index of each match; becomes the row's first entry offset during flush
-    float mx[kMCap];           // multiplier of the row: query value, or the bias
-    uint32_t off[kMCap + 4];   // exclusive prefix of the matched rows' entry counts
+    uint32_t ms[MCAP];         // chunk-row index of each match; becomes the row's first entry offset during flush
+    float mx[MCAP];            // multiplier of the row: query value, or the bias
+    uint32_t off[MCAP + 4];    // exclusive prefix of the matched rows' entry counts
     uint2 stage[kECap];        // staged {col_offset, bits of x*w}
     float out[kCSmem];         // dense output block of the chunk
 };
@@ -80,12 +83,13 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 }
 
 // Apply the matched rows collected in ws (in ascending feature order) to the output block.
-__device__ __noinline__ void xl_flush(WarpScratch& ws, int m, const uint32_t* __restrict__ rp,
+template <int MCAP>
+__device__ __noinline__ void xl_flush(WarpScratch<MCAP>& ws, int m, const uint32_t* __restrict__ rp,
                                       const uint2* __restrict__ ent, float* out, int has_dup, int lane,
                                       unsigned long long& e_total) {
     if (m == 0) return;
     __syncwarp();
-    constexpr int PER = kMCap / 32;
+    constexpr int PER = MCAP / 32;
     uint32_t a[PER], c[PER];
     uint32_t local = 0;
 #pragma unroll
@@ -132,9 +136,22 @@ __device__ __noinline__ void xl_flush(WarpScratch& ws, int m, const uint32_t* __
                 const uint32_t n = ws.off[i + 1] - ws.off[i];
                 const uint32_t o = ws.off[i] - base;
                 const float x = ws.mx[i];
-                for (uint32_t j = 0; j < n; ++j) {
-                    const uint2 en = __ldg(ent + a + j);
-                    ws.stage[o + j] = make_uint2(en.x, __float_as_uint(__fmul_rn(x, __uint_as_float(en.y))));
+                const uint2* src = ent + a;
+                uint32_t j = 0;
+                for (; j + 4 <= n; j += 4) {  // four independent loads in flight per lane
+                    const uint2 e0 = __ldg(src + j), e1 = __ldg(src + j + 1), e2 = __ldg(src + j + 2), e3 = __ldg(src + j + 3);
+                    ws.stage[o + j] = make_uint2(e0.x, __float_as_uint(__fmul_rn(x, __uint_as_float(e0.y))));
+                    ws.stage[o + j + 1] = make_uint2(e1.x, __float_as_uint(__fmul_rn(x, __uint_as_float(e1.y))));
+                    ws.stage[o + j + 2] = make_uint2(e2.x, __float_as_uint(__fmul_rn(x, __uint_as_float(e2.y))));
+                    ws.stage[o + j + 3] = make_uint2(e3.x, __float_as_uint(__fmul_rn(x, __uint_as_float(e3.y))));
+                }
+                if (j < n) {
+                    const uint2 e0 = __ldg(src + j);
+                    const uint2 e1 = (j + 1 < n) ? __ldg(src + j + 1) : e0;
+                    const uint2 e2 = (j + 2 < n) ? __ldg(src + j + 2) : e0;
+                    ws.stage[o + j] = make_uint2(e0.x, __float_as_uint(__fmul_rn(x, __uint_as_float(e0.y))));
+                    if (j + 1 < n) ws.stage[o + j + 1] = make_uint2(e1.x, __float_as_uint(__fmul_rn(x, __uint_as_float(e1.y))));
+                    if (j + 2 < n) ws.stage[o + j + 2] = make_uint2(e2.x, __float_as_uint(__fmul_rn(x, __uint_as_float(e2.y))));
                 }
             }
             ne = ws.off[i1] - base;
@@ -156,12 +173,11 @@ __device__ __noinline__ void xl_flush(WarpScratch& ws, int m, const uint32_t* __
             const bool valid = g < ne;
             const uint2 s = valid ? ws.stage[g] : make_uint2(0xFFFFFFFFu - lane, 0u);
             const unsigned peers = __match_any_sync(kFull, s.x);
-            const int rank = __popc(peers & ((1u << lane) - 1u));
-            unsigned pending = __ballot_sync(kFull, valid);
-            for (int r = 0; pending; ++r) {
+            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+            const uint32_t rounds = __reduce_max_sync(kFull, valid ? rank : 0u);
+            for (uint32_t r = 0; r <= rounds; ++r) {
                 if (valid && rank == r) out[s.x] = __fadd_rn(out[s.x], __uint_as_float(s.y));
                 __syncwarp();
-                pending = __ballot_sync(kFull, valid && rank > r);
             }
         }
         __syncwarp();
@@ -180,7 +196,8 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* q_idx_s = reinterpret_cast<uint32_t*>(smem_raw);
     float* q_val_s = reinterpret_cast<float*>(smem_raw + kQCap * 4);
-    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem_raw + kQCap * 8);
+    constexpr int MCAP = LOOKUP ? kMCapLookup : kMCap;
+    WarpScratch<MCAP>* scratch = reinterpret_cast<WarpScratch<MCAP>*>(smem_raw + kQCap * 8);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -208,7 +225,7 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
     }
 
     const uint32_t cnt = beam_cnt[q];
-    WarpScratch& ws = scratch[warp];
+    WarpScratch<MCAP>& ws = scratch[warp];
     unsigned long long st_chunks = 0, st_rows = 0, st_match = 0, st_ent = 0, st_cols = 0;
 
     for (uint32_t j = warp; j < cnt; j += nwarps) {
@@ -283,7 +300,7 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
                             ws.mx[pos] = qval[t];
                         }
                         m += __popc(mask);
-                        if (m > kMCap - 33) {  // keep room for the next 32 matches and the bias row
+                        if (m > MCAP - 33) {  // keep room for the next 32 matches and the bias row
                             m_total += m;
                             xl_flush(ws, m, rp, ent, out, L.has_dup_cols, lane, e_total);
                             m = 0;
@@ -629,7 +646,9 @@ uint32_t next_pow2_host(uint64_t v) {
     return static_cast<uint32_t>(p);
 }
 
-size_t chunk_kernel_smem(int warps) { return static_cast<size_t>(kQCap) * 8 + static_cast<size_t>(warps) * sizeof(WarpScratch); }
+size_t chunk_kernel_smem(int warps, bool lookup) {
+    return static_cast<size_t>(kQCap) * 8 + static_cast<size_t>(warps) * (lookup ? sizeof(WarpScratch<kMCapLookup>) : sizeof(WarpScratch<kMCap>));
+}
 size_t topk_kernel_smem(uint32_t b_prev) { return static_cast<size_t>(kSortCap) * 8 + (static_cast<size_t>(b_prev) * 3 + 1) * 4; }
 
 }  // namespace
@@ -795,12 +814,12 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
         unsigned long long* stats = collect_stats ? stats_dev_.get() + 8 * d : nullptr;
         if (profile_) PB200_CUDA(cudaEventRecord(ev_[0], stream_));
         const dim3 grid(rows), block(warps * 32);
-        const size_t smem1 = chunk_kernel_smem(warps);
+        const bool lookup = !dense && L.featmap != nullptr;
+        const size_t smem1 = chunk_kernel_smem(warps, lookup);
         auto launch = [&](auto kernel) {
             kernel<<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(),
                                                    cand_stride_q, c_stride, stats);
         };
-        const bool lookup = !dense && L.featmap != nullptr;
         if (dense) {
             if (collect_stats) launch(xl_chunk_scores_kernel<true, true, false>);
             else launch(xl_chunk_scores_kernel<true, false, false>);
