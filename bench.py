@@ -633,4 +633,12 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    # Exactly ONE line goes to stdout (the JSON record): libraries that write banners to fd 1 (e.g. "NCCL version ...")
+    # are diverted to stderr for the whole run; print() is re-pointed at the saved descriptor.
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
+    rc = main()
+    sys.stdout.flush()
+    sys.exit(rc)

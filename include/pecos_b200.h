@@ -118,6 +118,22 @@ double pb200_xlinear_resident_predict(void* ptr, uint32_t overridden_beam_size, 
                                       uint32_t overridden_only_topk, int collect_stats);
 void pb200_xlinear_resident_fetch(void* ptr, py_sparse_allocator_t pred_alloc);
 
+/* Index sharding of the leaf layer over `shard_world` GPUs (one process per GPU).  Upper layers are
+ * replicated, so every rank walks the identical global beam; rank r keeps the weights of a contiguous range of leaf
+ * chunks and scores only those.  weight_matrix_type < 0 loads an mmap folder.
+ *   local:  runs all layers, writes this rank's top-k {u64 key, u32 id, f32 value}[rows][stride] and u32 count[rows]
+ *           into CALLER-OWNED DEVICE buffers (the send buffers of ONE ncclAllGather); returns stride (<= capacity).
+ *   merge:  gathered [world][rows][stride] lists -> global top-k, returned through pred_alloc like c_xlinear_predict_*.
+ * The result is bit-identical to the unsharded prediction (keys carry the candidate's global position). */
+void* pb200_xlinear_load_sharded(const char* model_path, int weight_matrix_type, uint32_t shard_rank, uint32_t shard_world);
+void pb200_xlinear_get_shard(void* ptr, uint32_t* out /* rank, world, leaf_chunk_begin, leaf_chunk_end */);
+uint32_t pb200_xlinear_sharded_local_csr(void* ptr, const ScipyCsrF32* input_x, uint32_t overridden_beam_size,
+                                         const char* overridden_post_processor_str, uint32_t overridden_only_topk,
+                                         uint32_t stride_capacity, void* keys_dev, void* ids_dev, void* vals_dev, void* cnt_dev);
+void pb200_xlinear_sharded_merge(void* ptr, uint32_t world, uint32_t rows, uint32_t stride, uint32_t overridden_only_topk,
+                                 const void* g_keys, const void* g_ids, const void* g_vals, const void* g_cnt,
+                                 py_sparse_allocator_t pred_alloc);
+
 /* Per-layer kernel timing (CUDA events) and algorithmic-byte counters.
  *   profile: out[2*d] = chunk-score kernel ms, out[2*d+1] = top-k kernel ms   (accumulated since reset)
  *   stats:   out[7*d + {0..6}] = chunks, sum R, sum m, sum e, sum c, sum nnz(x), sum beam-out   (last stats pass) */

@@ -210,6 +210,39 @@ void pb200_xlinear_resident_fetch(void* ptr, py_sparse_allocator_t pred_alloc) {
     PB200_API_END("pb200_xlinear_resident_fetch")
 }
 
+void* pb200_xlinear_load_sharded(const char* model_path, int weight_matrix_type, uint32_t shard_rank, uint32_t shard_world) {
+    PB200_API_BEGIN
+    if (weight_matrix_type < 0) return make_engine(pb200::load_xlinear_mmap_model(model_path, false, shard_rank, shard_world));
+    return make_engine(pb200::load_xlinear_npz_model(model_path, weight_matrix_type, shard_rank, shard_world));
+    PB200_API_END("pb200_xlinear_load_sharded")
+}
+
+void pb200_xlinear_get_shard(void* ptr, uint32_t* out) {
+    PB200_API_BEGIN
+    const auto& m = engine_of(ptr).host();
+    out[0] = m.shard_rank; out[1] = m.shard_world; out[2] = m.leaf_chunk_begin; out[3] = m.leaf_chunk_end;
+    PB200_API_END("pb200_xlinear_get_shard")
+}
+
+uint32_t pb200_xlinear_sharded_local_csr(void* ptr, const ScipyCsrF32* X, uint32_t beam, const char* pp, uint32_t topk,
+                                         uint32_t stride_capacity, void* keys_dev, void* ids_dev, void* vals_dev, void* cnt_dev) {
+    PB200_API_BEGIN
+    return engine_of(ptr).sharded_local_csr(X->row_ptr, X->col_idx, X->val, X->rows, X->cols, beam, pp, topk, stride_capacity,
+                                            static_cast<unsigned long long*>(keys_dev), static_cast<uint32_t*>(ids_dev),
+                                            static_cast<float*>(vals_dev), static_cast<uint32_t*>(cnt_dev));
+    PB200_API_END("pb200_xlinear_sharded_local_csr")
+}
+
+void pb200_xlinear_sharded_merge(void* ptr, uint32_t world, uint32_t rows, uint32_t stride, uint32_t topk, const void* g_keys,
+                                 const void* g_ids, const void* g_vals, const void* g_cnt, py_sparse_allocator_t pred_alloc) {
+    PB200_API_BEGIN
+    auto r = engine_of(ptr).sharded_merge(world, rows, stride, topk, static_cast<const unsigned long long*>(g_keys),
+                                          static_cast<const uint32_t*>(g_ids), static_cast<const float*>(g_vals),
+                                          static_cast<const uint32_t*>(g_cnt));
+    emit_result(r, pred_alloc);
+    PB200_API_END("pb200_xlinear_sharded_merge")
+}
+
 void pb200_xlinear_set_profile(void* ptr, int on) {
     PB200_API_BEGIN
     engine_of(ptr).set_profile(on != 0);

@@ -231,6 +231,8 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
     for (uint32_t j = warp; j < cnt; j += nwarps) {
         const uint32_t p = beam_id[static_cast<uint64_t>(q) * beam_stride + j];
         const ChunkHeader h = L.chunks[p];
+        if (h.has_bias & kChunkAbsent) continue;  // leaf chunk owned by another GPU (index sharding): not scored here
+        const bool chunk_bias = (h.has_bias & 1u) != 0u;
         const uint32_t R = h.nnz_rows;
         const uint32_t R4 = (R + 3u) & ~3u;
         const uint32_t* ridx = L.meta + h.meta_off;
@@ -247,8 +249,8 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
 
         if (DENSE) {
             // chunk_ops<drm, bin_search>: bias row first, then every chunk row (inference.hpp:823-837)
-            const uint32_t r_lim = h.has_bias ? R - 1u : R;
-            if (h.has_bias) {
+            const uint32_t r_lim = chunk_bias ? R - 1u : R;
+            if (chunk_bias) {
                 if (lane == 0) { ws.ms[0] = R - 1u; ws.mx[0] = L.bias; }
                 m = 1;
                 __syncwarp();
@@ -342,7 +344,7 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
                     }
                 }
             }
-            if (h.has_bias) {
+            if (chunk_bias) {
                 __syncwarp();
                 if (lane == 0) { ws.ms[m] = R - 1u; ws.mx[m] = L.bias; }
                 ++m;
@@ -451,7 +453,7 @@ xl_topk_kernel(const LayerDev L, const int pp_kind, const int pp_p, const int co
                const uint64_t cand_stride_q, const uint32_t c_stride, uint32_t* __restrict__ out_id,
                float* __restrict__ out_val, uint32_t* __restrict__ out_cnt, const uint32_t out_stride,
                unsigned long long* sortbuf, const uint64_t sortbuf_stride, const uint32_t b_prev,
-               unsigned long long* stats) {
+               unsigned long long* stats, unsigned long long* __restrict__ out_key) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     uint32_t* s_base = reinterpret_cast<uint32_t*>(smem_raw + kSortCap * 8);  // [b_prev + 1]
@@ -464,18 +466,24 @@ xl_topk_kernel(const LayerDev L, const int pp_kind, const int pp_p, const int co
         const uint32_t p = beam_id[static_cast<uint64_t>(q) * beam_stride + j];
         const ChunkHeader h = L.chunks[p];
         s_base[j + 1] = h.n_cols;
-        s_colbeg[j] = h.col_begin;
+        s_colbeg[j] = (h.has_bias & kChunkAbsent) ? 0xFFFFFFFFu : h.col_begin;  // absent: candidates exist elsewhere
         s_pval[j] = beam_val[static_cast<uint64_t>(q) * beam_stride + j];
     }
     __syncthreads();
+    __shared__ uint32_t s_owned;
     if (threadIdx.x == 0) {
-        uint32_t run = 0;
+        uint32_t run = 0, owned = 0;
         s_base[0] = 0;
-        for (uint32_t j = 0; j < cnt; ++j) { run += s_base[j + 1]; s_base[j + 1] = run; }
+        for (uint32_t j = 0; j < cnt; ++j) {
+            if (s_colbeg[j] != 0xFFFFFFFFu) owned += s_base[j + 1];
+            run += s_base[j + 1];
+            s_base[j + 1] = run;
+        }
+        s_owned = owned;
     }
     __syncthreads();
-    const uint32_t n_valid = s_base[cnt];
-    const uint32_t kk = min(k, n_valid);
+    const uint32_t n_valid = s_base[cnt];       // positions are global (all beam slots), keys only for owned slots
+    const uint32_t kk = min(k, s_owned);
     if (threadIdx.x == 0) {
         out_cnt[q] = kk;
         if (stats) atomicAdd(&stats[6], static_cast<unsigned long long>(kk));
@@ -491,13 +499,19 @@ xl_topk_kernel(const LayerDev L, const int pp_kind, const int pp_p, const int co
         label = s_colbeg[j] + off;
         return v;
     };
+    auto key_at = [&](uint32_t cpos) -> unsigned long long {
+        const uint32_t j = static_cast<uint32_t>(last_le_u32(s_base, static_cast<int>(cnt), cpos));
+        if (s_colbeg[j] == 0xFFFFFFFFu) return 0ull;  // scored on another GPU
+        uint32_t lab;
+        return xl_make_key(score_at(cpos, lab), cpos);
+    };
 
     unsigned long long* sorted = keys;
     if (n_valid <= static_cast<uint32_t>(kSortCap)) {
         const uint32_t P = next_pow2_u32(n_valid);
         for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
             unsigned long long key = 0ull;
-            if (i < n_valid) { uint32_t lab; key = xl_make_key(score_at(i, lab), i); }
+            if (i < n_valid) key = key_at(i);
             keys[i] = key;
         }
         __syncthreads();
@@ -511,7 +525,7 @@ xl_topk_kernel(const LayerDev L, const int pp_kind, const int pp_p, const int co
             for (uint32_t i = threadIdx.x; i < tile; i += blockDim.x) {
                 const uint32_t cpos = t0 + i;
                 unsigned long long key = 0ull;
-                if (cpos < n_valid) { uint32_t lab; key = xl_make_key(score_at(cpos, lab), cpos); }
+                if (cpos < n_valid) key = key_at(cpos);
                 keys[KP + i] = key;
             }
             __syncthreads();
@@ -523,7 +537,7 @@ xl_topk_kernel(const LayerDev L, const int pp_kind, const int pp_p, const int co
         const uint32_t P = next_pow2_u32(n_valid);
         for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
             unsigned long long key = 0ull;
-            if (i < n_valid) { uint32_t lab; key = xl_make_key(score_at(i, lab), i); }
+            if (i < n_valid) key = key_at(i);
             sorted[i] = key;
         }
         __syncthreads();
@@ -537,6 +551,7 @@ xl_topk_kernel(const LayerDev L, const int pp_kind, const int pp_p, const int co
         if (L.label_of_col) label = L.label_of_col[label];
         out_id[static_cast<uint64_t>(q) * out_stride + r] = label;
         out_val[static_cast<uint64_t>(q) * out_stride + r] = v;
+        if (out_key) out_key[static_cast<uint64_t>(q) * out_stride + r] = sorted[r];
     }
 }
 
@@ -562,7 +577,7 @@ xl_topk_warp_kernel(const LayerDev L, const int pp_kind, const int pp_p, const i
                     const uint32_t* __restrict__ beam_cnt, const uint32_t beam_stride, const float* __restrict__ cand,
                     const uint64_t cand_stride_q, const uint32_t c_stride, uint32_t* __restrict__ out_id,
                     float* __restrict__ out_val, uint32_t* __restrict__ out_cnt, const uint32_t out_stride,
-                    const uint32_t rows, unsigned long long* stats) {
+                    const uint32_t rows, unsigned long long* stats, unsigned long long* __restrict__ out_key) {
     __shared__ SelScratch scratch[kSelWarps];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -574,18 +589,24 @@ xl_topk_warp_kernel(const LayerDev L, const int pp_kind, const int pp_p, const i
         const uint32_t p = beam_id[static_cast<uint64_t>(q) * beam_stride + j];
         const ChunkHeader h = L.chunks[p];
         S.base[j + 1] = h.n_cols;
-        S.colbeg[j] = h.col_begin;
+        S.colbeg[j] = (h.has_bias & kChunkAbsent) ? 0xFFFFFFFFu : h.col_begin;
         S.pval[j] = beam_val[static_cast<uint64_t>(q) * beam_stride + j];
     }
     __syncwarp();
+    uint32_t owned = 0;
     if (lane == 0) {
         uint32_t run = 0;
         S.base[0] = 0;
-        for (uint32_t j = 0; j < cnt; ++j) { run += S.base[j + 1]; S.base[j + 1] = run; }
+        for (uint32_t j = 0; j < cnt; ++j) {
+            if (S.colbeg[j] != 0xFFFFFFFFu) owned += S.base[j + 1];
+            run += S.base[j + 1];
+            S.base[j + 1] = run;
+        }
     }
+    owned = __shfl_sync(kFull, owned, 0);
     __syncwarp();
     const uint32_t n_valid = S.base[cnt];
-    const uint32_t kk = min(k, n_valid);
+    const uint32_t kk = min(k, owned);
     if (lane == 0) {
         out_cnt[q] = kk;
         if (stats) atomicAdd(&stats[6], static_cast<unsigned long long>(kk));
@@ -603,7 +624,8 @@ xl_topk_warp_kernel(const LayerDev L, const int pp_kind, const int pp_p, const i
     unsigned long long best = 0ull;  // lane-local maximum over positions lane, lane+32, ...
     for (uint32_t i = lane; i < n_valid; i += 32) {
         uint32_t lab;
-        const unsigned long long key = xl_make_key(score_at(i, lab), i);
+        const uint32_t ji = static_cast<uint32_t>(last_le_u32(S.base, static_cast<int>(cnt), i));
+        const unsigned long long key = (S.colbeg[ji] == 0xFFFFFFFFu) ? 0ull : xl_make_key(score_at(i, lab), i);
         S.keys[i] = key;
         best = key > best ? key : best;
     }
@@ -622,9 +644,67 @@ xl_topk_warp_kernel(const LayerDev L, const int pp_kind, const int pp_p, const i
             if (L.label_of_col) label = L.label_of_col[label];
             out_id[static_cast<uint64_t>(q) * out_stride + r] = label;
             out_val[static_cast<uint64_t>(q) * out_stride + r] = v;
+            if (out_key) out_key[static_cast<uint64_t>(q) * out_stride + r] = top;
             S.keys[cpos] = 0ull;
             best = 0ull;
             for (uint32_t i = lane; i < n_valid; i += 32) { const unsigned long long key = S.keys[i]; best = key > best ? key : best; }
+        }
+        __syncwarp();
+    }
+}
+
+// K3 (index sharding): merge the per-GPU top-k lists gathered by ONE all-gather into the global top-k.
+// gathered layout: [world][rows][stride] for keys / ids / vals and [world][rows] for counts.  Keys are globally unique
+// (they embed the candidate's position in the full prolongated row), so the merge is an exact arg-max selection.
+__global__ void __launch_bounds__(kSelWarps * 32)
+xl_merge_topk_kernel(const unsigned long long* __restrict__ g_keys, const uint32_t* __restrict__ g_ids,
+                     const float* __restrict__ g_vals, const uint32_t* __restrict__ g_cnt, const uint32_t world,
+                     const uint32_t rows, const uint32_t stride, const uint32_t k, uint32_t* __restrict__ out_id,
+                     float* __restrict__ out_val, uint32_t* __restrict__ out_cnt) {
+    __shared__ unsigned long long s_keys[kSelWarps][kSelKeys];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * kSelWarps + warp;
+    if (q >= rows) return;
+    unsigned long long* keys = s_keys[warp];
+    const uint32_t n = world * stride;
+    unsigned long long best = 0ull;
+    uint32_t total = 0;
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t g = i / stride, r = i - g * stride;
+        const uint32_t c = g_cnt[static_cast<uint64_t>(g) * rows + q];
+        unsigned long long key = 0ull;
+        if (r < c) { key = g_keys[(static_cast<uint64_t>(g) * rows + q) * stride + r]; ++total; }
+        keys[i] = key;
+        best = key > best ? key : best;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(kFull, total, d);
+    __syncwarp();
+    const uint32_t kk = min(k, total);
+    if (lane == 0) out_cnt[q] = kk;
+    for (uint32_t rnk = 0; rnk < kk; ++rnk) {
+        unsigned long long top = best;
+        uint32_t who = best ? static_cast<uint32_t>(lane) : 0xFFFFFFFFu;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(kFull, top, d);
+            top = o > top ? o : top;
+        }
+        // the owner lane finds the slot of `top` among its stride-32 subset
+        (void)who;
+        uint32_t slot = 0xFFFFFFFFu;
+        if (best == top) {
+            for (uint32_t i = lane; i < n; i += 32) if (keys[i] == top) { slot = i; break; }
+        }
+        if (slot != 0xFFFFFFFFu) {
+            const uint32_t g = slot / stride, r = slot - g * stride;
+            const uint64_t src = (static_cast<uint64_t>(g) * rows + q) * stride + r;
+            out_id[static_cast<uint64_t>(q) * k + rnk] = g_ids[src];
+            out_val[static_cast<uint64_t>(q) * k + rnk] = g_vals[src];
+            keys[slot] = 0ull;
+            best = 0ull;
+            for (uint32_t i = lane; i < n; i += 32) { const unsigned long long key = keys[i]; best = key > best ? key : best; }
         }
         __syncwarp();
     }
@@ -836,7 +916,14 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
 
         const bool last = (d + 1 == depth);
         uint32_t* o_id; float* o_val; uint32_t* o_cnt; uint32_t o_stride;
-        if (last) {
+        unsigned long long* o_key = nullptr;
+        if (last && ext_ids_) {  // index-sharded run: local top-k goes straight into the caller's (NCCL send) buffers
+            o_id = ext_ids_ + static_cast<uint64_t>(res_rows_) * res_stride_;
+            o_val = ext_vals_ + static_cast<uint64_t>(res_rows_) * res_stride_;
+            o_cnt = ext_cnt_ + res_rows_;
+            o_key = ext_keys_ + static_cast<uint64_t>(res_rows_) * res_stride_;
+            o_stride = res_stride_;
+        } else if (last) {
             o_id = res_ids_dev_.get() + static_cast<uint64_t>(res_rows_) * res_stride_;
             o_val = res_vals_dev_.get() + static_cast<uint64_t>(res_rows_) * res_stride_;
             o_cnt = res_cnt_dev_.get() + res_rows_;
@@ -851,12 +938,12 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
         if (warp_select) {
             xl_topk_warp_kernel<<<(rows + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream_>>>(
                 L, lp.pp.kind, lp.pp.p, d == 0 ? 0 : 1, lp.k, beam_id_[cur].get(), beam_val_[cur].get(), beam_cnt_[cur].get(),
-                beam_stride_, cand_.get(), cand_stride_q, c_stride, o_id, o_val, o_cnt, o_stride, rows, stats);
+                beam_stride_, cand_.get(), cand_stride_q, c_stride, o_id, o_val, o_cnt, o_stride, rows, stats, o_key);
         } else {
             xl_topk_kernel<<<grid, kTopkThreads, topk_kernel_smem(lp.b_prev), stream_>>>(
                 L, lp.pp.kind, lp.pp.p, d == 0 ? 0 : 1, lp.k, beam_id_[cur].get(), beam_val_[cur].get(), beam_cnt_[cur].get(),
                 beam_stride_, cand_.get(), cand_stride_q, c_stride, o_id, o_val, o_cnt, o_stride, sortbuf_.get(), sort_stride,
-                lp.b_prev, stats);
+                lp.b_prev, stats, o_key);
         }
         PB200_CUDA(cudaGetLastError());
         ++launches_;
@@ -997,6 +1084,59 @@ double XLinearEngine::resident_predict(uint32_t beam_size, const char* post_proc
         }
     }
     return static_cast<double>(ms);
+}
+
+uint32_t XLinearEngine::sharded_local_csr(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, uint32_t rows,
+                                          uint32_t cols, uint32_t beam_size, const char* post_processor, uint32_t only_topk,
+                                          uint32_t stride_capacity, unsigned long long* keys_dev, uint32_t* ids_dev,
+                                          float* vals_dev, uint32_t* cnt_dev) {
+    PB200_CUDA(cudaSetDevice(device_));
+    const auto plan = make_plan_(beam_size, post_processor, only_topk);
+    const uint32_t stride = plan.back().k_cap;
+    if (stride > stride_capacity) throw std::runtime_error("pecos_b200: sharded output buffers are too narrow for this top-k");
+    const uint32_t tile = pick_tile_rows_(plan, rows);
+    ensure_workspace_(plan, tile);
+    res_stride_ = stride;
+    ext_keys_ = keys_dev; ext_ids_ = ids_dev; ext_vals_ = vals_dev; ext_cnt_ = cnt_dev;
+    try {
+        for (uint32_t r0 = 0; r0 < rows; r0 += tile) {
+            const uint32_t tr = std::min(tile, rows - r0);
+            const uint64_t base = row_ptr[r0], end = row_ptr[r0 + tr];
+            x_row_ptr_.upload(row_ptr + r0, static_cast<uint64_t>(tr) + 1, stream_);
+            x_col_idx_.upload(col_idx + base, end - base, stream_);
+            x_val_.upload(val + base, end - base, stream_);
+            QueryDev q{x_row_ptr_.get(), x_col_idx_.get(), x_val_.get(), base, tr, cols};
+            res_rows_ = r0;
+            run_tile_(q, plan, false);
+            PB200_CUDA(cudaStreamSynchronize(stream_));
+        }
+    } catch (...) {
+        ext_keys_ = nullptr; ext_ids_ = nullptr; ext_vals_ = nullptr; ext_cnt_ = nullptr;
+        throw;
+    }
+    ext_keys_ = nullptr; ext_ids_ = nullptr; ext_vals_ = nullptr; ext_cnt_ = nullptr;
+    return stride;
+}
+
+XLinearEngine::Result XLinearEngine::sharded_merge(uint32_t world, uint32_t rows, uint32_t stride, uint32_t only_topk,
+                                                   const unsigned long long* g_keys, const uint32_t* g_ids,
+                                                   const float* g_vals, const uint32_t* g_cnt) {
+    PB200_CUDA(cudaSetDevice(device_));
+    if (static_cast<uint64_t>(world) * stride > static_cast<uint64_t>(kSelKeys))
+        throw std::runtime_error("pecos_b200: world * top-k exceeds the merge kernel's capacity");
+    const uint32_t k = only_topk ? only_topk : static_cast<uint32_t>(host_->layers.back().only_topk);
+    const uint32_t k_out = std::min<uint32_t>(k, world * stride);
+    res_stride_ = k_out;
+    res_ids_dev_.reserve(static_cast<uint64_t>(rows) * k_out + 1);
+    res_vals_dev_.reserve(static_cast<uint64_t>(rows) * k_out + 1);
+    res_cnt_dev_.reserve(static_cast<uint64_t>(rows) + 1);
+    if (rows) {
+        xl_merge_topk_kernel<<<(rows + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream_>>>(
+            g_keys, g_ids, g_vals, g_cnt, world, rows, stride, k_out, res_ids_dev_.get(), res_vals_dev_.get(), res_cnt_dev_.get());
+        PB200_CUDA(cudaGetLastError());
+        ++launches_;
+    }
+    return finish_result_(rows, k_out);
 }
 
 XLinearEngine::Result XLinearEngine::resident_fetch() {

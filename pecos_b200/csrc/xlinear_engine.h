@@ -89,6 +89,16 @@ public:
     double resident_predict(uint32_t beam_size, const char* post_processor, uint32_t only_topk, bool collect_stats);
     Result resident_fetch();
 
+    // Index sharding (leaf layer split over `world` GPUs).  sharded_local_csr runs every layer on this GPU's
+    // shard and writes the LOCAL top-k {key, id, value}[rows][stride] + count[rows] into caller-owned device buffers
+    // (the NCCL all-gather send buffers); sharded_merge reduces the gathered [world][rows][stride] lists to the global
+    // top-k.  Returns the stride used.
+    uint32_t sharded_local_csr(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, uint32_t rows, uint32_t cols,
+                               uint32_t beam_size, const char* post_processor, uint32_t only_topk, uint32_t stride_capacity,
+                               unsigned long long* keys_dev, uint32_t* ids_dev, float* vals_dev, uint32_t* cnt_dev);
+    Result sharded_merge(uint32_t world, uint32_t rows, uint32_t stride, uint32_t only_topk, const unsigned long long* g_keys,
+                         const uint32_t* g_ids, const float* g_vals, const uint32_t* g_cnt);
+
     void set_profile(bool on) { profile_ = on; }
     // false = stream the chunk row lists (first-generation kernel) even when feature maps exist; for A/B tests
     void set_lookup(bool on);
@@ -147,6 +157,10 @@ private:
     DeviceBuffer<float> res_vals_dev_;
     DeviceBuffer<uint32_t> res_cnt_dev_;
     uint32_t res_rows_ = 0, res_stride_ = 0;
+    unsigned long long* ext_keys_ = nullptr;  // caller-owned leaf outputs of an index-sharded run
+    uint32_t* ext_ids_ = nullptr;
+    float* ext_vals_ = nullptr;
+    uint32_t* ext_cnt_ = nullptr;
 
     // host result staging (pinned)
     PinnedBuffer<uint32_t> out_ids_;

@@ -115,6 +115,8 @@ struct XLinearHostModel {
     std::vector<ChunkedLayerHost> layers;
     int layer_type = LT_BINARY_SEARCH_CHUNKED;  // what the caller asked for; reported back verbatim
     bool is_mmap = false;
+    uint32_t shard_rank = 0, shard_world = 1;   // leaf-layer index sharding (1 = whole model on this GPU)
+    uint32_t leaf_chunk_begin = 0, leaf_chunk_end = 0;
     uint32_t depth() const { return static_cast<uint32_t>(layers.size()); }
     uint32_t nr_features() const {
         const auto& l = layers.back();
@@ -300,6 +302,67 @@ inline void build_chunked_layer(const CscHost& W, const CscHost& C, float bias, 
     });
 }
 
+// ---------------------------------------------------------------------------------------------
+// index sharding of the leaf layer: rank r of `world` keeps the weights of a contiguous range of leaf
+// chunks, balanced by entry bytes; every other chunk keeps only its header (column range => candidate positions stay
+// global) and is flagged absent (bit 1 of has_bias).  Upper layers are replicated.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kChunkAbsent = 2u;
+
+inline void shard_ranges_by_weight(const std::vector<uint64_t>& weight, uint32_t world, std::vector<uint32_t>& begin) {
+    // begin[r] .. begin[r+1] = chunks of rank r; greedy split at the prefix-sum quantiles
+    const uint32_t n = static_cast<uint32_t>(weight.size());
+    uint64_t total = 0;
+    for (uint64_t w : weight) total += w + 1;
+    begin.assign(world + 1, n);
+    begin[0] = 0;
+    uint64_t run = 0;
+    uint32_t r = 1;
+    for (uint32_t i = 0; i < n && r < world; ++i) {
+        run += weight[i] + 1;
+        while (r < world && run * world >= static_cast<uint64_t>(r) * total) begin[r++] = i + 1;
+    }
+    for (; r < world; ++r) begin[r] = n;
+}
+
+inline void apply_leaf_shard(ChunkedLayerHost& L, uint32_t rank, uint32_t world, uint32_t& c0, uint32_t& c1) {
+    if (world <= 1) { c0 = 0; c1 = L.n_chunks; return; }
+    if (rank >= world) throw std::runtime_error("leaf shard: rank >= world");
+    std::vector<uint64_t> weight(L.n_chunks);
+    for (uint32_t p = 0; p < L.n_chunks; ++p) {
+        const ChunkHeader& h = L.chunks[p];
+        const uint32_t* rp = L.meta.data() + h.meta_off + round_up4(h.nnz_rows);
+        weight[p] = static_cast<uint64_t>(rp[h.nnz_rows]) * 8 + static_cast<uint64_t>(h.nnz_rows) * 8;
+    }
+    std::vector<uint32_t> begin;
+    shard_ranges_by_weight(weight, world, begin);
+    c0 = begin[rank];
+    c1 = begin[rank + 1];
+    std::vector<uint32_t> meta;
+    std::vector<ChunkEntry> entries;
+    for (uint32_t p = 0; p < L.n_chunks; ++p) {
+        ChunkHeader& h = L.chunks[p];
+        if (p >= c0 && p < c1) {
+            const uint64_t m_len = round_up4(h.nnz_rows) + round_up4(static_cast<uint64_t>(h.nnz_rows) + 1);
+            const uint32_t* src_m = L.meta.data() + h.meta_off;
+            const uint32_t n_ent = src_m[round_up4(h.nnz_rows) + h.nnz_rows];
+            const ChunkEntry* src_e = L.entries.data() + h.ent_off;
+            h.meta_off = meta.size();
+            h.ent_off = entries.size();
+            meta.insert(meta.end(), src_m, src_m + m_len);
+            entries.insert(entries.end(), src_e, src_e + n_ent);
+        } else {
+            h.nnz_rows = 0;
+            h.has_bias = kChunkAbsent;
+            h.meta_off = 0;
+            h.ent_off = 0;
+        }
+    }
+    if (meta.empty()) meta.assign(4, 0u);  // keep device pointers valid on ranks that own nothing
+    L.meta.swap(meta);
+    L.entries.swap(entries);
+}
+
 // Bytes the feature map of a layer would occupy.
 inline uint64_t feature_map_bytes(const ChunkedLayerHost& L) {
     return static_cast<uint64_t>(L.n_chunks) * ((static_cast<uint64_t>(L.w_rows) + 31) / 32) * 8;
@@ -477,7 +540,8 @@ inline HierMeta load_hier_meta(const std::string& path) {
     return m;
 }
 
-inline std::unique_ptr<XLinearHostModel> load_xlinear_npz_model(const std::string& folder, int layer_type) {
+inline std::unique_ptr<XLinearHostModel> load_xlinear_npz_model(const std::string& folder, int layer_type,
+                                                                uint32_t shard_rank = 0, uint32_t shard_world = 1) {
     HierMeta hm = load_hier_meta(folder + "/param.json");
     if (hm.is_mmap) throw std::runtime_error("This folder contains mmap model. Cannot load in npz format.");
     auto model = std::make_unique<XLinearHostModel>();
@@ -486,10 +550,14 @@ inline std::unique_ptr<XLinearHostModel> load_xlinear_npz_model(const std::strin
     model->layers.resize(hm.depth);
     for (int d = 0; d < hm.depth; ++d)
         load_npz_layer(folder + "/" + std::to_string(d) + ".model", static_cast<uint32_t>(d), model->layers[d]);
+    model->shard_rank = shard_rank;
+    model->shard_world = std::max<uint32_t>(shard_world, 1u);
+    apply_leaf_shard(model->layers.back(), shard_rank, model->shard_world, model->leaf_chunk_begin, model->leaf_chunk_end);
     return model;
 }
 
-inline std::unique_ptr<XLinearHostModel> load_xlinear_mmap_model(const std::string& folder, bool lazy_load) {
+inline std::unique_ptr<XLinearHostModel> load_xlinear_mmap_model(const std::string& folder, bool lazy_load,
+                                                                 uint32_t shard_rank = 0, uint32_t shard_world = 1) {
     HierMeta hm = load_hier_meta(folder + "/param.json");
     if (!hm.is_mmap) throw std::runtime_error("This folder contains npz model. Cannot load in mmap format.");
     auto model = std::make_unique<XLinearHostModel>();
@@ -498,6 +566,9 @@ inline std::unique_ptr<XLinearHostModel> load_xlinear_mmap_model(const std::stri
     model->layers.resize(hm.depth);
     for (int d = 0; d < hm.depth; ++d)
         load_mmap_layer(folder + "/" + std::to_string(d) + ".model", lazy_load, model->layers[d]);
+    model->shard_rank = shard_rank;
+    model->shard_world = std::max<uint32_t>(shard_world, 1u);
+    apply_leaf_shard(model->layers.back(), shard_rank, model->shard_world, model->leaf_chunk_begin, model->leaf_chunk_end);
     return model;
 }
 

@@ -62,3 +62,21 @@ def csr_with_empty_rows(X, rows):
     X = X.tocsr().astype(np.float32)
     X.sort_indices()
     return X
+
+
+def merge_topk_numpy(g_keys, g_ids, g_vals, g_cnt, k):
+    """Reference semantics of the index-sharding merge kernel (test-only): per query keep the k largest 64-bit keys
+    among the valid entries of all ranks.  g_* have shape [world, rows, stride], g_cnt [world, rows]."""
+    world, rows, stride = g_keys.shape
+    out_ids = np.zeros((rows, k), dtype=np.uint32)
+    out_vals = np.zeros((rows, k), dtype=np.float32)
+    out_cnt = np.zeros(rows, dtype=np.uint32)
+    for q in range(rows):
+        cand = [(int(np.uint64(g_keys[g, q, r])), int(g_ids[g, q, r]), float(g_vals[g, q, r]))
+                for g in range(world) for r in range(int(g_cnt[g, q]))]
+        cand.sort(key=lambda t: -t[0])
+        kk = min(k, len(cand))
+        out_cnt[q] = kk
+        for r in range(kk):
+            out_ids[q, r], out_vals[q, r] = cand[r][1], cand[r][2]
+    return out_ids, out_vals, out_cnt
