@@ -154,6 +154,9 @@ void pb200_hnsw_resident_upload(void* model_ptr, const ScipyDrmF32* pX);
 double pb200_hnsw_resident_predict(void* model_ptr, uint32_t efS, uint32_t topk);
 void pb200_hnsw_resident_fetch(void* model_ptr, uint32_t* ret_idx, float* ret_val);
 void pb200_hnsw_get_counters(void* model_ptr, uint64_t* out);
+/* base-vector rows kept in flight per warp by the bulk-copy (TMA) ring: 0 = direct loads, 4 (default) or 8; returns the
+ * value in effect.  Results are identical for every setting. */
+int pb200_hnsw_set_stages(void* model_ptr, int stages);
 void pb200_hnsw_get_info(void* model_ptr, uint64_t* out);
 
 /* Host-only model ingest (no GPU needed): loads + builds the chunk layout, for layout tests.

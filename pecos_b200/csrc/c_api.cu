@@ -413,6 +413,13 @@ void pb200_hnsw_resident_fetch(void* model_ptr, uint32_t* ret_idx, float* ret_va
     PB200_API_END("pb200_hnsw_resident_fetch")
 }
 
+int pb200_hnsw_set_stages(void* model_ptr, int stages) {
+    PB200_API_BEGIN
+    hnsw_of(model_ptr).set_stages(stages);
+    return hnsw_of(model_ptr).stages();
+    PB200_API_END("pb200_hnsw_set_stages")
+}
+
 void pb200_hnsw_get_counters(void* model_ptr, uint64_t* out) {
     PB200_API_BEGIN
     auto c = hnsw_of(model_ptr).counters();

@@ -42,19 +42,18 @@ __device__ __forceinline__ float chain_step(float acc, float x, float y) {
 
 // Distance between the staged (permuted) query and base vector `node`, computed by one half-warp.
 // Every lane of the warp must call it; the result is valid on lanes 0 and 16 (hl == 0).
-template <int METRIC>
-__device__ __forceinline__ float half_warp_distance(const HnswDev& ix, const float* qs, uint32_t node, int hl) {
-    const float* row = ix.vec + static_cast<uint64_t>(node) * ix.vstride;
+template <int METRIC, bool SMEM>
+__device__ __forceinline__ float half_warp_distance(const HnswDev& ix, const float* qs, const float* row, int hl) {
     const float4* v4 = reinterpret_cast<const float4*>(row);
     const float4* q4 = reinterpret_cast<const float4*>(qs);
     const uint32_t nK = ix.main_pad >> 6;
     float acc = 0.0f;
     uint32_t K = 0;
     for (; K + 4 <= nK; K += 4) {
-        const float4 y0 = ld_stream_f4(v4 + (K + 0) * 16 + hl);
-        const float4 y1 = ld_stream_f4(v4 + (K + 1) * 16 + hl);
-        const float4 y2 = ld_stream_f4(v4 + (K + 2) * 16 + hl);
-        const float4 y3 = ld_stream_f4(v4 + (K + 3) * 16 + hl);
+        const float4 y0 = SMEM ? v4[(K + 0) * 16 + hl] : ld_stream_f4(v4 + (K + 0) * 16 + hl);
+        const float4 y1 = SMEM ? v4[(K + 1) * 16 + hl] : ld_stream_f4(v4 + (K + 1) * 16 + hl);
+        const float4 y2 = SMEM ? v4[(K + 2) * 16 + hl] : ld_stream_f4(v4 + (K + 2) * 16 + hl);
+        const float4 y3 = SMEM ? v4[(K + 3) * 16 + hl] : ld_stream_f4(v4 + (K + 3) * 16 + hl);
         const float4 x0 = q4[(K + 0) * 16 + hl], x1 = q4[(K + 1) * 16 + hl], x2 = q4[(K + 2) * 16 + hl], x3 = q4[(K + 3) * 16 + hl];
         acc = chain_step<METRIC>(acc, x0.x, y0.x); acc = chain_step<METRIC>(acc, x0.y, y0.y);
         acc = chain_step<METRIC>(acc, x0.z, y0.z); acc = chain_step<METRIC>(acc, x0.w, y0.w);
@@ -66,7 +65,7 @@ __device__ __forceinline__ float half_warp_distance(const HnswDev& ix, const flo
         acc = chain_step<METRIC>(acc, x3.z, y3.z); acc = chain_step<METRIC>(acc, x3.w, y3.w);
     }
     for (; K < nK; ++K) {
-        const float4 y = ld_stream_f4(v4 + K * 16 + hl);
+        const float4 y = SMEM ? v4[K * 16 + hl] : ld_stream_f4(v4 + K * 16 + hl);
         const float4 x = q4[K * 16 + hl];
         acc = chain_step<METRIC>(acc, x.x, y.x); acc = chain_step<METRIC>(acc, x.y, y.y);
         acc = chain_step<METRIC>(acc, x.z, y.z); acc = chain_step<METRIC>(acc, x.w, y.w);
@@ -93,16 +92,67 @@ __device__ __forceinline__ float half_warp_distance(const HnswDev& ix, const flo
     return sum;
 }
 
-// distances of ids[0..n) -> dist[0..n), two per step
-template <int METRIC>
+// ---- bulk asynchronous copies (TMA engine, non-tensor form: SASS UBLKCP) + mbarrier completion -----------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// one elected lane: expect `bytes` on the barrier, then start the copy global -> shared
+__device__ __forceinline__ void bulk_load_row(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t done = 0;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+    } while (!done);
+}
+
+// distances of ids[0..n) -> dist[0..n), two per step (one per half-warp).
+// STAGES == 0: each lane loads its float4s straight from HBM.  STAGES > 0: base vectors are brought into a per-warp ring
+// of STAGES shared-memory slots by bulk asynchronous copies (one 16-byte-aligned contiguous row each), STAGES rows in
+// flight per warp, so the HBM latency of the next rows hides behind the arithmetic of the current pair.
+template <int METRIC, int STAGES>
 __device__ __forceinline__ void batch_distances(const HnswDev& ix, const float* qs, const uint32_t* ids, float* dist,
-                                                uint32_t n, int lane) {
+                                                uint32_t n, int lane, float* ring, uint32_t mbar0, uint32_t& phase_bits) {
     const int half = lane >> 4, hl = lane & 15;
+    if (STAGES == 0) {
+        for (uint32_t b = 0; b < n; b += 2) {
+            const uint32_t slot = b + half;
+            const uint32_t node = ids[min(slot, n - 1)];
+            const float d = half_warp_distance<METRIC, false>(ix, qs, ix.vec + static_cast<uint64_t>(node) * ix.vstride, hl);
+            if (hl == 0 && slot < n) dist[slot] = d;
+        }
+        __syncwarp();
+        return;
+    }
+    const uint32_t bytes = ix.vstride * 4u;
+    const uint32_t ring0 = smem_addr(ring);
+    if (lane == 0) {
+        const uint32_t first = min(static_cast<uint32_t>(STAGES), n);
+        for (uint32_t s = 0; s < first; ++s)
+            bulk_load_row(ring0 + s * bytes, ix.vec + static_cast<uint64_t>(ids[s]) * ix.vstride, bytes, mbar0 + 8u * s);
+    }
     for (uint32_t b = 0; b < n; b += 2) {
-        const uint32_t slot = b + half;
-        const uint32_t node = ids[min(slot, n - 1)];
-        const float d = half_warp_distance<METRIC>(ix, qs, node, hl);
-        if (hl == 0 && slot < n) dist[slot] = d;
+        const uint32_t slot0 = b % STAGES, slot1 = (b + 1) % STAGES;
+        const bool second = (b + 1) < n;
+        const uint32_t my = (half && second) ? slot1 : slot0;
+        mbar_wait(mbar0 + 8u * my, (phase_bits >> my) & 1u);
+        const float d = half_warp_distance<METRIC, true>(ix, qs, ring + static_cast<size_t>(my) * ix.vstride, hl);
+        if (hl == 0 && (b + half) < n) dist[b + half] = d;
+        phase_bits ^= (1u << slot0) | (second ? (1u << slot1) : 0u);
+        __syncwarp();  // both slots fully consumed before they are refilled
+        if (lane == 0) {
+            const uint32_t nxt = b + STAGES;
+            if (nxt < n) bulk_load_row(ring0 + slot0 * bytes, ix.vec + static_cast<uint64_t>(ids[nxt]) * ix.vstride, bytes, mbar0 + 8u * slot0);
+            if (nxt + 1 < n) bulk_load_row(ring0 + slot1 * bytes, ix.vec + static_cast<uint64_t>(ids[nxt + 1]) * ix.vstride, bytes, mbar0 + 8u * slot1);
+        }
     }
     __syncwarp();
 }
@@ -171,7 +221,7 @@ __device__ __forceinline__ uint32_t permuted_pos_dev(const HnswDev& ix, uint32_t
     return ix.main_pad + (i - m);
 }
 
-template <int METRIC>
+template <int METRIC, int STAGES>
 __global__ void __launch_bounds__(256)
 hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const uint32_t nq, const uint32_t efS, const uint32_t topk,
                    const uint32_t ef, uint32_t* __restrict__ out_idx, float* __restrict__ out_val, uint32_t* bitmap_all,
@@ -182,10 +232,22 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const uint32_t
     const int warp = threadIdx.x >> 5;
     const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;
     unsigned char* base = smem_raw + static_cast<size_t>(warp) * per_warp_bytes;
+    // per-warp slice: [query | STAGES ring slots | STAGES mbarriers | neighbour ids | distances | result heap]
     float* qs = reinterpret_cast<float*>(base);
-    uint32_t* nb_ids = reinterpret_cast<uint32_t*>(qs + ix.vstride);
+    float* ring = qs + ix.vstride;
+    unsigned long long* mbars = reinterpret_cast<unsigned long long*>(ring + static_cast<size_t>(STAGES) * ix.vstride);
+    uint32_t* nb_ids = reinterpret_cast<uint32_t*>(mbars + STAGES);
     float* nb_dist = reinterpret_cast<float*>(nb_ids + nbmax);
     uint2* topq = topk_all ? topk_all + static_cast<uint64_t>(gw) * (ef + 1) : reinterpret_cast<uint2*>(nb_dist + nbmax);
+    const uint32_t mbar0 = smem_addr(mbars);
+    uint32_t phase_bits = 0;
+    if (STAGES > 0) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) mbar_init(mbar0 + 8u * s, 1u);
+            fence_proxy_async_smem();
+        }
+        __syncwarp();
+    }
     uint32_t* bitmap = bitmap_all + static_cast<uint64_t>(gw) * bitmap_words;
     uint32_t* vlist = vlist_all + static_cast<uint64_t>(gw) * vcap;
     uint2* cand = cand_all + static_cast<uint64_t>(gw) * vcap;
@@ -210,7 +272,7 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const uint32_t
         uint32_t curr = ix.init_node;
         if (lane == 0) nb_ids[0] = curr;
         __syncwarp();
-        batch_distances<METRIC>(ix, qs, nb_ids, nb_dist, 1, lane);
+        batch_distances<METRIC, STAGES>(ix, qs, nb_ids, nb_dist, 1, lane, ring, mbar0, phase_bits);
         float curr_dist = nb_dist[0];
         n_dist += 1;
         __syncwarp();
@@ -223,7 +285,7 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const uint32_t
                 n_hops += 1;
                 for (uint32_t j = lane; j < deg; j += 32) nb_ids[j] = nb[1 + j];
                 __syncwarp();
-                if (deg) batch_distances<METRIC>(ix, qs, nb_ids, nb_dist, deg, lane);
+                if (deg) batch_distances<METRIC, STAGES>(ix, qs, nb_ids, nb_dist, deg, lane, ring, mbar0, phase_bits);
                 n_dist += deg;
                 if (lane == 0) {
                     for (uint32_t j = 0; j < deg; ++j) {
@@ -287,7 +349,7 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const uint32_t
             }
             nvis += nu;
             // B. all distances
-            if (nu) batch_distances<METRIC>(ix, qs, nb_ids, nb_dist, nu, lane);
+            if (nu) batch_distances<METRIC, STAGES>(ix, qs, nb_ids, nb_dist, nu, lane, ring, mbar0, phase_bits);
             n_dist += nu;
             // C. sequential replay of the queue updates (hnsw.hpp:904-914)
             if (lane == 0) {
@@ -411,8 +473,17 @@ HnswEngine::HnswEngine(std::unique_ptr<HnswHostIndex> host, int device) : host_(
     PB200_CUDA(cudaMemsetAsync(ctrl_.get(), 0, 8 * sizeof(unsigned long long), stream_));
     PB200_CUDA(cudaStreamSynchronize(stream_));
     const int max_smem = 200 * 1024;
-    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_IP>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_IP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_L2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_IP, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_L2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_IP, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_L2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    stages_ = 4;  // rows in flight per warp through the bulk-copy ring; 0 = direct loads (first-generation kernel)
+    if (const char* env = std::getenv("PB200_HNSW_STAGES")) {
+        const int v = std::atoi(env);
+        stages_ = (v <= 0) ? 0 : (v <= 4 ? 4 : 8);
+    }
     // the mapped file is no longer needed once the arrays live in HBM
     host_->l0_buffer = nullptr;
     host_->l1_buffer = nullptr;
@@ -426,11 +497,25 @@ HnswEngine::~HnswEngine() {
     if (stream_) cudaStreamDestroy(stream_);
 }
 
-void HnswEngine::ensure_scratch_(uint32_t ef) {
+uint32_t HnswEngine::per_warp_smem_(uint32_t ef, uint32_t* nbmax_out) const {
     const HnswHostIndex& H = *host_;
     const uint32_t nbmax = ((std::max(H.l0_max_degree, H.l1_max_degree) + 31u) / 32u) * 32u;
     const bool top_in_smem = ef <= kEfSmemMax;
-    const uint32_t per_warp = (H.vstride() * 4 + nbmax * 8 + (top_in_smem ? (ef + 1) * 8 : 0) + 15u) & ~15u;
+    if (nbmax_out) *nbmax_out = nbmax;
+    // [query | stages_ ring slots | stages_ mbarriers | ids | distances | result heap]
+    return (H.vstride() * 4 * (1u + static_cast<uint32_t>(stages_)) + static_cast<uint32_t>(stages_) * 8u + nbmax * 8 +
+            (top_in_smem ? (ef + 1) * 8 : 0) + 15u) & ~15u;
+}
+
+void HnswEngine::set_stages(int stages) {
+    stages_ = (stages <= 0) ? 0 : (stages <= 4 ? 4 : 8);
+    n_warps_ = 0;  // forces the scratch / launch geometry to be recomputed
+}
+
+void HnswEngine::ensure_scratch_(uint32_t ef) {
+    const HnswHostIndex& H = *host_;
+    const bool top_in_smem = ef <= kEfSmemMax;
+    const uint32_t per_warp = per_warp_smem_(ef, nullptr);
     uint32_t warps = 8;
     while (warps > 1 && static_cast<uint64_t>(warps) * per_warp > 96u * 1024u) warps >>= 1;
     if (static_cast<uint64_t>(warps) * per_warp > 200u * 1024u)
@@ -462,9 +547,9 @@ double HnswEngine::launch_(const float* q_dev, uint32_t nq, uint32_t efS, uint32
     const uint32_t ef = std::max(efS, topk);
     if (ef == 0) throw std::runtime_error("pecos_b200: efS and topk are both zero");
     ensure_scratch_(ef);
-    const uint32_t nbmax = ((std::max(H.l0_max_degree, H.l1_max_degree) + 31u) / 32u) * 32u;
+    uint32_t nbmax = 0;
     const bool top_in_smem = ef <= kEfSmemMax;
-    const uint32_t per_warp = (H.vstride() * 4 + nbmax * 8 + (top_in_smem ? (ef + 1) * 8 : 0) + 15u) & ~15u;
+    const uint32_t per_warp = per_warp_smem_(ef, &nbmax);
     const uint32_t words = static_cast<uint32_t>((static_cast<uint64_t>(H.num_node) + 31) / 32);
     PB200_CUDA(cudaMemsetAsync(ctrl_.get(), 0, 8 * sizeof(unsigned long long), stream_));
     PB200_CUDA(cudaMemsetAsync(out_idx_.get(), 0, static_cast<uint64_t>(nq) * topk * 4, stream_));
@@ -472,14 +557,15 @@ double HnswEngine::launch_(const float* q_dev, uint32_t nq, uint32_t efS, uint32
     const uint32_t ctas = std::max<uint32_t>(1, std::min<uint32_t>(n_ctas_, (nq + warps_per_cta_ - 1) / warps_per_cta_));
     const size_t smem = static_cast<size_t>(warps_per_cta_) * per_warp;
     PB200_CUDA(cudaEventRecord(ev_[0], stream_));
-    if (H.metric == HNSW_IP)
-        hnsw_search_kernel<HNSW_IP><<<ctas, warps_per_cta_ * 32, smem, stream_>>>(
-            view_, q_dev, nq, efS, topk, ef, out_idx_.get(), out_val_.get(), bitmap_.get(), words, vlist_.get(), cand_.get(), vcap_,
-            top_in_smem ? nullptr : topk_heap_.get(), nbmax, per_warp, ctrl_.get());
-    else
-        hnsw_search_kernel<HNSW_L2><<<ctas, warps_per_cta_ * 32, smem, stream_>>>(
-            view_, q_dev, nq, efS, topk, ef, out_idx_.get(), out_val_.get(), bitmap_.get(), words, vlist_.get(), cand_.get(), vcap_,
-            top_in_smem ? nullptr : topk_heap_.get(), nbmax, per_warp, ctrl_.get());
+    auto launch = [&](auto kernel) {
+        kernel<<<ctas, warps_per_cta_ * 32, smem, stream_>>>(view_, q_dev, nq, efS, topk, ef, out_idx_.get(), out_val_.get(),
+                                                             bitmap_.get(), words, vlist_.get(), cand_.get(), vcap_,
+                                                             top_in_smem ? nullptr : topk_heap_.get(), nbmax, per_warp, ctrl_.get());
+    };
+    const bool ip = H.metric == HNSW_IP;
+    if (stages_ == 0) { if (ip) launch(hnsw_search_kernel<HNSW_IP, 0>); else launch(hnsw_search_kernel<HNSW_L2, 0>); }
+    else if (stages_ == 4) { if (ip) launch(hnsw_search_kernel<HNSW_IP, 4>); else launch(hnsw_search_kernel<HNSW_L2, 4>); }
+    else { if (ip) launch(hnsw_search_kernel<HNSW_IP, 8>); else launch(hnsw_search_kernel<HNSW_L2, 8>); }
     PB200_CUDA(cudaGetLastError());
     PB200_CUDA(cudaEventRecord(ev_[1], stream_));
     ++launches_;

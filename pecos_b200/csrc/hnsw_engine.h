@@ -53,9 +53,13 @@ public:
     uint64_t launches() const { return launches_; }
     uint64_t index_bytes() const { return index_bytes_; }
     double last_kernel_ms() const { return last_ms_; }
+    // rows kept in flight per warp by the bulk-copy ring: 0 (direct loads), 4 or 8
+    void set_stages(int stages);
+    int stages() const { return stages_; }
 
 private:
     void ensure_scratch_(uint32_t ef);
+    uint32_t per_warp_smem_(uint32_t ef, uint32_t* nbmax_out) const;
     double launch_(const float* q_dev, uint32_t nq, uint32_t efS, uint32_t topk);
 
     std::unique_ptr<HnswHostIndex> host_;
@@ -86,6 +90,7 @@ private:
 
     uint64_t launches_ = 0;
     double last_ms_ = 0.0;
+    int stages_ = 4;
 };
 
 }  // namespace pb200

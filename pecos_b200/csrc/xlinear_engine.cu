@@ -560,16 +560,21 @@ xl_topk_kernel(const LayerDev L, const int pp_kind, const int pp_p, const int co
 // unique because they embed the candidate position), the winning lane rescanning only its own stride-32 subset.
 // Same keys, same order, same values as xl_topk_kernel.
 constexpr int kSelWarps = 4;
-constexpr int kSelKeys = 1024;
+constexpr int kSelKeys = 1024;   // merge kernel capacity (static shared memory)
+constexpr int kSelKeysMax = 4096; // warp top-k capacity (dynamic shared memory, sized per launch)
 constexpr int kSelSlots = 64;
 constexpr int kSelK = 64;
 
-struct __align__(16) SelScratch {
-    unsigned long long keys[kSelKeys];
-    uint32_t base[kSelSlots + 1];
-    uint32_t colbeg[kSelSlots];
-    float pval[kSelSlots];
+struct SelScratch {  // view into the warp's slice of dynamic shared memory
+    unsigned long long* keys;
+    uint32_t* base;    // [kSelSlots + 1]
+    uint32_t* colbeg;  // [kSelSlots]
+    float* pval;       // [kSelSlots]
 };
+
+__host__ __device__ inline size_t sel_warp_bytes(uint32_t key_cap) {
+    return static_cast<size_t>(key_cap) * 8 + (kSelSlots + 1 + kSelSlots + kSelSlots) * 4 + 12;  // padded to 16 below
+}
 
 __global__ void __launch_bounds__(kSelWarps * 32)
 xl_topk_warp_kernel(const LayerDev L, const int pp_kind, const int pp_p, const int combine, const uint32_t k,
@@ -577,13 +582,19 @@ xl_topk_warp_kernel(const LayerDev L, const int pp_kind, const int pp_p, const i
                     const uint32_t* __restrict__ beam_cnt, const uint32_t beam_stride, const float* __restrict__ cand,
                     const uint64_t cand_stride_q, const uint32_t c_stride, uint32_t* __restrict__ out_id,
                     float* __restrict__ out_val, uint32_t* __restrict__ out_cnt, const uint32_t out_stride,
-                    const uint32_t rows, unsigned long long* stats, unsigned long long* __restrict__ out_key) {
-    __shared__ SelScratch scratch[kSelWarps];
+                    const uint32_t rows, unsigned long long* stats, unsigned long long* __restrict__ out_key,
+                    const uint32_t key_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * kSelWarps + warp;
     if (q >= rows) return;
-    SelScratch& S = scratch[warp];
+    const size_t slice = (sel_warp_bytes(key_cap) + 15) & ~static_cast<size_t>(15);
+    SelScratch S;
+    S.keys = reinterpret_cast<unsigned long long*>(smem_raw + warp * slice);
+    S.base = reinterpret_cast<uint32_t*>(S.keys + key_cap);
+    S.colbeg = S.base + (kSelSlots + 1);
+    S.pval = reinterpret_cast<float*>(S.colbeg + kSelSlots);
     const uint32_t cnt = beam_cnt[q];
     for (uint32_t j = lane; j < cnt; j += 32) {
         const uint32_t p = beam_id[static_cast<uint64_t>(q) * beam_stride + j];
@@ -790,6 +801,7 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
     PB200_CUDA(cudaFuncSetAttribute(xl_chunk_scores_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_chunk_scores_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(xl_topk_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     stats_dev_.reserve(8 * layers_.size());
     layer_profile_.assign(layers_.size(), XLinearLayerProfile{});
     layer_stats_.assign(layers_.size(), XLinearStats{});
@@ -934,11 +946,13 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
         }
         const uint64_t sort_stride = next_pow2_host(cand_stride_q);
         const bool warp_select = !force_block_topk_ && lp.b_prev <= static_cast<uint32_t>(kSelSlots) &&
-                                 cand_stride_q <= static_cast<uint64_t>(kSelKeys) && lp.k <= static_cast<uint32_t>(kSelK);
+                                 cand_stride_q <= static_cast<uint64_t>(kSelKeysMax) && lp.k <= static_cast<uint32_t>(kSelK);
         if (warp_select) {
-            xl_topk_warp_kernel<<<(rows + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream_>>>(
+            const uint32_t key_cap = static_cast<uint32_t>((cand_stride_q + 31) & ~static_cast<uint64_t>(31));
+            const size_t sel_smem = kSelWarps * ((sel_warp_bytes(key_cap) + 15) & ~static_cast<size_t>(15));
+            xl_topk_warp_kernel<<<(rows + kSelWarps - 1) / kSelWarps, kSelWarps * 32, sel_smem, stream_>>>(
                 L, lp.pp.kind, lp.pp.p, d == 0 ? 0 : 1, lp.k, beam_id_[cur].get(), beam_val_[cur].get(), beam_cnt_[cur].get(),
-                beam_stride_, cand_.get(), cand_stride_q, c_stride, o_id, o_val, o_cnt, o_stride, rows, stats, o_key);
+                beam_stride_, cand_.get(), cand_stride_q, c_stride, o_id, o_val, o_cnt, o_stride, rows, stats, o_key, key_cap);
         } else {
             xl_topk_kernel<<<grid, kTopkThreads, topk_kernel_smem(lp.b_prev), stream_>>>(
                 L, lp.pp.kind, lp.pp.p, d == 0 ? 0 : 1, lp.k, beam_id_[cur].get(), beam_val_[cur].get(), beam_cnt_[cur].get(),

@@ -138,6 +138,27 @@ def test_duplicate_points_and_ties(tmp_path, gpu_clib, have_ref):
             assert np.array_equal(idx, ri) and np.array_equal(dist.view(np.uint32), rd.view(np.uint32))
 
 
+def test_bulk_copy_ring_depths_give_identical_results(tmp_path, gpu_clib, have_ref):
+    """0 = direct loads, 4 / 8 = base vectors staged through the per-warp TMA bulk-copy ring: same bits."""
+    if not have_ref:
+        pytest.skip("needs oracle/_ref to build the index")
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((5000, 200)).astype(np.float32)   # d = 200: permuted main part + 8-element tail
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    Q = rng.standard_normal((300, 200)).astype(np.float32)
+    folder = str(tmp_path / "idx")
+    _save_index(folder, X, 12, 60, "ip")
+    m = _load(folder)
+    c = gpu_clib.clib_float32
+    ref_out = None
+    for stages in (0, 4, 8, 4):
+        assert c.pb200_hnsw_set_stages(m.model_ptr, stages) == stages
+        out = m.predict(Q, pred_params=_pp(100, 10), ret_csr=False)
+        if ref_out is None:
+            ref_out = out
+        assert np.array_equal(out[0], ref_out[0]) and np.array_equal(out[1].view(np.uint32), ref_out[1].view(np.uint32))
+
+
 def test_resident_batch_and_counters(golden, gpu_clib):
     from ctypes import POINTER, byref, c_float, c_uint32, c_uint64
 

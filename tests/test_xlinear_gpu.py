@@ -160,6 +160,9 @@ def test_wide_chunks_long_queries_and_flat_model(tmp_path, gpu_clib, have_ref):
     m, oracles = _load(folder), _oracles(folder, have_ref)
     _check(m, oracles, X, "flat k=10", only_topk=10)
     _check(m, oracles, X, "flat k=1500 (global sort path)", only_topk=1500)
+    gpu_clib.clib_float32.pb200_xlinear_set_lookup(m.model.model_chain, 0)  # first-generation kernels
+    _check(m, oracles, X, "flat k=10, block-wide streaming top-k + row-list streaming scores", only_topk=10)
+    gpu_clib.clib_float32.pb200_xlinear_set_lookup(m.model.model_chain, 1)
     _check(m, oracles, X[:3].toarray(), "flat dense", only_topk=10)
 
 
