@@ -36,14 +36,15 @@ constexpr int kQCap = 1024;      // query non-zeros staged in shared memory (lon
 constexpr int kSortCap = 2048;   // keys sorted in shared memory per pass of the top-k kernel
 constexpr int kTopkThreads = 256;
 
+constexpr int kECapLookup = 128; // staged entries per pass of the lookup kernel
 constexpr int kMCapLookup = 128; // the lookup kernel adds at most 32 matches per pass: a shorter list => higher occupancy
 
-template <int MCAP>
+template <int MCAP, int ECAP>
 struct __align__(16) WarpScratch {
     uint32_t ms[MCAP];         // chunk-row index of each match; becomes the row's first entry offset during flush
     float mx[MCAP];            // multiplier of the row: query value, or the bias
     uint32_t off[MCAP + 4];    // exclusive prefix of the matched rows' entry counts
-    uint2 stage[kECap];        // staged {col_offset, bits of x*w}
+    uint2 stage[ECAP];         // staged {col_offset, bits of x*w}
     float out[kCSmem];         // dense output block of the chunk
 };
 
@@ -83,8 +84,8 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 }
 
 // Apply the matched rows collected in ws (in ascending feature order) to the output block.
-template <int MCAP>
-__device__ __noinline__ void xl_flush(WarpScratch<MCAP>& ws, int m, const uint32_t* __restrict__ rp,
+template <int MCAP, int ECAP>
+__device__ __noinline__ void xl_flush(WarpScratch<MCAP, ECAP>& ws, int m, const uint32_t* __restrict__ rp,
                                       const uint2* __restrict__ ent, float* out, int has_dup, int lane,
                                       unsigned long long& e_total) {
     if (m == 0) return;
@@ -129,8 +130,8 @@ __device__ __noinline__ void xl_flush(WarpScratch<MCAP>& ws, int m, const uint32
         const uint32_t base = row_begin + part;
         int i_next;
         uint32_t part_next = 0, ne;
-        if (part == 0 && ws.off[i0 + 1] - row_begin <= static_cast<uint32_t>(kECap)) {
-            const int i1 = last_le_u32(ws.off, m + 1, base + kECap);  // rows [i0, i1) fit entirely; i1 > i0
+        if (part == 0 && ws.off[i0 + 1] - row_begin <= static_cast<uint32_t>(ECAP)) {
+            const int i1 = last_le_u32(ws.off, m + 1, base + ECAP);  // rows [i0, i1) fit entirely; i1 > i0
             for (int i = i0 + lane; i < i1; i += 32) {
                 const uint32_t a = ws.ms[i];
                 const uint32_t n = ws.off[i + 1] - ws.off[i];
@@ -158,7 +159,7 @@ __device__ __noinline__ void xl_flush(WarpScratch<MCAP>& ws, int m, const uint32
             i_next = i1;
         } else {
             const uint32_t n_left = ws.off[i0 + 1] - base;
-            ne = min(static_cast<uint32_t>(kECap), n_left);
+            ne = min(static_cast<uint32_t>(ECAP), n_left);
             const uint32_t a = ws.ms[i0] + part;
             const float x = ws.mx[i0];
             for (uint32_t g = lane; g < ne; g += 32) {
@@ -192,12 +193,14 @@ template <bool DENSE, bool STATS, bool LOOKUP>
 __global__ void __launch_bounds__(kWarpsMax * 32)
 xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __restrict__ beam_id,
                        const uint32_t* __restrict__ beam_cnt, const uint32_t beam_stride, float* __restrict__ cand,
-                       const uint64_t cand_stride_q, const uint32_t c_stride, unsigned long long* stats) {
+                       const uint64_t cand_stride_q, const uint32_t c_stride, unsigned long long* stats,
+                       const uint32_t q_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* q_idx_s = reinterpret_cast<uint32_t*>(smem_raw);
-    float* q_val_s = reinterpret_cast<float*>(smem_raw + kQCap * 4);
+    float* q_val_s = reinterpret_cast<float*>(smem_raw + q_cap * 4);
     constexpr int MCAP = LOOKUP ? kMCapLookup : kMCap;
-    WarpScratch<MCAP>* scratch = reinterpret_cast<WarpScratch<MCAP>*>(smem_raw + kQCap * 8);
+    constexpr int ECAP = LOOKUP ? kECapLookup : kECap;
+    WarpScratch<MCAP, ECAP>* scratch = reinterpret_cast<WarpScratch<MCAP, ECAP>*>(smem_raw + q_cap * 8);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -213,7 +216,7 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
         qn = static_cast<int>(e - b);
         const uint32_t* gi = X.col_idx + b;
         const float* gv = X.val + b;
-        if (qn <= kQCap) {
+        if (qn <= static_cast<int>(q_cap)) {
             for (int i = threadIdx.x; i < qn; i += blockDim.x) { q_idx_s[i] = gi[i]; q_val_s[i] = gv[i]; }
             qidx = q_idx_s; qval = q_val_s;
         } else {
@@ -225,7 +228,7 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
     }
 
     const uint32_t cnt = beam_cnt[q];
-    WarpScratch<MCAP>& ws = scratch[warp];
+    WarpScratch<MCAP, ECAP>& ws = scratch[warp];
     unsigned long long st_chunks = 0, st_rows = 0, st_match = 0, st_ent = 0, st_cols = 0;
 
     for (uint32_t j = warp; j < cnt; j += nwarps) {
@@ -731,14 +734,21 @@ __global__ void xl_init_beam_kernel(uint32_t* beam_id, float* beam_val, uint32_t
     }
 }
 
+uint32_t max_row_nnz(const uint64_t* row_ptr, uint32_t rows) {
+    uint64_t m = 0;
+    for (uint32_t r = 0; r < rows; ++r) m = std::max<uint64_t>(m, row_ptr[r + 1] - row_ptr[r]);
+    return static_cast<uint32_t>(std::min<uint64_t>(m, 0xFFFFFFFFull));
+}
+
 uint32_t next_pow2_host(uint64_t v) {
     uint64_t p = 2;
     while (p < v) p <<= 1;
     return static_cast<uint32_t>(p);
 }
 
-size_t chunk_kernel_smem(int warps, bool lookup) {
-    return static_cast<size_t>(kQCap) * 8 + static_cast<size_t>(warps) * (lookup ? sizeof(WarpScratch<kMCapLookup>) : sizeof(WarpScratch<kMCap>));
+size_t chunk_kernel_smem(int warps, bool lookup, uint32_t q_cap) {
+    return static_cast<size_t>(q_cap) * 8 + static_cast<size_t>(warps) * (lookup ? sizeof(WarpScratch<kMCapLookup, kECapLookup>)
+                                                                                 : sizeof(WarpScratch<kMCap, kECap>));
 }
 size_t topk_kernel_smem(uint32_t b_prev) { return static_cast<size_t>(kSortCap) * 8 + (static_cast<size_t>(b_prev) * 3 + 1) * 4; }
 
@@ -907,10 +917,12 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
         if (profile_) PB200_CUDA(cudaEventRecord(ev_[0], stream_));
         const dim3 grid(rows), block(warps * 32);
         const bool lookup = !dense && L.featmap != nullptr;
-        const size_t smem1 = chunk_kernel_smem(warps, lookup);
+        // query staging area: as small as the batch's longest row allows (occupancy), at most kQCap non-zeros
+        const uint32_t q_cap = dense ? 32u : std::min<uint32_t>(kQCap, std::max<uint32_t>(32u, (q.max_row_nnz + 31u) & ~31u));
+        const size_t smem1 = chunk_kernel_smem(warps, lookup, q_cap);
         auto launch = [&](auto kernel) {
             kernel<<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(),
-                                                   cand_stride_q, c_stride, stats);
+                                                   cand_stride_q, c_stride, stats, q_cap);
         };
         if (dense) {
             if (collect_stats) launch(xl_chunk_scores_kernel<true, true, false>);
@@ -1013,7 +1025,7 @@ XLinearEngine::Result XLinearEngine::predict_csr(const uint64_t* row_ptr, const 
         x_row_ptr_.upload(row_ptr + r0, static_cast<uint64_t>(tr) + 1, stream_);
         x_col_idx_.upload(col_idx + base, end - base, stream_);
         x_val_.upload(val + base, end - base, stream_);
-        QueryDev q{x_row_ptr_.get(), x_col_idx_.get(), x_val_.get(), base, tr, cols};
+        QueryDev q{x_row_ptr_.get(), x_col_idx_.get(), x_val_.get(), base, tr, cols, max_row_nnz(row_ptr + r0, tr)};
         res_rows_ = r0;
         run_tile_(q, plan, false);
         if (r0 + tr < rows) PB200_CUDA(cudaStreamSynchronize(stream_));  // staging buffers are reused by the next tile
@@ -1037,7 +1049,7 @@ XLinearEngine::Result XLinearEngine::predict_drm(const float* dense, uint32_t ro
     for (uint32_t r0 = 0; r0 < rows; r0 += tile) {
         const uint32_t tr = std::min(tile, rows - r0);
         x_val_.upload(dense + static_cast<uint64_t>(r0) * cols, static_cast<uint64_t>(tr) * cols, stream_);
-        QueryDev q{nullptr, nullptr, x_val_.get(), 0, tr, cols};
+        QueryDev q{nullptr, nullptr, x_val_.get(), 0, tr, cols, cols};
         res_rows_ = r0;
         run_tile_(q, plan, false);
         if (r0 + tr < rows) PB200_CUDA(cudaStreamSynchronize(stream_));
@@ -1053,7 +1065,7 @@ void XLinearEngine::resident_upload_csr(const uint64_t* row_ptr, const uint32_t*
     x_col_idx_.upload(col_idx, nnz, stream_);
     x_val_.upload(val, nnz, stream_);
     PB200_CUDA(cudaStreamSynchronize(stream_));
-    resident_ = QueryDev{x_row_ptr_.get(), x_col_idx_.get(), x_val_.get(), 0, rows, cols};
+    resident_ = QueryDev{x_row_ptr_.get(), x_col_idx_.get(), x_val_.get(), 0, rows, cols, max_row_nnz(row_ptr, rows)};
     has_resident_ = true;
 }
 
@@ -1119,7 +1131,7 @@ uint32_t XLinearEngine::sharded_local_csr(const uint64_t* row_ptr, const uint32_
             x_row_ptr_.upload(row_ptr + r0, static_cast<uint64_t>(tr) + 1, stream_);
             x_col_idx_.upload(col_idx + base, end - base, stream_);
             x_val_.upload(val + base, end - base, stream_);
-            QueryDev q{x_row_ptr_.get(), x_col_idx_.get(), x_val_.get(), base, tr, cols};
+            QueryDev q{x_row_ptr_.get(), x_col_idx_.get(), x_val_.get(), base, tr, cols, max_row_nnz(row_ptr + r0, tr)};
             res_rows_ = r0;
             run_tile_(q, plan, false);
             PB200_CUDA(cudaStreamSynchronize(stream_));

@@ -42,6 +42,7 @@ struct QueryDev {
     uint64_t nnz_base;
     uint32_t rows;
     uint32_t cols;
+    uint32_t max_row_nnz;     // longest row of the batch (sizes the shared-memory staging of the query)
 };
 
 struct XLinearStats {  // algorithmic-byte counters of SURVEY.md section 8(d), accumulated by the STATS kernel variant
