@@ -635,14 +635,34 @@ xl_topk_warp_kernel(const LayerDev L, const int pp_kind, const int pp_p, const i
         label = S.colbeg[j] + off;
         return v;
     };
-    unsigned long long best = 0ull;  // lane-local maximum over positions lane, lane+32, ...
-    for (uint32_t i = lane; i < n_valid; i += 32) {
-        uint32_t lab;
-        const uint32_t ji = static_cast<uint32_t>(last_le_u32(S.base, static_cast<int>(cnt), i));
-        const unsigned long long key = (S.colbeg[ji] == 0xFFFFFFFFu) ? 0ull : xl_make_key(score_at(i, lab), i);
-        S.keys[i] = key;
-        best = key > best ? key : best;
+    // pass 1 (slot-major, loads only => many in flight): raw scores -> shared memory
+    for (uint32_t j = 0; j < cnt; ++j) {
+        const uint32_t b0 = S.base[j], nc = S.base[j + 1] - b0;
+        const bool absent = S.colbeg[j] == 0xFFFFFFFFu;  // leaf chunk scored on another GPU (index sharding)
+        const float* src = cq + static_cast<uint64_t>(j) * c_stride;
+#pragma unroll 4
+        for (uint32_t off = lane; off < nc; off += 32)
+            S.keys[b0 + off] = absent ? 0xFFFFFFFFFFFFFFFFull : static_cast<unsigned long long>(__float_as_uint(src[off]));
     }
+    __syncwarp();
+    // pass 2 (slot-major, no position search): post-processor, combine, composite key
+    for (uint32_t j = 0; j < cnt; ++j) {
+        const uint32_t b0 = S.base[j], nc = S.base[j + 1] - b0;
+        const float pv = S.pval[j];
+        for (uint32_t off = lane; off < nc; off += 32) {
+            const unsigned long long raw = S.keys[b0 + off];
+            unsigned long long key = 0ull;
+            if (raw != 0xFFFFFFFFFFFFFFFFull) {
+                float v = xl_transform(__uint_as_float(static_cast<uint32_t>(raw)), pp_kind, pp_p);
+                if (combine) v = xl_combine(v, pv, pp_kind);
+                key = xl_make_key(v, b0 + off);
+            }
+            S.keys[b0 + off] = key;
+        }
+    }
+    __syncwarp();
+    unsigned long long best = 0ull;  // lane-local maximum over positions lane, lane+32, ...
+    for (uint32_t i = lane; i < n_valid; i += 32) { const unsigned long long key = S.keys[i]; best = key > best ? key : best; }
     __syncwarp();
     for (uint32_t r = 0; r < kk; ++r) {
         unsigned long long top = best;
