@@ -190,7 +190,7 @@ __device__ __noinline__ void xl_flush(WarpScratch<MCAP, ECAP>& ws, int m, const 
 // DENSE: row-major dense queries.  LOOKUP: sparse queries probe the chunk's feature map (one 8-byte cell per query
 // feature) instead of streaming the chunk's row list -- same matches in the same order, far fewer bytes/instructions.
 template <bool DENSE, bool STATS, bool LOOKUP>
-__global__ void __launch_bounds__(kWarpsMax * 32)
+__global__ void __launch_bounds__(kWarpsMax * 32, LOOKUP ? 3 : 1)  // lookup variant: 40 registers => 5 x 10-warp CTAs per SM
 xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __restrict__ beam_id,
                        const uint32_t* __restrict__ beam_cnt, const uint32_t beam_stride, float* __restrict__ cand,
                        const uint64_t cand_stride_q, const uint32_t c_stride, unsigned long long* stats,
@@ -645,19 +645,32 @@ xl_topk_warp_kernel(const LayerDev L, const int pp_kind, const int pp_p, const i
             S.keys[b0 + off] = absent ? 0xFFFFFFFFFFFFFFFFull : static_cast<unsigned long long>(__float_as_uint(src[off]));
     }
     __syncwarp();
-    // pass 2 (slot-major, no position search): post-processor, combine, composite key
-    for (uint32_t j = 0; j < cnt; ++j) {
-        const uint32_t b0 = S.base[j], nc = S.base[j + 1] - b0;
-        const float pv = S.pval[j];
-        for (uint32_t off = lane; off < nc; off += 32) {
-            const unsigned long long raw = S.keys[b0 + off];
-            unsigned long long key = 0ull;
-            if (raw != 0xFFFFFFFFFFFFFFFFull) {
-                float v = xl_transform(__uint_as_float(static_cast<uint32_t>(raw)), pp_kind, pp_p);
-                if (combine) v = xl_combine(v, pv, pp_kind);
-                key = xl_make_key(v, b0 + off);
+    // pass 2: post-processor (double-precision libm chains), combine, composite key.  Four independent candidates per lane
+    // and step, so the long dependent exp/log chains of different candidates overlap.
+    for (uint32_t i0 = lane; i0 < n_valid; i0 += 128) {
+        unsigned long long raw[4];
+        float pv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + 32u * u;
+            raw[u] = 0xFFFFFFFFFFFFFFFFull;
+            pv[u] = 0.0f;
+            if (i < n_valid) {
+                raw[u] = S.keys[i];
+                pv[u] = S.pval[last_le_u32(S.base, static_cast<int>(cnt), i)];
             }
-            S.keys[b0 + off] = key;
+        }
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = xl_transform(__uint_as_float(static_cast<uint32_t>(raw[u])), pp_kind, pp_p);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + 32u * u;
+            if (i < n_valid) {
+                float w = v[u];
+                if (combine) w = xl_combine(w, pv[u], pp_kind);
+                S.keys[i] = (raw[u] == 0xFFFFFFFFFFFFFFFFull) ? 0ull : xl_make_key(w, i);
+            }
         }
     }
     __syncwarp();
