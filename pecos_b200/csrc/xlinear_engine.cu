@@ -27,7 +27,7 @@ namespace pb200 {
 namespace {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
-constexpr int kWarpsMax = 16;    // warps per CTA of the chunk kernel
+constexpr int kWarpsMax = 10;    // warps per CTA of the chunk kernel
 constexpr int kMCap = 256;       // match list capacity per warp
 constexpr int kMFlush = 128;     // flush the match list once it holds this many rows (kMCap - 128 new per pass)
 constexpr int kECap = 256;       // staged entries per accumulate pass
@@ -190,17 +190,18 @@ __device__ __noinline__ void xl_flush(WarpScratch<MCAP, ECAP>& ws, int m, const 
 // DENSE: row-major dense queries.  LOOKUP: sparse queries probe the chunk's feature map (one 8-byte cell per query
 // feature) instead of streaming the chunk's row list -- same matches in the same order, far fewer bytes/instructions.
 template <bool DENSE, bool STATS, bool LOOKUP>
-__global__ void __launch_bounds__(kWarpsMax * 32, LOOKUP ? 3 : 1)  // lookup variant: 40 registers => 5 x 10-warp CTAs per SM
+__global__ void __launch_bounds__(kWarpsMax * 32, LOOKUP ? 4 : 1)  // lookup variant: <= 51 registers => 4 x 10-warp CTAs per SM
 xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __restrict__ beam_id,
                        const uint32_t* __restrict__ beam_cnt, const uint32_t beam_stride, float* __restrict__ cand,
                        const uint64_t cand_stride_q, const uint32_t c_stride, unsigned long long* stats,
-                       const uint32_t q_cap) {
+                       const uint32_t q_cap, const uint32_t sb_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* q_idx_s = reinterpret_cast<uint32_t*>(smem_raw);
     float* q_val_s = reinterpret_cast<float*>(smem_raw + q_cap * 4);
+    uint32_t* slot_base = reinterpret_cast<uint32_t*>(smem_raw + q_cap * 8);  // [cnt + 1] first candidate of each beam slot
     constexpr int MCAP = LOOKUP ? kMCapLookup : kMCap;
     constexpr int ECAP = LOOKUP ? kECapLookup : kECap;
-    WarpScratch<MCAP, ECAP>* scratch = reinterpret_cast<WarpScratch<MCAP, ECAP>*>(smem_raw + q_cap * 8);
+    WarpScratch<MCAP, ECAP>* scratch = reinterpret_cast<WarpScratch<MCAP, ECAP>*>(smem_raw + q_cap * 8 + sb_cap * 4);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -222,12 +223,21 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
         } else {
             qidx = gi; qval = gv;
         }
-        __syncthreads();
     } else {
         qval = X.val + static_cast<uint64_t>(q) * X.cols;
     }
 
+    // candidates of a query are stored compactly in prolongation order: slot j starts at the sum of the widths before it
     const uint32_t cnt = beam_cnt[q];
+    for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x)
+        slot_base[j + 1] = L.chunks[beam_id[static_cast<uint64_t>(q) * beam_stride + j]].n_cols;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        slot_base[0] = 0;
+        for (uint32_t j = 0; j < cnt; ++j) { run += slot_base[j + 1]; slot_base[j + 1] = run; }
+    }
+    __syncthreads();
     WarpScratch<MCAP, ECAP>& ws = scratch[warp];
     unsigned long long st_chunks = 0, st_rows = 0, st_match = 0, st_ent = 0, st_cols = 0;
 
@@ -241,7 +251,7 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
         const uint32_t* ridx = L.meta + h.meta_off;
         const uint32_t* rp = ridx + R4;
         const uint2* ent = L.entries + h.ent_off;
-        float* blk = cand + static_cast<uint64_t>(q) * cand_stride_q + static_cast<uint64_t>(j) * c_stride;
+        float* blk = cand + static_cast<uint64_t>(q) * cand_stride_q + slot_base[j];
         const bool in_smem = h.n_cols <= static_cast<uint32_t>(kCSmem);
         float* out = in_smem ? ws.out : blk;
         for (uint32_t c = lane; c < h.n_cols; c += 32) out[c] = 0.0f;
@@ -282,33 +292,43 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
             if (LOOKUP) {
                 if (R > 0) {
                     const uint2* fm = L.featmap + static_cast<uint64_t>(p) * L.fm_words;
-                    for (int tb = 0; tb < qn; tb += 32) {
-                        const int t = tb + lane;
-                        bool hit = false;
-                        uint32_t slot = 0;
-                        if (t < qn) {
-                            const uint32_t f = qidx[t];
-                            // a repeated column index only counts once: the reference's marching loop consumes the first
-                            const bool dup = (t > 0) && (qidx[t - 1] == f);
-                            if (!dup && f < L.w_rows) {
-                                const uint2 cell = __ldg(fm + (f >> 5));
-                                const uint32_t bit = f & 31u;
-                                hit = (cell.x >> bit) & 1u;
-                                slot = cell.y + __popc(cell.x & ((1u << bit) - 1u));
+                    for (int tb0 = 0; tb0 < qn; tb0 += 128) {
+                        // four probe rounds issued back to back: 4 independent cell loads in flight per lane
+                        uint2 cell[4];
+                        uint32_t feat[4];
+                        bool live[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int t = tb0 + 32 * u + lane;
+                            live[u] = false;
+                            feat[u] = 0;
+                            cell[u] = make_uint2(0u, 0u);
+                            if (t < qn) {
+                                const uint32_t f = qidx[t];
+                                // a repeated column index only counts once: the reference's marching loop consumes the first
+                                const bool dup = (t > 0) && (qidx[t - 1] == f);
+                                if (!dup && f < L.w_rows) { live[u] = true; feat[u] = f; cell[u] = __ldg(fm + (f >> 5)); }
                             }
                         }
-                        const unsigned mask = __ballot_sync(kFull, hit);
-                        if (mask == 0u) continue;
-                        if (hit) {
-                            const uint32_t pos = m + __popc(mask & ((1u << lane) - 1u));
-                            ws.ms[pos] = slot;
-                            ws.mx[pos] = qval[t];
-                        }
-                        m += __popc(mask);
-                        if (m > MCAP - 33) {  // keep room for the next 32 matches and the bias row
-                            m_total += m;
-                            xl_flush(ws, m, rp, ent, out, L.has_dup_cols, lane, e_total);
-                            m = 0;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (tb0 + 32 * u >= qn) break;
+                            const int t = tb0 + 32 * u + lane;
+                            const uint32_t bit = feat[u] & 31u;
+                            const bool hit = live[u] && ((cell[u].x >> bit) & 1u);
+                            const unsigned mask = __ballot_sync(kFull, hit);
+                            if (mask == 0u) continue;
+                            if (hit) {
+                                const uint32_t pos = m + __popc(mask & ((1u << lane) - 1u));
+                                ws.ms[pos] = cell[u].y + __popc(cell[u].x & ((1u << bit) - 1u));
+                                ws.mx[pos] = qval[t];
+                            }
+                            m += __popc(mask);
+                            if (m > MCAP - 33) {  // keep room for the next 32 matches and the bias row
+                                m_total += m;
+                                xl_flush(ws, m, rp, ent, out, L.has_dup_cols, lane, e_total);
+                                m = 0;
+                            }
                         }
                     }
                 }
@@ -497,7 +517,7 @@ xl_topk_kernel(const LayerDev L, const int pp_kind, const int pp_p, const int co
     auto score_at = [&](uint32_t cpos, uint32_t& label) -> float {
         const uint32_t j = static_cast<uint32_t>(last_le_u32(s_base, static_cast<int>(cnt), cpos));
         const uint32_t off = cpos - s_base[j];
-        float v = xl_transform(cq[static_cast<uint64_t>(j) * c_stride + off], pp_kind, pp_p);
+        float v = xl_transform(cq[cpos], pp_kind, pp_p);
         if (combine) v = xl_combine(v, s_pval[j], pp_kind);
         label = s_colbeg[j] + off;
         return v;
@@ -630,21 +650,28 @@ xl_topk_warp_kernel(const LayerDev L, const int pp_kind, const int pp_p, const i
     auto score_at = [&](uint32_t cpos, uint32_t& label) -> float {
         const uint32_t j = static_cast<uint32_t>(last_le_u32(S.base, static_cast<int>(cnt), cpos));
         const uint32_t off = cpos - S.base[j];
-        float v = xl_transform(cq[static_cast<uint64_t>(j) * c_stride + off], pp_kind, pp_p);
+        float v = xl_transform(cq[cpos], pp_kind, pp_p);
         if (combine) v = xl_combine(v, S.pval[j], pp_kind);
         label = S.colbeg[j] + off;
         return v;
     };
-    // pass 1 (slot-major, loads only => many in flight): raw scores -> shared memory
-    for (uint32_t j = 0; j < cnt; ++j) {
-        const uint32_t b0 = S.base[j], nc = S.base[j + 1] - b0;
-        const bool absent = S.colbeg[j] == 0xFFFFFFFFu;  // leaf chunk scored on another GPU (index sharding)
-        const float* src = cq + static_cast<uint64_t>(j) * c_stride;
-#pragma unroll 4
-        for (uint32_t off = lane; off < nc; off += 32)
-            S.keys[b0 + off] = absent ? 0xFFFFFFFFFFFFFFFFull : static_cast<unsigned long long>(__float_as_uint(src[off]));
+    // pass 1: raw scores -> shared memory; the candidates of a query are contiguous, so this is a flat coalesced copy
+    // with eight independent loads in flight per lane
+    for (uint32_t i0 = lane; i0 < n_valid; i0 += 256) {
+        float r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + 32u * u; r[u] = (i < n_valid) ? cq[i] : 0.0f; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const uint32_t i = i0 + 32u * u; if (i < n_valid) S.keys[i] = static_cast<unsigned long long>(__float_as_uint(r[u])); }
     }
     __syncwarp();
+    if (owned != n_valid) {  // index sharding: the ranges of leaf chunks scored on other GPUs hold no data
+        for (uint32_t j = 0; j < cnt; ++j) {
+            if (S.colbeg[j] != 0xFFFFFFFFu) continue;
+            for (uint32_t i = S.base[j] + lane; i < S.base[j + 1]; i += 32) S.keys[i] = 0xFFFFFFFFFFFFFFFFull;
+        }
+        __syncwarp();
+    }
     // pass 2: post-processor (double-precision libm chains), combine, composite key.  Four independent candidates per lane
     // and step, so the long dependent exp/log chains of different candidates overlap.
     for (uint32_t i0 = lane; i0 < n_valid; i0 += 128) {
@@ -779,8 +806,8 @@ uint32_t next_pow2_host(uint64_t v) {
     return static_cast<uint32_t>(p);
 }
 
-size_t chunk_kernel_smem(int warps, bool lookup, uint32_t q_cap) {
-    return static_cast<size_t>(q_cap) * 8 + static_cast<size_t>(warps) * (lookup ? sizeof(WarpScratch<kMCapLookup, kECapLookup>)
+size_t chunk_kernel_smem(int warps, bool lookup, uint32_t q_cap, uint32_t sb_cap) {
+    return static_cast<size_t>(q_cap) * 8 + static_cast<size_t>(sb_cap) * 4 + static_cast<size_t>(warps) * (lookup ? sizeof(WarpScratch<kMCapLookup, kECapLookup>)
                                                                                  : sizeof(WarpScratch<kMCap, kECap>));
 }
 size_t topk_kernel_smem(uint32_t b_prev) { return static_cast<size_t>(kSortCap) * 8 + (static_cast<size_t>(b_prev) * 3 + 1) * 4; }
@@ -952,10 +979,11 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
         const bool lookup = !dense && L.featmap != nullptr;
         // query staging area: as small as the batch's longest row allows (occupancy), at most kQCap non-zeros
         const uint32_t q_cap = dense ? 32u : std::min<uint32_t>(kQCap, std::max<uint32_t>(32u, (q.max_row_nnz + 31u) & ~31u));
-        const size_t smem1 = chunk_kernel_smem(warps, lookup, q_cap);
+        const uint32_t sb_cap = (lp.b_prev + 1u + 3u) & ~3u;
+        const size_t smem1 = chunk_kernel_smem(warps, lookup, q_cap, sb_cap);
         auto launch = [&](auto kernel) {
             kernel<<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(),
-                                                   cand_stride_q, c_stride, stats, q_cap);
+                                                   cand_stride_q, c_stride, stats, q_cap, sb_cap);
         };
         if (dense) {
             if (collect_stats) launch(xl_chunk_scores_kernel<true, true, false>);
