@@ -194,43 +194,65 @@ __global__ void __launch_bounds__(kWarpsMax * 32, LOOKUP ? 4 : 1)  // lookup var
 xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __restrict__ beam_id,
                        const uint32_t* __restrict__ beam_cnt, const uint32_t beam_stride, float* __restrict__ cand,
                        const uint64_t cand_stride_q, const uint32_t c_stride, unsigned long long* stats,
-                       const uint32_t q_cap, const uint32_t sb_cap) {
+                       const uint32_t q_cap, const uint32_t sb_cap, const uint32_t hdr_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* q_idx_s = reinterpret_cast<uint32_t*>(smem_raw);
     float* q_val_s = reinterpret_cast<float*>(smem_raw + q_cap * 4);
     uint32_t* slot_base = reinterpret_cast<uint32_t*>(smem_raw + q_cap * 8);  // [cnt + 1] first candidate of each beam slot
+    ChunkHeader* hdr_s = reinterpret_cast<ChunkHeader*>(smem_raw + q_cap * 8 + sb_cap * 4);  // [hdr_cap] beam chunk headers
     constexpr int MCAP = LOOKUP ? kMCapLookup : kMCap;
     constexpr int ECAP = LOOKUP ? kECapLookup : kECap;
-    WarpScratch<MCAP, ECAP>* scratch = reinterpret_cast<WarpScratch<MCAP, ECAP>*>(smem_raw + q_cap * 8 + sb_cap * 4);
+    WarpScratch<MCAP, ECAP>* scratch =
+        reinterpret_cast<WarpScratch<MCAP, ECAP>*>(smem_raw + q_cap * 8 + sb_cap * 4 + static_cast<size_t>(hdr_cap) * sizeof(ChunkHeader));
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
     const uint32_t q = blockIdx.x;
 
+    // ---- prologue.  All global loads are issued before the first shared-memory store (issue is in order: a store that
+    // waits for its operand would otherwise serialise the independent load chains below).
+    const uint32_t cnt = beam_cnt[q];
+    uint64_t qb = 0, qe = 0;
+    if (!DENSE) { qb = X.row_ptr[q] - X.nnz_base; qe = X.row_ptr[q + 1] - X.nnz_base; }
+    const uint32_t my_p = (threadIdx.x < cnt) ? beam_id[static_cast<uint64_t>(q) * beam_stride + threadIdx.x] : 0u;
     const uint32_t* qidx = nullptr;
     const float* qval = nullptr;
     int qn = 0;
+    uint32_t first_idx = 0;
+    float first_val = 0.0f;
+    bool staged = false;
     if (!DENSE) {
-        const uint64_t b = X.row_ptr[q] - X.nnz_base;
-        const uint64_t e = X.row_ptr[q + 1] - X.nnz_base;
-        qn = static_cast<int>(e - b);
-        const uint32_t* gi = X.col_idx + b;
-        const float* gv = X.val + b;
-        if (qn <= static_cast<int>(q_cap)) {
-            for (int i = threadIdx.x; i < qn; i += blockDim.x) { q_idx_s[i] = gi[i]; q_val_s[i] = gv[i]; }
-            qidx = q_idx_s; qval = q_val_s;
-        } else {
-            qidx = gi; qval = gv;
-        }
+        qn = static_cast<int>(qe - qb);
+        qidx = X.col_idx + qb;
+        qval = X.val + qb;
+        staged = qn <= static_cast<int>(q_cap);
+        if (staged && static_cast<int>(threadIdx.x) < qn) { first_idx = qidx[threadIdx.x]; first_val = qval[threadIdx.x]; }
     } else {
         qval = X.val + static_cast<uint64_t>(q) * X.cols;
     }
-
+    ChunkHeader my_h;
+    my_h.n_cols = 0;
+    if (threadIdx.x < cnt) my_h = L.chunks[my_p];
+    if (staged) {
+        if (static_cast<int>(threadIdx.x) < qn) { q_idx_s[threadIdx.x] = first_idx; q_val_s[threadIdx.x] = first_val; }
+        for (int i = threadIdx.x + blockDim.x; i < qn; i += blockDim.x) { q_idx_s[i] = qidx[i]; q_val_s[i] = qval[i]; }
+        qidx = q_idx_s;
+        qval = q_val_s;
+    }
     // candidates of a query are stored compactly in prolongation order: slot j starts at the sum of the widths before it
-    const uint32_t cnt = beam_cnt[q];
-    for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x)
-        slot_base[j + 1] = L.chunks[beam_id[static_cast<uint64_t>(q) * beam_stride + j]].n_cols;
+    if (threadIdx.x < cnt) {
+        slot_base[threadIdx.x + 1] = my_h.n_cols;
+        my_h.col_begin = my_p;  // this kernel never needs col_begin: the cached copy carries the chunk id instead
+        if (threadIdx.x < hdr_cap) hdr_s[threadIdx.x] = my_h;
+    }
+    for (uint32_t j = threadIdx.x + blockDim.x; j < cnt; j += blockDim.x) {
+        const uint32_t pj = beam_id[static_cast<uint64_t>(q) * beam_stride + j];
+        ChunkHeader hh = L.chunks[pj];
+        slot_base[j + 1] = hh.n_cols;
+        hh.col_begin = pj;
+        if (j < hdr_cap) hdr_s[j] = hh;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t run = 0;
@@ -242,8 +264,15 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
     unsigned long long st_chunks = 0, st_rows = 0, st_match = 0, st_ent = 0, st_cols = 0;
 
     for (uint32_t j = warp; j < cnt; j += nwarps) {
-        const uint32_t p = beam_id[static_cast<uint64_t>(q) * beam_stride + j];
-        const ChunkHeader h = L.chunks[p];
+        uint32_t p;
+        ChunkHeader h;
+        if (j < hdr_cap) {
+            h = hdr_s[j];
+            p = h.col_begin;
+        } else {
+            p = beam_id[static_cast<uint64_t>(q) * beam_stride + j];
+            h = L.chunks[p];
+        }
         if (h.has_bias & kChunkAbsent) continue;  // leaf chunk owned by another GPU (index sharding): not scored here
         const bool chunk_bias = (h.has_bias & 1u) != 0u;
         const uint32_t R = h.nnz_rows;
@@ -806,8 +835,9 @@ uint32_t next_pow2_host(uint64_t v) {
     return static_cast<uint32_t>(p);
 }
 
-size_t chunk_kernel_smem(int warps, bool lookup, uint32_t q_cap, uint32_t sb_cap) {
-    return static_cast<size_t>(q_cap) * 8 + static_cast<size_t>(sb_cap) * 4 + static_cast<size_t>(warps) * (lookup ? sizeof(WarpScratch<kMCapLookup, kECapLookup>)
+size_t chunk_kernel_smem(int warps, bool lookup, uint32_t q_cap, uint32_t sb_cap, uint32_t hdr_cap) {
+    return static_cast<size_t>(q_cap) * 8 + static_cast<size_t>(sb_cap) * 4 + static_cast<size_t>(hdr_cap) * sizeof(ChunkHeader) +
+           static_cast<size_t>(warps) * (lookup ? sizeof(WarpScratch<kMCapLookup, kECapLookup>)
                                                                                  : sizeof(WarpScratch<kMCap, kECap>));
 }
 size_t topk_kernel_smem(uint32_t b_prev) { return static_cast<size_t>(kSortCap) * 8 + (static_cast<size_t>(b_prev) * 3 + 1) * 4; }
@@ -980,10 +1010,11 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
         // query staging area: as small as the batch's longest row allows (occupancy), at most kQCap non-zeros
         const uint32_t q_cap = dense ? 32u : std::min<uint32_t>(kQCap, std::max<uint32_t>(32u, (q.max_row_nnz + 31u) & ~31u));
         const uint32_t sb_cap = (lp.b_prev + 1u + 3u) & ~3u;
-        const size_t smem1 = chunk_kernel_smem(warps, lookup, q_cap, sb_cap);
+        const uint32_t hdr_cap = lp.b_prev <= 128u ? lp.b_prev : 0u;  // beam chunk headers cached in shared memory
+        const size_t smem1 = chunk_kernel_smem(warps, lookup, q_cap, sb_cap, hdr_cap);
         auto launch = [&](auto kernel) {
             kernel<<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(),
-                                                   cand_stride_q, c_stride, stats, q_cap, sb_cap);
+                                                   cand_stride_q, c_stride, stats, q_cap, sb_cap, hdr_cap);
         };
         if (dense) {
             if (collect_stats) launch(xl_chunk_scores_kernel<true, true, false>);
