@@ -187,28 +187,6 @@ __device__ __noinline__ void xl_flush(WarpScratch<MCAP, ECAP>& ws, int m, const 
     }
 }
 
-__device__ __forceinline__ float xl_transform(float v, int kind, int p);
-__device__ __forceinline__ float xl_combine(float x, float parent, int kind);
-__device__ __forceinline__ unsigned long long xl_make_key(float v, uint32_t pos);
-
-// Fused epilogue of the chunk-score kernel: when the whole candidate row of a query fits in shared memory, the CTA applies
-// the post-processor and selects the top-k itself (no candidate round trip through HBM, no second launch).
-struct FuseArgs {
-    int enabled;
-    int pp_kind, pp_p, combine;
-    uint32_t k;
-    const float* beam_val;
-    uint32_t* out_id;
-    float* out_val;
-    uint32_t* out_cnt;
-    uint32_t out_stride;
-    unsigned long long* out_key;  // nullable
-    uint32_t n_cap;               // floats reserved for the candidate row (0 when not fused)
-};
-constexpr int kFuseK = 64;         // local lists of the fused selection live in the warp scratch (16 B x k <= 1 KB)
-constexpr uint32_t kFuseNCap = 4096;
-constexpr uint32_t kRemoved = 0xFFFFFFFFu;
-
 // DENSE: row-major dense queries.  LOOKUP: sparse queries probe the chunk's feature map (one 8-byte cell per query
 // feature) instead of streaming the chunk's row list -- same matches in the same order, far fewer bytes/instructions.
 template <bool DENSE, bool STATS, bool LOOKUP>
@@ -216,19 +194,16 @@ __global__ void __launch_bounds__(kWarpsMax * 32, LOOKUP ? 4 : 1)  // lookup var
 xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __restrict__ beam_id,
                        const uint32_t* __restrict__ beam_cnt, const uint32_t beam_stride, float* __restrict__ cand,
                        const uint64_t cand_stride_q, const uint32_t c_stride, unsigned long long* stats,
-                       const uint32_t q_cap, const uint32_t sb_cap, const uint32_t hdr_cap, const FuseArgs fuse) {
+                       const uint32_t q_cap, const uint32_t sb_cap, const uint32_t hdr_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* q_idx_s = reinterpret_cast<uint32_t*>(smem_raw);
     float* q_val_s = reinterpret_cast<float*>(smem_raw + q_cap * 4);
     uint32_t* slot_base = reinterpret_cast<uint32_t*>(smem_raw + q_cap * 8);  // [cnt + 1] first candidate of each beam slot
-    const uint32_t fsb = fuse.enabled ? sb_cap : 0u;
-    uint32_t* slot_colbeg = slot_base + sb_cap;                                  // [fsb] true col_begin (0xFFFFFFFF = absent)
-    float* slot_pval = reinterpret_cast<float*>(slot_colbeg + fsb);              // [fsb] parent path scores
-    ChunkHeader* hdr_s = reinterpret_cast<ChunkHeader*>(slot_pval + fsb);        // [hdr_cap] beam chunk headers
-    float* cand_s = reinterpret_cast<float*>(hdr_s + hdr_cap);                   // [fuse.n_cap] candidate row (fused mode)
+    ChunkHeader* hdr_s = reinterpret_cast<ChunkHeader*>(smem_raw + q_cap * 8 + sb_cap * 4);  // [hdr_cap] beam chunk headers
     constexpr int MCAP = LOOKUP ? kMCapLookup : kMCap;
     constexpr int ECAP = LOOKUP ? kECapLookup : kECap;
-    WarpScratch<MCAP, ECAP>* scratch = reinterpret_cast<WarpScratch<MCAP, ECAP>*>(cand_s + fuse.n_cap);
+    WarpScratch<MCAP, ECAP>* scratch =
+        reinterpret_cast<WarpScratch<MCAP, ECAP>*>(smem_raw + q_cap * 8 + sb_cap * 4 + static_cast<size_t>(hdr_cap) * sizeof(ChunkHeader));
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -241,7 +216,6 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
     uint64_t qb = 0, qe = 0;
     if (!DENSE) { qb = X.row_ptr[q] - X.nnz_base; qe = X.row_ptr[q + 1] - X.nnz_base; }
     const uint32_t my_p = (threadIdx.x < cnt) ? beam_id[static_cast<uint64_t>(q) * beam_stride + threadIdx.x] : 0u;
-    const float my_pval = (fuse.enabled && threadIdx.x < cnt) ? fuse.beam_val[static_cast<uint64_t>(q) * beam_stride + threadIdx.x] : 0.0f;
     const uint32_t* qidx = nullptr;
     const float* qval = nullptr;
     int qn = 0;
@@ -269,21 +243,13 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
     // candidates of a query are stored compactly in prolongation order: slot j starts at the sum of the widths before it
     if (threadIdx.x < cnt) {
         slot_base[threadIdx.x + 1] = my_h.n_cols;
-        if (fuse.enabled) {
-            slot_colbeg[threadIdx.x] = (my_h.has_bias & kChunkAbsent) ? 0xFFFFFFFFu : my_h.col_begin;
-            slot_pval[threadIdx.x] = my_pval;
-        }
-        my_h.col_begin = my_p;  // the cached header copy carries the chunk id in place of col_begin
+        my_h.col_begin = my_p;  // this kernel never needs col_begin: the cached copy carries the chunk id instead
         if (threadIdx.x < hdr_cap) hdr_s[threadIdx.x] = my_h;
     }
     for (uint32_t j = threadIdx.x + blockDim.x; j < cnt; j += blockDim.x) {
         const uint32_t pj = beam_id[static_cast<uint64_t>(q) * beam_stride + j];
         ChunkHeader hh = L.chunks[pj];
         slot_base[j + 1] = hh.n_cols;
-        if (fuse.enabled) {
-            slot_colbeg[j] = (hh.has_bias & kChunkAbsent) ? 0xFFFFFFFFu : hh.col_begin;
-            slot_pval[j] = fuse.beam_val[static_cast<uint64_t>(q) * beam_stride + j];
-        }
         hh.col_begin = pj;
         if (j < hdr_cap) hdr_s[j] = hh;
     }
@@ -315,8 +281,8 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
         const uint32_t* rp = ridx + R4;
         const uint2* ent = L.entries + h.ent_off;
         float* blk = cand + static_cast<uint64_t>(q) * cand_stride_q + slot_base[j];
-        const bool in_smem = !fuse.enabled && h.n_cols <= static_cast<uint32_t>(kCSmem);
-        float* out = fuse.enabled ? (cand_s + slot_base[j]) : (in_smem ? ws.out : blk);
+        const bool in_smem = h.n_cols <= static_cast<uint32_t>(kCSmem);
+        float* out = in_smem ? ws.out : blk;
         for (uint32_t c = lane; c < h.n_cols; c += 32) out[c] = 0.0f;
         __syncwarp();
 
@@ -444,91 +410,6 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
         }
         __syncwarp();
         if (STATS) { st_chunks += 1; st_rows += R; st_match += m_total; st_ent += e_total; st_cols += h.n_cols; }
-    }
-    if (fuse.enabled) {
-        __syncthreads();
-        const uint32_t n = slot_base[cnt];
-        // post-processor + combine, in place (double-precision chains: two independent candidates per thread and step)
-        for (uint32_t i0 = threadIdx.x; i0 < n; i0 += 2u * blockDim.x) {
-            const uint32_t i1 = i0 + blockDim.x;
-            const uint32_t j0 = static_cast<uint32_t>(last_le_u32(slot_base, static_cast<int>(cnt), i0));
-            const uint32_t j1 = (i1 < n) ? static_cast<uint32_t>(last_le_u32(slot_base, static_cast<int>(cnt), i1)) : j0;
-            const float r0 = cand_s[i0], r1 = (i1 < n) ? cand_s[i1] : 0.0f;
-            float v0 = xl_transform(r0, fuse.pp_kind, fuse.pp_p), v1 = xl_transform(r1, fuse.pp_kind, fuse.pp_p);
-            if (fuse.combine) { v0 = xl_combine(v0, slot_pval[j0], fuse.pp_kind); v1 = xl_combine(v1, slot_pval[j1], fuse.pp_kind); }
-            cand_s[i0] = (slot_colbeg[j0] == 0xFFFFFFFFu) ? __uint_as_float(kRemoved) : v0;
-            if (i1 < n) cand_s[i1] = (slot_colbeg[j1] == 0xFFFFFFFFu) ? __uint_as_float(kRemoved) : v1;
-        }
-        __syncthreads();
-        // local top-k of this warp's slice -> list of {key, value bits, label} in the warp scratch
-        const uint32_t per = (n + nwarps - 1) / nwarps;
-        const uint32_t lo = min(n, static_cast<uint32_t>(warp) * per), hi = min(n, lo + per);
-        uint4* list = reinterpret_cast<uint4*>(&scratch[warp]);
-        auto key_of = [&](uint32_t i) -> unsigned long long {
-            const uint32_t bits = __float_as_uint(cand_s[i]);
-            return bits == kRemoved ? 0ull : xl_make_key(__uint_as_float(bits), i);
-        };
-        unsigned long long best = 0ull;
-        for (uint32_t i = lo + lane; i < hi; i += 32) { const unsigned long long key = key_of(i); best = key > best ? key : best; }
-        uint32_t found = 0;
-        const uint32_t want = min(fuse.k, hi - lo);
-        for (; found < want; ++found) {
-            unsigned long long top = best;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(kFull, top, d); top = o > top ? o : top; }
-            if (top == 0ull) break;
-            if (best == top) {  // keys are unique: exactly one lane owns the winner
-                const uint32_t i = 0xFFFFFFFFu - static_cast<uint32_t>(top & 0xFFFFFFFFull);
-                const uint32_t jj = static_cast<uint32_t>(last_le_u32(slot_base, static_cast<int>(cnt), i));
-                list[found] = make_uint4(static_cast<uint32_t>(top & 0xFFFFFFFFull), static_cast<uint32_t>(top >> 32),
-                                         __float_as_uint(cand_s[i]), slot_colbeg[jj] + (i - slot_base[jj]));
-                cand_s[i] = __uint_as_float(kRemoved);
-                best = 0ull;
-                for (uint32_t t = lo + lane; t < hi; t += 32) { const unsigned long long key = key_of(t); best = key > best ? key : best; }
-            }
-            __syncwarp();
-        }
-        if (lane == 0) scratch[warp].off[0] = found;
-        __syncthreads();
-        // merge the per-warp lists (warp 0): k rounds of arg-max over at most nwarps * k keys
-        if (warp == 0) {
-            uint32_t total = 0;
-            for (int w = 0; w < nwarps; ++w) total += scratch[w].off[0];
-            const uint32_t kk = min(fuse.k, total);
-            if (lane == 0) {
-                fuse.out_cnt[q] = kk;
-                if (STATS) atomicAdd(&stats[6], static_cast<unsigned long long>(kk));
-            }
-            auto entry_key = [&](uint32_t e) -> unsigned long long {  // e = w * kFuseK + r
-                const uint32_t w = e / kFuseK, r = e - w * kFuseK;
-                if (r >= scratch[w].off[0]) return 0ull;
-                const uint4 en = reinterpret_cast<const uint4*>(&scratch[w])[r];
-                return (static_cast<unsigned long long>(en.y) << 32) | en.x;
-            };
-            const uint32_t n_ent = static_cast<uint32_t>(nwarps) * kFuseK;
-            unsigned long long mbest = 0ull;
-            uint32_t mwho = 0;
-            for (uint32_t e = lane; e < n_ent; e += 32) { const unsigned long long key = entry_key(e); if (key > mbest) { mbest = key; mwho = e; } }
-            for (uint32_t r = 0; r < kk; ++r) {
-                unsigned long long top = mbest;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(kFull, top, d); top = o > top ? o : top; }
-                if (mbest == top) {
-                    const uint32_t w = mwho / kFuseK, rr = mwho - w * kFuseK;
-                    uint4* wl = reinterpret_cast<uint4*>(&scratch[w]);
-                    const uint4 en = wl[rr];
-                    uint32_t label = en.w;
-                    if (L.label_of_col) label = L.label_of_col[label];
-                    fuse.out_id[static_cast<uint64_t>(q) * fuse.out_stride + r] = label;
-                    fuse.out_val[static_cast<uint64_t>(q) * fuse.out_stride + r] = __uint_as_float(en.z);
-                    if (fuse.out_key) fuse.out_key[static_cast<uint64_t>(q) * fuse.out_stride + r] = top;
-                    wl[rr] = make_uint4(0u, 0u, 0u, 0u);
-                    mbest = 0ull;
-                    for (uint32_t e = lane; e < n_ent; e += 32) { const unsigned long long key = entry_key(e); if (key > mbest) { mbest = key; mwho = e; } }
-                }
-                __syncwarp();
-            }
-        }
     }
     if (STATS) {
         if (lane == 0 && st_chunks) {
@@ -1130,6 +1011,24 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
         const uint32_t q_cap = dense ? 32u : std::min<uint32_t>(kQCap, std::max<uint32_t>(32u, (q.max_row_nnz + 31u) & ~31u));
         const uint32_t sb_cap = (lp.b_prev + 1u + 3u) & ~3u;
         const uint32_t hdr_cap = lp.b_prev <= 128u ? lp.b_prev : 0u;  // beam chunk headers cached in shared memory
+        const size_t smem1 = chunk_kernel_smem(warps, lookup, q_cap, sb_cap, hdr_cap);
+        auto launch = [&](auto kernel) {
+            kernel<<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(),
+                                                   cand_stride_q, c_stride, stats, q_cap, sb_cap, hdr_cap);
+        };
+        if (dense) {
+            if (collect_stats) launch(xl_chunk_scores_kernel<true, true, false>);
+            else launch(xl_chunk_scores_kernel<true, false, false>);
+        } else if (lookup) {
+            if (collect_stats) launch(xl_chunk_scores_kernel<false, true, true>);
+            else launch(xl_chunk_scores_kernel<false, false, true>);
+        } else {
+            if (collect_stats) launch(xl_chunk_scores_kernel<false, true, false>);
+            else launch(xl_chunk_scores_kernel<false, false, false>);
+        }
+        PB200_CUDA(cudaGetLastError());
+        ++launches_;
+        if (profile_) PB200_CUDA(cudaEventRecord(ev_[1], stream_));
 
         const bool last = (d + 1 == depth);
         uint32_t* o_id; float* o_val; uint32_t* o_cnt; uint32_t o_stride;
@@ -1149,42 +1048,10 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
             o_id = beam_id_[cur ^ 1].get(); o_val = beam_val_[cur ^ 1].get(); o_cnt = beam_cnt_[cur ^ 1].get();
             o_stride = beam_stride_;
         }
-        // fused post-processor + top-k inside the score kernel when the candidate row fits in shared memory
-        FuseArgs fuse{};
-        fuse.enabled = (!force_block_topk_ && hdr_cap != 0u && lp.k <= static_cast<uint32_t>(kFuseK) &&
-                        cand_stride_q <= static_cast<uint64_t>(kFuseNCap)) ? 1 : 0;
-        if (fuse.enabled) {
-            fuse.pp_kind = lp.pp.kind; fuse.pp_p = lp.pp.p; fuse.combine = d == 0 ? 0 : 1; fuse.k = lp.k;
-            fuse.beam_val = beam_val_[cur].get();
-            fuse.out_id = o_id; fuse.out_val = o_val; fuse.out_cnt = o_cnt; fuse.out_stride = o_stride; fuse.out_key = o_key;
-            fuse.n_cap = static_cast<uint32_t>((cand_stride_q + 3) & ~static_cast<uint64_t>(3));
-        }
-        const size_t smem1 = chunk_kernel_smem(warps, lookup, q_cap, sb_cap, hdr_cap) +
-                             (fuse.enabled ? static_cast<size_t>(sb_cap) * 8 + static_cast<size_t>(fuse.n_cap) * 4 : 0);
-        auto launch = [&](auto kernel) {
-            kernel<<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(),
-                                                   cand_stride_q, c_stride, stats, q_cap, sb_cap, hdr_cap, fuse);
-        };
-        if (dense) {
-            if (collect_stats) launch(xl_chunk_scores_kernel<true, true, false>);
-            else launch(xl_chunk_scores_kernel<true, false, false>);
-        } else if (lookup) {
-            if (collect_stats) launch(xl_chunk_scores_kernel<false, true, true>);
-            else launch(xl_chunk_scores_kernel<false, false, true>);
-        } else {
-            if (collect_stats) launch(xl_chunk_scores_kernel<false, true, false>);
-            else launch(xl_chunk_scores_kernel<false, false, false>);
-        }
-        PB200_CUDA(cudaGetLastError());
-        ++launches_;
-        if (profile_) PB200_CUDA(cudaEventRecord(ev_[1], stream_));
-
         const uint64_t sort_stride = next_pow2_host(cand_stride_q);
         const bool warp_select = !force_block_topk_ && lp.b_prev <= static_cast<uint32_t>(kSelSlots) &&
                                  cand_stride_q <= static_cast<uint64_t>(kSelKeysMax) && lp.k <= static_cast<uint32_t>(kSelK);
-        if (fuse.enabled) {
-            // nothing to launch: the score kernel already produced this layer's beam
-        } else if (warp_select) {
+        if (warp_select) {
             const uint32_t key_cap = static_cast<uint32_t>((cand_stride_q + 31) & ~static_cast<uint64_t>(31));
             const size_t sel_smem = kSelWarps * ((sel_warp_bytes(key_cap) + 15) & ~static_cast<size_t>(15));
             xl_topk_warp_kernel<<<(rows + kSelWarps - 1) / kSelWarps, kSelWarps * 32, sel_smem, stream_>>>(
@@ -1197,7 +1064,7 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
                 lp.b_prev, stats, o_key);
         }
         PB200_CUDA(cudaGetLastError());
-        if (!fuse.enabled) ++launches_;
+        ++launches_;
         if (profile_) {
             PB200_CUDA(cudaEventRecord(ev_[2], stream_));
             PB200_CUDA(cudaEventSynchronize(ev_[2]));
