@@ -251,7 +251,7 @@ void pb200_xlinear_set_profile(void* ptr, int on) {
 
 int pb200_xlinear_set_lookup(void* ptr, int on) {
     PB200_API_BEGIN
-    engine_of(ptr).set_lookup(on != 0);
+    engine_of(ptr).set_kernel_mode(on);
     return engine_of(ptr).has_feature_maps() ? 1 : 0;
     PB200_API_END("pb200_xlinear_set_lookup")
 }

@@ -476,6 +476,8 @@ __device__ __forceinline__ unsigned long long xl_make_key(float v, uint32_t pos)
     return (static_cast<unsigned long long>(u) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - pos);
 }
 
+#include "xlinear_qw_kernel.cuh"
+
 // descending bitonic sort of n (power of two) keys; a may live in shared or global memory
 __device__ void xl_bitonic_desc(unsigned long long* a, uint32_t n) {
     for (uint32_t k = 2; k <= n; k <<= 1) {
@@ -902,6 +904,8 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
     PB200_CUDA(cudaFuncSetAttribute(xl_chunk_scores_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     stats_dev_.reserve(8 * layers_.size());
     layer_profile_.assign(layers_.size(), XLinearLayerProfile{});
     layer_stats_.assign(layers_.size(), XLinearStats{});
@@ -914,9 +918,13 @@ XLinearEngine::~XLinearEngine() {
     if (stream_) cudaStreamDestroy(stream_);
 }
 
-void XLinearEngine::set_lookup(bool on) {
+void XLinearEngine::set_kernel_mode(int mode) {
+    // 0: first generation (row-list streaming + block-wide sort); 1: default (query-warp / feature-map kernels + warp top-k);
+    // 2: feature-map lookups with one warp per chunk (no query-warp kernel)
+    const bool on = mode != 0;
     for (auto& l : layers_) l.view.featmap = (on && l.featmap.capacity()) ? l.featmap.get() : nullptr;
     force_block_topk_ = !on;
+    no_query_warp_ = (mode == 2);
 }
 
 bool XLinearEngine::has_feature_maps() const {
@@ -1016,7 +1024,21 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
             kernel<<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(),
                                                    cand_stride_q, c_stride, stats, q_cap, sb_cap, hdr_cap);
         };
-        if (dense) {
+        // one warp per query over the whole beam (feature-major): narrow beams, sparse queries, feature maps present
+        const bool query_warp = lookup && !no_query_warp_ && lp.b_prev <= static_cast<uint32_t>(kQwSlots) &&
+                                cand_stride_q <= static_cast<uint64_t>(kQwNCap) && q.max_row_nnz <= kQwQCap;
+        if (query_warp) {
+            const uint32_t qw_qcap = std::max<uint32_t>(32u, (q.max_row_nnz + 31u) & ~31u);
+            const uint32_t qw_ncap = static_cast<uint32_t>((cand_stride_q + 31) & ~static_cast<uint64_t>(31));
+            const size_t qw_smem = kQwWarps * ((qw_warp_bytes(qw_qcap, qw_ncap) + 15) & ~static_cast<size_t>(15));
+            const dim3 qw_grid((rows + kQwWarps - 1) / kQwWarps);
+            if (collect_stats)
+                xl_query_warp_scores_kernel<true><<<qw_grid, kQwWarps * 32, qw_smem, stream_>>>(
+                    L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(), cand_stride_q, stats, qw_qcap, qw_ncap, rows);
+            else
+                xl_query_warp_scores_kernel<false><<<qw_grid, kQwWarps * 32, qw_smem, stream_>>>(
+                    L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(), cand_stride_q, stats, qw_qcap, qw_ncap, rows);
+        } else if (dense) {
             if (collect_stats) launch(xl_chunk_scores_kernel<true, true, false>);
             else launch(xl_chunk_scores_kernel<true, false, false>);
         } else if (lookup) {

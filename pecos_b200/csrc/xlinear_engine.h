@@ -102,7 +102,7 @@ public:
 
     void set_profile(bool on) { profile_ = on; }
     // false = stream the chunk row lists (first-generation kernel) even when feature maps exist; for A/B tests
-    void set_lookup(bool on);
+    void set_kernel_mode(int mode);
     bool has_feature_maps() const;
     const std::vector<XLinearLayerProfile>& layer_profile() const { return layer_profile_; }
     void reset_profile();
@@ -169,6 +169,7 @@ private:
     PinnedBuffer<uint32_t> out_cnt_;
 
     bool profile_ = false;
+    bool no_query_warp_ = false;
     bool force_block_topk_ = false;  // A/B switch: first-generation kernels (row-list streaming + block-wide sort)
     std::vector<XLinearLayerProfile> layer_profile_;
     std::vector<XLinearStats> layer_stats_;
