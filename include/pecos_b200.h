@@ -139,7 +139,8 @@ void pb200_xlinear_sharded_merge(void* ptr, uint32_t world, uint32_t rows, uint3
  *   stats:   out[7*d + {0..6}] = chunks, sum R, sum m, sum e, sum c, sum nnz(x), sum beam-out   (last stats pass) */
 void pb200_xlinear_set_profile(void* ptr, int on);
 /* Kernel generation selector for A/B tests (results are identical): 0 = row-list streaming + block-wide sort,
- * 1 = default (query-warp / feature-map kernels + warp top-k), 2 = feature-map lookups with one warp per chunk.
+ * 1 = default (feature-map kernels + warp top-k; query-warp kernel for beams of many narrow chunks), 2 = feature-map
+ * lookups with one warp per chunk only, 3 = query-warp kernel wherever it is eligible.
  * Returns 1 when every layer has a feature map (PB200_FEATMAP_MB caps their total size at load time, default 32768). */
 int pb200_xlinear_set_lookup(void* ptr, int on);
 void pb200_xlinear_reset_profile(void* ptr);

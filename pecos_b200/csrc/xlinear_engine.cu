@@ -920,11 +920,12 @@ XLinearEngine::~XLinearEngine() {
 
 void XLinearEngine::set_kernel_mode(int mode) {
     // 0: first generation (row-list streaming + block-wide sort); 1: default (query-warp / feature-map kernels + warp top-k);
-    // 2: feature-map lookups with one warp per chunk (no query-warp kernel)
+    // 2: feature-map lookups with one warp per chunk (no query-warp kernel); 3: query-warp kernel wherever eligible
     const bool on = mode != 0;
     for (auto& l : layers_) l.view.featmap = (on && l.featmap.capacity()) ? l.featmap.get() : nullptr;
     force_block_topk_ = !on;
     no_query_warp_ = (mode == 2);
+    force_query_warp_ = (mode == 3);
 }
 
 bool XLinearEngine::has_feature_maps() const {
@@ -1024,9 +1025,14 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
             kernel<<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(),
                                                    cand_stride_q, c_stride, stats, q_cap, sb_cap, hdr_cap);
         };
-        // one warp per query over the whole beam (feature-major): narrow beams, sparse queries, feature maps present
-        const bool query_warp = lookup && !no_query_warp_ && lp.b_prev <= static_cast<uint32_t>(kQwSlots) &&
-                                cand_stride_q <= static_cast<uint64_t>(kQwNCap) && q.max_row_nnz <= kQwQCap;
+        // One warp per query over the whole beam (feature-major).  Measured on B200: it wins when the beam consists of
+        // MANY NARROW chunks (per-chunk bookkeeping dominates: S layers 1-4, 20 x 8 columns: 2.1-2.9 ms vs 3.1 ms), and
+        // loses on wide chunks where one warp per chunk keeps more loads in flight (E leaf 2.2 vs 1.45 ms, S leaf 12.7 vs
+        // 8.4 ms).  force_query_warp_ (kernel mode 3) selects it whenever it is eligible, for tests.
+        const bool qw_eligible = lookup && lp.b_prev <= static_cast<uint32_t>(kQwSlots) &&
+                                 cand_stride_q <= static_cast<uint64_t>(kQwNCap) && q.max_row_nnz <= kQwQCap;
+        const bool query_warp = qw_eligible && !no_query_warp_ &&
+                                (force_query_warp_ || (lp.b_prev >= 16u && cand_stride_q <= 256u));
         if (query_warp) {
             const uint32_t qw_qcap = std::max<uint32_t>(32u, (q.max_row_nnz + 31u) & ~31u);
             const uint32_t qw_ncap = static_cast<uint32_t>((cand_stride_q + 31) & ~static_cast<uint64_t>(31));

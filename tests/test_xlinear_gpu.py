@@ -215,9 +215,14 @@ def test_streaming_and_lookup_kernels_agree(tmp_path, gpu_clib, have_ref):
     c.pb200_xlinear_set_lookup(m.model.model_chain, 2)   # feature-map lookups, one warp per chunk (no query-warp kernel)
     c2 = _check(m, oracles, X, "lookup, warp per chunk", beam_size=8, only_topk=10)
     c2_dup = m.predict(Xd, beam_size=8, only_topk=10)
+    c.pb200_xlinear_set_lookup(m.model.model_chain, 3)   # query-warp kernel on every eligible layer
+    c3 = _check(m, oracles, X, "query-warp kernel", beam_size=8, only_topk=10)
+    c3_dup = m.predict(Xd, beam_size=8, only_topk=10)
     c.pb200_xlinear_set_lookup(m.model.model_chain, 1)
-    assert_csr_parity(a, c2, rtol=0.0, what="query-warp vs warp-per-chunk")
-    assert_csr_parity(a_dup, c2_dup, rtol=0.0, what="query-warp vs warp-per-chunk, duplicated column indices")
+    assert_csr_parity(a, c2, rtol=0.0, what="default vs warp-per-chunk")
+    assert_csr_parity(a_dup, c2_dup, rtol=0.0, what="default vs warp-per-chunk, duplicated column indices")
+    assert_csr_parity(a, c3, rtol=0.0, what="default vs query-warp")
+    assert_csr_parity(a_dup, c3_dup, rtol=0.0, what="default vs query-warp, duplicated column indices")
     assert_csr_parity(a, b, rtol=0.0, what="lookup vs streaming")
     assert_csr_parity(a_dup, b_dup, rtol=0.0, what="lookup vs streaming, duplicated column indices")
     if "reference" in oracles:
