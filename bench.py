@@ -382,7 +382,13 @@ def main_hnsw(args):
     value = n_gpus * nq / (ms_per_step * 1e-3)
     peak, peak_src = measured_peak_gbs()
     achieved = bytes_per_step / (ms_per_step * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    ncu_traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            ncu_traffic = json.load(f).get(args.workload, {}).get("hnsw_search_kernel")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic,
                 "kernel": "hnsw_search_kernel", "kernel_ms": ms_per_step, "algorithmic_bytes_per_launch": bytes_per_step,
                 "peak_source": peak_src, "per_query": {"distance_evals": n_dist / nq, "expansions": n_expand / nq,
                                                        "upper_level_reads": n_hops / nq, "bytes": bytes_per_step / nq}}
