@@ -140,7 +140,8 @@ void pb200_xlinear_sharded_merge(void* ptr, uint32_t world, uint32_t rows, uint3
 void pb200_xlinear_set_profile(void* ptr, int on);
 /* Kernel generation selector for A/B tests (results are identical): 0 = row-list streaming + block-wide sort,
  * 1 = default (feature-map kernels + warp top-k; query-warp kernel for beams of many narrow chunks), 2 = feature-map
- * lookups with one warp per chunk only, 3 = query-warp kernel wherever it is eligible.
+ * lookups with one warp per chunk only, 3 = query-warp kernel wherever it is eligible, 4 = as 1 but the warp top-k
+ * evaluates the post-processor for every candidate (no single-precision estimate filter).
  * Returns 1 when every layer has a feature map (PB200_FEATMAP_MB caps their total size at load time, default 32768). */
 int pb200_xlinear_set_lookup(void* ptr, int on);
 void pb200_xlinear_reset_profile(void* ptr);

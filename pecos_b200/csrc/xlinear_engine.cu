@@ -758,6 +758,8 @@ xl_topk_warp_kernel(const LayerDev L, const int pp_kind, const int pp_p, const i
     }
 }
 
+#include "xlinear_topk_filter.cuh"
+
 // K3 (index sharding): merge the per-GPU top-k lists gathered by ONE all-gather into the global top-k.
 // gathered layout: [world][rows][stride] for keys / ids / vals and [world][rows] for counts.  Keys are globally unique
 // (they embed the candidate's position in the full prolongated row), so the merge is an exact arg-max selection.
@@ -904,6 +906,7 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
     PB200_CUDA(cudaFuncSetAttribute(xl_chunk_scores_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(xl_topk_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     stats_dev_.reserve(8 * layers_.size());
@@ -920,12 +923,14 @@ XLinearEngine::~XLinearEngine() {
 
 void XLinearEngine::set_kernel_mode(int mode) {
     // 0: first generation (row-list streaming + block-wide sort); 1: default (query-warp / feature-map kernels + warp top-k);
-    // 2: feature-map lookups with one warp per chunk (no query-warp kernel); 3: query-warp kernel wherever eligible
+    // 2: feature-map lookups with one warp per chunk (no query-warp kernel); 3: query-warp kernel wherever eligible;
+    // 4: as 1 but the warp top-k evaluates the post-processor for every candidate (no estimate filter)
     const bool on = mode != 0;
     for (auto& l : layers_) l.view.featmap = (on && l.featmap.capacity()) ? l.featmap.get() : nullptr;
     force_block_topk_ = !on;
     no_query_warp_ = (mode == 2);
     force_query_warp_ = (mode == 3);
+    no_topk_filter_ = (mode == 4);
 }
 
 bool XLinearEngine::has_feature_maps() const {
@@ -1079,7 +1084,18 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
         const uint64_t sort_stride = next_pow2_host(cand_stride_q);
         const bool warp_select = !force_block_topk_ && lp.b_prev <= static_cast<uint32_t>(kSelSlots) &&
                                  cand_stride_q <= static_cast<uint64_t>(kSelKeysMax) && lp.k <= static_cast<uint32_t>(kSelK);
-        if (warp_select) {
+        const bool hinge = lp.pp.kind == PP_LP_HINGE || lp.pp.kind == PP_LOG_LP_HINGE;
+        const bool filter_select = !force_block_topk_ && !no_topk_filter_ && lp.k <= 32u &&
+                                   lp.b_prev <= static_cast<uint32_t>(kFltSlots) &&
+                                   cand_stride_q <= static_cast<uint64_t>(kFltKeysMax) &&
+                                   (!hinge || (lp.pp.p >= 0 && lp.pp.p <= 4));
+        if (filter_select) {
+            const uint32_t key_cap = static_cast<uint32_t>((cand_stride_q + 127) & ~static_cast<uint64_t>(127));
+            const size_t flt_smem = kFltWarps * flt_warp_bytes(key_cap);
+            xl_topk_filter_kernel<<<(rows + kFltWarps - 1) / kFltWarps, kFltWarps * 32, flt_smem, stream_>>>(
+                L, lp.pp.kind, lp.pp.p, d == 0 ? 0 : 1, lp.k, beam_id_[cur].get(), beam_val_[cur].get(), beam_cnt_[cur].get(),
+                beam_stride_, cand_.get(), cand_stride_q, o_id, o_val, o_cnt, o_stride, rows, stats, o_key, key_cap);
+        } else if (warp_select) {
             const uint32_t key_cap = static_cast<uint32_t>((cand_stride_q + 31) & ~static_cast<uint64_t>(31));
             const size_t sel_smem = kSelWarps * ((sel_warp_bytes(key_cap) + 15) & ~static_cast<size_t>(15));
             xl_topk_warp_kernel<<<(rows + kSelWarps - 1) / kSelWarps, kSelWarps * 32, sel_smem, stream_>>>(

@@ -171,6 +171,7 @@ private:
     bool profile_ = false;
     bool no_query_warp_ = false;
     bool force_query_warp_ = false;
+    bool no_topk_filter_ = false;
     bool force_block_topk_ = false;  // A/B switch: first-generation kernels (row-list streaming + block-wide sort)
     std::vector<XLinearLayerProfile> layer_profile_;
     std::vector<XLinearStats> layer_stats_;

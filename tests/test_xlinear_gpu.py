@@ -264,3 +264,28 @@ def test_eurlex_shaped_sample_matches_reference(tmp_path, gpu_clib, have_ref):
         oracles = {"reference": oracles["reference"]}  # the scalar restatement is slow at this width
     got = _check(m, oracles, X, "eurlex-4k", beam_size=cfg["beam_size"], only_topk=cfg["only_topk"])
     assert (got.getnnz(axis=1) == 10).all()
+
+
+@pytest.mark.parametrize("scale", [1.0, 8.0, 60.0])
+def test_topk_estimate_filter_is_exact(tmp_path, gpu_clib, have_ref, scale):
+    """xl_topk_filter_kernel (single-precision estimates pick the candidates that get the exact post-processor) must return
+    the bits of the kernel that evaluates every candidate (kernel mode 4) and of the oracles: plain, saturated (hundreds
+    of exact ties) and extreme (exp under/overflow, log-sigmoid asymptote) score ranges, wide rows (> 32 survivors per
+    batch), k = 32 (the filter's limit) and k = 33 (falls back)."""
+    folder = str(tmp_path / "m")
+    layers = random_tree(81, [8, 64, 2400], 700, 30, bias=1.0, permute=True)
+    layers = [(smat.csc_matrix(W * np.float32(scale), dtype=np.float32), C) for W, C in layers]
+    synth.save_xlinear_model(folder, layers, bias=1.0, only_topk=10)
+    X = synth.make_queries(82, 160, 700, 60)
+    m, oracles = _load(folder), _oracles(folder, have_ref)
+    c = gpu_clib.clib_float32
+    for pp in POST_PROCESSORS:
+        for beam, topk in [(10, 10), (32, 32), (20, 33), (64, 7)]:
+            if pp not in ("l3-hinge", "log-l3-hinge", "sigmoid") and (beam, topk) != (10, 10):
+                continue
+            c.pb200_xlinear_set_lookup(m.model.model_chain, 1)
+            a = _check(m, oracles, X, f"filter scale={scale}", post_processor=pp, beam_size=beam, only_topk=topk)
+            c.pb200_xlinear_set_lookup(m.model.model_chain, 4)
+            b = m.predict(X, post_processor=pp, beam_size=beam, only_topk=topk)
+            assert_csr_parity(a, b, rtol=0.0, what=f"filter vs evaluate-all {pp} beam={beam} k={topk} scale={scale}")
+    c.pb200_xlinear_set_lookup(m.model.model_chain, 1)
