@@ -140,7 +140,8 @@ __device__ __forceinline__ void batch_distances(const HnswDev& ix, const float* 
             bulk_load_row(ring0 + s * bytes, ix.vec + static_cast<uint64_t>(ids[s]) * ix.vstride, bytes, mbar0 + 8u * s);
     }
     for (uint32_t b = 0; b < n; b += 2) {
-        const uint32_t slot0 = b % STAGES, slot1 = (b + 1) % STAGES;
+        constexpr uint32_t kRing = STAGES > 0 ? STAGES : 1;  // (STAGES == 0 never reaches this path)
+        const uint32_t slot0 = b % kRing, slot1 = (b + 1) % kRing;
         const bool second = (b + 1) < n;
         const uint32_t my = (half && second) ? slot1 : slot0;
         mbar_wait(mbar0 + 8u * my, (phase_bits >> my) & 1u);

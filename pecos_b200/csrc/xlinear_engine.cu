@@ -30,21 +30,18 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kWarpsMax = 10;    // warps per CTA of the chunk kernel
 constexpr int kMCap = 256;       // match list capacity per warp
 constexpr int kMFlush = 128;     // flush the match list once it holds this many rows (kMCap - 128 new per pass)
-constexpr int kECap = 256;       // staged entries per accumulate pass
 constexpr int kCSmem = 128;      // chunk widths up to this accumulate in shared memory, wider ones in the HBM block
 constexpr int kQCap = 1024;      // query non-zeros staged in shared memory (longer queries are read through L1/L2)
 constexpr int kSortCap = 2048;   // keys sorted in shared memory per pass of the top-k kernel
 constexpr int kTopkThreads = 256;
 
-constexpr int kECapLookup = 128; // staged entries per pass of the lookup kernel
 constexpr int kMCapLookup = 128; // the lookup kernel adds at most 32 matches per pass: a shorter list => higher occupancy
 
-template <int MCAP, int ECAP>
+template <int MCAP>
 struct __align__(16) WarpScratch {
     uint32_t ms[MCAP];         // chunk-row index of each match; becomes the row's first entry offset during flush
     float mx[MCAP];            // multiplier of the row: query value, or the bias
     uint32_t off[MCAP + 4];    // exclusive prefix of the matched rows' entry counts
-    uint2 stage[ECAP];         // staged {col_offset, bits of x*w}
     float out[kCSmem];         // dense output block of the chunk
 };
 
@@ -84,10 +81,16 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 }
 
 // Apply the matched rows collected in ws (in ascending feature order) to the output block.
-template <int MCAP, int ECAP>
-__device__ __noinline__ void xl_flush(WarpScratch<MCAP, ECAP>& ws, int m, const uint32_t* __restrict__ rp,
-                                      const uint2* __restrict__ ent, float* out, int has_dup, int lane,
-                                      unsigned long long& e_total) {
+//
+// Entry-parallel: the m matched rows hold `total` entries; lane L of group g owns entry 32g + L of their concatenation
+// (its row found by a binary search in the rows' prefix sums), so ragged rows -- one entry for a rare feature, every column
+// for the bias row -- cost the same per entry, consecutive lanes read consecutive entries, and nothing is staged in
+// shared memory.  Entries of one 32-group that hit the same column (they come from different rows, or from a row that
+// repeats a column) are added in lane order = concatenation order = ascending feature order; __match_any_sync finds the
+// collisions, so the common collision-free group costs a single round.  Groups are applied in order.
+template <int MCAP>
+__device__ __noinline__ void xl_flush(WarpScratch<MCAP>& ws, int m, const uint32_t* __restrict__ rp,
+                                      const uint2* __restrict__ ent, float* out, int lane, unsigned long long& e_total) {
     if (m == 0) return;
     __syncwarp();
     constexpr int PER = MCAP / 32;
@@ -118,72 +121,33 @@ __device__ __noinline__ void xl_flush(WarpScratch<MCAP, ECAP>& ws, int m, const 
     __syncwarp();
     e_total += total;
 
-    // Stage tiles of whole matched rows (one lane per row: rows are short), then apply the staged entries to the
-    // output block 32 at a time.  Entries of one 32-group that hit the same column (they come from different rows, or
-    // from a row that repeats a column) are applied in staged order = ascending feature order; __match_any_sync finds
-    // the collisions, so the common collision-free group costs a single round.
-    (void)has_dup;
-    int i0 = 0;
-    uint32_t part = 0;  // entries of row i0 already applied (only rows longer than the staging area are split)
-    while (i0 < m) {
-        const uint32_t row_begin = ws.off[i0];
-        const uint32_t base = row_begin + part;
-        int i_next;
-        uint32_t part_next = 0, ne;
-        if (part == 0 && ws.off[i0 + 1] - row_begin <= static_cast<uint32_t>(ECAP)) {
-            const int i1 = last_le_u32(ws.off, m + 1, base + ECAP);  // rows [i0, i1) fit entirely; i1 > i0
-            for (int i = i0 + lane; i < i1; i += 32) {
-                const uint32_t a = ws.ms[i];
-                const uint32_t n = ws.off[i + 1] - ws.off[i];
-                const uint32_t o = ws.off[i] - base;
-                const float x = ws.mx[i];
-                const uint2* src = ent + a;
-                uint32_t j = 0;
-                for (; j + 4 <= n; j += 4) {  // four independent loads in flight per lane
-                    const uint2 e0 = __ldg(src + j), e1 = __ldg(src + j + 1), e2 = __ldg(src + j + 2), e3 = __ldg(src + j + 3);
-                    ws.stage[o + j] = make_uint2(e0.x, __float_as_uint(__fmul_rn(x, __uint_as_float(e0.y))));
-                    ws.stage[o + j + 1] = make_uint2(e1.x, __float_as_uint(__fmul_rn(x, __uint_as_float(e1.y))));
-                    ws.stage[o + j + 2] = make_uint2(e2.x, __float_as_uint(__fmul_rn(x, __uint_as_float(e2.y))));
-                    ws.stage[o + j + 3] = make_uint2(e3.x, __float_as_uint(__fmul_rn(x, __uint_as_float(e3.y))));
-                }
-                if (j < n) {
-                    const uint2 e0 = __ldg(src + j);
-                    const uint2 e1 = (j + 1 < n) ? __ldg(src + j + 1) : e0;
-                    const uint2 e2 = (j + 2 < n) ? __ldg(src + j + 2) : e0;
-                    ws.stage[o + j] = make_uint2(e0.x, __float_as_uint(__fmul_rn(x, __uint_as_float(e0.y))));
-                    if (j + 1 < n) ws.stage[o + j + 1] = make_uint2(e1.x, __float_as_uint(__fmul_rn(x, __uint_as_float(e1.y))));
-                    if (j + 2 < n) ws.stage[o + j + 2] = make_uint2(e2.x, __float_as_uint(__fmul_rn(x, __uint_as_float(e2.y))));
-                }
+    for (uint32_t g0 = 0; g0 < total; g0 += 128u) {
+        uint2 e[4];
+        float x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {  // four independent (search, load) chains in flight per lane
+            const uint32_t g = g0 + 32u * u + lane;
+            e[u] = make_uint2(0xFFFFFFFFu - lane, 0u);  // idle lanes: distinct pseudo-columns, never applied
+            x[u] = 0.0f;
+            if (g < total) {
+                const int i = last_le_u32(ws.off, m, g);  // off[i] <= g < off[i + 1]
+                e[u] = __ldg(ent + ws.ms[i] + (g - ws.off[i]));
+                x[u] = ws.mx[i];
             }
-            ne = ws.off[i1] - base;
-            i_next = i1;
-        } else {
-            const uint32_t n_left = ws.off[i0 + 1] - base;
-            ne = min(static_cast<uint32_t>(ECAP), n_left);
-            const uint32_t a = ws.ms[i0] + part;
-            const float x = ws.mx[i0];
-            for (uint32_t g = lane; g < ne; g += 32) {
-                const uint2 en = __ldg(ent + a + g);
-                ws.stage[g] = make_uint2(en.x, __float_as_uint(__fmul_rn(x, __uint_as_float(en.y))));
-            }
-            if (ne == n_left) { i_next = i0 + 1; } else { i_next = i0; part_next = part + ne; }
         }
-        __syncwarp();
-        for (uint32_t g0 = 0; g0 < ne; g0 += 32) {
-            const uint32_t g = g0 + lane;
-            const bool valid = g < ne;
-            const uint2 s = valid ? ws.stage[g] : make_uint2(0xFFFFFFFFu - lane, 0u);
-            const unsigned peers = __match_any_sync(kFull, s.x);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (g0 + 32u * u >= total) break;
+            const bool valid = (g0 + 32u * u + lane) < total;
+            const float v = __fmul_rn(x[u], __uint_as_float(e[u].y));
+            const unsigned peers = __match_any_sync(kFull, e[u].x);
             const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
             const uint32_t rounds = __reduce_max_sync(kFull, valid ? rank : 0u);
             for (uint32_t r = 0; r <= rounds; ++r) {
-                if (valid && rank == r) out[s.x] = __fadd_rn(out[s.x], __uint_as_float(s.y));
+                if (valid && rank == r) out[e[u].x] = __fadd_rn(out[e[u].x], v);
                 __syncwarp();
             }
         }
-        __syncwarp();
-        i0 = i_next;
-        part = part_next;
     }
 }
 
@@ -201,9 +165,8 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
     uint32_t* slot_base = reinterpret_cast<uint32_t*>(smem_raw + q_cap * 8);  // [cnt + 1] first candidate of each beam slot
     ChunkHeader* hdr_s = reinterpret_cast<ChunkHeader*>(smem_raw + q_cap * 8 + sb_cap * 4);  // [hdr_cap] beam chunk headers
     constexpr int MCAP = LOOKUP ? kMCapLookup : kMCap;
-    constexpr int ECAP = LOOKUP ? kECapLookup : kECap;
-    WarpScratch<MCAP, ECAP>* scratch =
-        reinterpret_cast<WarpScratch<MCAP, ECAP>*>(smem_raw + q_cap * 8 + sb_cap * 4 + static_cast<size_t>(hdr_cap) * sizeof(ChunkHeader));
+    WarpScratch<MCAP>* scratch =
+        reinterpret_cast<WarpScratch<MCAP>*>(smem_raw + q_cap * 8 + sb_cap * 4 + static_cast<size_t>(hdr_cap) * sizeof(ChunkHeader));
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -260,7 +223,7 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
         for (uint32_t j = 0; j < cnt; ++j) { run += slot_base[j + 1]; slot_base[j + 1] = run; }
     }
     __syncthreads();
-    WarpScratch<MCAP, ECAP>& ws = scratch[warp];
+    WarpScratch<MCAP>& ws = scratch[warp];
     unsigned long long st_chunks = 0, st_rows = 0, st_match = 0, st_ent = 0, st_cols = 0;
 
     for (uint32_t j = warp; j < cnt; j += nwarps) {
@@ -312,7 +275,7 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
                 m += static_cast<int>(tot);
                 if (m >= kMFlush) {
                     m_total += m;
-                    xl_flush(ws, m, rp, ent, out, L.has_dup_cols, lane, e_total);
+                    xl_flush(ws, m, rp, ent, out, lane, e_total);
                     m = 0;
                 }
             }
@@ -355,7 +318,7 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
                             m += __popc(mask);
                             if (m > MCAP - 33) {  // keep room for the next 32 matches and the bias row
                                 m_total += m;
-                                xl_flush(ws, m, rp, ent, out, L.has_dup_cols, lane, e_total);
+                                xl_flush(ws, m, rp, ent, out, lane, e_total);
                                 m = 0;
                             }
                         }
@@ -391,7 +354,7 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
                     m += static_cast<int>(tot);
                     if (m >= kMFlush) {
                         m_total += m;
-                        xl_flush(ws, m, rp, ent, out, L.has_dup_cols, lane, e_total);
+                        xl_flush(ws, m, rp, ent, out, lane, e_total);
                         m = 0;
                     }
                 }
@@ -403,7 +366,7 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
             }
         }
         m_total += m;
-        xl_flush(ws, m, rp, ent, out, L.has_dup_cols, lane, e_total);
+        xl_flush(ws, m, rp, ent, out, lane, e_total);
         __syncwarp();
         if (in_smem) {
             for (uint32_t c = lane; c < h.n_cols; c += 32) blk[c] = ws.out[c];
@@ -792,14 +755,12 @@ xl_merge_topk_kernel(const unsigned long long* __restrict__ g_keys, const uint32
     if (lane == 0) out_cnt[q] = kk;
     for (uint32_t rnk = 0; rnk < kk; ++rnk) {
         unsigned long long top = best;
-        uint32_t who = best ? static_cast<uint32_t>(lane) : 0xFFFFFFFFu;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             const unsigned long long o = __shfl_xor_sync(kFull, top, d);
             top = o > top ? o : top;
         }
         // the owner lane finds the slot of `top` among its stride-32 subset
-        (void)who;
         uint32_t slot = 0xFFFFFFFFu;
         if (best == top) {
             for (uint32_t i = lane; i < n; i += 32) if (keys[i] == top) { slot = i; break; }
@@ -841,8 +802,7 @@ uint32_t next_pow2_host(uint64_t v) {
 
 size_t chunk_kernel_smem(int warps, bool lookup, uint32_t q_cap, uint32_t sb_cap, uint32_t hdr_cap) {
     return static_cast<size_t>(q_cap) * 8 + static_cast<size_t>(sb_cap) * 4 + static_cast<size_t>(hdr_cap) * sizeof(ChunkHeader) +
-           static_cast<size_t>(warps) * (lookup ? sizeof(WarpScratch<kMCapLookup, kECapLookup>)
-                                                                                 : sizeof(WarpScratch<kMCap, kECap>));
+           static_cast<size_t>(warps) * (lookup ? sizeof(WarpScratch<kMCapLookup>) : sizeof(WarpScratch<kMCap>));
 }
 size_t topk_kernel_smem(uint32_t b_prev) { return static_cast<size_t>(kSortCap) * 8 + (static_cast<size_t>(b_prev) * 3 + 1) * 4; }
 
@@ -855,6 +815,10 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
     PB200_CUDA(cudaSetDevice(device_));
     PB200_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     for (auto& e : ev_) PB200_CUDA(cudaEventCreate(&e));
+    PB200_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    for (auto& e : up_ev_) PB200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : use_ev_) PB200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (const char* env = std::getenv("PB200_XL_PIPELINE")) pipeline_uploads_ = std::atoi(env) != 0;
     layers_.resize(host_->layers.size());
     uint64_t featmap_budget = 32ull << 30;  // bytes of HBM the feature maps may take in total
     if (const char* env = std::getenv("PB200_FEATMAP_MB")) featmap_budget = std::strtoull(env, nullptr, 10) << 20;
@@ -918,6 +882,10 @@ XLinearEngine::~XLinearEngine() {
     cudaSetDevice(device_);
     if (stream_) cudaStreamSynchronize(stream_);
     for (auto& e : ev_) if (e) cudaEventDestroy(e);
+    if (copy_stream_) cudaStreamSynchronize(copy_stream_);
+    for (auto& e : up_ev_) if (e) cudaEventDestroy(e);
+    for (auto& e : use_ev_) if (e) cudaEventDestroy(e);
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
     if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -1155,16 +1123,42 @@ XLinearEngine::Result XLinearEngine::predict_csr(const uint64_t* row_ptr, const 
     res_ids_dev_.reserve(static_cast<uint64_t>(rows) * stride + 1);
     res_vals_dev_.reserve(static_cast<uint64_t>(rows) * stride + 1);
     res_cnt_dev_.reserve(static_cast<uint64_t>(rows) + 1);
-    for (uint32_t r0 = 0; r0 < rows; r0 += tile) {
-        const uint32_t tr = std::min(tile, rows - r0);
+    // Host buffers: the batch is cut into sub-tiles whose uploads (copy stream, two staging sets) overlap the scoring of
+    // the previous sub-tile; results stay on the device until the last sub-tile is done.
+    uint32_t sub = tile;
+    if (pipeline_uploads_ && rows >= 4096u) {
+        const uint32_t quarter = ((rows + 3u) / 4u + 31u) & ~31u;
+        sub = std::min(tile, std::max<uint32_t>(1024u, quarter));
+    }
+    uint64_t max_nnz = 0;
+    for (uint32_t r0 = 0; r0 < rows; r0 += sub) max_nnz = std::max(max_nnz, row_ptr[r0 + std::min(sub, rows - r0)] - row_ptr[r0]);
+    DeviceBuffer<uint64_t>* s_rp[2] = {&x_row_ptr_, &x2_row_ptr_};
+    DeviceBuffer<uint32_t>* s_ci[2] = {&x_col_idx_, &x2_col_idx_};
+    DeviceBuffer<float>* s_va[2] = {&x_val_, &x2_val_};
+    const bool two_sets = rows > sub;
+    for (int b = 0; b < (two_sets ? 2 : 1); ++b) {  // no (synchronising) reallocation inside the pipeline
+        s_rp[b]->reserve(static_cast<uint64_t>(sub) + 1);
+        s_ci[b]->reserve(max_nnz);
+        s_va[b]->reserve(max_nnz);
+    }
+    uint32_t t = 0;
+    for (uint32_t r0 = 0; r0 < rows; r0 += sub, ++t) {
+        const uint32_t tr = std::min(sub, rows - r0);
         const uint64_t base = row_ptr[r0], end = row_ptr[r0 + tr];
-        x_row_ptr_.upload(row_ptr + r0, static_cast<uint64_t>(tr) + 1, stream_);
-        x_col_idx_.upload(col_idx + base, end - base, stream_);
-        x_val_.upload(val + base, end - base, stream_);
-        QueryDev q{x_row_ptr_.get(), x_col_idx_.get(), x_val_.get(), base, tr, cols, max_row_nnz(row_ptr + r0, tr)};
+        const int b = two_sets ? static_cast<int>(t & 1u) : 0;
+        cudaStream_t up = two_sets ? copy_stream_ : stream_;
+        if (two_sets && t >= 2) PB200_CUDA(cudaStreamWaitEvent(copy_stream_, use_ev_[b], 0));
+        s_rp[b]->upload(row_ptr + r0, static_cast<uint64_t>(tr) + 1, up);
+        s_ci[b]->upload(col_idx + base, end - base, up);
+        s_va[b]->upload(val + base, end - base, up);
+        if (two_sets) {
+            PB200_CUDA(cudaEventRecord(up_ev_[b], copy_stream_));
+            PB200_CUDA(cudaStreamWaitEvent(stream_, up_ev_[b], 0));
+        }
+        QueryDev q{s_rp[b]->get(), s_ci[b]->get(), s_va[b]->get(), base, tr, cols, max_row_nnz(row_ptr + r0, tr)};
         res_rows_ = r0;
         run_tile_(q, plan, false);
-        if (r0 + tr < rows) PB200_CUDA(cudaStreamSynchronize(stream_));  // staging buffers are reused by the next tile
+        if (two_sets) PB200_CUDA(cudaEventRecord(use_ev_[b], stream_));
     }
     return finish_result_(rows, stride);
 }

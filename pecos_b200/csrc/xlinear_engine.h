@@ -152,6 +152,14 @@ private:
     DeviceBuffer<uint64_t> x_row_ptr_;
     DeviceBuffer<uint32_t> x_col_idx_;
     DeviceBuffer<float> x_val_;
+    // second staging set + copy stream: predict_csr uploads sub-tile t+1 while sub-tile t is being scored
+    DeviceBuffer<uint64_t> x2_row_ptr_;
+    DeviceBuffer<uint32_t> x2_col_idx_;
+    DeviceBuffer<float> x2_val_;
+    cudaStream_t copy_stream_ = nullptr;
+    cudaEvent_t up_ev_[2] = {nullptr, nullptr};   // staging set uploaded
+    cudaEvent_t use_ev_[2] = {nullptr, nullptr};  // staging set consumed by the score kernels
+    bool pipeline_uploads_ = true;
     QueryDev resident_{};
     bool has_resident_ = false;
     DeviceBuffer<uint32_t> res_ids_dev_;

@@ -289,3 +289,17 @@ def test_topk_estimate_filter_is_exact(tmp_path, gpu_clib, have_ref, scale):
             b = m.predict(X, post_processor=pp, beam_size=beam, only_topk=topk)
             assert_csr_parity(a, b, rtol=0.0, what=f"filter vs evaluate-all {pp} beam={beam} k={topk} scale={scale}")
     c.pb200_xlinear_set_lookup(m.model.model_chain, 1)
+
+
+def test_pipelined_uploads_equal_unpipelined_calls(small_model):
+    """Batches of >= 4096 rows are cut into sub-tiles whose host->device copies overlap the scoring of the previous
+    sub-tile (two staging sets, copy stream).  Same bits as calls small enough not to be pipelined, and as the oracle;
+    ragged rows make the sub-tiles uneven."""
+    folder, X, m, oracles = small_model
+    big = smat.vstack([X] * 60, format="csr").astype(np.float32)[:5531]
+    big = csr_with_empty_rows(big, [0, 1, 4095, 4096, 5530])
+    a = _check(m, {"restatement": oracles["restatement"]}, big, "pipelined", beam_size=6, only_topk=5)
+    b = m.predict(big, beam_size=6, only_topk=5, max_pred_chunk=1000)
+    assert_csr_parity(a, b, rtol=0.0, what="pipelined vs small calls")
+    a2 = m.predict(big, beam_size=6, only_topk=5)  # staging sets are reused by the next call
+    assert_csr_parity(a2, a, rtol=0.0, what="second pipelined call")
