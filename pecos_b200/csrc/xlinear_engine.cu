@@ -35,7 +35,7 @@ constexpr int kQCap = 1024;      // query non-zeros staged in shared memory (lon
 constexpr int kSortCap = 2048;   // keys sorted in shared memory per pass of the top-k kernel
 constexpr int kTopkThreads = 256;
 
-constexpr int kMCapLookup = 128; // the lookup kernel adds at most 32 matches per pass: a shorter list => higher occupancy
+constexpr int kMCapLookup = 256; // the lookup kernel collects a block of <= 128 matches (+ bias row) between flush checks
 
 template <int MCAP>
 struct __align__(16) WarpScratch {
@@ -89,33 +89,32 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 // repeats a column) are added in lane order = concatenation order = ascending feature order; __match_any_sync finds the
 // collisions, so the common collision-free group costs a single round.  Groups are applied in order.
 template <int MCAP>
-__device__ __noinline__ void xl_flush(WarpScratch<MCAP>& ws, int m, const uint32_t* __restrict__ rp,
-                                      const uint2* __restrict__ ent, float* out, int lane, unsigned long long& e_total) {
+__device__ __forceinline__ void xl_flush_impl(WarpScratch<MCAP>& ws, int m, const uint2* __restrict__ ext,
+                                              const uint2* __restrict__ ent, float* out, int lane,
+                                              unsigned long long& e_total) {
     if (m == 0) return;
     __syncwarp();
     constexpr int PER = MCAP / 32;
-    uint32_t a[PER], c[PER];
+    uint32_t c[PER];
     uint32_t local = 0;
 #pragma unroll
-    for (int u = 0; u < PER; ++u) {
+    for (int u = 0; u < PER; ++u) {  // PER independent 8-byte loads per lane; ms[i]: chunk row -> its first entry
         const int i = lane * PER + u;
-        a[u] = 0; c[u] = 0;
+        c[u] = 0;
         if (i < m) {
-            const uint32_t s = ws.ms[i];
-            const uint32_t lo = __ldg(rp + s);
-            const uint32_t hi = __ldg(rp + s + 1);
-            a[u] = lo; c[u] = hi - lo;
+            const uint2 lh = __ldg(ext + ws.ms[i]);
+            ws.ms[i] = lh.x;
+            c[u] = lh.y - lh.x;
         }
         local += c[u];
     }
     const uint32_t incl = warp_incl_scan(local, lane);
     uint32_t run = incl - local;
     const uint32_t total = __shfl_sync(kFull, incl, 31);
-    __syncwarp();
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
         const int i = lane * PER + u;
-        if (i < m) { ws.ms[i] = a[u]; ws.off[i] = run; run += c[u]; }
+        if (i < m) { ws.off[i] = run; run += c[u]; }
     }
     if (lane == 0) ws.off[m] = total;
     __syncwarp();
@@ -149,6 +148,13 @@ __device__ __noinline__ void xl_flush(WarpScratch<MCAP>& ws, int m, const uint32
             }
         }
     }
+}
+
+// out-of-line copy for the kernels that flush from several places
+template <int MCAP>
+__device__ __noinline__ void xl_flush(WarpScratch<MCAP>& ws, int m, const uint2* __restrict__ ext,
+                                      const uint2* __restrict__ ent, float* out, int lane, unsigned long long& e_total) {
+    xl_flush_impl(ws, m, ext, ent, out, lane, e_total);
 }
 
 // DENSE: row-major dense queries.  LOOKUP: sparse queries probe the chunk's feature map (one 8-byte cell per query
@@ -217,10 +223,16 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
         if (j < hdr_cap) hdr_s[j] = hh;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (warp == 0) {  // widths -> first candidate position of every slot (warp scan, 32 slots per step)
         uint32_t run = 0;
-        slot_base[0] = 0;
-        for (uint32_t j = 0; j < cnt; ++j) { run += slot_base[j + 1]; slot_base[j + 1] = run; }
+        for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            const uint32_t w = (j < cnt) ? slot_base[j + 1] : 0u;
+            const uint32_t incl = warp_incl_scan(w, lane);
+            if (j < cnt) slot_base[j + 1] = run + incl;
+            run += __shfl_sync(kFull, incl, 31);
+        }
+        if (lane == 0) slot_base[0] = 0;
     }
     __syncthreads();
     WarpScratch<MCAP>& ws = scratch[warp];
@@ -241,7 +253,7 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
         const uint32_t R = h.nnz_rows;
         const uint32_t R4 = (R + 3u) & ~3u;
         const uint32_t* ridx = L.meta + h.meta_off;
-        const uint32_t* rp = ridx + R4;
+        const uint2* ext = reinterpret_cast<const uint2*>(L.rowext + h.meta_off);  // {begin, end} of every chunk row
         const uint2* ent = L.entries + h.ent_off;
         float* blk = cand + static_cast<uint64_t>(q) * cand_stride_q + slot_base[j];
         const bool in_smem = h.n_cols <= static_cast<uint32_t>(kCSmem);
@@ -275,17 +287,20 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
                 m += static_cast<int>(tot);
                 if (m >= kMFlush) {
                     m_total += m;
-                    xl_flush(ws, m, rp, ent, out, lane, e_total);
+                    xl_flush(ws, m, ext, ent, out, lane, e_total);
                     m = 0;
                 }
             }
         } else {
             // chunk_ops<csr, bin_search>: matched rows in ascending feature order, bias row last (inference.hpp:788-811)
             if (LOOKUP) {
-                if (R > 0) {
-                    const uint2* fm = L.featmap + static_cast<uint64_t>(p) * L.fm_words;
-                    for (int tb0 = 0; tb0 < qn; tb0 += 128) {
-                        // four probe rounds issued back to back: 4 independent cell loads in flight per lane
+                // Blocks of 128 query features: four probe rounds issued back to back (4 independent cell loads in flight
+                // per lane), matches compacted in feature order.  The match list takes a whole block (+ the bias row), so
+                // the single flush site sits outside the probe registers' live range.
+                const uint2* fm = L.featmap + static_cast<uint64_t>(p) * L.fm_words;
+                int tb0 = 0;
+                do {
+                    if (R > 0 && tb0 < qn) {
                         uint2 cell[4];
                         uint32_t feat[4];
                         bool live[4];
@@ -316,14 +331,21 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
                                 ws.mx[pos] = qval[t];
                             }
                             m += __popc(mask);
-                            if (m > MCAP - 33) {  // keep room for the next 32 matches and the bias row
-                                m_total += m;
-                                xl_flush(ws, m, rp, ent, out, lane, e_total);
-                                m = 0;
-                            }
                         }
                     }
-                }
+                    tb0 += 128;
+                    const bool last_block = tb0 >= qn;
+                    if (last_block && chunk_bias) {
+                        __syncwarp();
+                        if (lane == 0) { ws.ms[m] = R - 1u; ws.mx[m] = L.bias; }
+                        ++m;
+                    }
+                    if (last_block || m > MCAP - 130) {  // room for the next block of <= 128 matches and the bias row
+                        m_total += m;
+                        xl_flush_impl(ws, m, ext, ent, out, lane, e_total);
+                        m = 0;
+                    }
+                } while (tb0 < qn);
             } else if (qn > 0 && R > 0) {
                 const uint32_t qmin = qidx[0];
                 const uint32_t qmax = qidx[qn - 1];
@@ -354,19 +376,21 @@ xl_chunk_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* __res
                     m += static_cast<int>(tot);
                     if (m >= kMFlush) {
                         m_total += m;
-                        xl_flush(ws, m, rp, ent, out, lane, e_total);
+                        xl_flush(ws, m, ext, ent, out, lane, e_total);
                         m = 0;
                     }
                 }
             }
-            if (chunk_bias) {
+            if (!LOOKUP && chunk_bias) {
                 __syncwarp();
                 if (lane == 0) { ws.ms[m] = R - 1u; ws.mx[m] = L.bias; }
                 ++m;
             }
         }
-        m_total += m;
-        xl_flush(ws, m, rp, ent, out, lane, e_total);
+        if (!LOOKUP || DENSE) {
+            m_total += m;
+            xl_flush(ws, m, ext, ent, out, lane, e_total);
+        }
         __syncwarp();
         if (in_smem) {
             for (uint32_t c = lane; c < h.n_cols; c += 32) blk[c] = ws.out[c];
@@ -778,6 +802,23 @@ xl_merge_topk_kernel(const unsigned long long* __restrict__ g_keys, const uint32
     }
 }
 
+// Row extents as one 8-byte record per chunk row, derived on the device from the row_ptr array of the chunk (the score
+// kernels then need ONE load per matched row).  The chunk's region of meta[] holds R4 + roundup4(R + 1) >= 2R words, so
+// rowext[] simply mirrors meta[]'s indexing.
+__global__ void xl_build_rowext_kernel(const ChunkHeader* __restrict__ chunks, const uint32_t* __restrict__ meta,
+                                       uint32_t* __restrict__ rowext, const uint32_t n_chunks) {
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < n_chunks; c += warps) {
+        const ChunkHeader h = chunks[c];
+        if (h.has_bias & kChunkAbsent) continue;
+        const uint32_t R = h.nnz_rows;
+        const uint32_t* rp = meta + h.meta_off + ((R + 3u) & ~3u);
+        uint2* dst = reinterpret_cast<uint2*>(rowext + h.meta_off);
+        for (uint32_t r = lane; r < R; r += 32) dst[r] = make_uint2(rp[r], rp[r + 1]);
+    }
+}
+
 __global__ void xl_init_beam_kernel(uint32_t* beam_id, float* beam_val, uint32_t* beam_cnt, uint32_t beam_stride,
                                     uint32_t rows) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -842,8 +883,13 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
             model_bytes_ += src.featmap.size() * 8;
             std::vector<uint2_host>().swap(src.featmap);
         }
+        dst.rowext.reserve(std::max<uint64_t>(src.meta.size(), 4));
+        xl_build_rowext_kernel<<<148 * 8, 256, 0, stream_>>>(dst.chunks.get(), dst.meta.get(), dst.rowext.get(), src.n_chunks);
+        PB200_CUDA(cudaGetLastError());
+        model_bytes_ += src.meta.size() * 4;
         dst.view.chunks = dst.chunks.get();
         dst.view.meta = dst.meta.get();
+        dst.view.rowext = dst.rowext.get();
         dst.view.entries = dst.entries.get();
         dst.view.label_of_col = src.reordered ? dst.label_of_col.get() : nullptr;
         dst.view.n_cols = src.n_cols;

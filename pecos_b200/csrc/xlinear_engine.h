@@ -22,6 +22,7 @@ namespace pb200 {
 struct LayerDev {
     const ChunkHeader* chunks;
     const uint32_t* meta;
+    const uint32_t* rowext;        // same indexing as meta: chunk region [meta_off, meta_off + 2R) = {begin, end} per row
     const uint2* entries;
     const uint32_t* label_of_col;  // nullptr when the layer is contiguously ordered
     const uint2* featmap;          // per-chunk {bits, prefix} cells for query-driven lookups; nullptr = stream row lists
@@ -120,6 +121,7 @@ private:
     struct LayerStore {
         DeviceBuffer<ChunkHeader> chunks;
         DeviceBuffer<uint32_t> meta;
+        DeviceBuffer<uint32_t> rowext;
         DeviceBuffer<uint2> entries;
         DeviceBuffer<uint32_t> label_of_col;
         DeviceBuffer<uint2> featmap;

@@ -2,15 +2,17 @@
 //
 // Included by xlinear_engine.cu (inside its anonymous namespace, after the small device helpers).
 //
-// Why: scoring a (query, chunk) pair touches only a few hundred {col, val} entries, and the per-pair bookkeeping of the
-// warp-per-chunk kernel (flush set-up, scans, conflict rounds inside a 60..90 column block) costs more than the
-// arithmetic.  Here LANE j owns beam slot j (its feature-map pointer lives in registers) and the warp walks the query's
-// features in order, eight at a time: every lane probes "is feature f a row of my chunk" with ONE 8-byte load, all
-// eight loads of a lane in flight together.  The matches of the whole beam are collected feature-major:
+// Why: scoring a (query, chunk) pair of a narrow chunk touches a few dozen {col, val} entries, and the per-pair
+// bookkeeping of the warp-per-chunk kernel (flush set-up, scans) costs more than the arithmetic.  Here one warp probes
+// the chunks of the beam one after the other -- lane = query feature, one 8-byte feature-map cell per probe, the probes of
+// two chunks (8 loads per lane) in flight together -- and collects the matches of SEVERAL chunks before it applies them:
 //
-//   * entries of one feature hit different chunks => different output columns => no ordering constraint between them;
-//   * 32 consecutive entries spread over (beam x chunk-width) ~ 160..1800 targets, so two of them rarely collide
-//     (collisions are still resolved exactly, in concatenation order, through __match_any_sync);
+//   * lanes of one load instruction probe the SAME chunk with ascending features, so the popular (small) feature ids
+//     share 128-byte lines: the L1 pipeline, which processes one line per ~2 cycles and instruction, sees about half the
+//     lines of a lane-per-chunk arrangement (measured limiter: 2,560 probes per query and layer);
+//   * matches are chunk-major, feature-ascending inside a chunk; entries of different chunks hit different columns, and
+//     entries of one 32-group that hit the same column are added in concatenation order (__match_any_sync), i.e. in
+//     ascending feature order;
 //   * the apply pass is entry-parallel (lane = entry of the concatenated matched rows, row found by a binary search in
 //     the prefix sums), so ragged rows cost the same per entry and nothing is staged.
 //
@@ -26,7 +28,8 @@ constexpr uint32_t kQwNCap = 2048; // candidate row capacity (floats)
 constexpr uint32_t kQwQCap = 512;  // query non-zeros staged per warp
 
 struct QwSlot {
-    const uint32_t* rp;    // row_ptr (u32, relative to ent)
+    const uint2* fm;       // feature-map cells of the chunk (nullptr: nothing to probe)
+    const uint2* ext;      // {first entry, end} of every chunk row, relative to ent
     const uint2* ent;      // entries of the chunk
     uint32_t base;         // first candidate position of this slot
     uint32_t n_rows;       // R
@@ -85,11 +88,10 @@ xl_query_warp_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* 
     const uint32_t n_total = __shfl_sync(kFull, incl, 31);
     const bool scored = static_cast<uint32_t>(lane) < cnt && !(my_h.has_bias & kChunkAbsent);  // absent: another GPU's chunk
     const bool probing = scored && my_h.nnz_rows > 0;
-    const uint2* my_fm = L.featmap + static_cast<uint64_t>(my_p) * L.fm_words;
     if (static_cast<uint32_t>(lane) < cnt) {
         QwSlot s;
-        const uint32_t R4 = (my_h.nnz_rows + 3u) & ~3u;
-        s.rp = L.meta + my_h.meta_off + R4;
+        s.fm = probing ? L.featmap + static_cast<uint64_t>(my_p) * L.fm_words : nullptr;
+        s.ext = reinterpret_cast<const uint2*>(L.rowext + my_h.meta_off);
         s.ent = L.entries + my_h.ent_off;
         s.base = incl - my_h.n_cols;
         s.n_rows = my_h.nnz_rows;
@@ -116,8 +118,8 @@ xl_query_warp_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* 
             if (i < m) {
                 const uint2 rj = mrow[i];
                 const QwSlot sl = slots[rj.y];
-                const uint32_t lo = __ldg(sl.rp + rj.x), hi = __ldg(sl.rp + rj.x + 1);
-                a[u] = sl.ent + lo; c[u] = hi - lo; bs[u] = sl.base;
+                const uint2 lh = __ldg(sl.ext + rj.x);  // one 8-byte load per matched row
+                a[u] = sl.ent + lh.x; c[u] = lh.y - lh.x; bs[u] = sl.base;
             }
             local += c[u];
         }
@@ -167,37 +169,57 @@ xl_query_warp_scores_kernel(const LayerDev L, const QueryDev X, const uint32_t* 
         __syncwarp();
     };
 
-    // ---- probes: lane = beam slot, eight query features per step
+    // ---- probes: two chunks per step, lane = query feature (4 x 32 features per chunk and pass)
     if (__ballot_sync(kFull, probing) != 0u && qn > 0) {
         int m = 0;
-        for (int t0 = 0; t0 < qn; t0 += 8) {
-            uint2 cell[8];
-            uint32_t bitpos[8];
+        for (uint32_t j0 = 0; j0 < cnt; j0 += 2) {
+            const uint2* fm[2];
+            fm[0] = slots[j0].fm;
+            fm[1] = (j0 + 1 < cnt) ? slots[j0 + 1].fm : nullptr;
+            if (fm[0] == nullptr && fm[1] == nullptr) continue;
+            for (int tb = 0; tb < qn; tb += 128) {
+                uint32_t bitpos[4];
+                uint32_t word[4];
+                bool live[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int t = t0 + u;
-                cell[u] = make_uint2(0u, 0u);
-                bitpos[u] = 0;
-                if (t < qn) {  // warp-uniform
-                    const uint32_t f = qidx[t];
-                    const bool dup = (t > 0) && (qidx[t - 1] == f);  // only the first of repeated indices counts
-                    bitpos[u] = f & 31u;
-                    if (!dup && f < L.w_rows && probing) cell[u] = __ldg(my_fm + (f >> 5));
+                for (int u = 0; u < 4; ++u) {
+                    const int t = tb + 32 * u + lane;
+                    live[u] = false; bitpos[u] = 0; word[u] = 0;
+                    if (t < qn) {
+                        const uint32_t f = qidx[t];
+                        const bool dup = (t > 0) && (qidx[t - 1] == f);  // only the first of repeated indices counts
+                        live[u] = !dup && f < L.w_rows;
+                        bitpos[u] = f & 31u;
+                        word[u] = f >> 5;
+                    }
                 }
-            }
+                uint2 cell[2][4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (t0 + u >= qn) break;
-                const bool hit = (cell[u].x >> bitpos[u]) & 1u;
-                const unsigned mask = __ballot_sync(kFull, hit);
-                if (mask == 0u) continue;
-                if (hit) {
-                    const uint32_t pos = m + __popc(mask & ((1u << lane) - 1u));
-                    mrow[pos] = make_uint2(cell[u].y + __popc(cell[u].x & ((1u << bitpos[u]) - 1u)), static_cast<uint32_t>(lane));
-                    mx[pos] = qval[t0 + u];
+                for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        cell[c][u] = make_uint2(0u, 0u);
+                        if (fm[c] != nullptr && live[u]) cell[c][u] = __ldg(fm[c] + word[u]);
+                    }
                 }
-                m += __popc(mask);
-                if (m > kQwPairs - 32) { flush(m); m = 0; }
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (fm[c] == nullptr) continue;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (tb + 32 * u >= qn) break;
+                        const bool hit = (cell[c][u].x >> bitpos[u]) & 1u;
+                        const unsigned mask = __ballot_sync(kFull, hit);
+                        if (mask == 0u) continue;
+                        if (hit) {
+                            const uint32_t pos = m + __popc(mask & ((1u << lane) - 1u));
+                            mrow[pos] = make_uint2(cell[c][u].y + __popc(cell[c][u].x & ((1u << bitpos[u]) - 1u)), j0 + c);
+                            mx[pos] = qval[tb + 32 * u + lane];
+                        }
+                        m += __popc(mask);
+                        if (m > kQwPairs - 32) { flush(m); m = 0; }
+                    }
+                }
             }
         }
         flush(m);
