@@ -229,6 +229,9 @@ def workload_config(name, cfg, X, extra=None):
     return c
 
 
+SCORE_KERNELS = ["xl_chunk_scores_kernel<stream>", "xl_chunk_scores_kernel", "xl_chunk_scores_kernel<dense>", "xl_query_warp_scores_kernel"]
+TOPK_KERNELS = ["xl_topk_kernel", "xl_topk_warp_kernel", "xl_topk_filter_kernel"]
+
 HNSW_WORKLOADS = {
     # BASELINE.json configs[3] shape (dense d=768, ip, M=32, efS=200, top-10) at sizes the reference trainer can build
     # inside a GPU lease; the index is built once per box by the reference's own HNSW.train (oracle/_ref), all host threads
@@ -462,7 +465,7 @@ def main():
     n_gpus = max(world, 1)
 
     import __graft_entry__ as entry
-    from ctypes import byref, c_double, c_uint64
+    from ctypes import byref, c_double, c_int, c_uint64
 
     from pecos_b200 import core
     from pecos_b200.core import ScipyCompressedSparseAllocator, ScipyCsrF32
@@ -548,13 +551,15 @@ def main():
         one_step()
     prof = (c_double * (2 * depth))()
     c.pb200_xlinear_get_profile(h, prof)
+    kid = (c_int * (2 * depth))()
+    c.pb200_xlinear_get_kernel_ids(h, kid)
     c.pb200_xlinear_set_profile(h, 0)
     pm = np.array(list(prof), dtype=np.float64).reshape(depth, 2) / prof_steps
     peak, peak_src = measured_peak_gbs()
     kernels = []
     for d in range(depth):
-        kernels.append({"kernel": f"xl_chunk_scores_kernel[layer {d}]", "ms": pm[d, 0], "algorithmic_bytes": float(scores_bytes[d])})
-        kernels.append({"kernel": f"xl_topk_kernel[layer {d}]", "ms": pm[d, 1], "algorithmic_bytes": float(topk_bytes[d])})
+        kernels.append({"kernel": f"{SCORE_KERNELS[kid[2 * d]]}[layer {d}]", "ms": pm[d, 0], "algorithmic_bytes": float(scores_bytes[d])})
+        kernels.append({"kernel": f"{TOPK_KERNELS[kid[2 * d + 1]]}[layer {d}]", "ms": pm[d, 1], "algorithmic_bytes": float(topk_bytes[d])})
     dom = max(kernels, key=lambda k: k["ms"])
     achieved = dom["algorithmic_bytes"] / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
     ncu_traffic = None

@@ -146,6 +146,10 @@ void pb200_xlinear_set_profile(void* ptr, int on);
 int pb200_xlinear_set_lookup(void* ptr, int on);
 void pb200_xlinear_reset_profile(void* ptr);
 void pb200_xlinear_get_profile(void* ptr, double* out);
+/* out[2*depth]: per layer {score kernel, top-k kernel} of the last call.  Score: 0 row-list streaming, 1 feature-map
+ * lookup (xl_chunk_scores_kernel), 2 dense, 3 xl_query_warp_scores_kernel.  Top-k: 0 xl_topk_kernel, 1 xl_topk_warp_kernel,
+ * 2 xl_topk_filter_kernel. */
+void pb200_xlinear_get_kernel_ids(void* ptr, int* out);
 void pb200_xlinear_get_stats(void* ptr, uint64_t* out);
 uint64_t pb200_xlinear_launches(void* ptr);
 uint64_t pb200_xlinear_model_bytes(void* ptr);

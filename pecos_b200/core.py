@@ -280,6 +280,7 @@ class B200CoreLib(object):
         fp(c.pb200_xlinear_reset_profile, None, [c_void_p])
         fp(c.pb200_xlinear_set_lookup, c_int, [c_void_p, c_int])
         fp(c.pb200_xlinear_get_profile, None, [c_void_p, POINTER(c_double)])
+        fp(c.pb200_xlinear_get_kernel_ids, None, [c_void_p, POINTER(c_int)])
         fp(c.pb200_xlinear_get_stats, None, [c_void_p, POINTER(c_uint64)])
         fp(c.pb200_xlinear_launches, c_uint64, [c_void_p])
         fp(c.pb200_xlinear_model_bytes, c_uint64, [c_void_p])

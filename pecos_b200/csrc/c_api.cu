@@ -269,6 +269,13 @@ void pb200_xlinear_get_profile(void* ptr, double* out) {
     PB200_API_END("pb200_xlinear_get_profile")
 }
 
+void pb200_xlinear_get_kernel_ids(void* ptr, int* out) {
+    PB200_API_BEGIN
+    const auto& p = engine_of(ptr).layer_profile();
+    for (size_t d = 0; d < p.size(); ++d) { out[2 * d] = p[d].scores_kernel; out[2 * d + 1] = p[d].topk_kernel; }
+    PB200_API_END("pb200_xlinear_get_kernel_ids")
+}
+
 void pb200_xlinear_get_stats(void* ptr, uint64_t* out) {
     PB200_API_BEGIN
     const auto& s = engine_of(ptr).layer_stats();

@@ -80,6 +80,25 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
     return v;
 }
 
+// Rows of the 32 consecutive entries [G, G + 32) of the concatenated matched rows (off[] = their prefix sums, off[m] =
+// total, every row non-empty).  row_first = row holding entry G (warp-uniform; updated to the row holding entry G + 32).
+// Lane L looks at candidate row row_first + 1 + L: if it starts inside the group it sets the bit of its first entry; a
+// lane's row is then row_first + (number of row starts at or before the lane).  ~12 instructions instead of a
+// log2(m)-step binary search per entry.
+__device__ __forceinline__ int xl_rows_of_group(const uint32_t* off, int m, uint32_t G, int& row_first, int lane) {
+    const int r = row_first + 1 + lane;
+    uint32_t bit = 0;
+    if (r < m) {
+        const uint32_t p = off[r] - G;
+        if (p < 32u) bit = 1u << p;
+    }
+    const uint32_t starts = __reduce_or_sync(kFull, bit);
+    const int my_row = row_first + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
+    const int r31 = __shfl_sync(kFull, my_row, 31);
+    row_first = (off[r31 + 1] == G + 32u) ? r31 + 1 : r31;
+    return my_row;
+}
+
 // Apply the matched rows collected in ws (in ascending feature order) to the output block.
 //
 // Entry-parallel: the m matched rows hold `total` entries; lane L of group g owns entry 32g + L of their concatenation
@@ -97,6 +116,7 @@ __device__ __forceinline__ void xl_flush_impl(WarpScratch<MCAP>& ws, int m, cons
     constexpr int PER = MCAP / 32;
     uint32_t c[PER];
     uint32_t local = 0;
+    bool empty_row = false;
 #pragma unroll
     for (int u = 0; u < PER; ++u) {  // PER independent 8-byte loads per lane; ms[i]: chunk row -> its first entry
         const int i = lane * PER + u;
@@ -105,9 +125,11 @@ __device__ __forceinline__ void xl_flush_impl(WarpScratch<MCAP>& ws, int m, cons
             const uint2 lh = __ldg(ext + ws.ms[i]);
             ws.ms[i] = lh.x;
             c[u] = lh.y - lh.x;
+            empty_row |= (c[u] == 0u);
         }
         local += c[u];
     }
+    const bool search = __any_sync(kFull, empty_row);  // never for chunks built from a CSC matrix (rows have >= 1 entry)
     const uint32_t incl = warp_incl_scan(local, lane);
     uint32_t run = incl - local;
     const uint32_t total = __shfl_sync(kFull, incl, 31);
@@ -120,18 +142,24 @@ __device__ __forceinline__ void xl_flush_impl(WarpScratch<MCAP>& ws, int m, cons
     __syncwarp();
     e_total += total;
 
+    int row_first = 0;
     for (uint32_t g0 = 0; g0 < total; g0 += 128u) {
         uint2 e[4];
         float x[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {  // four independent (search, load) chains in flight per lane
-            const uint32_t g = g0 + 32u * u + lane;
+        for (int u = 0; u < 4; ++u) {  // four entry loads in flight per lane
+            const uint32_t G = g0 + 32u * u;
+            const uint32_t g = G + lane;
             e[u] = make_uint2(0xFFFFFFFFu - lane, 0u);  // idle lanes: distinct pseudo-columns, never applied
             x[u] = 0.0f;
-            if (g < total) {
-                const int i = last_le_u32(ws.off, m, g);  // off[i] <= g < off[i + 1]
-                e[u] = __ldg(ent + ws.ms[i] + (g - ws.off[i]));
-                x[u] = ws.mx[i];
+            if (G < total) {
+                int i = 0;
+                if (!search) i = xl_rows_of_group(ws.off, m, G, row_first, lane);
+                if (g < total) {
+                    if (search) i = last_le_u32(ws.off, m, g);  // off[i] <= g < off[i + 1]
+                    e[u] = __ldg(ent + ws.ms[i] + (g - ws.off[i]));
+                    x[u] = ws.mx[i];
+                }
             }
         }
 #pragma unroll
@@ -859,7 +887,11 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
     PB200_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
     for (auto& e : up_ev_) PB200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : use_ev_) PB200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    if (const char* env = std::getenv("PB200_XL_PIPELINE")) pipeline_uploads_ = std::atoi(env) != 0;
+    if (const char* env = std::getenv("PB200_XL_PIPELINE")) {  // 0 = off, n >= 2 = number of sub-tiles (default 4)
+        const int v = std::atoi(env);
+        pipeline_uploads_ = v != 0;
+        if (v >= 2) pipeline_parts_ = static_cast<uint32_t>(std::min(v, 64));
+    }
     layers_.resize(host_->layers.size());
     uint64_t featmap_budget = 32ull << 30;  // bytes of HBM the feature maps may take in total
     if (const char* env = std::getenv("PB200_FEATMAP_MB")) featmap_budget = std::strtoull(env, nullptr, 10) << 20;
@@ -1075,6 +1107,7 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
         }
         PB200_CUDA(cudaGetLastError());
         ++launches_;
+        layer_profile_[d].scores_kernel = query_warp ? 3 : dense ? 2 : lookup ? 1 : 0;
         if (profile_) PB200_CUDA(cudaEventRecord(ev_[1], stream_));
 
         const bool last = (d + 1 == depth);
@@ -1123,6 +1156,7 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
         }
         PB200_CUDA(cudaGetLastError());
         ++launches_;
+        layer_profile_[d].topk_kernel = filter_select ? 2 : warp_select ? 1 : 0;
         if (profile_) {
             PB200_CUDA(cudaEventRecord(ev_[2], stream_));
             PB200_CUDA(cudaEventSynchronize(ev_[2]));
@@ -1173,8 +1207,8 @@ XLinearEngine::Result XLinearEngine::predict_csr(const uint64_t* row_ptr, const 
     // the previous sub-tile; results stay on the device until the last sub-tile is done.
     uint32_t sub = tile;
     if (pipeline_uploads_ && rows >= 4096u) {
-        const uint32_t quarter = ((rows + 3u) / 4u + 31u) & ~31u;
-        sub = std::min(tile, std::max<uint32_t>(1024u, quarter));
+        const uint32_t part = ((rows + pipeline_parts_ - 1u) / pipeline_parts_ + 31u) & ~31u;
+        sub = std::min(tile, std::max<uint32_t>(1024u, part));
     }
     uint64_t max_nnz = 0;
     for (uint32_t r0 = 0; r0 < rows; r0 += sub) max_nnz = std::max(max_nnz, row_ptr[r0 + std::min(sub, rows - r0)] - row_ptr[r0]);

@@ -57,9 +57,11 @@ struct XLinearStats {  // algorithmic-byte counters of SURVEY.md section 8(d), a
 };
 
 struct XLinearLayerProfile {
-    double scores_ms = 0.0;  // xl_chunk_scores_kernel
-    double topk_ms = 0.0;    // xl_topk_kernel
+    double scores_ms = 0.0;  // score kernel of the layer
+    double topk_ms = 0.0;    // top-k kernel of the layer
     uint64_t launches = 0;
+    int scores_kernel = 0;   // last launch: 0 row-list streaming, 1 feature-map lookup, 2 dense, 3 query-warp
+    int topk_kernel = 0;     // last launch: 0 block-wide sort, 1 warp arg-max, 2 estimate filter
 };
 
 class XLinearEngine {
@@ -162,6 +164,7 @@ private:
     cudaEvent_t up_ev_[2] = {nullptr, nullptr};   // staging set uploaded
     cudaEvent_t use_ev_[2] = {nullptr, nullptr};  // staging set consumed by the score kernels
     bool pipeline_uploads_ = true;
+    uint32_t pipeline_parts_ = 4;
     QueryDev resident_{};
     bool has_resident_ = false;
     DeviceBuffer<uint32_t> res_ids_dev_;
