@@ -54,17 +54,68 @@ def dist_env():
 
 
 class ClockSampler(object):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    """Samples SM clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe).
+
+    Primary source: NVML polled every ~2 ms from a thread (the timed region of the default run is only tens of
+    milliseconds, far below nvidia-smi's sampling period); fallback: `nvidia-smi -lms 100`.  Every NVML call is guarded:
+    a sampling failure must never fail the bench."""
 
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
         self.gpu_index = gpu_index
         self.proc = None
         self.lines = []
+        self.nvml_samples = []   # (sm_mhz, reasons bitmask)
+        self.nvml_max = None
+        self.nvml_thread = None
+        self.stop_flag = False
+        self.mark_at = 0
+        self.nvml_mark_at = 0
+
+    def _nvml_index(self):
+        # CUDA_VISIBLE_DEVICES may renumber the devices; NVML counts physical ones
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        try:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if ids and all(v.isdigit() for v in ids) and self.gpu_index < len(ids):
+                return int(ids[self.gpu_index])
+        except Exception:
+            pass
+        return self.gpu_index
+
+    def _nvml_loop(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            try:
+                self.nvml_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            except Exception:
+                self.nvml_max = None
+            while not self.stop_flag:
+                try:
+                    mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                    try:
+                        bits = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    except Exception:
+                        bits = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                    self.nvml_samples.append((mhz, bits))
+                except Exception:
+                    break
+                time.sleep(0.002)
+        except Exception:
+            pass
 
     def start(self):
+        try:
+            self.nvml_thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.nvml_thread.start()
+        except Exception:
+            self.nvml_thread = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
@@ -75,23 +126,40 @@ class ClockSampler(object):
             self.proc = None
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        try:
+            for line in self.proc.stdout:
+                self.lines.append(line.strip())
+        except Exception:
+            pass
 
     def mark(self):
         """Samples taken before this call (warm-up) are dropped if enough samples follow."""
         self.mark_at = len(self.lines)
+        self.nvml_mark_at = len(self.nvml_samples)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        lines = self.lines[getattr(self, "mark_at", 0):]
+        self.stop_flag = True
+        if self.nvml_thread is not None:
+            try:
+                self.nvml_thread.join(timeout=1.0)
+            except Exception:
+                pass
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        timed = self.nvml_samples[self.nvml_mark_at:]
+        if len(timed) >= 3:
+            sm = [m for m, _ in timed]
+            reasons = sorted({name for _, bits in timed for name, mask in self.NVML_REASONS if bits & mask})
+            return {"sm_mhz": statistics.median(sm), "sm_max_mhz": self.nvml_max if self.nvml_max else max(sm),
+                    "reasons": reasons, "samples": len(sm), "source": "nvml, ~2 ms period, timed region only"}
+        if self.proc is None and not self.nvml_samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi and NVML unavailable"], "samples": 0}
+        lines = self.lines[self.mark_at:]
         if len(lines) < 3:
             lines = self.lines
         sm, smax, reasons = [], [], set()
@@ -108,8 +176,12 @@ class ClockSampler(object):
             for name, val in zip(names, parts[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
+        if not sm and self.nvml_samples:  # NVML gave something, but not enough inside the timed region
+            sm = [m for m, _ in self.nvml_samples]
+            smax = [self.nvml_max] if self.nvml_max else [max(sm)]
+            reasons = {name for _, bits in self.nvml_samples for name, mask in self.NVML_REASONS if bits & mask}
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100 (incl. warm-up if the timed region was too short)"}
 
 
 def measured_peak_gbs():
