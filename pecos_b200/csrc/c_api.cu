@@ -29,7 +29,16 @@ std::atomic<int> g_device{0};
 
 struct XLinearHandle {
     std::unique_ptr<pb200::XLinearEngine> engine;
+    // The reference's handles are immutable after load and may be shared between threads (ctypes drops the GIL during a
+    // call).  Ours own device workspaces, so calls on ONE handle are serialised; different handles run concurrently.
+    std::mutex mu;
 };
+
+std::mutex& mutex_of(void* ptr) {
+    if (!ptr) throw std::runtime_error("null model handle");
+    return static_cast<XLinearHandle*>(ptr)->mu;
+}
+#define PB200_LOCK_XL(ptr) std::lock_guard<std::mutex> pb200_handle_lock(mutex_of(ptr));
 
 pb200::XLinearEngine& engine_of(void* ptr) {
     if (!ptr) throw std::runtime_error("null model handle");
@@ -128,6 +137,7 @@ void c_xlinear_predict_csr_f32(void* ptr, const ScipyCsrF32* X, const uint32_t o
                                const int threads, py_sparse_allocator_t pred_alloc) {
     (void)threads;
     PB200_API_BEGIN
+    PB200_LOCK_XL(ptr)
     auto& eng = engine_of(ptr);
     auto r = eng.predict_csr(X->row_ptr, X->col_idx, X->val, X->rows, X->cols, overridden_beam_size,
                              overridden_post_processor_str, overridden_only_topk);
@@ -140,6 +150,7 @@ void c_xlinear_predict_drm_f32(void* ptr, const ScipyDrmF32* X, const uint32_t o
                                const int threads, py_sparse_allocator_t pred_alloc) {
     (void)threads;
     PB200_API_BEGIN
+    PB200_LOCK_XL(ptr)
     auto& eng = engine_of(ptr);
     if (X->cols != eng.host().nr_features()) throw std::runtime_error("dense query width != nr_features");
     auto r = eng.predict_drm(X->val, X->rows, X->cols, overridden_beam_size, overridden_post_processor_str,
@@ -194,18 +205,21 @@ void pb200_l2_flush(void) {
 
 void pb200_xlinear_resident_upload_csr(void* ptr, const ScipyCsrF32* X) {
     PB200_API_BEGIN
+    PB200_LOCK_XL(ptr)
     engine_of(ptr).resident_upload_csr(X->row_ptr, X->col_idx, X->val, X->rows, X->cols);
     PB200_API_END("pb200_xlinear_resident_upload_csr")
 }
 
 double pb200_xlinear_resident_predict(void* ptr, uint32_t beam, const char* pp, uint32_t topk, int collect_stats) {
     PB200_API_BEGIN
+    PB200_LOCK_XL(ptr)
     return engine_of(ptr).resident_predict(beam, pp, topk, collect_stats != 0);
     PB200_API_END("pb200_xlinear_resident_predict")
 }
 
 void pb200_xlinear_resident_fetch(void* ptr, py_sparse_allocator_t pred_alloc) {
     PB200_API_BEGIN
+    PB200_LOCK_XL(ptr)
     emit_result(engine_of(ptr).resident_fetch(), pred_alloc);
     PB200_API_END("pb200_xlinear_resident_fetch")
 }
@@ -227,6 +241,7 @@ void pb200_xlinear_get_shard(void* ptr, uint32_t* out) {
 uint32_t pb200_xlinear_sharded_local_csr(void* ptr, const ScipyCsrF32* X, uint32_t beam, const char* pp, uint32_t topk,
                                          uint32_t stride_capacity, void* keys_dev, void* ids_dev, void* vals_dev, void* cnt_dev) {
     PB200_API_BEGIN
+    PB200_LOCK_XL(ptr)
     return engine_of(ptr).sharded_local_csr(X->row_ptr, X->col_idx, X->val, X->rows, X->cols, beam, pp, topk, stride_capacity,
                                             static_cast<unsigned long long*>(keys_dev), static_cast<uint32_t*>(ids_dev),
                                             static_cast<float*>(vals_dev), static_cast<uint32_t*>(cnt_dev));
@@ -236,6 +251,7 @@ uint32_t pb200_xlinear_sharded_local_csr(void* ptr, const ScipyCsrF32* X, uint32
 void pb200_xlinear_sharded_merge(void* ptr, uint32_t world, uint32_t rows, uint32_t stride, uint32_t topk, const void* g_keys,
                                  const void* g_ids, const void* g_vals, const void* g_cnt, py_sparse_allocator_t pred_alloc) {
     PB200_API_BEGIN
+    PB200_LOCK_XL(ptr)
     auto r = engine_of(ptr).sharded_merge(world, rows, stride, topk, static_cast<const unsigned long long*>(g_keys),
                                           static_cast<const uint32_t*>(g_ids), static_cast<const float*>(g_vals),
                                           static_cast<const uint32_t*>(g_cnt));
@@ -245,12 +261,14 @@ void pb200_xlinear_sharded_merge(void* ptr, uint32_t world, uint32_t rows, uint3
 
 void pb200_xlinear_set_profile(void* ptr, int on) {
     PB200_API_BEGIN
+    PB200_LOCK_XL(ptr)
     engine_of(ptr).set_profile(on != 0);
     PB200_API_END("pb200_xlinear_set_profile")
 }
 
 int pb200_xlinear_set_lookup(void* ptr, int on) {
     PB200_API_BEGIN
+    PB200_LOCK_XL(ptr)
     engine_of(ptr).set_kernel_mode(on);
     return engine_of(ptr).has_feature_maps() ? 1 : 0;
     PB200_API_END("pb200_xlinear_set_lookup")
@@ -258,12 +276,14 @@ int pb200_xlinear_set_lookup(void* ptr, int on) {
 
 void pb200_xlinear_reset_profile(void* ptr) {
     PB200_API_BEGIN
+    PB200_LOCK_XL(ptr)
     engine_of(ptr).reset_profile();
     PB200_API_END("pb200_xlinear_reset_profile")
 }
 
 void pb200_xlinear_get_profile(void* ptr, double* out) {
     PB200_API_BEGIN
+    PB200_LOCK_XL(ptr)
     const auto& p = engine_of(ptr).layer_profile();
     for (size_t d = 0; d < p.size(); ++d) { out[2 * d] = p[d].scores_ms; out[2 * d + 1] = p[d].topk_ms; }
     PB200_API_END("pb200_xlinear_get_profile")
@@ -271,6 +291,7 @@ void pb200_xlinear_get_profile(void* ptr, double* out) {
 
 void pb200_xlinear_get_kernel_ids(void* ptr, int* out) {
     PB200_API_BEGIN
+    PB200_LOCK_XL(ptr)
     const auto& p = engine_of(ptr).layer_profile();
     for (size_t d = 0; d < p.size(); ++d) { out[2 * d] = p[d].scores_kernel; out[2 * d + 1] = p[d].topk_kernel; }
     PB200_API_END("pb200_xlinear_get_kernel_ids")
@@ -278,6 +299,7 @@ void pb200_xlinear_get_kernel_ids(void* ptr, int* out) {
 
 void pb200_xlinear_get_stats(void* ptr, uint64_t* out) {
     PB200_API_BEGIN
+    PB200_LOCK_XL(ptr)
     const auto& s = engine_of(ptr).layer_stats();
     for (size_t d = 0; d < s.size(); ++d) {
         out[7 * d + 0] = s[d].chunks; out[7 * d + 1] = s[d].chunk_rows; out[7 * d + 2] = s[d].matched;
@@ -339,7 +361,14 @@ namespace {
 
 struct HnswHandle {
     std::unique_ptr<pb200::HnswEngine> engine;
+    std::mutex mu;  // per-warp search scratch lives with the engine: calls on one handle are serialised
 };
+
+std::mutex& hnsw_mutex_of(void* ptr) {
+    if (!ptr) throw std::runtime_error("null HNSW handle");
+    return static_cast<HnswHandle*>(ptr)->mu;
+}
+#define PB200_LOCK_HNSW(ptr) std::lock_guard<std::mutex> pb200_handle_lock(hnsw_mutex_of(ptr));
 
 struct HnswSearchers {  // the reference hands out a vector<Searcher>; our scratch lives with the engine (per warp)
     HnswHandle* owner;
@@ -363,6 +392,7 @@ void* hnsw_load(const char* model_dir, bool lazy_load, int metric) {
 
 void hnsw_predict(void* model_ptr, const ScipyDrmF32* pX, uint32_t* ret_idx, float* ret_val, uint32_t efS, uint32_t topk,
                   int metric) {
+    PB200_LOCK_HNSW(model_ptr)
     auto& eng = hnsw_of(model_ptr);
     if (eng.metric() != metric) throw std::runtime_error("HNSW handle was loaded with a different metric");
     eng.predict(pX->val, pX->rows, pX->cols, efS, topk, ret_idx, ret_val);
@@ -404,24 +434,28 @@ PB200_HNSW_API(_drm_l2_f32, pb200::HNSW_L2)
 
 void pb200_hnsw_resident_upload(void* model_ptr, const ScipyDrmF32* pX) {
     PB200_API_BEGIN
+    PB200_LOCK_HNSW(model_ptr)
     hnsw_of(model_ptr).resident_upload(pX->val, pX->rows, pX->cols);
     PB200_API_END("pb200_hnsw_resident_upload")
 }
 
 double pb200_hnsw_resident_predict(void* model_ptr, uint32_t efS, uint32_t topk) {
     PB200_API_BEGIN
+    PB200_LOCK_HNSW(model_ptr)
     return hnsw_of(model_ptr).resident_predict(efS, topk);
     PB200_API_END("pb200_hnsw_resident_predict")
 }
 
 void pb200_hnsw_resident_fetch(void* model_ptr, uint32_t* ret_idx, float* ret_val) {
     PB200_API_BEGIN
+    PB200_LOCK_HNSW(model_ptr)
     hnsw_of(model_ptr).resident_fetch(ret_idx, ret_val);
     PB200_API_END("pb200_hnsw_resident_fetch")
 }
 
 int pb200_hnsw_set_stages(void* model_ptr, int stages) {
     PB200_API_BEGIN
+    PB200_LOCK_HNSW(model_ptr)
     hnsw_of(model_ptr).set_stages(stages);
     return hnsw_of(model_ptr).stages();
     PB200_API_END("pb200_hnsw_set_stages")
@@ -429,6 +463,7 @@ int pb200_hnsw_set_stages(void* model_ptr, int stages) {
 
 void pb200_hnsw_get_counters(void* model_ptr, uint64_t* out) {
     PB200_API_BEGIN
+    PB200_LOCK_HNSW(model_ptr)
     auto c = hnsw_of(model_ptr).counters();
     out[0] = c.n_dist; out[1] = c.n_expand; out[2] = c.n_hops; out[3] = c.n_queries;
     PB200_API_END("pb200_hnsw_get_counters")
