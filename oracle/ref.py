@@ -13,6 +13,7 @@ import scipy.sparse as smat
 from pecos_b200.core import (
     XLINEAR_INFERENCE_MODEL_TYPES,
     ScipyCompressedSparseAllocator,
+    ScipyCscF32,
     ScipyCsrF32,
     ScipyDrmF32,
 )
@@ -43,6 +44,12 @@ def lib():
         L.c_xlinear_predict_csr_f32.argtypes = [c_void_p, POINTER(ScipyCsrF32)] + pred
         L.c_xlinear_predict_drm_f32.restype = None
         L.c_xlinear_predict_drm_f32.argtypes = [c_void_p, POINTER(ScipyDrmF32)] + pred
+        single = [POINTER(ScipyCsrF32), POINTER(ScipyCscF32), POINTER(ScipyCscF32), c_char_p, c_uint32, c_int, c_float,
+                  ScipyCompressedSparseAllocator.CFUNCTYPE]  # pecos/core/base.py:880-905
+        L.c_xlinear_single_layer_predict_csr_f32.restype = None
+        L.c_xlinear_single_layer_predict_csr_f32.argtypes = [POINTER(ScipyCsrF32)] + single
+        L.c_xlinear_single_layer_predict_drm_f32.restype = None
+        L.c_xlinear_single_layer_predict_drm_f32.argtypes = [POINTER(ScipyDrmF32)] + single
         for metric in ("ip", "l2"):
             sfx = f"drm_{metric}_f32"
             f = getattr(L, "c_ann_hnsw_train_" + sfx)
@@ -105,6 +112,27 @@ class RefXLinear(object):
             cx = ScipyDrmF32.init_from(np.ascontiguousarray(X, dtype=np.float32))
             L.c_xlinear_predict_drm_f32(self.h, byref(cx), beam_size or 0, pp, only_topk or 0, threads, alloc.cfunc)
         return alloc.get()
+
+
+def single_layer_predict(X, csr_codes, W, C, post_processor, only_topk, bias, threads=-1):
+    """c_xlinear_single_layer_predict_{csr,drm}_f32 of the reference (pecos/core/libpecos.cpp:201-235): one layer of the
+    python prediction chain, `csr_codes` = the previous layer's prediction (None for the first layer)."""
+    L = lib()
+    alloc = ScipyCompressedSparseAllocator()
+    cw = ScipyCscF32.init_from(smat.csc_matrix(W, dtype=np.float32))
+    cc = ScipyCscF32.init_from(smat.csc_matrix(C, dtype=np.float32))
+    codes = None
+    if csr_codes is not None:
+        codes = byref(ScipyCsrF32.init_from(smat.csr_matrix(csr_codes, dtype=np.float32)))
+    if isinstance(X, smat.csr_matrix):
+        assert X.has_sorted_indices
+        cx = ScipyCsrF32.init_from(X)
+        fn = L.c_xlinear_single_layer_predict_csr_f32
+    else:
+        cx = ScipyDrmF32.init_from(np.ascontiguousarray(X, dtype=np.float32))
+        fn = L.c_xlinear_single_layer_predict_drm_f32
+    fn(byref(cx), codes, byref(cw), byref(cc), post_processor.encode(), only_topk, threads, bias, alloc.cfunc)
+    return alloc.get()
 
 
 def compile_mmap_model(npz_ranker_folder, mmap_folder):

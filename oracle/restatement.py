@@ -36,6 +36,9 @@ def lib():
         L.xlo_predict.restype = c_int
         L.xlo_predict.argtypes = [c_int, POINTER(_Csc), POINTER(_Csc), POINTER(c_float), POINTER(c_int), POINTER(c_int),
                                   POINTER(c_uint32), POINTER(_Query), POINTER(_Result)]
+        L.xlo_predict_from.restype = c_int
+        L.xlo_predict_from.argtypes = [c_int, POINTER(_Csc), POINTER(_Csc), POINTER(c_float), POINTER(c_int), POINTER(c_int),
+                                       POINTER(c_uint32), POINTER(_Query), POINTER(_Query), POINTER(_Result)]
         L.xlo_free_result.restype = None
         L.xlo_free_result.argtypes = [POINTER(_Result)]
         _lib = L
@@ -55,6 +58,59 @@ def parse_post_processor(name):
     if name.startswith("l") and name.endswith("-hinge"):
         return 3, int(name[1:-len("-hinge")] or 0)
     return 0, 0
+
+
+def _query_struct(X, keep):
+    q = _Query()
+    if isinstance(X, smat.csr_matrix):
+        ip = np.ascontiguousarray(X.indptr, dtype=np.uint64)
+        ix = np.ascontiguousarray(X.indices, dtype=np.uint32)
+        dv = np.ascontiguousarray(X.data, dtype=np.float32)
+        keep.extend([ip, ix, dv])
+        q.rows, q.cols = X.shape
+        q.row_ptr = ip.ctypes.data_as(POINTER(c_uint64))
+        q.col_idx = ix.ctypes.data_as(POINTER(c_uint32))
+        q.val = dv.ctypes.data_as(POINTER(c_float))
+    else:
+        Xd = np.ascontiguousarray(X, dtype=np.float32)
+        keep.append(Xd)
+        q.rows, q.cols = Xd.shape
+        q.row_ptr = None
+        q.col_idx = None
+        q.val = Xd.ctypes.data_as(POINTER(c_float))
+    return q
+
+
+def _take_result(L, res):
+    n = int(res.nnz)
+    indptr = np.ctypeslib.as_array(res.indptr, shape=(res.rows + 1,)).astype(np.int64)
+    indices = np.ctypeslib.as_array(res.indices, shape=(max(n, 1),))[:n].astype(np.int64)
+    data = np.ctypeslib.as_array(res.data, shape=(max(n, 1),))[:n].copy()
+    out = smat.csr_matrix((data, indices, indptr), shape=(res.rows, res.cols))
+    L.xlo_free_result(byref(res))
+    return out
+
+
+def single_layer_predict(X, csr_codes, W, C, post_processor, only_topk, bias):
+    """Restatement of c_xlinear_single_layer_predict_{csr,drm}_f32 (pecos/core/libpecos.cpp:201-235): one layer of the
+    python prediction chain; `csr_codes` (previous layer's prediction, entries in stored order) or None."""
+    L = lib()
+    keep = []
+    W = smat.csc_matrix(W, dtype=np.float32)
+    W.sort_indices()
+    C = smat.csc_matrix(C, dtype=np.float32)
+    Ws = (_Csc * 1)(OracleXLinear._csc_struct(W, keep))
+    Cs = (_Csc * 1)(OracleXLinear._csc_struct(C, keep))
+    kind, p = parse_post_processor(post_processor)
+    q = _query_struct(X, keep)
+    codes = None
+    if csr_codes is not None:
+        codes = byref(_query_struct(smat.csr_matrix(csr_codes, dtype=np.float32), keep))
+    res = _Result()
+    rc = L.xlo_predict_from(1, Ws, Cs, (c_float * 1)(bias), (c_int * 1)(kind), (c_int * 1)(p), (c_uint32 * 1)(only_topk),
+                            byref(q), codes, byref(res))
+    assert rc == 0
+    return _take_result(L, res)
 
 
 class OracleXLinear(object):
@@ -106,36 +162,13 @@ class OracleXLinear(object):
             ps.append(p)
             local = only_topk if d == D - 1 else beam_size   # inference.hpp:2471
             ks.append(local if local else l["only_topk"])    # inference.hpp:2055
-        q = _Query()
-        if isinstance(X, smat.csr_matrix):
-            ip = np.ascontiguousarray(X.indptr, dtype=np.uint64)
-            ix = np.ascontiguousarray(X.indices, dtype=np.uint32)
-            dv = np.ascontiguousarray(X.data, dtype=np.float32)
-            keep.extend([ip, ix, dv])
-            q.rows, q.cols = X.shape
-            q.row_ptr = ip.ctypes.data_as(POINTER(c_uint64))
-            q.col_idx = ix.ctypes.data_as(POINTER(c_uint32))
-            q.val = dv.ctypes.data_as(POINTER(c_float))
-        else:
-            Xd = np.ascontiguousarray(X, dtype=np.float32)
-            keep.append(Xd)
-            q.rows, q.cols = Xd.shape
-            q.row_ptr = None
-            q.col_idx = None
-            q.val = Xd.ctypes.data_as(POINTER(c_float))
+        q = _query_struct(X, keep)
         res = _Result()
         rc = L.xlo_predict(D, Ws, Cs, bias, (c_int * D)(*kinds), (c_int * D)(*ps), (c_uint32 * D)(*ks), byref(q), byref(res))
         assert rc == 0
-        n = int(res.nnz)
-        indptr = np.ctypeslib.as_array(res.indptr, shape=(res.rows + 1,)).astype(np.int64)
-        indices = np.ctypeslib.as_array(res.indices, shape=(max(n, 1),))[:n].astype(np.int64)
-        data = np.ctypeslib.as_array(res.data, shape=(max(n, 1),))[:n].copy()
-        out = smat.csr_matrix((data, indices, indptr), shape=(res.rows, res.cols))
-        L.xlo_free_result(byref(res))
-        return out
+        return _take_result(L, res)
 
 
-# ------------------------------------------------------------------------------------------------------ HNSW
 class _HnswIndex(Structure):
     _fields_ = [("num_node", c_uint32), ("maxM", c_uint32), ("maxM0", c_uint32), ("efC", c_uint32),
                 ("max_level", c_uint32), ("init_node", c_uint32),

@@ -11,6 +11,7 @@
  * (paths relative to the reference checkout):
  *
  *   xlo_predict ................ HierarchicalMLModel::predict       pecos/core/xmc/inference.hpp:2446-2488
+ *   xlo_predict_from ........... c_xlinear_single_layer_predict_*   pecos/core/libpecos.cpp:201-235 (given previous beam)
  *   layer_predict .............. MLModel::predict_internal          pecos/core/xmc/inference.hpp:2029-2080
  *   candidates (prolongation) .. prolongate_predictions             pecos/core/xmc/inference.hpp:1155-1219
  *   score_sparse ............... chunk_ops<csr, bin_search>         pecos/core/xmc/inference.hpp:769-813 (+ :506-518)
@@ -150,15 +151,37 @@ static int cmp_desc_then_pos(const void* pa, const void* pb) {
 
 /* Sorted-by-row copy of a CSC column is assumed (scipy writes sorted indices; the reference would stable-sort). */
 
-int xlo_predict(int depth, const xlo_csc_t* W, const xlo_csc_t* C, const float* bias, const int* pp_kind,
-                const int* pp_p, const uint32_t* only_topk, const xlo_query_t* X, xlo_result_t* out) {
+/* Layers [0, depth) starting from a given beam.  codes == NULL: prev_layer_pred = ones(Q x C[0].cols) and the first
+ * layer does not combine (HierarchicalMLModel::predict, inference.hpp:2462-2463; c_xlinear_single_layer_predict with
+ * csr_codes == NULL, libpecos.cpp:213-219).  codes != NULL: a CSR matrix Q x C[0].cols (row_ptr / col_idx / val) whose
+ * entries, in stored order, are the beam entering layer 0, and layer 0 combines with their values
+ * (libpecos.cpp:209-212: no_prev_pred = false). */
+int xlo_predict_from(int depth, const xlo_csc_t* W, const xlo_csc_t* C, const float* bias, const int* pp_kind,
+                     const int* pp_p, const uint32_t* only_topk, const xlo_query_t* X, const xlo_query_t* codes,
+                     xlo_result_t* out) {
     const uint32_t Q = X->rows;
     /* beam per query: ids / vals, ragged */
     uint64_t* beam_ptr = (uint64_t*)malloc(sizeof(uint64_t) * ((size_t)Q + 1));
-    uint32_t* beam_id = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(Q ? Q : 1));
-    float* beam_val = (float*)malloc(sizeof(float) * (size_t)(Q ? Q : 1));
-    for (uint32_t q = 0; q < Q; ++q) { beam_ptr[q] = q; beam_id[q] = 0; beam_val[q] = 1.0f; } /* ones(Q x 1) */
-    beam_ptr[Q] = Q;
+    uint32_t* beam_id;
+    float* beam_val;
+    if (codes) {
+        const uint64_t n = codes->row_ptr[Q];
+        beam_id = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(n ? n : 1));
+        beam_val = (float*)malloc(sizeof(float) * (size_t)(n ? n : 1));
+        memcpy(beam_ptr, codes->row_ptr, sizeof(uint64_t) * ((size_t)Q + 1));
+        memcpy(beam_id, codes->col_idx, sizeof(uint32_t) * (size_t)n);
+        memcpy(beam_val, codes->val, sizeof(float) * (size_t)n);
+    } else {
+        const uint32_t nc = depth > 0 ? C[0].cols : 1; /* fill_ones(X.rows, C->cols) */
+        beam_id = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(Q ? (size_t)Q * nc : 1));
+        beam_val = (float*)malloc(sizeof(float) * (size_t)(Q ? (size_t)Q * nc : 1));
+        for (uint32_t q = 0; q < Q; ++q) {
+            beam_ptr[q] = (uint64_t)q * nc;
+            for (uint32_t j = 0; j < nc; ++j) { beam_id[(size_t)q * nc + j] = j; beam_val[(size_t)q * nc + j] = 1.0f; }
+        }
+        beam_ptr[Q] = (uint64_t)Q * nc;
+    }
+    const int combine_first = codes != NULL;
     uint32_t out_cols = 1;
 
     for (int d = 0; d < depth; ++d) {
@@ -194,7 +217,7 @@ int xlo_predict(int depth, const xlo_csc_t* W, const xlo_csc_t* C, const float* 
                     const uint32_t label = Cd->row_idx[c]; /* == c when the tree is contiguously ordered */
                     float raw = X->row_ptr ? score_sparse(Wd, label, qidx, qval, qn, bias[d]) : score_dense(Wd, label, xd, bias[d]);
                     float v = xlo_transform(raw, pp_kind[d], pp_p[d]);
-                    if (d > 0) v = xlo_combine(v, beam_val[j], pp_kind[d]);
+                    if (d > 0 || combine_first) v = xlo_combine(v, beam_val[j], pp_kind[d]);
                     cand[n].val = v; cand[n].pos = n; cand[n].label = label;
                     ++n;
                 }
@@ -215,6 +238,11 @@ int xlo_predict(int depth, const xlo_csc_t* W, const xlo_csc_t* C, const float* 
     out->rows = Q;
     out->cols = out_cols;
     return 0;
+}
+
+int xlo_predict(int depth, const xlo_csc_t* W, const xlo_csc_t* C, const float* bias, const int* pp_kind,
+                const int* pp_p, const uint32_t* only_topk, const xlo_query_t* X, xlo_result_t* out) {
+    return xlo_predict_from(depth, W, C, bias, pp_kind, pp_p, only_topk, X, NULL, out);
 }
 
 void xlo_free_result(xlo_result_t* r) {

@@ -83,6 +83,37 @@ class ScipyCsrF32(ctypes.Structure):
         return self
 
 
+class ScipyCscF32(ctypes.Structure):
+    """C view of a float32 scipy CSC matrix (pecos/core/base.py:177-216); same layout as ScipyCsrF32 with col_ptr /
+    row_idx in place of row_ptr / col_idx."""
+
+    _fields_ = [
+        ("rows", c_uint32),
+        ("cols", c_uint32),
+        ("indptr", POINTER(c_uint64)),
+        ("indices", POINTER(c_uint32)),
+        ("data", POINTER(c_float)),
+    ]
+
+    @classmethod
+    def init_from(cls, A):
+        if not isinstance(A, smat.csc_matrix):
+            raise ValueError("type(A) = {} is not supported".format(type(A)))
+        if A.dtype != np.float32:
+            raise ValueError("A.dtype = {} is not float32".format(A.dtype))
+        self = cls()
+        self.py_buf = {
+            "indptr": np.ascontiguousarray(A.indptr, dtype=np.uint64),
+            "indices": np.ascontiguousarray(A.indices, dtype=np.uint32),
+            "data": np.ascontiguousarray(A.data, dtype=np.float32),
+        }
+        self.rows, self.cols = A.shape
+        self.indptr = self.py_buf["indptr"].ctypes.data_as(POINTER(c_uint64))
+        self.indices = self.py_buf["indices"].ctypes.data_as(POINTER(c_uint32))
+        self.data = self.py_buf["data"].ctypes.data_as(POINTER(c_float))
+        return self
+
+
 class ScipyDrmF32(ctypes.Structure):
     """C view of a C-contiguous float32 ndarray (pecos/core/base.py:269-310)."""
 

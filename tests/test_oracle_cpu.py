@@ -97,3 +97,54 @@ def test_reference_library_layer_types_agree(tmp_path, built, have_ref):
         other = ref.RefXLinear(os.path.join(folder, "ranker"), t).predict(X, 5, None, 5)
         assert np.array_equal(base.indices, other.indices)
         assert np.allclose(base.data, other.data, atol=1e-6)
+
+
+@pytest.mark.parametrize("permute,prune", [(False, 0.0), (True, 0.25)])
+def test_single_layer_restatement_equals_reference_library(built, have_ref, permute, prune):
+    """Next scope row: c_xlinear_single_layer_predict_{csr,drm}_f32, the per-layer entry point of the python
+    prediction chain (pecos/core/libpecos.cpp:201-235, pecos/xmc/base.py:890-949).  Pins the restatement
+    (xlo_predict_from) bit-for-bit against oracle/_ref: with and without csr_codes, csr and dense queries, every kind of
+    post-processor, previous-layer entries in NON-sorted stored order, empty code rows; and checks that chaining the
+    single-layer calls reproduces the predict-only model (same arithmetic: bias + dot == dot + bias)."""
+    if not have_ref:
+        pytest.skip("oracle/_ref is not built (no /root/reference here)")
+    from oracle import ref, restatement
+
+    layers = random_tree(91, [5, 30, 240], 150, 20, bias=1.0, permute=permute, prune=prune)
+    X = synth.make_queries(92, 40, 150, 25)
+    rng = np.random.default_rng(93)
+    prev = None
+    for d, (W, C) in enumerate(layers):
+        for pp in ["l3-hinge", "noop", "sigmoid", "log-sigmoid", "log-l2-hinge"]:
+            for Xq in (X, X[:7].toarray()):
+                codes = prev if (prev is None or isinstance(Xq, smat.csr_matrix)) else prev[:7]
+                want = ref.single_layer_predict(Xq, codes, W, C, pp, 6, 1.0)
+                got = restatement.single_layer_predict(Xq, codes, W, C, pp, 6, 1.0)
+                assert_csr_parity(got, want, rtol=0.0, what=f"layer {d} {pp} {'csr' if Xq is X else 'drm'}")
+        prev = ref.single_layer_predict(X, prev, W, C, "l3-hinge", 4, 1.0)
+        # the beam is consumed in stored order: shuffle the entries inside every row and empty two rows
+        lil = prev.tolil()
+        lil.rows[3], lil.data[3] = [], []
+        lil.rows[11], lil.data[11] = [], []
+        shuffled = lil.tocsr().astype(np.float32)
+        for r in range(shuffled.shape[0]):
+            s, e = shuffled.indptr[r], shuffled.indptr[r + 1]
+            perm = rng.permutation(e - s)
+            shuffled.indices[s:e] = shuffled.indices[s:e][perm]
+            shuffled.data[s:e] = shuffled.data[s:e][perm]
+        shuffled.has_sorted_indices = False
+        if d + 1 < len(layers):
+            Wn, Cn = layers[d + 1]
+            want = ref.single_layer_predict(X, shuffled, Wn, Cn, "l3-hinge", 6, 1.0)
+            got = restatement.single_layer_predict(X, shuffled, Wn, Cn, "l3-hinge", 6, 1.0)
+            assert_csr_parity(got, want, rtol=0.0, what=f"layer {d + 1}, shuffled codes")
+    # chain of single-layer calls == one predict-only call (beam 4, top-6 at the leaf)
+    chain = None
+    for d, (W, C) in enumerate(layers):
+        chain = ref.single_layer_predict(X, chain, W, C, "l3-hinge", 6 if d == len(layers) - 1 else 4, 1.0)
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as folder:
+        synth.save_xlinear_model(folder, layers, bias=1.0, only_topk=6)
+        full = ref.RefXLinear(os.path.join(folder, "ranker")).predict(X, 4, "l3-hinge", 6)
+    assert_csr_parity(chain, full, rtol=0.0, what="python chain vs predict-only")
