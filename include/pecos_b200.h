@@ -78,6 +78,26 @@ void c_xlinear_predict_drm_f32(void* ptr, const ScipyDrmF32* input_x, const uint
                                const char* overridden_post_processor_str, const uint32_t overridden_only_topk,
                                const int threads, py_sparse_allocator_t pred_alloc);
 
+/* libpecos.cpp:201-235  One layer of the python prediction chain (pecos/xmc/base.py:890-949, is_predict_only=False
+ * models): W ((nr_features [+1 bias row]) x nr_labels) and C (nr_labels x nr_codes) are handed over on every call;
+ * csr_codes = the previous layer's prediction (rows x nr_codes, entries consumed in stored order) or NULL for the first
+ * layer (= ones, no combine).  post_processor_str must be given; only_topk as passed (0 keeps nothing, like the
+ * reference).  The chunked HBM layout of (W, C, bias) is built on first use and kept in a small LRU cache keyed by the
+ * matrices' shapes, value pointer and a sampled content fingerprint (PB200_LAYER_CACHE entries, default 8): the
+ * matrices are assumed immutable while cached (pb200_layer_cache_clear() drops them).
+ * STATUS: written at the end of round 1 without GPU time left -- parity-pinned on the CPU side (oracle vs reference,
+ * tests/test_oracle_cpu.py), GPU tests in tests/test_single_layer_gpu.py run only with PB200_UNVALIDATED=1. */
+void c_xlinear_single_layer_predict_csr_f32(const ScipyCsrF32* input_x, const ScipyCsrF32* csr_codes, ScipyCscF32* W,
+                                            ScipyCscF32* C, const char* post_processor_str, const uint32_t only_topk,
+                                            const int num_threads, const float bias, py_sparse_allocator_t pred_alloc);
+void c_xlinear_single_layer_predict_drm_f32(const ScipyDrmF32* input_x, const ScipyCsrF32* csr_codes, ScipyCscF32* W,
+                                            ScipyCscF32* C, const char* post_processor_str, const uint32_t only_topk,
+                                            const int num_threads, const float bias, py_sparse_allocator_t pred_alloc);
+/* drops every cached single-layer engine; returns how many were held */
+uint32_t pb200_layer_cache_clear(void);
+/* out[0] = entries held, out[1] = hits, out[2] = misses (builds) since load */
+void pb200_layer_cache_info(uint64_t* out);
+
 /* ========================================= HNSW (reference-compatible) ========================================== */
 
 /* libpecos.cpp:471-480  model_dir = ".../c_model" holding config.json + index.mmap_store (hnsw.hpp:534-552). */
@@ -170,6 +190,8 @@ void pb200_hnsw_get_info(void* model_ptr, uint64_t* out);
  *   kind: 0 = npz folder, 1 = mmap folder.  dims out[8] = {w_rows, n_cols, out_cols, n_chunks, c_max, meta_len,
  *   n_entries, label_of_col_len}.  export copies the arrays into caller buffers (any may be NULL). */
 void* pb200_xlinear_host_load(const char* model_path, int kind);
+/* host-only: the one-layer model c_xlinear_single_layer_predict_* builds from in-memory W / C (same handle type) */
+void* pb200_xlinear_host_from_csc(const ScipyCscF32* W, const ScipyCscF32* C, float bias);
 void pb200_xlinear_host_free(void* hptr);
 uint32_t pb200_xlinear_host_depth(void* hptr);
 void pb200_xlinear_host_layer_dims(void* hptr, uint32_t layer, uint64_t* out);

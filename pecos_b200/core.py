@@ -203,6 +203,53 @@ class B200CoreLib(object):
         fp(c.c_xlinear_predict_csr_f32, None, [c_void_p, POINTER(ScipyCsrF32)] + pred_args)
         fp(c.c_xlinear_predict_drm_f32, None, [c_void_p, POINTER(ScipyDrmF32)] + pred_args)
 
+        single = [POINTER(ScipyCsrF32), POINTER(ScipyCscF32), POINTER(ScipyCscF32), c_char_p, c_uint32, c_int, c_float,
+                  ScipyCompressedSparseAllocator.CFUNCTYPE]  # pecos/core/base.py:880-933
+        fp(c.c_xlinear_single_layer_predict_csr_f32, None, [POINTER(ScipyCsrF32)] + single)
+        fp(c.c_xlinear_single_layer_predict_drm_f32, None, [POINTER(ScipyDrmF32)] + single)
+        fp(c.pb200_xlinear_host_from_csc, c_void_p, [POINTER(ScipyCscF32), POINTER(ScipyCscF32), c_float])
+        fp(c.pb200_layer_cache_clear, c_uint32, [])
+        fp(c.pb200_layer_cache_info, None, [POINTER(c_uint64)])
+
+    def xlinear_single_layer_predict(self, X, csr_codes, W, C, post_processor_str, only_topk, num_threads, bias, pred_alloc):
+        """Same contract as corelib.xlinear_single_layer_predict (pecos/core/base.py:1160-1226): one layer of the python
+        prediction chain.  W / C: csc_matrix (or ScipyCscF32), csr_codes: csr_matrix or None."""
+        self.require_gpu()
+        clib = self.clib_float32
+        if isinstance(X, smat.csr_matrix):
+            if not X.has_sorted_indices:
+                raise ValueError("Query matrix does not have sorted indices!")
+            X = ScipyCsrF32.init_from(X)
+        elif isinstance(X, np.ndarray):
+            X = ScipyDrmF32.init_from(X)
+        if isinstance(X, ScipyCsrF32):
+            c_predict = clib.c_xlinear_single_layer_predict_csr_f32
+        elif isinstance(X, ScipyDrmF32):
+            c_predict = clib.c_xlinear_single_layer_predict_drm_f32
+        else:
+            raise NotImplementedError("type(X) = {} not implemented".format(type(X)))
+        if isinstance(W, smat.csc_matrix):
+            W = ScipyCscF32.init_from(W)
+        if isinstance(C, smat.csc_matrix):
+            C = ScipyCscF32.init_from(C)
+        if not isinstance(W, ScipyCscF32) or not isinstance(C, ScipyCscF32):
+            raise NotImplementedError("W and C must be csc_matrix / ScipyCscF32")
+        if csr_codes is not None and isinstance(csr_codes, smat.csr_matrix):
+            csr_codes = ScipyCsrF32.init_from(csr_codes)
+        if csr_codes is not None and not isinstance(csr_codes, ScipyCsrF32):
+            raise NotImplementedError("type(csr_codes) = {} not implemented".format(type(csr_codes)))
+        c_predict(
+            byref(X),
+            byref(csr_codes) if csr_codes is not None else None,
+            byref(W),
+            byref(C),
+            post_processor_str.encode("utf-8"),
+            only_topk,
+            num_threads,
+            bias,
+            pred_alloc.cfunc,
+        )
+
     def require_gpu(self):
         if self.clib_float32.pb200_device_count() <= 0:
             raise RuntimeError("pecos_b200: no CUDA device visible and there is no CPU fallback")
@@ -346,10 +393,21 @@ class B200CoreLib(object):
         arr = np.frombuffer(owner.buf, dtype=dtype, count=int(n))
         return _PinnedArray(arr, owner)
 
+    def host_layer_layout_from_csc(self, W, C, bias):
+        """Host-only: the chunk layout the single-layer entry point builds from in-memory W / C (csc_matrix)."""
+        cw = ScipyCscF32.init_from(smat.csc_matrix(W, dtype=np.float32))
+        cc = ScipyCscF32.init_from(smat.csc_matrix(C, dtype=np.float32))
+        h = c_void_p(self.clib_float32.pb200_xlinear_host_from_csc(byref(cw), byref(cc), c_float(bias)))
+        return self._export_host_model(h)
+
     def host_model_layout(self, model_path, is_mmap=False):
         """Host-only: load a model folder and return its chunk layout per layer as numpy arrays (no GPU needed)."""
         c = self.clib_float32
         h = c_void_p(c.pb200_xlinear_host_load(model_path.encode("utf-8"), 1 if is_mmap else 0))
+        return self._export_host_model(h)
+
+    def _export_host_model(self, h):
+        c = self.clib_float32
         try:
             layers = []
             for d in range(c.pb200_xlinear_host_depth(h)):

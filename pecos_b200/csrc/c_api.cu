@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
+#include <vector>
 
 #include "hnsw_engine.h"
 #include "xlinear_engine.h"
@@ -157,6 +159,157 @@ void c_xlinear_predict_drm_f32(void* ptr, const ScipyDrmF32* X, const uint32_t o
                              overridden_only_topk);
     emit_result(r, pred_alloc);
     PB200_API_END("c_xlinear_predict_drm_f32")
+}
+
+// ------------------------------------------------ single layer (python chain) ------------------------------------
+}  // extern "C"
+
+namespace {
+
+// Cache of one-layer engines.  The python chain re-sends W and C with every call (pecos/xmc/base.py:934-944), and its
+// ctypes shim re-creates the index arrays each time, so pointers of col_ptr / row_idx are useless as identity: the key is
+// shape + nnz + value pointer + bias + a content fingerprint over strided samples of all five arrays.
+struct LayerKey {
+    uint32_t w_rows, w_cols, c_rows, c_cols;
+    uint64_t w_nnz, c_nnz;
+    const float* w_val;
+    uint32_t bias_bits;
+    uint64_t fingerprint;
+    bool operator==(const LayerKey& o) const {
+        return w_rows == o.w_rows && w_cols == o.w_cols && c_rows == o.c_rows && c_cols == o.c_cols && w_nnz == o.w_nnz &&
+               c_nnz == o.c_nnz && w_val == o.w_val && bias_bits == o.bias_bits && fingerprint == o.fingerprint;
+    }
+};
+
+inline uint64_t mix64(uint64_t h, uint64_t v) {
+    h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    return h;
+}
+
+template <typename T>
+uint64_t sample_hash(uint64_t h, const T* a, uint64_t n) {
+    if (n == 0) return mix64(h, 0x51ull);
+    const uint64_t samples = 4096;
+    const uint64_t step = n > samples ? n / samples : 1;
+    for (uint64_t i = 0; i < n; i += step) {
+        uint64_t v = 0;
+        std::memcpy(&v, &a[i], sizeof(T) < 8 ? sizeof(T) : 8);
+        h = mix64(h, v + i);
+    }
+    uint64_t v = 0;
+    std::memcpy(&v, &a[n - 1], sizeof(T) < 8 ? sizeof(T) : 8);
+    return mix64(h, v);
+}
+
+LayerKey make_layer_key(const ScipyCscF32* W, const ScipyCscF32* C, float bias) {
+    LayerKey k{};
+    k.w_rows = W->rows; k.w_cols = W->cols; k.c_rows = C->rows; k.c_cols = C->cols;
+    k.w_nnz = W->col_ptr[W->cols];
+    k.c_nnz = C->col_ptr[C->cols];
+    k.w_val = W->val;
+    std::memcpy(&k.bias_bits, &bias, 4);
+    uint64_t h = 0x0123456789ABCDEFull;
+    h = sample_hash(h, W->col_ptr, static_cast<uint64_t>(W->cols) + 1);
+    h = sample_hash(h, W->row_idx, k.w_nnz);
+    h = sample_hash(h, W->val, k.w_nnz);
+    h = sample_hash(h, C->col_ptr, static_cast<uint64_t>(C->cols) + 1);
+    h = sample_hash(h, C->row_idx, k.c_nnz);
+    k.fingerprint = h;
+    return k;
+}
+
+struct CachedLayer {
+    LayerKey key;
+    std::shared_ptr<XLinearHandle> handle;
+    uint64_t last_use;
+};
+
+std::mutex g_layer_cache_mutex;
+// heap-allocated and never destroyed: engines must not run CUDA calls from static destructors at process exit
+std::vector<CachedLayer>& g_layer_cache = *new std::vector<CachedLayer>();
+uint64_t g_layer_clock = 0, g_layer_hits = 0, g_layer_misses = 0;
+
+std::shared_ptr<XLinearHandle> layer_engine(const ScipyCscF32* W, const ScipyCscF32* C, float bias) {
+    if (!W || !C) throw std::runtime_error("single layer: W and C are required");
+    if (W->cols != C->rows) throw std::runtime_error("single layer: W.cols != C.rows");
+    const LayerKey key = make_layer_key(W, C, bias);
+    std::lock_guard<std::mutex> lock(g_layer_cache_mutex);
+    for (auto& e : g_layer_cache)
+        if (e.key == key) { e.last_use = ++g_layer_clock; ++g_layer_hits; return e.handle; }
+    ++g_layer_misses;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0)
+        throw std::runtime_error("no CUDA device visible: pecos_b200 has no CPU fallback");
+    size_t cap = 8;
+    if (const char* env = std::getenv("PB200_LAYER_CACHE")) cap = static_cast<size_t>(std::max(1, std::atoi(env)));
+    while (g_layer_cache.size() >= cap) {  // evict the least recently used engine (frees its HBM once callers are done)
+        size_t victim = 0;
+        for (size_t i = 1; i < g_layer_cache.size(); ++i)
+            if (g_layer_cache[i].last_use < g_layer_cache[victim].last_use) victim = i;
+        g_layer_cache.erase(g_layer_cache.begin() + static_cast<std::ptrdiff_t>(victim));
+    }
+    const pb200::CscRaw w{W->rows, W->cols, W->col_ptr, W->row_idx, W->val};
+    const pb200::CscRaw c{C->rows, C->cols, C->col_ptr, C->row_idx, C->val};
+    auto h = std::make_shared<XLinearHandle>();
+    h->engine = std::make_unique<pb200::XLinearEngine>(pb200::make_single_layer_model(w, c, bias), g_device.load());
+    g_layer_cache.push_back(CachedLayer{key, h, ++g_layer_clock});
+    return h;
+}
+
+void single_layer_predict(const ScipyCsrF32* Xs, const ScipyDrmF32* Xd, const ScipyCsrF32* codes, ScipyCscF32* W,
+                          ScipyCscF32* C, const char* pp, uint32_t only_topk, float bias, py_sparse_allocator_t pred_alloc) {
+    if (!pp) throw std::runtime_error("single layer: post_processor_str is required");
+    const uint32_t rows = Xs ? Xs->rows : Xd->rows;
+    const uint32_t cols = Xs ? Xs->cols : Xd->cols;
+    auto h = layer_engine(W, C, bias);
+    std::lock_guard<std::mutex> lock(h->mu);
+    auto& eng = *h->engine;
+    // MLModel::predict_internal checks (inference.hpp:2041-2051)
+    if (codes && codes->rows != rows) throw std::runtime_error("Instance dimension of query and prev_layer_pred matrix do not match");
+    if (codes && codes->cols != C->cols) throw std::runtime_error("Label dimension of prev_layer_pred and C matrix do not match");
+    if (Xd && cols != eng.host().nr_features()) throw std::runtime_error("dense query width != nr_features");
+    auto r = eng.predict_single_layer(Xs ? Xs->row_ptr : nullptr, Xs ? Xs->col_idx : nullptr, Xs ? Xs->val : nullptr,
+                                      Xd ? Xd->val : nullptr, rows, cols, codes ? codes->row_ptr : nullptr,
+                                      codes ? codes->col_idx : nullptr, codes ? codes->val : nullptr, pp, only_topk);
+    emit_result(r, pred_alloc);
+}
+
+}  // namespace
+
+extern "C" {
+
+void c_xlinear_single_layer_predict_csr_f32(const ScipyCsrF32* input_x, const ScipyCsrF32* csr_codes, ScipyCscF32* W,
+                                            ScipyCscF32* C, const char* post_processor_str, const uint32_t only_topk,
+                                            const int num_threads, const float bias, py_sparse_allocator_t pred_alloc) {
+    (void)num_threads;
+    PB200_API_BEGIN
+    single_layer_predict(input_x, nullptr, csr_codes, W, C, post_processor_str, only_topk, bias, pred_alloc);
+    PB200_API_END("c_xlinear_single_layer_predict_csr_f32")
+}
+
+void c_xlinear_single_layer_predict_drm_f32(const ScipyDrmF32* input_x, const ScipyCsrF32* csr_codes, ScipyCscF32* W,
+                                            ScipyCscF32* C, const char* post_processor_str, const uint32_t only_topk,
+                                            const int num_threads, const float bias, py_sparse_allocator_t pred_alloc) {
+    (void)num_threads;
+    PB200_API_BEGIN
+    single_layer_predict(nullptr, input_x, csr_codes, W, C, post_processor_str, only_topk, bias, pred_alloc);
+    PB200_API_END("c_xlinear_single_layer_predict_drm_f32")
+}
+
+uint32_t pb200_layer_cache_clear(void) {
+    PB200_API_BEGIN
+    std::lock_guard<std::mutex> lock(g_layer_cache_mutex);
+    const uint32_t n = static_cast<uint32_t>(g_layer_cache.size());
+    g_layer_cache.clear();
+    return n;
+    PB200_API_END("pb200_layer_cache_clear")
+}
+
+void pb200_layer_cache_info(uint64_t* out) {
+    PB200_API_BEGIN
+    std::lock_guard<std::mutex> lock(g_layer_cache_mutex);
+    out[0] = g_layer_cache.size(); out[1] = g_layer_hits; out[2] = g_layer_misses;
+    PB200_API_END("pb200_layer_cache_info")
 }
 
 // ------------------------------------------------ additions ------------------------------------------------------
@@ -329,6 +482,14 @@ void* pb200_xlinear_host_load(const char* model_path, int kind) {
                   : pb200::load_xlinear_npz_model(model_path, pb200::LT_BINARY_SEARCH_CHUNKED);
     return m.release();
     PB200_API_END("pb200_xlinear_host_load")
+}
+
+void* pb200_xlinear_host_from_csc(const ScipyCscF32* W, const ScipyCscF32* C, float bias) {
+    PB200_API_BEGIN
+    const pb200::CscRaw w{W->rows, W->cols, W->col_ptr, W->row_idx, W->val};
+    const pb200::CscRaw c{C->rows, C->cols, C->col_ptr, C->row_idx, C->val};
+    return pb200::make_single_layer_model(w, c, bias).release();
+    PB200_API_END("pb200_xlinear_host_from_csc")
 }
 
 void pb200_xlinear_host_free(void* hptr) { delete static_cast<pb200::XLinearHostModel*>(hptr); }

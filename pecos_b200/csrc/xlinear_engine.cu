@@ -1032,7 +1032,7 @@ void XLinearEngine::ensure_workspace_(const std::vector<LayerPlan>& plan, uint32
     for (size_t d = 0; d < plan.size(); ++d) {
         const uint64_t c = static_cast<uint64_t>(plan[d].b_prev) * std::max<uint32_t>(host_->layers[d].c_max, 1u);
         cand_max = std::max(cand_max, c);
-        beam_stride = std::max<uint64_t>(beam_stride, plan[d].k_cap);
+        beam_stride = std::max<uint64_t>(beam_stride, std::max<uint32_t>(plan[d].k_cap, plan[d].b_prev));
         if (c > static_cast<uint64_t>(kSortCap) && plan[d].k > static_cast<uint32_t>(kSortCap / 2)) sort_max = std::max<uint64_t>(sort_max, next_pow2_host(c));
     }
     beam_stride_ = static_cast<uint32_t>(beam_stride);
@@ -1046,18 +1046,24 @@ void XLinearEngine::ensure_workspace_(const std::vector<LayerPlan>& plan, uint32
 }
 
 // Runs every layer over one tile of queries.  The last layer writes into res_*_dev_ at row offset res_row0_.
-void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& plan, bool collect_stats) {
+// ext_beam: beam_*_[0] already hold the beam entering the first layer (single-layer entry point); combine_first: that
+// layer combines its scores with the beam values (a previous prediction was given).
+void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& plan, bool collect_stats, bool ext_beam,
+                              int combine_first) {
     const uint32_t rows = q.rows;
     if (rows == 0) return;
     const bool dense = (q.row_ptr == nullptr);
     int cur = 0;
-    xl_init_beam_kernel<<<(rows + 255) / 256, 256, 0, stream_>>>(beam_id_[cur].get(), beam_val_[cur].get(),
-                                                                 beam_cnt_[cur].get(), beam_stride_, rows);
-    ++launches_;
+    if (!ext_beam) {
+        xl_init_beam_kernel<<<(rows + 255) / 256, 256, 0, stream_>>>(beam_id_[cur].get(), beam_val_[cur].get(),
+                                                                     beam_cnt_[cur].get(), beam_stride_, rows);
+        ++launches_;
+    }
     const size_t depth = plan.size();
     for (size_t d = 0; d < depth; ++d) {
         const LayerDev& L = layers_[d].view;
         const LayerPlan& lp = plan[d];
+        const int combine = (d == 0) ? combine_first : 1;
         const uint32_t c_stride = std::max<uint32_t>(L.c_max, 1u);
         const uint64_t cand_stride_q = static_cast<uint64_t>(lp.b_prev) * c_stride;
         // spread the beam slots evenly: b = 10 -> 10 warps x 1 slot, b = 20 -> 10 warps x 2 slots
@@ -1140,17 +1146,17 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
             const uint32_t key_cap = static_cast<uint32_t>((cand_stride_q + 127) & ~static_cast<uint64_t>(127));
             const size_t flt_smem = kFltWarps * flt_warp_bytes(key_cap);
             xl_topk_filter_kernel<<<(rows + kFltWarps - 1) / kFltWarps, kFltWarps * 32, flt_smem, stream_>>>(
-                L, lp.pp.kind, lp.pp.p, d == 0 ? 0 : 1, lp.k, beam_id_[cur].get(), beam_val_[cur].get(), beam_cnt_[cur].get(),
+                L, lp.pp.kind, lp.pp.p, combine, lp.k, beam_id_[cur].get(), beam_val_[cur].get(), beam_cnt_[cur].get(),
                 beam_stride_, cand_.get(), cand_stride_q, o_id, o_val, o_cnt, o_stride, rows, stats, o_key, key_cap);
         } else if (warp_select) {
             const uint32_t key_cap = static_cast<uint32_t>((cand_stride_q + 31) & ~static_cast<uint64_t>(31));
             const size_t sel_smem = kSelWarps * ((sel_warp_bytes(key_cap) + 15) & ~static_cast<size_t>(15));
             xl_topk_warp_kernel<<<(rows + kSelWarps - 1) / kSelWarps, kSelWarps * 32, sel_smem, stream_>>>(
-                L, lp.pp.kind, lp.pp.p, d == 0 ? 0 : 1, lp.k, beam_id_[cur].get(), beam_val_[cur].get(), beam_cnt_[cur].get(),
+                L, lp.pp.kind, lp.pp.p, combine, lp.k, beam_id_[cur].get(), beam_val_[cur].get(), beam_cnt_[cur].get(),
                 beam_stride_, cand_.get(), cand_stride_q, c_stride, o_id, o_val, o_cnt, o_stride, rows, stats, o_key, key_cap);
         } else {
             xl_topk_kernel<<<grid, kTopkThreads, topk_kernel_smem(lp.b_prev), stream_>>>(
-                L, lp.pp.kind, lp.pp.p, d == 0 ? 0 : 1, lp.k, beam_id_[cur].get(), beam_val_[cur].get(), beam_cnt_[cur].get(),
+                L, lp.pp.kind, lp.pp.p, combine, lp.k, beam_id_[cur].get(), beam_val_[cur].get(), beam_cnt_[cur].get(),
                 beam_stride_, cand_.get(), cand_stride_q, c_stride, o_id, o_val, o_cnt, o_stride, sortbuf_.get(), sort_stride,
                 lp.b_prev, stats, o_key);
         }
@@ -1263,6 +1269,88 @@ XLinearEngine::Result XLinearEngine::predict_drm(const float* dense, uint32_t ro
         res_rows_ = r0;
         run_tile_(q, plan, false);
         if (r0 + tr < rows) PB200_CUDA(cudaStreamSynchronize(stream_));
+    }
+    return finish_result_(rows, stride);
+}
+
+XLinearEngine::Result XLinearEngine::predict_single_layer(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val,
+                                                          const float* dense, uint32_t rows, uint32_t cols,
+                                                          const uint64_t* codes_row_ptr, const uint32_t* codes_col_idx,
+                                                          const float* codes_val, const char* post_processor,
+                                                          uint32_t only_topk) {
+    PB200_CUDA(cudaSetDevice(device_));
+    if (host_->layers.size() != 1) throw std::runtime_error("pecos_b200: predict_single_layer needs a one-layer model");
+    const auto& HL = host_->layers[0];
+    const bool have_codes = codes_row_ptr != nullptr;
+    // beam entering the layer: the given previous prediction, or every parent with value 1 (libpecos.cpp:209-219)
+    uint32_t b_prev = have_codes ? 1u : std::max<uint32_t>(HL.n_chunks, 1u);
+    if (have_codes) {
+        for (uint32_t r = 0; r < rows; ++r)
+            b_prev = std::max<uint32_t>(b_prev, static_cast<uint32_t>(std::min<uint64_t>(codes_row_ptr[r + 1] - codes_row_ptr[r], 0xFFFFFFFFull)));
+        const uint64_t n = codes_row_ptr[rows] - codes_row_ptr[0];
+        for (uint64_t i = 0; i < n; ++i)
+            if (codes_col_idx[codes_row_ptr[0] + i] >= HL.n_chunks)
+                throw std::runtime_error("pecos_b200: csr_codes column index >= C.cols");
+    }
+    std::vector<LayerPlan> plan(1);
+    plan[0].k = only_topk;  // only_topk_to_use = overridden > 0 ? overridden : metadata.only_topk, both = this argument
+    plan[0].pp = parse_post_processor(post_processor ? post_processor : HL.post_processor_name.c_str());
+    plan[0].b_prev = b_prev;
+    const uint64_t cand_max = static_cast<uint64_t>(b_prev) * std::max<uint32_t>(HL.c_max, 1u);
+    plan[0].k_cap = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(only_topk, cand_max)));
+    if (topk_kernel_smem(b_prev) > 200u * 1024u || b_prev > 32768u)
+        throw std::runtime_error("pecos_b200: beam of " + std::to_string(b_prev) + " nodes exceeds the supported maximum");
+    const uint32_t stride = plan[0].k_cap;
+    res_stride_ = stride;
+    res_ids_dev_.reserve(static_cast<uint64_t>(rows) * stride + 1);
+    res_vals_dev_.reserve(static_cast<uint64_t>(rows) * stride + 1);
+    res_cnt_dev_.reserve(static_cast<uint64_t>(rows) + 1);
+    if (only_topk == 0) {  // sorted_csr keeps min(nnz, 0) entries per row (inference.hpp:1237)
+        if (rows) PB200_CUDA(cudaMemsetAsync(res_cnt_dev_.get(), 0, static_cast<uint64_t>(rows) * 4, stream_));
+        return finish_result_(rows, stride);
+    }
+    uint32_t tile = pick_tile_rows_(plan, rows);
+    if (dense) {
+        const uint64_t max_dense_rows = std::max<uint64_t>(1, (4ull << 30) / (static_cast<uint64_t>(std::max<uint32_t>(cols, 1u)) * 4));
+        tile = static_cast<uint32_t>(std::min<uint64_t>(tile, max_dense_rows));
+    }
+    ensure_workspace_(plan, tile);
+    beam_id_host_.reserve(static_cast<uint64_t>(tile) * beam_stride_ + 1);
+    beam_val_host_.reserve(static_cast<uint64_t>(tile) * beam_stride_ + 1);
+    beam_cnt_host_.reserve(static_cast<uint64_t>(tile) + 1);
+    for (uint32_t r0 = 0; r0 < rows; r0 += tile) {
+        const uint32_t tr = std::min(tile, rows - r0);
+        for (uint32_t r = 0; r < tr; ++r) {
+            uint32_t* ids = beam_id_host_.get() + static_cast<uint64_t>(r) * beam_stride_;
+            float* vals = beam_val_host_.get() + static_cast<uint64_t>(r) * beam_stride_;
+            if (have_codes) {
+                const uint64_t b = codes_row_ptr[r0 + r], e = codes_row_ptr[r0 + r + 1];
+                const uint32_t n = static_cast<uint32_t>(e - b);
+                std::memcpy(ids, codes_col_idx + b, static_cast<size_t>(n) * 4);
+                std::memcpy(vals, codes_val + b, static_cast<size_t>(n) * 4);
+                beam_cnt_host_.get()[r] = n;
+            } else {
+                for (uint32_t j = 0; j < HL.n_chunks; ++j) { ids[j] = j; vals[j] = 1.0f; }
+                beam_cnt_host_.get()[r] = HL.n_chunks;
+            }
+        }
+        PB200_CUDA(cudaMemcpyAsync(beam_id_[0].get(), beam_id_host_.get(), static_cast<uint64_t>(tr) * beam_stride_ * 4, cudaMemcpyHostToDevice, stream_));
+        PB200_CUDA(cudaMemcpyAsync(beam_val_[0].get(), beam_val_host_.get(), static_cast<uint64_t>(tr) * beam_stride_ * 4, cudaMemcpyHostToDevice, stream_));
+        PB200_CUDA(cudaMemcpyAsync(beam_cnt_[0].get(), beam_cnt_host_.get(), static_cast<uint64_t>(tr) * 4, cudaMemcpyHostToDevice, stream_));
+        QueryDev q{};
+        if (dense) {
+            x_val_.upload(dense + static_cast<uint64_t>(r0) * cols, static_cast<uint64_t>(tr) * cols, stream_);
+            q = QueryDev{nullptr, nullptr, x_val_.get(), 0, tr, cols, cols};
+        } else {
+            const uint64_t base = row_ptr[r0], end = row_ptr[r0 + tr];
+            x_row_ptr_.upload(row_ptr + r0, static_cast<uint64_t>(tr) + 1, stream_);
+            x_col_idx_.upload(col_idx + base, end - base, stream_);
+            x_val_.upload(val + base, end - base, stream_);
+            q = QueryDev{x_row_ptr_.get(), x_col_idx_.get(), x_val_.get(), base, tr, cols, max_row_nnz(row_ptr + r0, tr)};
+        }
+        res_rows_ = r0;
+        run_tile_(q, plan, false, /*ext_beam=*/true, /*combine_first=*/have_codes ? 1 : 0);
+        PB200_CUDA(cudaStreamSynchronize(stream_));  // the pinned beam staging area is refilled by the next tile
     }
     return finish_result_(rows, stride);
 }

@@ -87,6 +87,13 @@ public:
     Result predict_drm(const float* dense, uint32_t rows, uint32_t cols, uint32_t beam_size, const char* post_processor,
                        uint32_t only_topk);
 
+    // One layer of the python prediction chain (c_xlinear_single_layer_predict_*, pecos/core/libpecos.cpp:201-235): the
+    // engine must hold a one-layer model.  Queries: CSR (row_ptr != nullptr) or row-major dense.  codes_*: the previous
+    // layer's prediction as CSR rows x n_chunks, consumed in stored order (nullptr: ones(rows x n_chunks), no combine).
+    Result predict_single_layer(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, const float* dense,
+                                uint32_t rows, uint32_t cols, const uint64_t* codes_row_ptr, const uint32_t* codes_col_idx,
+                                const float* codes_val, const char* post_processor, uint32_t only_topk);
+
     // Device-resident queries (bench "value" leg: inputs already in HBM when the timed region starts).
     void resident_upload_csr(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, uint32_t rows, uint32_t cols);
     // Runs all layers over the resident batch; results stay in HBM (fetch with resident_fetch). Returns device ms.
@@ -133,7 +140,8 @@ private:
     std::vector<LayerPlan> make_plan_(uint32_t beam_size, const char* post_processor, uint32_t only_topk) const;
     void ensure_workspace_(const std::vector<LayerPlan>& plan, uint32_t tile_rows);
     uint32_t pick_tile_rows_(const std::vector<LayerPlan>& plan, uint32_t rows) const;
-    void run_tile_(const QueryDev& q, const std::vector<LayerPlan>& plan, bool collect_stats);
+    void run_tile_(const QueryDev& q, const std::vector<LayerPlan>& plan, bool collect_stats, bool ext_beam = false,
+                   int combine_first = 0);
     Result finish_result_(uint32_t rows, uint32_t stride);
 
     std::unique_ptr<XLinearHostModel> host_;
@@ -164,6 +172,9 @@ private:
     cudaEvent_t up_ev_[2] = {nullptr, nullptr};   // staging set uploaded
     cudaEvent_t use_ev_[2] = {nullptr, nullptr};  // staging set consumed by the score kernels
     bool pipeline_uploads_ = true;
+    PinnedBuffer<uint32_t> beam_id_host_;   // single-layer entry point: the given beam, staged per tile
+    PinnedBuffer<float> beam_val_host_;
+    PinnedBuffer<uint32_t> beam_cnt_host_;
     uint32_t pipeline_parts_ = 4;
     QueryDev resident_{};
     bool has_resident_ = false;

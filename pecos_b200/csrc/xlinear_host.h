@@ -433,6 +433,47 @@ inline void load_npz_layer(const std::string& folder, uint32_t depth, ChunkedLay
     apply_meta(meta, L);
 }
 
+// One-layer model from in-memory CSC matrices (c_xlinear_single_layer_predict_*: the python prediction chain hands W and
+// C of a layer to the native side on every call, pecos/core/libpecos.cpp:201-235).  The arrays are copied.
+struct CscRaw {
+    uint32_t rows, cols;
+    const uint64_t* col_ptr;
+    const uint32_t* row_idx;
+    const float* val;
+};
+
+inline CscHost copy_csc(const CscRaw& A) {
+    if (A.cols && !A.col_ptr) throw std::runtime_error("single layer: null col_ptr");
+    CscHost H;
+    H.rows = A.rows;
+    H.cols = A.cols;
+    H.col_ptr.assign(A.col_ptr, A.col_ptr + static_cast<size_t>(A.cols) + 1);
+    const uint64_t nnz = H.col_ptr[A.cols];
+    if (H.col_ptr[0] != 0) throw std::runtime_error("single layer: col_ptr[0] != 0");
+    for (uint32_t c = 0; c < A.cols; ++c)
+        if (H.col_ptr[c] > H.col_ptr[c + 1]) throw std::runtime_error("single layer: col_ptr is not monotone");
+    H.row_idx.assign(A.row_idx, A.row_idx + nnz);
+    H.val.assign(A.val, A.val + nnz);
+    for (uint64_t i = 0; i < nnz; ++i)
+        if (H.row_idx[i] >= A.rows) throw std::runtime_error("single layer: row index out of range");
+    return H;
+}
+
+inline std::unique_ptr<XLinearHostModel> make_single_layer_model(const CscRaw& W, const CscRaw& C, float bias) {
+    auto m = std::make_unique<XLinearHostModel>();
+    m->layer_type = LT_CSC;  // what the reference instantiates here: MLModel<csc_t> (same results)
+    m->layers.resize(1);
+    const CscHost Wh = copy_csc(W);
+    const CscHost Ch = copy_csc(C);
+    build_chunked_layer(Wh, Ch, bias, m->layers[0]);
+    LayerMeta meta;
+    meta.bias = bias;
+    apply_meta(meta, m->layers[0]);
+    m->leaf_chunk_begin = 0;
+    m->leaf_chunk_end = m->layers[0].n_chunks;
+    return m;
+}
+
 // Compiled layer: W.mmap_store already holds the reference's chunked arrays; we only re-pack them.
 inline void load_mmap_layer(const std::string& folder, bool lazy_load, ChunkedLayerHost& L) {
     LayerMeta meta = load_layer_meta(folder + "/param.json");

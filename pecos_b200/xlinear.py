@@ -7,8 +7,12 @@ Same names, argument meaning and error behaviour as the reference for the predic
 * ``HierarchicalMLModel.load / predict`` (predict-only branch) ....................... pecos/xmc/base.py:1326-1369, :1577-1668
 * ``PredParams.override_with_kwargs`` ............................................... pecos/xmc/base.py:1140-1173
 
-Training, pruning, ``predict_on_selected_outputs`` and the Python-chain (``is_predict_only=False``) stay on the
-reference CPU library; they are outside this engine's scope and raise ``NotImplementedError`` here.
+* ``MLModel.load / predict`` (one layer of the python chain, ``is_predict_only=False``) .. pecos/xmc/base.py:832-878, :890-949
+
+Training, pruning and ``predict_on_selected_outputs`` stay on the reference CPU library; they are outside this engine's
+scope and raise ``NotImplementedError`` here.  The python chain (``MLModel``, ``is_predict_only=False``) was written at the
+end of round 1 without GPU time left: its oracle is pinned on the CPU side, its GPU tests are opt-in
+(``PB200_UNVALIDATED=1``).
 """
 import copy
 import dataclasses as dc
@@ -64,6 +68,110 @@ class HierarchicalPredParams(object):
         return self
 
 
+class MLModel(object):
+    """One layer of the python prediction chain (pecos/xmc/base.py:598-949): holds ``W`` ((nr_features [+1]) x nr_labels,
+    csc) and ``C`` (nr_labels x nr_codes, csc) on the host like the reference and predicts through
+    ``c_xlinear_single_layer_predict_*``; the native side keeps the layer's chunked HBM layout in an LRU cache."""
+
+    PredParams = MLModelPredParams
+
+    def __init__(self, W, C=None, bias=-1.0, pred_params=None, **kwargs):
+        if C is not None:
+            if isinstance(C, smat.csr_matrix):
+                C = C.tocsc()
+            elif not isinstance(C, smat.csc_matrix):
+                raise ValueError(f"type(C)={type(C)} is not supported")
+        else:
+            C = smat.csc_matrix(np.ones((W.shape[1], 1), dtype=W.dtype))  # pecos/xmc/base.py:632-634
+        self.W = smat.csc_matrix(W, dtype=np.float32)
+        self.W.sort_indices()
+        self.C = smat.csc_matrix(C, dtype=np.float32)
+        self.bias = float(bias)
+        self.pred_params = self.PredParams() if pred_params is None else pred_params
+        if self.C.shape[0] != self.W.shape[1]:
+            raise ValueError("C.shape[0] != W.shape[1]")
+        self._clib = get_clib()
+
+    @property
+    def nr_labels(self):
+        return self.W.shape[1]
+
+    @property
+    def nr_codes(self):
+        return self.C.shape[1]
+
+    @property
+    def nr_features(self):
+        return self.W.shape[0] - (1 if self.bias > 0 else 0)
+
+    @classmethod
+    def load(cls, folder):
+        """A ``<d>.model`` folder written by the reference's ``MLModel.save`` (param.json, W.npz, C.npz)."""
+        param = json.loads(open(f"{folder}/param.json", "r", encoding="utf-8").read())
+        assert param["model"] == "MLModel"
+        W = smat.load_npz(f"{folder}/W.npz").tocsc().astype(np.float32)
+        C = smat.load_npz(f"{folder}/C.npz").tocsc().astype(np.float32) if path.exists(f"{folder}/C.npz") else None
+        return cls(W, C, float(param["bias"]), MLModelPredParams.from_layer_folder(folder))
+
+    def get_pred_params(self):
+        return copy.deepcopy(self.pred_params)
+
+    def predict(self, X, csr_codes=None, pred_params=None, **kwargs):
+        if X.shape[1] != self.nr_features:
+            raise ValueError("Feature dimension of query matrix does not match weight matrix")
+        pred_params = self.get_pred_params() if pred_params is None else copy.deepcopy(pred_params)
+        if kwargs.get("only_topk", None):
+            pred_params.only_topk = kwargs["only_topk"]
+        if kwargs.get("post_processor", None):
+            pred_params.post_processor = kwargs["post_processor"]
+        if isinstance(X, smat.csr_matrix) and not X.has_sorted_indices:
+            raise ValueError("Query matrix does not have sorted indices!")
+        pred_alloc = ScipyCompressedSparseAllocator()
+        self._clib.xlinear_single_layer_predict(
+            X,
+            csr_codes,
+            self.W,
+            self.C,
+            pred_params.post_processor,
+            pred_params.only_topk if pred_params.only_topk else 0,
+            kwargs.get("threads", -1),
+            self.bias,
+            pred_alloc,
+        )
+        return pred_alloc.get()
+
+
+class _PythonChain(object):
+    """``HierarchicalMLModel`` with ``is_predict_only=False``: a list of ``MLModel`` (pecos/xmc/base.py:1669-1679)."""
+
+    PredParams = HierarchicalPredParams
+
+    def __init__(self, chain):
+        self.model_chain = chain
+        self.is_predict_only = False
+
+    depth = property(lambda self: len(self.model_chain))
+    nr_features = property(lambda self: self.model_chain[0].nr_features)
+    nr_labels = property(lambda self: self.model_chain[-1].nr_labels)
+    nr_codes = property(lambda self: self.model_chain[-1].nr_codes)
+
+    def get_pred_params(self):
+        return self.PredParams(model_chain=[m.get_pred_params() for m in self.model_chain])
+
+    def predict(self, X, csr_codes=None, pred_params=None, **kwargs):
+        assert X.dtype == np.float32
+        if pred_params is None:
+            pred_params = self.get_pred_params()
+        else:
+            pred_params = copy.deepcopy(pred_params)
+        pred_params.override_with_kwargs(kwargs)
+        pred_csr = csr_codes
+        for d in range(self.depth):
+            pred_csr = self.model_chain[d].predict(X, csr_codes=pred_csr, pred_params=pred_params.model_chain[d],
+                                                   threads=kwargs.get("threads", -1))
+        return pred_csr
+
+
 class HierarchicalMLModel(object):
     """Predict-only ``HierarchicalMLModel`` whose layers live in HBM behind an opaque C handle."""
 
@@ -105,14 +213,14 @@ class HierarchicalMLModel(object):
 
     @classmethod
     def load(cls, model_folder, is_predict_only=True, **kwargs):
-        if not is_predict_only:
-            raise NotImplementedError(
-                "pecos_b200 only serves is_predict_only=True models; use the reference library for the Python chain"
-            )
         clib = get_clib()
         param = json.loads(open(f"{model_folder}/param.json", "r", encoding="utf-8").read())
         assert param["model"] == "HierarchicalMLModel"
         depth = int(param.get("depth", len(glob("{}/*.model".format(model_folder)))))
+        if not is_predict_only:
+            if bool(param.get("is_mmap", False)):
+                raise NotImplementedError("mmap single-layer handles (c_mlmodel_*) stay on the reference library")
+            return _PythonChain([MLModel.load(f"{model_folder}/{d}.model") for d in range(depth)])
         is_mmap = bool(param.get("is_mmap", False))
         if is_mmap:
             model = clib.xlinear_load_mmap(model_folder, **kwargs)
@@ -203,7 +311,7 @@ class XLinearModel(object):
 
     @property
     def is_predict_only(self):
-        return True
+        return self.model.is_predict_only
 
     @classmethod
     def load(cls, model_folder, is_predict_only=True, **kwargs):

@@ -39,8 +39,12 @@ def test_no_gpu_means_loud_failure_not_fallback(clib, tmp_path):
 
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         XLinearModel.load(os.path.join(GOLD, "model"), is_predict_only=True)
-    with pytest.raises(NotImplementedError):
-        XLinearModel.load(os.path.join(GOLD, "model"), is_predict_only=False)
+    # the python chain keeps W / C on the host like the reference (loading needs no GPU), predicting raises loudly
+    chain = XLinearModel.load(os.path.join(GOLD, "model"), is_predict_only=False)
+    assert not chain.is_predict_only and chain.depth >= 1
+    X = np.zeros((1, chain.nr_features), dtype=np.float32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        chain.predict(X)
 
 
 def test_product_never_imports_the_oracle():
@@ -169,3 +173,21 @@ def test_ctypes_views_keep_reference_struct_layout():
     assert (v.rows, v.cols) == (5, 20) and v.indptr[5] == X.nnz
     with pytest.raises(ValueError):
         ScipyCsrF32.init_from(X.astype(np.float64))
+
+
+@pytest.mark.parametrize("permute,prune,bias", [(False, 0.0, 1.0), (True, 0.3, 1.0), (False, 0.0, -1.0)])
+def test_single_layer_model_from_in_memory_csc_equals_the_folder_loader(clib, tmp_path, permute, prune, bias):
+    """c_xlinear_single_layer_predict_* receives W and C as in-memory CSC matrices (pecos/core/libpecos.cpp:201-235); the
+    one-layer host model built from them must be the layer the npz loader builds."""
+    folder = str(tmp_path / "m")
+    layers = random_tree(13, [4, 18, 120], 90, 10, bias=bias, permute=permute, prune=prune)
+    synth.save_xlinear_model(folder, layers, bias=bias, only_topk=4)
+    from_folder = clib.host_model_layout(os.path.join(folder, "ranker"))
+    for d, (W, C) in enumerate(layers):
+        got = clib.host_layer_layout_from_csc(W, C, bias)
+        assert len(got) == 1
+        for k in ("w_rows", "n_cols", "out_cols", "n_chunks", "c_max"):
+            assert got[0][k] == from_folder[d][k], k
+        for k in ("chunks", "meta", "entries", "label_of_col"):
+            assert np.array_equal(got[0][k], from_folder[d][k]), k
+    _check_layout([clib.host_layer_layout_from_csc(*layers[-1], bias)[0]], [layers[-1][0]], [layers[-1][1]], bias)
