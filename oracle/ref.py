@@ -44,6 +44,11 @@ def lib():
         L.c_xlinear_predict_csr_f32.argtypes = [c_void_p, POINTER(ScipyCsrF32)] + pred
         L.c_xlinear_predict_drm_f32.restype = None
         L.c_xlinear_predict_drm_f32.argtypes = [c_void_p, POINTER(ScipyDrmF32)] + pred
+        sel = [POINTER(ScipyCsrF32), c_char_p, c_int, ScipyCompressedSparseAllocator.CFUNCTYPE]  # pecos/core/base.py:846-876
+        L.c_xlinear_predict_on_selected_outputs_csr_f32.restype = None
+        L.c_xlinear_predict_on_selected_outputs_csr_f32.argtypes = [c_void_p, POINTER(ScipyCsrF32)] + sel
+        L.c_xlinear_predict_on_selected_outputs_drm_f32.restype = None
+        L.c_xlinear_predict_on_selected_outputs_drm_f32.argtypes = [c_void_p, POINTER(ScipyDrmF32)] + sel
         single = [POINTER(ScipyCsrF32), POINTER(ScipyCscF32), POINTER(ScipyCscF32), c_char_p, c_uint32, c_int, c_float,
                   ScipyCompressedSparseAllocator.CFUNCTYPE]  # pecos/core/base.py:880-905
         L.c_xlinear_single_layer_predict_csr_f32.restype = None
@@ -112,6 +117,23 @@ class RefXLinear(object):
             cx = ScipyDrmF32.init_from(np.ascontiguousarray(X, dtype=np.float32))
             L.c_xlinear_predict_drm_f32(self.h, byref(cx), beam_size or 0, pp, only_topk or 0, threads, alloc.cfunc)
         return alloc.get()
+
+
+def predict_on_selected_outputs(model, X, selected_outputs_csr, post_processor=None, threads=-1):
+    """c_xlinear_predict_on_selected_outputs_{csr,drm}_f32 (pecos/core/libpecos.cpp:179-198); `model` must be a RefXLinear
+    loaded with weight_matrix_type="CSC" (inference.hpp:2143-2147)."""
+    L = lib()
+    alloc = ScipyCompressedSparseAllocator()
+    cs = ScipyCsrF32.init_from(smat.csr_matrix(selected_outputs_csr, dtype=np.float32))
+    pp = post_processor.encode() if post_processor else None
+    if isinstance(X, smat.csr_matrix):
+        assert X.has_sorted_indices
+        cx = ScipyCsrF32.init_from(X)
+        L.c_xlinear_predict_on_selected_outputs_csr_f32(model.h, byref(cx), byref(cs), pp, threads, alloc.cfunc)
+    else:
+        cx = ScipyDrmF32.init_from(np.ascontiguousarray(X, dtype=np.float32))
+        L.c_xlinear_predict_on_selected_outputs_drm_f32(model.h, byref(cx), byref(cs), pp, threads, alloc.cfunc)
+    return alloc.get()
 
 
 def single_layer_predict(X, csr_codes, W, C, post_processor, only_topk, bias, threads=-1):

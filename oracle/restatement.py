@@ -39,6 +39,9 @@ def lib():
         L.xlo_predict_from.restype = c_int
         L.xlo_predict_from.argtypes = [c_int, POINTER(_Csc), POINTER(_Csc), POINTER(c_float), POINTER(c_int), POINTER(c_int),
                                        POINTER(c_uint32), POINTER(_Query), POINTER(_Query), POINTER(_Result)]
+        L.xlo_predict_selected.restype = c_int
+        L.xlo_predict_selected.argtypes = [c_int, POINTER(_Csc), POINTER(_Csc), POINTER(c_float), POINTER(c_int), POINTER(c_int),
+                                           POINTER(_Query), POINTER(_Query), POINTER(_Result)]
         L.xlo_free_result.restype = None
         L.xlo_free_result.argtypes = [POINTER(_Result)]
         _lib = L
@@ -147,6 +150,26 @@ class OracleXLinear(object):
         s.row_idx = ix.ctypes.data_as(POINTER(c_uint32))
         s.val = dv.ctypes.data_as(POINTER(c_float))
         return s
+
+    def predict_on_selected_outputs(self, X, selected_outputs_csr, post_processor=None):
+        """Restatement of c_xlinear_predict_on_selected_outputs_* (pecos/core/libpecos.cpp:179-198)."""
+        L = lib()
+        keep = []
+        D = self.depth
+        Ws = (_Csc * D)(*[self._csc_struct(l["W"], keep) for l in self.layers])
+        Cs = (_Csc * D)(*[self._csc_struct(l["C"], keep) for l in self.layers])
+        bias = (c_float * D)(*[l["bias"] for l in self.layers])
+        kinds, ps = [], []
+        for l in self.layers:
+            kind, p = parse_post_processor(post_processor if post_processor else l["post_processor"])
+            kinds.append(kind)
+            ps.append(p)
+        q = _query_struct(X, keep)
+        sel = _query_struct(smat.csr_matrix(selected_outputs_csr, dtype=np.float32), keep)
+        res = _Result()
+        rc = L.xlo_predict_selected(D, Ws, Cs, bias, (c_int * D)(*kinds), (c_int * D)(*ps), byref(q), byref(sel), byref(res))
+        assert rc == 0
+        return _take_result(L, res)
 
     def predict(self, X, beam_size=0, post_processor=None, only_topk=0):
         L = lib()

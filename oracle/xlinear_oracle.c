@@ -11,6 +11,7 @@
  * (paths relative to the reference checkout):
  *
  *   xlo_predict ................ HierarchicalMLModel::predict       pecos/core/xmc/inference.hpp:2446-2488
+ *   xlo_predict_selected ....... HierarchicalMLModel::predict_on_selected_outputs  inference.hpp:2507-2571, :2129-2180, :1302-1358
  *   xlo_predict_from ........... c_xlinear_single_layer_predict_*   pecos/core/libpecos.cpp:201-235 (given previous beam)
  *   layer_predict .............. MLModel::predict_internal          pecos/core/xmc/inference.hpp:2029-2080
  *   candidates (prolongation) .. prolongate_predictions             pecos/core/xmc/inference.hpp:1155-1219
@@ -243,6 +244,110 @@ int xlo_predict_from(int depth, const xlo_csc_t* W, const xlo_csc_t* C, const fl
 int xlo_predict(int depth, const xlo_csc_t* W, const xlo_csc_t* C, const float* bias, const int* pp_kind,
                 const int* pp_p, const uint32_t* only_topk, const xlo_query_t* X, xlo_result_t* out) {
     return xlo_predict_from(depth, W, C, bias, pp_kind, pp_p, only_topk, X, NULL, out);
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * predict_on_selected_outputs (next scope row): score exactly the given (query, label) pairs through the
+ * hierarchy, no top-k.  Restates HierarchicalMLModel::predict_on_selected_outputs (inference.hpp:2507-2571), per layer
+ * MLModel::predict_on_selected_outputs_internal (:2129-2180) with prolongate_sparse_predictions (:1302-1358).
+ *   - selected set of layer l-1 = parents (through C[l]) of the selected set of layer l, as a SORTED set (smat_x_smat with
+ *     sorted output, :2531-2540);
+ *   - entries of a row at layer l: for every entry of the previous layer's row, in order, its children in C's column
+ *     order that belong to the layer's selected set;
+ *   - score = CSC path (bias term + sparse dot product, :1019-1035) == score_sparse bit for bit (float add commutes);
+ *     transform, then combine with the parent's value except at layer 0.
+ * selected: CSR pattern rows x n_labels (values ignored, column indices unique per row).
+ * --------------------------------------------------------------------------------------------------------------- */
+static int cmp_u32(const void* a, const void* b) {
+    const uint32_t x = *(const uint32_t*)a, y = *(const uint32_t*)b;
+    return (x > y) - (x < y);
+}
+
+static int sorted_contains(const uint32_t* a, uint32_t n, uint32_t key) {
+    const uint32_t t = lower_bound_u32(a, n, key);
+    return t < n && a[t] == key;
+}
+
+int xlo_predict_selected(int depth, const xlo_csc_t* W, const xlo_csc_t* C, const float* bias, const int* pp_kind,
+                         const int* pp_p, const xlo_query_t* X, const xlo_query_t* selected, xlo_result_t* out) {
+    const uint32_t Q = X->rows;
+    /* child -> parent maps */
+    uint32_t** parent_of = (uint32_t**)calloc((size_t)depth, sizeof(uint32_t*));
+    for (int d = 0; d < depth; ++d) {
+        parent_of[d] = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(C[d].rows ? C[d].rows : 1));
+        for (uint32_t r = 0; r < C[d].rows; ++r) parent_of[d][r] = 0xFFFFFFFFu;
+        for (uint32_t p = 0; p < C[d].cols; ++p)
+            for (uint64_t j = C[d].col_ptr[p]; j < C[d].col_ptr[p + 1]; ++j) parent_of[d][C[d].row_idx[j]] = p;
+    }
+    uint64_t* res_ptr = (uint64_t*)malloc(sizeof(uint64_t) * ((size_t)Q + 1));
+    memcpy(res_ptr, selected->row_ptr, sizeof(uint64_t) * ((size_t)Q + 1));
+    const uint64_t total = res_ptr[Q];
+    uint32_t* res_id = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(total ? total : 1));
+    float* res_val = (float*)malloc(sizeof(float) * (size_t)(total ? total : 1));
+    for (uint32_t q = 0; q < Q; ++q) {
+        const uint32_t n_leaf = (uint32_t)(selected->row_ptr[q + 1] - selected->row_ptr[q]);
+        /* selected sets per layer (sorted, unique) */
+        uint32_t** sel = (uint32_t**)calloc((size_t)depth, sizeof(uint32_t*));
+        uint32_t* sel_n = (uint32_t*)calloc((size_t)depth, sizeof(uint32_t));
+        sel[depth - 1] = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(n_leaf ? n_leaf : 1));
+        memcpy(sel[depth - 1], selected->col_idx + selected->row_ptr[q], sizeof(uint32_t) * n_leaf);
+        qsort(sel[depth - 1], n_leaf, sizeof(uint32_t), cmp_u32);
+        sel_n[depth - 1] = n_leaf;
+        for (int d = depth - 1; d > 0; --d) {
+            sel[d - 1] = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(sel_n[d] ? sel_n[d] : 1));
+            uint32_t m = 0;
+            for (uint32_t i = 0; i < sel_n[d]; ++i) {
+                const uint32_t par = parent_of[d][sel[d][i]];
+                if (par != 0xFFFFFFFFu) sel[d - 1][m++] = par;
+            }
+            qsort(sel[d - 1], m, sizeof(uint32_t), cmp_u32);
+            uint32_t u = 0;
+            for (uint32_t i = 0; i < m; ++i) if (i == 0 || sel[d - 1][i] != sel[d - 1][i - 1]) sel[d - 1][u++] = sel[d - 1][i];
+            sel_n[d - 1] = u;
+        }
+        const uint32_t* qidx = NULL; const float* qval = NULL; uint32_t qn = 0; const float* xd = NULL;
+        if (X->row_ptr) {
+            qidx = X->col_idx + X->row_ptr[q]; qval = X->val + X->row_ptr[q];
+            qn = (uint32_t)(X->row_ptr[q + 1] - X->row_ptr[q]);
+        } else {
+            xd = X->val + (size_t)q * X->cols;
+        }
+        uint32_t prev_n = 1;
+        uint32_t* prev_id = (uint32_t*)malloc(sizeof(uint32_t));
+        float* prev_val = (float*)malloc(sizeof(float));
+        prev_id[0] = 0; prev_val[0] = 1.0f;
+        for (int d = 0; d < depth; ++d) {
+            uint32_t* cur_id = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(sel_n[d] ? sel_n[d] : 1));
+            float* cur_val = (float*)malloc(sizeof(float) * (size_t)(sel_n[d] ? sel_n[d] : 1));
+            uint32_t k = 0;
+            for (uint32_t i = 0; i < prev_n; ++i) {
+                const uint32_t par = prev_id[i];
+                for (uint64_t j = C[d].col_ptr[par]; j < C[d].col_ptr[par + 1]; ++j) {
+                    const uint32_t label = C[d].row_idx[j];
+                    if (!sorted_contains(sel[d], sel_n[d], label) || k >= sel_n[d]) continue;
+                    const float raw = X->row_ptr ? score_sparse(&W[d], label, qidx, qval, qn, bias[d]) : score_dense(&W[d], label, xd, bias[d]);
+                    float v = xlo_transform(raw, pp_kind[d], pp_p[d]);
+                    if (d > 0) v = xlo_combine(v, prev_val[i], pp_kind[d]);
+                    cur_id[k] = label; cur_val[k] = v; ++k;
+                }
+            }
+            free(prev_id); free(prev_val);
+            prev_id = cur_id; prev_val = cur_val; prev_n = k;
+        }
+        /* the reference copies the selected row's length; entries it could not reach stay unspecified (zero here) */
+        for (uint32_t i = 0; i < n_leaf; ++i) {
+            res_id[res_ptr[q] + i] = i < prev_n ? prev_id[i] : 0u;
+            res_val[res_ptr[q] + i] = i < prev_n ? prev_val[i] : 0.0f;
+        }
+        free(prev_id); free(prev_val);
+        for (int d = 0; d < depth; ++d) free(sel[d]);
+        free(sel); free(sel_n);
+    }
+    for (int d = 0; d < depth; ++d) free(parent_of[d]);
+    free(parent_of);
+    out->indptr = res_ptr; out->indices = res_id; out->data = res_val;
+    out->nnz = total; out->rows = Q; out->cols = selected->cols;
+    return 0;
 }
 
 void xlo_free_result(xlo_result_t* r) {

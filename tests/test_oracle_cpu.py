@@ -148,3 +148,40 @@ def test_single_layer_restatement_equals_reference_library(built, have_ref, perm
         synth.save_xlinear_model(folder, layers, bias=1.0, only_topk=6)
         full = ref.RefXLinear(os.path.join(folder, "ranker")).predict(X, 4, "l3-hinge", 6)
     assert_csr_parity(chain, full, rtol=0.0, what="python chain vs predict-only")
+
+
+@pytest.mark.parametrize("permute", [False, True])
+def test_selected_outputs_restatement_equals_reference_library(tmp_path, built, have_ref, permute):
+    """Next scope row: c_xlinear_predict_on_selected_outputs_{csr,drm}_f32 (pecos/core/libpecos.cpp:179-198):
+    scores of exactly the given (query, label) pairs through the hierarchy, no top-k, CSC layers only.  Pins the restatement
+    (xlo_predict_selected) bit-for-bit: entry order (parents in the previous layer's order, children in C's column order),
+    every kind of post-processor, csr and dense queries, empty rows."""
+    if not have_ref:
+        pytest.skip("oracle/_ref is not built (no /root/reference here)")
+    from oracle import ref, restatement
+
+    folder = str(tmp_path / "m")
+    layers = random_tree(95, [6, 40, 300], 200, 25, bias=1.0, permute=permute)
+    synth.save_xlinear_model(folder, layers, bias=1.0, only_topk=6)
+    X = synth.make_queries(96, 50, 200, 30)
+    rng = np.random.default_rng(97)
+    rows, cols = [], []
+    for q in range(50):
+        c = rng.choice(300, size=int(rng.integers(0, 12)), replace=False)  # some rows select nothing
+        rows += [q] * len(c)
+        cols += list(c)
+    S = smat.csr_matrix((np.ones(len(rows), dtype=np.float32), (rows, cols)), shape=(50, 300))
+    m = ref.RefXLinear(os.path.join(folder, "ranker"), weight_matrix_type="CSC")
+    o = restatement.OracleXLinear(os.path.join(folder, "ranker"))
+    for pp in [None, "noop", "sigmoid", "log-sigmoid", "l2-hinge", "log-l3-hinge"]:
+        for Xq, Sq in ((X, S), (X.toarray()[:9], S[:9])):
+            want = ref.predict_on_selected_outputs(m, Xq, Sq, pp)
+            got = o.predict_on_selected_outputs(Xq, Sq, pp)
+            assert want.nnz == Sq.nnz
+            assert_csr_parity(got, want, rtol=0.0, what=f"selected outputs {pp} {'csr' if Xq is X else 'drm'}")
+    # consistency with beam search: a label returned by predict has the same score when selected explicitly
+    full = ref.RefXLinear(os.path.join(folder, "ranker")).predict(X, 40, None, 5)  # beam 40 = exhaustive at the middle layer
+    sel_scores = ref.predict_on_selected_outputs(m, X, smat.csr_matrix(full, dtype=np.float32), None)
+    a = smat.csr_matrix(full).toarray()
+    b = sel_scores.toarray()
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
