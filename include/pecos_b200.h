@@ -161,13 +161,14 @@ void pb200_xlinear_set_profile(void* ptr, int on);
 /* Kernel generation selector for A/B tests (results are identical): 0 = row-list streaming + block-wide sort,
  * 1 = default (feature-map kernels + warp top-k; query-warp kernel for beams of many narrow chunks), 2 = feature-map
  * lookups with one warp per chunk only, 3 = query-warp kernel wherever it is eligible, 4 = as 1 but the warp top-k
- * evaluates the post-processor for every candidate (no single-precision estimate filter).
+ * evaluates the post-processor for every candidate (no single-precision estimate filter), 5 = as 1 plus the EXPERIMENTAL
+ * chunk-major score kernel on eligible layers (written without GPU access at the end of round 1, not validated yet).
  * Returns 1 when every layer has a feature map (PB200_FEATMAP_MB caps their total size at load time, default 32768). */
 int pb200_xlinear_set_lookup(void* ptr, int on);
 void pb200_xlinear_reset_profile(void* ptr);
 void pb200_xlinear_get_profile(void* ptr, double* out);
 /* out[2*depth]: per layer {score kernel, top-k kernel} of the last call.  Score: 0 row-list streaming, 1 feature-map
- * lookup (xl_chunk_scores_kernel), 2 dense, 3 xl_query_warp_scores_kernel.  Top-k: 0 xl_topk_kernel, 1 xl_topk_warp_kernel,
+ * lookup (xl_chunk_scores_kernel), 2 dense, 3 xl_query_warp_scores_kernel, 4 xl_cm_scores_kernel (experimental).  Top-k: 0 xl_topk_kernel, 1 xl_topk_warp_kernel,
  * 2 xl_topk_filter_kernel. */
 void pb200_xlinear_get_kernel_ids(void* ptr, int* out);
 void pb200_xlinear_get_stats(void* ptr, uint64_t* out);

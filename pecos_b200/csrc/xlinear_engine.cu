@@ -492,6 +492,7 @@ __device__ __forceinline__ unsigned long long xl_make_key(float v, uint32_t pos)
 }
 
 #include "xlinear_qw_kernel.cuh"
+#include "xlinear_cm_kernel.cuh"
 
 // descending bitonic sort of n (power of two) keys; a may live in shared or global memory
 __device__ void xl_bitonic_desc(unsigned long long* a, uint32_t n) {
@@ -915,6 +916,12 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
             model_bytes_ += src.featmap.size() * 8;
             std::vector<uint2_host>().swap(src.featmap);
         }
+        dst.e_max = 0;
+        for (const ChunkHeader& ch : src.chunks) {
+            if ((ch.has_bias & kChunkAbsent) || ch.nnz_rows == 0) continue;
+            const uint32_t* rp = src.meta.data() + ch.meta_off + round_up4(ch.nnz_rows);
+            dst.e_max = std::max(dst.e_max, rp[ch.nnz_rows]);
+        }
         dst.rowext.reserve(std::max<uint64_t>(src.meta.size(), 4));
         xl_build_rowext_kernel<<<148 * 8, 256, 0, stream_>>>(dst.chunks.get(), dst.meta.get(), dst.rowext.get(), src.n_chunks);
         PB200_CUDA(cudaGetLastError());
@@ -949,6 +956,8 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     stats_dev_.reserve(8 * layers_.size());
@@ -970,13 +979,15 @@ XLinearEngine::~XLinearEngine() {
 void XLinearEngine::set_kernel_mode(int mode) {
     // 0: first generation (row-list streaming + block-wide sort); 1: default (query-warp / feature-map kernels + warp top-k);
     // 2: feature-map lookups with one warp per chunk (no query-warp kernel); 3: query-warp kernel wherever eligible;
-    // 4: as 1 but the warp top-k evaluates the post-processor for every candidate (no estimate filter)
+    // 4: as 1 but the warp top-k evaluates the post-processor for every candidate (no estimate filter);
+    // 5: as 1 plus the EXPERIMENTAL chunk-major score kernel on the layers it is eligible for (xlinear_cm_kernel.cuh)
     const bool on = mode != 0;
     for (auto& l : layers_) l.view.featmap = (on && l.featmap.capacity()) ? l.featmap.get() : nullptr;
     force_block_topk_ = !on;
     no_query_warp_ = (mode == 2);
     force_query_warp_ = (mode == 3);
     no_topk_filter_ = (mode == 4);
+    chunk_major_ = (mode == 5);
 }
 
 bool XLinearEngine::has_feature_maps() const {
@@ -1041,6 +1052,19 @@ void XLinearEngine::ensure_workspace_(const std::vector<LayerPlan>& plan, uint32
         beam_val_[b].reserve(static_cast<uint64_t>(tile_rows) * beam_stride);
         beam_cnt_[b].reserve(tile_rows);
     }
+    if (chunk_major_) {
+        uint64_t b_max = 1, chunks_max = 1;
+        for (size_t d = 0; d < plan.size(); ++d) {
+            b_max = std::max<uint64_t>(b_max, plan[d].b_prev);
+            chunks_max = std::max<uint64_t>(chunks_max, host_->layers[d].n_chunks);
+        }
+        cm_slot_pos_.reserve(static_cast<uint64_t>(tile_rows) * beam_stride);
+        cm_pair_q_.reserve(static_cast<uint64_t>(tile_rows) * b_max);
+        cm_pair_pos_.reserve(static_cast<uint64_t>(tile_rows) * b_max);
+        cm_count_.reserve(chunks_max + 1);
+        cm_bucket_ptr_.reserve(chunks_max + 1);
+        cm_item_ptr_.reserve(chunks_max + 1);
+    }
     cand_.reserve(static_cast<uint64_t>(tile_rows) * cand_max);
     if (sort_max) sortbuf_.reserve(static_cast<uint64_t>(tile_rows) * sort_max);
 }
@@ -1090,7 +1114,28 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
                                  cand_stride_q <= static_cast<uint64_t>(kQwNCap) && q.max_row_nnz <= kQwQCap;
         const bool query_warp = qw_eligible && !no_query_warp_ &&
                                 (force_query_warp_ || (lp.b_prev >= 16u && cand_stride_q <= 256u));
-        if (query_warp) {
+        // EXPERIMENTAL (kernel mode 5): chunk-major scoring when the layer's chunks are narrow, small enough to stage in
+        // shared memory, and visited by many pairs each
+        const uint32_t cm_r = host_->layers[d].r_max, cm_e = layers_[d].e_max;
+        const bool chunk_major = chunk_major_ && lookup && L.c_max <= static_cast<uint32_t>(kCmCols) && L.n_chunks > 0 &&
+                                 static_cast<uint64_t>(cm_hash_slots(cm_r)) * 8 + (static_cast<uint64_t>(cm_r) + cm_e + 2) * 8 <= kCmChunkBytes &&
+                                 cm_smem_bytes(cm_r, cm_e) <= 200u * 1024u &&
+                                 static_cast<uint64_t>(rows) * lp.b_prev >= static_cast<uint64_t>(kCmMinReuse) * L.n_chunks;
+        if (chunk_major) {
+            CmWork w{cm_slot_pos_.get(), cm_count_.get(), cm_bucket_ptr_.get(), cm_item_ptr_.get(), cm_pair_q_.get(), cm_pair_pos_.get()};
+            PB200_CUDA(cudaMemsetAsync(w.count, 0, (static_cast<uint64_t>(L.n_chunks) + 1) * 4, stream_));
+            const uint32_t warp_grid = (rows * 32u + 127u) / 128u;
+            xl_cm_count_kernel<<<warp_grid, 128, 0, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w, stats);
+            xl_cm_scan_kernel<<<1, 1024, 0, stream_>>>(L.n_chunks, w);
+            xl_cm_scatter_kernel<<<warp_grid, 128, 0, stream_>>>(L, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w);
+            const uint64_t max_items = (static_cast<uint64_t>(rows) * lp.b_prev + kCmPairs - 1) / kCmPairs + L.n_chunks;
+            const size_t cm_smem = cm_smem_bytes(cm_r, cm_e);
+            if (collect_stats)
+                xl_cm_scores_kernel<true><<<static_cast<uint32_t>(max_items), kCmWarps * 32, cm_smem, stream_>>>(L, q, w, cand_.get(), cand_stride_q, stats, cm_r, cm_e);
+            else
+                xl_cm_scores_kernel<false><<<static_cast<uint32_t>(max_items), kCmWarps * 32, cm_smem, stream_>>>(L, q, w, cand_.get(), cand_stride_q, stats, cm_r, cm_e);
+            launches_ += 3;  // + the score kernel counted below
+        } else if (query_warp) {
             const uint32_t qw_qcap = std::max<uint32_t>(32u, (q.max_row_nnz + 31u) & ~31u);
             const uint32_t qw_ncap = static_cast<uint32_t>((cand_stride_q + 31) & ~static_cast<uint64_t>(31));
             const size_t qw_smem = kQwWarps * ((qw_warp_bytes(qw_qcap, qw_ncap) + 15) & ~static_cast<size_t>(15));
@@ -1113,7 +1158,7 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
         }
         PB200_CUDA(cudaGetLastError());
         ++launches_;
-        layer_profile_[d].scores_kernel = query_warp ? 3 : dense ? 2 : lookup ? 1 : 0;
+        layer_profile_[d].scores_kernel = chunk_major ? 4 : query_warp ? 3 : dense ? 2 : lookup ? 1 : 0;
         if (profile_) PB200_CUDA(cudaEventRecord(ev_[1], stream_));
 
         const bool last = (d + 1 == depth);

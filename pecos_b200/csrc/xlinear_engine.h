@@ -60,7 +60,7 @@ struct XLinearLayerProfile {
     double scores_ms = 0.0;  // score kernel of the layer
     double topk_ms = 0.0;    // top-k kernel of the layer
     uint64_t launches = 0;
-    int scores_kernel = 0;   // last launch: 0 row-list streaming, 1 feature-map lookup, 2 dense, 3 query-warp
+    int scores_kernel = 0;   // last launch: 0 row-list streaming, 1 feature-map lookup, 2 dense, 3 query-warp, 4 chunk-major
     int topk_kernel = 0;     // last launch: 0 block-wide sort, 1 warp arg-max, 2 estimate filter
 };
 
@@ -134,6 +134,7 @@ private:
         DeviceBuffer<uint2> entries;
         DeviceBuffer<uint32_t> label_of_col;
         DeviceBuffer<uint2> featmap;
+        uint32_t e_max = 0;  // most entries of one chunk (sizes the chunk-major kernel's shared-memory staging)
         LayerDev view{};
     };
 
@@ -196,6 +197,8 @@ private:
     bool no_query_warp_ = false;
     bool force_query_warp_ = false;
     bool no_topk_filter_ = false;
+    bool chunk_major_ = false;  // kernel mode 5 (experimental): chunk-major scoring for layers of small, reused chunks
+    DeviceBuffer<uint32_t> cm_slot_pos_, cm_count_, cm_bucket_ptr_, cm_item_ptr_, cm_pair_q_, cm_pair_pos_;
     bool force_block_topk_ = false;  // A/B switch: first-generation kernels (row-list streaming + block-wide sort)
     std::vector<XLinearLayerProfile> layer_profile_;
     std::vector<XLinearStats> layer_stats_;

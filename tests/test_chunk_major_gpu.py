@@ -1,0 +1,91 @@
+"""Opt-in GPU tests for the EXPERIMENTAL chunk-major score kernel (pecos_b200/csrc/xlinear_cm_kernel.cuh, kernel mode 5).
+
+STATUS: the kernel was written at the end of round 1 after the round's GPU budget was spent; it compiles for sm_100a but has
+not run on a GPU yet and is OFF by default.  Run with PB200_UNVALIDATED=1 python -m pytest tests -m gpu.
+"""
+import os
+from ctypes import c_int
+
+import numpy as np
+import pytest
+import scipy.sparse as smat
+
+from pecos_b200 import synth
+
+from .util import assert_csr_parity, csr_with_empty_rows, random_tree
+
+pytestmark = [
+    pytest.mark.gpu,
+    pytest.mark.skipif(os.environ.get("PB200_UNVALIDATED") != "1",
+                       reason="chunk-major kernel was written without GPU access (end of round 1); opt in with PB200_UNVALIDATED=1"),
+]
+
+
+def _oracles(folder, have_ref):
+    from oracle import ref, restatement
+
+    out = {"restatement": restatement.OracleXLinear(os.path.join(folder, "ranker"))}
+    if have_ref:
+        out["reference"] = ref.RefXLinear(os.path.join(folder, "ranker"))
+    return out
+
+
+@pytest.mark.parametrize("permute,prune", [(False, 0.0), (True, 0.2)])
+def test_chunk_major_kernel_equals_default_kernels_and_oracles(tmp_path, gpu_clib, have_ref, permute, prune):
+    from pecos_b200.xlinear import XLinearModel
+
+    folder = str(tmp_path / "m")
+    # narrow chunks (8 children per node), enough queries that every chunk is visited by >= 32 pairs on average
+    layers = random_tree(131, [8, 64, 512], 400, 24, bias=1.0, permute=permute, prune=prune)
+    synth.save_xlinear_model(folder, layers, bias=1.0, only_topk=8)
+    X = synth.make_queries(132, 3000, 400, 48)
+    X = csr_with_empty_rows(X, [0, 7, 2999])
+    # repeated column indices: only the first occurrence counts (inference.hpp:788-803)
+    Xd = X.copy()
+    for r in (3, 11, 500):
+        s, e = Xd.indptr[r], Xd.indptr[r + 1]
+        if e - s >= 4:
+            Xd.indices[s + 1] = Xd.indices[s]
+            Xd.indices[s + 3] = Xd.indices[s + 2]
+    Xd.has_sorted_indices = True
+    m, oracles = XLinearModel.load(folder, is_predict_only=True), _oracles(folder, have_ref)
+    c = gpu_clib.clib_float32
+    h = m.model.model_chain
+    for pp in ("l3-hinge", "noop", "log-sigmoid"):
+        for Xq in (X, Xd):
+            c.pb200_xlinear_set_lookup(h, 1)
+            base = m.predict(Xq, beam_size=10, only_topk=8, post_processor=pp)
+            c.pb200_xlinear_set_lookup(h, 5)
+            got = m.predict(Xq, beam_size=10, only_topk=8, post_processor=pp)
+            kid = (c_int * 6)()
+            c.pb200_xlinear_get_kernel_ids(h, kid)
+            assert 4 in [kid[0], kid[2], kid[4]], "the chunk-major kernel did not run on any layer"
+            assert_csr_parity(got, base, rtol=0.0, what=f"chunk-major vs default {pp}")
+            if Xq is X:
+                for name, o in oracles.items():
+                    sub = slice(0, 200)
+                    assert_csr_parity(got[sub], o.predict(Xq[sub], 10, pp, 8), what=f"chunk-major vs {name} {pp}")
+    c.pb200_xlinear_set_lookup(h, 1)
+
+
+def test_chunk_major_tiles_and_small_batches(tmp_path, gpu_clib, have_ref):
+    """Few queries => the reuse heuristic keeps the default kernels; max_pred_chunk tiles re-run the bucketing per call."""
+    from pecos_b200.xlinear import XLinearModel
+
+    folder = str(tmp_path / "m")
+    layers = random_tree(141, [8, 64, 512], 300, 20, bias=1.0)
+    synth.save_xlinear_model(folder, layers, bias=1.0, only_topk=6)
+    X = synth.make_queries(142, 2500, 300, 40)
+    m = XLinearModel.load(folder, is_predict_only=True)
+    c = gpu_clib.clib_float32
+    h = m.model.model_chain
+    c.pb200_xlinear_set_lookup(h, 1)
+    base = m.predict(X, beam_size=8, only_topk=6)
+    c.pb200_xlinear_set_lookup(h, 5)
+    assert_csr_parity(m.predict(X, beam_size=8, only_topk=6, max_pred_chunk=1300), base, rtol=0.0, what="tiled")
+    small = m.predict(X[:5], beam_size=8, only_topk=6)
+    kid = (c_int * 6)()
+    c.pb200_xlinear_get_kernel_ids(h, kid)
+    assert kid[4] != 4, "5 queries x beam 8 must not pay for staging 512 chunks"
+    assert_csr_parity(small, base[:5], rtol=0.0, what="small batch")
+    c.pb200_xlinear_set_lookup(h, 1)
