@@ -961,6 +961,7 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     stats_dev_.reserve(8 * layers_.size());
+    if (const char* env = std::getenv("PB200_XL_KERNEL_MODE")) set_kernel_mode(std::atoi(env));  // A/B runs of bench.py
     layer_profile_.assign(layers_.size(), XLinearLayerProfile{});
     layer_stats_.assign(layers_.size(), XLinearStats{});
 }
