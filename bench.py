@@ -208,40 +208,73 @@ def prepare_workload(args, rank, world, barrier):
     return folder, X, cfg
 
 
-def time_reference(folder, X, cfg, steps, warmup, threads=-1, budget_s=120.0):
-    """Times the reference's own OpenMP C++ library (oracle/_ref) -- or the scalar C port when _ref is absent."""
+class ReferenceUnavailable(RuntimeError):
+    pass
+
+
+def _require_ref():
+    """The reference arm is the UNMODIFIED reference library (oracle/_ref), never the scalar restatement."""
     import oracle
 
+    if not oracle.have_ref():
+        raise ReferenceUnavailable(
+            "oracle/_ref/libpecos_float32.so is missing: build it where /root/reference exists (`make -C oracle`, "
+            "done by __graft_entry__.build()); it is git-ignored but travels to the GPU box with the snapshot")
+
+
+def _thread_grid(n_cores):
+    """Thread counts the reference is tried with (pecos/core/utils/parallel.hpp:27-34: -1 = omp_get_num_procs())."""
+    g = sorted({t for t in (1, 8, 32, n_cores) if 1 <= t <= n_cores})
+    return g
+
+
+def time_reference(folder, X, cfg, steps, warmup, budget_s=120.0, layouts=None):
+    """Times the reference's own OpenMP C++ library (oracle/_ref) on this box's host cores.
+
+    The headline is the reference's BEST configuration on this box: a short sweep over its two chunked weight layouts
+    (BINARY_SEARCH_CHUNKED = its default, HASH_CHUNKED; pecos/core/xmc/inference.hpp:43) and over thread counts
+    {1, 8, 32, all} picks the fastest (layout, threads); the K timed steps then run that configuration on a bounded
+    sample of the workload.  The whole sweep is reported next to it."""
+    _require_ref()
+    from oracle import ref
+
     n_cores = os.cpu_count() or 1
-    if oracle.have_ref():
-        from oracle import ref
+    if layouts is None:
+        layouts = ["BINARY_SEARCH_CHUNKED", "HASH_CHUNKED"]
+        if cfg["layer_sizes"][-1] > 1_000_000:
+            layouts = ["BINARY_SEARCH_CHUNKED"]  # the reference builds a layout single-threaded at load: minutes each on S
+    beam, topk = cfg["beam_size"], cfg["only_topk"]
+    probe = X[: min(X.shape[0], 4096)]
+    sweep, best = [], None
+    models = {}
+    t_sweep0 = time.perf_counter()
+    for lay in layouts:
+        t0 = time.perf_counter()
+        models[lay] = ref.RefXLinear(os.path.join(folder, "ranker"), weight_matrix_type=lay)
+        load_s = time.perf_counter() - t0
+        for th in _thread_grid(n_cores):
+            rows = probe if th > 1 else probe[: min(probe.shape[0], 512)]
+            models[lay].predict(rows[:64], beam, None, topk, th)
+            t0 = time.perf_counter()
+            models[lay].predict(rows, beam, None, topk, th)
+            dt = time.perf_counter() - t0
+            qps = rows.shape[0] / dt
+            sweep.append({"layout": lay, "threads": th, "queries": int(rows.shape[0]), "qps": qps, "load_s": round(load_s, 3)})
+            if best is None or qps > best[2]:
+                best = (lay, th, qps)
+            if time.perf_counter() - t_sweep0 > budget_s * 0.4:
+                break
+    lay, th, qps_est = best
+    model = models[lay]
+    # bound the sample so that warmup + steps stays within the remaining budget
+    remaining = max(5.0, budget_s - (time.perf_counter() - t_sweep0))
+    rows = int(min(X.shape[0], max(256, qps_est * remaining / max(1, steps + warmup))))
+    sample = X[:rows]
 
-        model = ref.RefXLinear(os.path.join(folder, "ranker"))
-        kind, cores = "reference", n_cores
-        sample = X
+    def run():
+        return model.predict(sample, beam, None, topk, th)
 
-        def run():
-            return model.predict(sample, cfg["beam_size"], None, cfg["only_topk"], threads)
-    else:
-        from oracle import restatement
-
-        model = restatement.OracleXLinear(os.path.join(folder, "ranker"))
-        kind, cores = "port", 1
-        sample = X[: min(X.shape[0], 256)]
-
-        def run():
-            return model.predict(sample, cfg["beam_size"], None, cfg["only_topk"])
-
-    # bound the sample so that warmup + steps stays within the budget
-    t0 = time.perf_counter()
-    run()
-    first = time.perf_counter() - t0
-    max_rows = sample.shape[0]
-    est_total = first * (steps + warmup)
-    if est_total > budget_s and max_rows > 64:
-        rows = max(64, int(max_rows * budget_s / est_total))
-        sample = sample[:rows]
-    for _ in range(max(0, warmup - 1)):
+    for _ in range(max(1, warmup)):
         run()
     times = []
     for _ in range(steps):
@@ -253,9 +286,14 @@ def time_reference(folder, X, cfg, steps, warmup, threads=-1, budget_s=120.0):
         "value": sample.shape[0] / mean_t,
         "best": sample.shape[0] / min(times),
         "ms_per_step": 1e3 * mean_t,
-        "kind": kind,
-        "cores": cores,
-        "sample": f"{sample.shape[0]} of {X.shape[0]} queries of the workload per step, {steps} steps, threads={threads} (all host threads)",
+        "kind": "reference",
+        "cores": n_cores,
+        "threads": th,
+        "layout": lay,
+        "sweep": sweep,
+        "sample": (f"{sample.shape[0]} of {X.shape[0]} queries of the workload per step, {steps} steps; reference library "
+                   f"oracle/_ref (unmodified libpecos.cpp, -fopenmp -O3), best of the sweep over layouts x threads "
+                   f"{_thread_grid(n_cores)}: {lay}, threads={th} on a {n_cores}-thread host"),
     }
 
 
@@ -263,9 +301,11 @@ def run_reference_arm(args):
     rank, world, local = dist_env()
     if rank != 0:
         return 0
-    import oracle
-
-    oracle.build()
+    try:
+        _require_ref()
+    except ReferenceUnavailable as e:
+        print(f"bench.py --impl reference: {e}", file=sys.stderr)
+        return 3  # never silently time something else
     folder, X, cfg = prepare_workload(args, 0, 1, lambda: None)
     r = time_reference(folder, X, cfg, args.steps, args.warmup)
     line = {
@@ -273,8 +313,9 @@ def run_reference_arm(args):
         "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, cfg, X, extra={"l2": "n/a (host cores)"}),
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "config": workload_config(args.workload, cfg, X),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                         "threads": r["threads"], "layout": r["layout"], "sweep": r["sweep"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -525,6 +566,39 @@ def main_hnsw(args):
     return 0
 
 
+def parity_gate_xlinear(got, folder, X, cfg, rows=1024, what="resident batch"):
+    """no timing counts before parity.  The first `rows` queries of the timed batch are predicted by the
+    reference library (oracle/_ref; the pinned restatement only if the library is absent) and compared with the GPU result:
+    label ids and ranks bit-equal, scores within 1e-5 relative.  Raises on any difference."""
+    import oracle
+
+    rows = int(min(rows, X.shape[0]))
+    beam, topk = cfg["beam_size"], cfg["only_topk"]
+    if oracle.have_ref():
+        from oracle import ref
+
+        want = ref.RefXLinear(os.path.join(folder, "ranker")).predict(X[:rows], beam, None, topk, -1)
+        checker = "reference library (oracle/_ref)"
+    else:
+        from oracle import restatement
+
+        want = restatement.OracleXLinear(os.path.join(folder, "ranker")).predict(X[:rows], beam, None, topk)
+        checker = "C restatement (oracle/liboracle.so; oracle/_ref absent)"
+    g = got[:rows]
+    if not np.array_equal(np.asarray(g.indptr, dtype=np.int64), np.asarray(want.indptr, dtype=np.int64)):
+        raise RuntimeError(f"parity gate ({what}): row sizes differ from the {checker}")
+    if not np.array_equal(np.asarray(g.indices, dtype=np.int64), np.asarray(want.indices, dtype=np.int64)):
+        bad = int(np.count_nonzero(np.asarray(g.indices, dtype=np.int64) != np.asarray(want.indices, dtype=np.int64)))
+        raise RuntimeError(f"parity gate ({what}): {bad} label ids / ranks differ from the {checker}")
+    gd, wd = np.asarray(g.data, dtype=np.float64), np.asarray(want.data, dtype=np.float64)
+    rel = float(np.max(np.abs(gd - wd) / np.maximum(np.abs(wd), 1e-30))) if gd.size else 0.0
+    if rel > 1e-5:
+        raise RuntimeError(f"parity gate ({what}): max relative score error {rel:.3e} > 1e-5 vs the {checker}")
+    bits = float(np.mean(np.asarray(g.data, dtype=np.float32).view(np.uint32) == np.asarray(want.data, dtype=np.float32).view(np.uint32))) if gd.size else 1.0
+    return {"checked_queries": rows, "checker": checker, "ids_bit_equal": True, "max_rel_score_err": rel,
+            "scores_bit_equal_frac": bits}
+
+
 def main():
     args = parse_args()
     if args.workload.startswith("hnsw"):
@@ -616,6 +690,12 @@ def main():
     ms_per_step = total_ms / args.steps
     value = n_gpus * Q / (ms_per_step * 1e-3)
 
+    # ------------------------------------------------------------ parity gate on the result of the LAST timed step
+    fetch = ScipyCompressedSparseAllocator()
+    c.pb200_xlinear_resident_fetch(h, fetch.cfunc)
+    got_resident = fetch.get()
+    parity = parity_gate_xlinear(got_resident, folder, X, cfg, rows=(1024 if rank == 0 else 128), what="resident batch")
+
     # ------------------------------------------------------------ per-kernel timing (CUDA events on the launch stream)
     c.pb200_xlinear_set_profile(h, 1)
     c.pb200_xlinear_reset_profile(h)
@@ -684,26 +764,47 @@ def main():
     e2e_value = n_gpus * Q * args.steps / e2e_total
     h2d = int(ip.array.nbytes + ix.array.nbytes + dv.array.nbytes)
     d2h = int(out.indices.nbytes + out.data.nbytes + 4 * Q)
+    got_e2e = out.get()
+    if not (np.array_equal(got_e2e.indptr, got_resident.indptr) and np.array_equal(got_e2e.indices, got_resident.indices)
+            and np.array_equal(got_e2e.data.view(np.uint32), got_resident.data.view(np.uint32))):
+        raise RuntimeError("parity gate (e2e): the C-ABI result of the host-buffer call differs from the resident-batch result")
+    parity["e2e_equals_resident_bits"] = True
+    # the same call with PAGEABLE host memory (what scipy hands the reference's ctypes shim)
+    cx_pageable = ScipyCsrF32.init_from(X)
+    pg_times = []
+    for i in range(2 + min(args.steps, 10)):
+        c.pb200_l2_flush()
+        t0 = time.perf_counter()
+        alloc = ScipyCompressedSparseAllocator()
+        c.c_xlinear_predict_csr_f32(h, byref(cx_pageable), beam, None, topk, -1, alloc.cfunc)
+        if i >= 2:
+            pg_times.append(time.perf_counter() - t0)
+    e2e_pageable = Q / (sum(pg_times) / len(pg_times))
 
     # ------------------------------------------------------------ CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
-        r = time_reference(folder, X, cfg, steps=5, warmup=2, budget_s=30.0)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
-               "best": r["best"]}
+        try:
+            r = time_reference(folder, X, cfg, steps=5, warmup=2, budget_s=30.0)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                   "best": r["best"], "threads": r["threads"], "layout": r["layout"], "sweep": r["sweep"]}
+        except ReferenceUnavailable as e:  # never substitute the scalar port for the reference
+            print(f"bench.py: cpu_baseline unavailable: {e}", file=sys.stderr)
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, cfg, X, extra={
-                "l2": "flushed between timed iterations (512 MiB memset outside the event-timed region)",
-                "timing": "CUDA events on the engine stream per step, summed over steps, max over ranks",
-            }),
+            "config": workload_config(args.workload, cfg, X),
+            "l2": "flushed between timed iterations (512 MiB memset outside the event-timed region)",
+            "timing": "CUDA events on the engine stream per step, summed over steps, max over ranks",
+            "parity": parity,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_total / args.steps, "api": "c_xlinear_predict_csr_f32 (pinned host CSR in, scipy CSR out)"},
+                    "ms_per_step": 1e3 * e2e_total / args.steps, "api": "c_xlinear_predict_csr_f32 (pinned host CSR in, scipy CSR out)",
+                    "pageable_value_per_gpu": e2e_pageable},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,

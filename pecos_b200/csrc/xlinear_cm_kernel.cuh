@@ -1,58 +1,89 @@
-// Chunk-major scoring for layers of MANY SMALL, HEAVILY REUSED chunks (e.g. the 64 / 512 / 4,096 eight-column chunks of the
-// 3M-label tree's middle layers, each visited by 500 .. 30,000 (query, beam slot) pairs of a 100k-query batch).
+// Chunk-major scoring: the (query, beam slot) pairs of a layer are bucketed by weight chunk, a CTA stages ONE chunk in
+// shared memory and every LANE walks ITS OWN pair.
 //
 // Included by xlinear_engine.cu (inside its anonymous namespace, after the small device helpers).
 //
-// STATUS: EXPERIMENTAL, OFF BY DEFAULT (kernel mode 5).  Written at the end of round 1 after the round's GPU budget was
-// spent: it compiles for sm_100a but has not run on a GPU yet; tests/test_chunk_major_gpu.py is opt-in
-// (PB200_UNVALIDATED=1).  DESIGN.md section 8 item 4 explains why this is the next step.
+// Why (profiles/r02_*): the query-major kernels spend 600 - 3,900 warp-instructions per pair on match compaction, prefix
+// sums and on putting colliding entries of a 32-entry group back into feature order, and every probe / extent / entry
+// access is a scattered global load (one L1 line each).  Here
+//   * pairs are bucketed by chunk on the device (count -> scan -> scatter; the reference's b_sort_by_chunk,
+//     pecos/core/xmc/inference.hpp:985-993);
+//   * a work item = one chunk + up to W x 32 of its pairs.  The CTA stages the chunk's FEATURE MAP -- one bit per
+//     feature plus a 16-bit row prefix per 32 features: "is feature f a row of this chunk, and which one" is one
+//     shared-memory word + a popcount, no probing loop, no divergence -- and its row pointers (u16) and entries
+//     (u8 column + f32 weight, split arrays);
+//   * a lane walks its pair's query features in ascending order (staged through shared memory in coalesced rounds of 16),
+//     compacts the hits of a round in place, then adds the hit rows' entries to the lane's PRIVATE accumulators
+//     acc[column][lane] -- literally the reference's marching loop (inference.hpp:788-811): ascending feature order,
+//     separate multiply and add, bias row last.  No compaction across lanes, no conflict resolution: the order is right
+//     by construction, and a column is only ever touched by the lane that owns the pair.
 //
-// Why: the query-warp kernel spends one L1 line (~2 cycles of the SM's L1 pipeline) on every (feature, chunk) probe --
-// 2,560 per query and layer -- and ~600 warp-instructions per pair on compaction, prefix sums and conflict rounds.  Here
-// the pairs of a layer are bucketed by chunk (the reference's b_sort_by_chunk, pecos/core/xmc/inference.hpp:985-993); a
-// CTA takes one chunk and up to kCmPairs of its pairs, stages the chunk -- entries, row extents and an open-addressing
-// hash of its row ids -- in shared memory, and then every LANE walks ITS OWN pair: the query's features in ascending
-// order, one hash probe each, the matched row's entries added to the lane's private accumulators, bias row last.  That
-// is literally the reference's marching loop (inference.hpp:788-811): same arithmetic order by construction, no
-// compaction, no prefix sums, no conflict resolution, and every access except the query read and the result write hits
-// shared memory.  Query features are staged through shared memory in coalesced 32-feature rounds (row stride 33 words, so
-// the lane-per-row reads are bank-conflict free).
-//
-// Pipeline per layer: xl_cm_count_kernel (slot positions + pairs per chunk) -> xl_cm_scan_kernel (bucket and work-item
-// offsets) -> xl_cm_scatter_kernel (pair lists) -> xl_cm_scores_kernel.  Eligibility (host): sparse queries, chunk width
-// <= kCmCols, staged chunk <= kCmChunkBytes, at least kCmMinReuse pairs per chunk on average.
+// Bit-identical to the query-major kernels (tests/test_chunk_major_gpu.py); eligibility is decided per layer on the
+// host (cm_plan): sparse queries, feature map + chunk fit in shared memory, chunk rows / entries < 65536, width <= 256,
+// enough pairs per chunk to amortise the staging.
 #pragma once
 
-constexpr int kCmWarps = 8;                 // warps per CTA
-constexpr int kCmPairs = kCmWarps * 32;     // pairs per work item
 constexpr int kCmFeat = 16;                 // query features staged per pair and round
-constexpr int kCmCols = 16;                 // widest chunk served (accumulators: kCmCols x 32 floats per warp)
-constexpr uint32_t kCmChunkBytes = 64u << 10;  // staged chunk budget (hash + extents + entries)
-constexpr uint32_t kCmMinReuse = 32;        // average pairs per chunk below which the per-chunk staging does not pay
+constexpr int kCmMaxWarps = 16;
+constexpr int kCmMinWarps = 4;
+constexpr uint32_t kCmSmemBudget = 224u << 10;  // dynamic shared memory a CTA may take (227 KB is the sm_100a maximum)
+constexpr uint32_t kCmMinReuse = 24;        // average pairs per chunk below which the per-chunk staging does not pay
 constexpr uint32_t kCmEmpty = 0xFFFFFFFFu;
 
 struct CmWork {
     uint32_t* slot_pos;     // [rows x beam_stride] first candidate position of every beam slot
     uint32_t* count;        // [n_chunks] pairs per chunk, reused as the scatter cursor
     uint32_t* bucket_ptr;   // [n_chunks + 1]
-    uint32_t* item_ptr;     // [n_chunks + 1] work items (<= kCmPairs pairs each) per chunk
+    uint32_t* item_ptr;     // [n_chunks + 1] work items (<= item_pairs pairs each) per chunk
     uint32_t* pair_q;       // [pairs] query of a pair, grouped by chunk
     uint32_t* pair_pos;     // [pairs] candidate position of the pair's first column inside the query's row
+    uint32_t item_pairs;    // pairs per work item = 32 x warps of the score kernel
 };
 
-__host__ __device__ inline uint32_t cm_hash_slots(uint32_t r_max) {  // power of two >= 2 * rows (load factor <= 0.5)
-    uint32_t h = 16;
-    while (h < 2u * r_max) h <<= 1;
-    return h;
+struct CmPlan {  // host-side launch plan of one layer
+    bool eligible = false;
+    uint32_t warps = 0;
+    uint32_t fm_words = 0;   // feature-map cells staged
+    uint32_t r_cap = 0;      // rows of the largest chunk
+    uint32_t e_cap = 0;      // entries of the largest chunk
+    uint32_t acc_cols = 0;   // accumulator rows per warp (= widest chunk)
+    size_t smem = 0;
+};
+
+__host__ __device__ inline size_t cm_align16(size_t x) { return (x + 15) & ~static_cast<size_t>(15); }
+
+__host__ __device__ inline size_t cm_chunk_bytes(uint32_t fm_words, uint32_t r_cap, uint32_t e_cap) {
+    return cm_align16(static_cast<size_t>(fm_words) * 4)      // bits
+           + cm_align16(static_cast<size_t>(fm_words) * 2)    // row prefix per cell (u16)
+           + cm_align16(static_cast<size_t>(r_cap + 2) * 2)   // row pointers (u16, relative to the chunk's first entry)
+           + cm_align16(static_cast<size_t>(e_cap + 1) * 4)   // entry weights
+           + cm_align16(static_cast<size_t>(e_cap + 1));      // entry columns (u8)
 }
 
-__host__ __device__ inline size_t cm_smem_bytes(uint32_t r_max, uint32_t e_max) {
-    return static_cast<size_t>(cm_hash_slots(r_max)) * 8           // hash keys + values
-           + static_cast<size_t>(r_max + 1) * 8                     // row extents
-           + static_cast<size_t>(e_max + 1) * 8                     // entries
-           + static_cast<size_t>(kCmWarps) * (32 * (kCmFeat + 1) * 8    // staged query features (idx + val), stride 33
-                                              + kCmCols * 32 * 4)      // accumulators [col][lane]
-           + 16;
+__host__ __device__ inline size_t cm_warp_bytes(uint32_t acc_cols) {
+    return static_cast<size_t>(32) * (kCmFeat + 1) * 8        // staged query features / compacted hits (idx + val), stride 17
+           + static_cast<size_t>(acc_cols) * 32 * 4;          // accumulators [col][lane]
+}
+
+inline CmPlan cm_plan(uint32_t fm_words, uint32_t r_max, uint32_t e_max, uint32_t c_max, uint32_t n_chunks, uint64_t pairs) {
+    CmPlan p;
+    if (fm_words == 0 || n_chunks == 0 || c_max == 0 || c_max > 256u || r_max >= 65535u || e_max >= 65535u) return p;
+    if (pairs < static_cast<uint64_t>(kCmMinReuse) * n_chunks) return p;
+    const size_t chunk = cm_chunk_bytes(fm_words, r_max, e_max);
+    const size_t per_warp = cm_warp_bytes(c_max);
+    if (chunk + kCmMinWarps * per_warp + 64 > kCmSmemBudget) return p;
+    uint32_t warps = static_cast<uint32_t>(std::min<size_t>(kCmMaxWarps, (kCmSmemBudget - chunk - 64) / per_warp));
+    // no point in more lanes than the average bucket holds
+    const uint64_t avg = pairs / n_chunks;
+    while (warps > kCmMinWarps && static_cast<uint64_t>(warps - 1) * 32 >= avg) --warps;
+    p.eligible = true;
+    p.warps = warps;
+    p.fm_words = fm_words;
+    p.r_cap = r_max;
+    p.e_cap = e_max;
+    p.acc_cols = c_max;
+    p.smem = chunk + warps * per_warp + 64;
+    return p;
 }
 
 // one warp per query: candidate position of every beam slot (prefix of the chunk widths) and pairs per chunk
@@ -97,7 +128,7 @@ xl_cm_scan_kernel(const uint32_t n_chunks, CmWork w) {
     for (uint32_t c0 = 0; c0 < n_chunks; c0 += 1024) {
         const uint32_t c = c0 + threadIdx.x;
         const uint32_t n = (c < n_chunks) ? w.count[c] : 0u;
-        const uint32_t it = (n + kCmPairs - 1) / kCmPairs;
+        const uint32_t it = (n + w.item_pairs - 1) / w.item_pairs;
         const uint32_t in_p = warp_incl_scan(n, lane), in_i = warp_incl_scan(it, lane);
         if (lane == 31) { s_pairs[warp] = in_p; s_items[warp] = in_i; }
         __syncthreads();
@@ -142,22 +173,24 @@ xl_cm_scatter_kernel(const LayerDev L, const uint32_t* __restrict__ beam_id, con
 }
 
 template <bool STATS>
-__global__ void __launch_bounds__(kCmWarps * 32)
+__global__ void __launch_bounds__(kCmMaxWarps * 32)
 xl_cm_scores_kernel(const LayerDev L, const QueryDev X, const CmWork w, float* __restrict__ cand,
-                    const uint64_t cand_stride_q, unsigned long long* stats, const uint32_t r_cap, const uint32_t e_cap) {
+                    const uint64_t cand_stride_q, unsigned long long* stats, const uint32_t fm_words, const uint32_t r_cap,
+                    const uint32_t e_cap, const uint32_t acc_cols) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint32_t H = cm_hash_slots(r_cap);
-    uint32_t* hk = reinterpret_cast<uint32_t*>(smem_raw);            // [H] feature id or kCmEmpty
-    uint32_t* hv = hk + H;                                           // [H] chunk row
-    uint2* ext_s = reinterpret_cast<uint2*>(hv + H);                 // [r_cap + 1] {first entry, end} per chunk row
-    uint2* ent_s = ext_s + (r_cap + 1);                              // [e_cap + 1] {col offset, weight}
-    unsigned char* per_warp = reinterpret_cast<unsigned char*>(ent_s + (e_cap + 1));
+    unsigned char* sp = smem_raw;
+    uint32_t* bits_s = reinterpret_cast<uint32_t*>(sp);            sp += cm_align16(static_cast<size_t>(fm_words) * 4);
+    unsigned short* pre_s = reinterpret_cast<unsigned short*>(sp); sp += cm_align16(static_cast<size_t>(fm_words) * 2);
+    unsigned short* rp_s = reinterpret_cast<unsigned short*>(sp);  sp += cm_align16(static_cast<size_t>(r_cap + 2) * 2);
+    float* ew_s = reinterpret_cast<float*>(sp);                    sp += cm_align16(static_cast<size_t>(e_cap + 1) * 4);
+    unsigned char* ec_s = sp;                                      sp += cm_align16(static_cast<size_t>(e_cap + 1));
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     constexpr int kStride = kCmFeat + 1;
-    uint32_t* st_idx = reinterpret_cast<uint32_t*>(per_warp + static_cast<size_t>(warp) * (32 * kStride * 8 + kCmCols * 32 * 4));
+    unsigned char* mine = sp + static_cast<size_t>(warp) * cm_warp_bytes(acc_cols);
+    uint32_t* st_idx = reinterpret_cast<uint32_t*>(mine);
     float* st_val = reinterpret_cast<float*>(st_idx + 32 * kStride);
-    float* acc = st_val + 32 * kStride;                              // [kCmCols][32]
+    float* acc = st_val + 32 * kStride;                            // [acc_cols][32]
 
     // ---- which (chunk, slice) is this CTA's work item
     __shared__ uint32_t s_chunk, s_first, s_last;
@@ -172,8 +205,8 @@ xl_cm_scores_kernel(const LayerDev L, const QueryDev X, const CmWork w, float* _
             }
             c = lo;
             const uint32_t slice = blockIdx.x - w.item_ptr[c];
-            s_first = w.bucket_ptr[c] + slice * kCmPairs;
-            s_last = min(s_first + kCmPairs, w.bucket_ptr[c + 1]);
+            s_first = w.bucket_ptr[c] + slice * w.item_pairs;
+            s_last = min(s_first + w.item_pairs, w.bucket_ptr[c + 1]);
         }
         s_chunk = c;
     }
@@ -181,32 +214,9 @@ xl_cm_scores_kernel(const LayerDev L, const QueryDev X, const CmWork w, float* _
     const uint32_t c = s_chunk;
     if (c == kCmEmpty) return;
 
-    // ---- stage the chunk: entries, row extents, hash of the row ids
-    const ChunkHeader h = L.chunks[c];
-    const uint32_t R = h.nnz_rows;
-    const uint32_t R4 = (R + 3u) & ~3u;
-    const uint32_t* ridx = L.meta + h.meta_off;
-    const uint2* ext_g = reinterpret_cast<const uint2*>(L.rowext + h.meta_off);
-    const uint2* ent_g = L.entries + h.ent_off;
-    (void)R4;
-    for (uint32_t i = threadIdx.x; i < H; i += blockDim.x) hk[i] = kCmEmpty;
-    for (uint32_t i = threadIdx.x; i < R; i += blockDim.x) ext_s[i] = ext_g[i];
-    __syncthreads();
-    const uint32_t E = R ? ext_s[R - 1].y : 0u;
-    for (uint32_t i = threadIdx.x; i < E; i += blockDim.x) ent_s[i] = ent_g[i];
-    const uint32_t shift = 32u - static_cast<uint32_t>(__ffs(static_cast<int>(H)) - 1);  // H = 2^k: top k bits of the product
-    for (uint32_t r = threadIdx.x; r < R; r += blockDim.x) {
-        const uint32_t f = ridx[r];
-        uint32_t slot = (f * 2654435761u) >> shift;
-        while (atomicCAS(&hk[slot], kCmEmpty, f) != kCmEmpty) slot = (slot + 1u) & (H - 1u);  // row ids are distinct
-        hv[slot] = r;
-    }
-    __syncthreads();
-
-    // ---- one pair per lane
+    // ---- this lane's pair: issue its loads before the staging traffic
     const uint32_t pidx = s_first + static_cast<uint32_t>(warp) * 32u + lane;
     const bool have = pidx < s_last;
-    if (__ballot_sync(kFull, have) == 0u) return;
     uint32_t q = 0, pos = 0;
     uint64_t qb = 0;
     uint32_t qn = 0;
@@ -216,66 +226,101 @@ xl_cm_scores_kernel(const LayerDev L, const QueryDev X, const CmWork w, float* _
         qb = X.row_ptr[q] - X.nnz_base;
         qn = static_cast<uint32_t>(X.row_ptr[q + 1] - X.nnz_base - qb);
     }
+
+    // ---- stage the chunk: feature map (bits + 16-bit row prefix), row pointers, entries (split columns / weights)
+    const ChunkHeader h = L.chunks[c];
+    const uint32_t R = h.nnz_rows;
+    const uint32_t R4 = (R + 3u) & ~3u;
+    const uint32_t* rp_g = L.meta + h.meta_off + R4;               // row_ptr[R + 1], relative to the chunk's first entry
+    const uint2* ent_g = L.entries + h.ent_off;
+    const uint2* fm_g = L.featmap + static_cast<uint64_t>(c) * L.fm_words;
+    const uint32_t nthreads = blockDim.x;
+#pragma unroll 4
+    for (uint32_t i = threadIdx.x; i < fm_words; i += nthreads) {  // unrolled: four independent 8-byte loads in flight per thread
+        const uint2 cell = __ldg(fm_g + i);
+        bits_s[i] = cell.x;
+        pre_s[i] = static_cast<unsigned short>(cell.y);
+    }
+    for (uint32_t i = threadIdx.x; i <= R; i += nthreads) rp_s[i] = static_cast<unsigned short>(__ldg(rp_g + i));
+    const uint32_t E = R ? __ldg(rp_g + R) : 0u;
+#pragma unroll 4
+    for (uint32_t i = threadIdx.x; i < E; i += nthreads) {
+        const uint2 en = __ldg(ent_g + i);
+        ec_s[i] = static_cast<unsigned char>(en.x);
+        ew_s[i] = __uint_as_float(en.y);
+    }
     const uint32_t n_cols = h.n_cols;
     for (uint32_t col = 0; col < n_cols; ++col) acc[col * 32 + lane] = 0.0f;
+    __syncthreads();
+
+    // ---- one pair per lane
+    if (__ballot_sync(kFull, have) == 0u) return;
     uint32_t qn_max = qn;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) qn_max = max(qn_max, __shfl_xor_sync(kFull, qn_max, d));
 
     unsigned long long st_match = 0, st_ent = 0;
     uint32_t prev_f = kCmEmpty;
+    uint32_t* my_idx = st_idx + lane * kStride;
+    float* my_val = st_val + lane * kStride;
+    float* my_acc = acc + lane;
     for (uint32_t t0 = 0; t0 < qn_max; t0 += kCmFeat) {
         // coalesced staging: for every pair of the warp, its next kCmFeat features (idx, val) -> row i of the stage
         __syncwarp();
         constexpr int kPerIter = 32 / kCmFeat;  // pairs staged per warp-wide load
         const int sub = lane / kCmFeat, fl = lane % kCmFeat;
+#pragma unroll 4
         for (int i0 = 0; i0 < 32; i0 += kPerIter) {
             const int i = i0 + sub;
             const uint64_t b_i = __shfl_sync(kFull, qb, i);
             const uint32_t n_i = __shfl_sync(kFull, qn, i);
             if (t0 + fl < n_i) {
-                st_idx[i * kStride + fl] = X.col_idx[b_i + t0 + fl];
-                st_val[i * kStride + fl] = X.val[b_i + t0 + fl];
+                st_idx[i * kStride + fl] = __ldg(X.col_idx + b_i + t0 + fl);
+                st_val[i * kStride + fl] = __ldg(X.val + b_i + t0 + fl);
             }
         }
         __syncwarp();
         const uint32_t n_here = (qn > t0) ? min(static_cast<uint32_t>(kCmFeat), qn - t0) : 0u;
+        // phase 1: probe the feature map, compact the hits of this round IN PLACE (slot cnt <= k was already consumed)
+        uint32_t cnt = 0;
         for (uint32_t k = 0; k < n_here; ++k) {
-            const uint32_t f = st_idx[lane * kStride + k];
+            const uint32_t f = my_idx[k];
             const bool dup = (f == prev_f);  // a repeated column index only counts once (the first occurrence)
             prev_f = f;
             if (dup || f >= L.w_rows) continue;
-            uint32_t slot = (f * 2654435761u) >> shift;
-            uint32_t row = kCmEmpty;
-            for (;;) {
-                const uint32_t key = hk[slot];
-                if (key == f) { row = hv[slot]; break; }
-                if (key == kCmEmpty) break;
-                slot = (slot + 1u) & (H - 1u);
+            const uint32_t word = bits_s[f >> 5];
+            const uint32_t bit = f & 31u;
+            if ((word >> bit) & 1u) {
+                const float x = my_val[k];
+                my_idx[cnt] = static_cast<uint32_t>(pre_s[f >> 5]) + __popc(word & ((1u << bit) - 1u));
+                my_val[cnt] = x;
+                ++cnt;
             }
-            if (row == kCmEmpty) continue;
-            const float x = st_val[lane * kStride + k];
-            const uint2 lh = ext_s[row];
-            for (uint32_t e = lh.x; e < lh.y; ++e) {
-                const uint2 en = ent_s[e];
-                float* a = acc + en.x * 32 + lane;
-                *a = __fadd_rn(*a, __fmul_rn(x, __uint_as_float(en.y)));
-            }
-            if (STATS) { st_match += 1; st_ent += lh.y - lh.x; }
         }
+        // phase 2: the hit rows' entries, in feature order, into this lane's accumulators
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const uint32_t row = my_idx[i];
+            const float x = my_val[i];
+            const uint32_t eb = rp_s[row], ee = rp_s[row + 1];
+            for (uint32_t e = eb; e < ee; ++e) {
+                float* a = my_acc + static_cast<uint32_t>(ec_s[e]) * 32u;
+                *a = __fadd_rn(*a, __fmul_rn(x, ew_s[e]));
+            }
+            if (STATS) st_ent += ee - eb;
+        }
+        if (STATS) st_match += cnt;
     }
     if (have && (h.has_bias & 1u)) {  // bias row last (inference.hpp:806-811)
-        const uint2 lh = ext_s[R - 1u];
-        for (uint32_t e = lh.x; e < lh.y; ++e) {
-            const uint2 en = ent_s[e];
-            float* a = acc + en.x * 32 + lane;
-            *a = __fadd_rn(*a, __fmul_rn(L.bias, __uint_as_float(en.y)));
+        const uint32_t eb = rp_s[R - 1u], ee = rp_s[R];
+        for (uint32_t e = eb; e < ee; ++e) {
+            float* a = my_acc + static_cast<uint32_t>(ec_s[e]) * 32u;
+            *a = __fadd_rn(*a, __fmul_rn(L.bias, ew_s[e]));
         }
-        if (STATS) { st_match += 1; st_ent += lh.y - lh.x; }
+        if (STATS) { st_match += 1; st_ent += ee - eb; }
     }
     if (have) {
         float* dst = cand + static_cast<uint64_t>(q) * cand_stride_q + pos;
-        for (uint32_t col = 0; col < n_cols; ++col) dst[col] = acc[col * 32 + lane];
+        for (uint32_t col = 0; col < n_cols; ++col) dst[col] = my_acc[col * 32];
     }
     if (STATS) {
         unsigned long long pairs = have ? 1ull : 0ull, rows_sum = have ? R : 0ull, cols_sum = have ? n_cols : 0ull;

@@ -956,8 +956,8 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     stats_dev_.reserve(8 * layers_.size());
@@ -981,14 +981,14 @@ void XLinearEngine::set_kernel_mode(int mode) {
     // 0: first generation (row-list streaming + block-wide sort); 1: default (query-warp / feature-map kernels + warp top-k);
     // 2: feature-map lookups with one warp per chunk (no query-warp kernel); 3: query-warp kernel wherever eligible;
     // 4: as 1 but the warp top-k evaluates the post-processor for every candidate (no estimate filter);
-    // 5: as 1 plus the EXPERIMENTAL chunk-major score kernel on the layers it is eligible for (xlinear_cm_kernel.cuh)
+    // 5: as 1 (kept for older scripts); 6: as 1 WITHOUT the chunk-major score kernel (query-major kernels only, for A/B tests)
     const bool on = mode != 0;
     for (auto& l : layers_) l.view.featmap = (on && l.featmap.capacity()) ? l.featmap.get() : nullptr;
     force_block_topk_ = !on;
     no_query_warp_ = (mode == 2);
     force_query_warp_ = (mode == 3);
     no_topk_filter_ = (mode == 4);
-    chunk_major_ = (mode == 5);
+    chunk_major_ = on && (mode != 6);
 }
 
 bool XLinearEngine::has_feature_maps() const {
@@ -1053,7 +1053,7 @@ void XLinearEngine::ensure_workspace_(const std::vector<LayerPlan>& plan, uint32
         beam_val_[b].reserve(static_cast<uint64_t>(tile_rows) * beam_stride);
         beam_cnt_[b].reserve(tile_rows);
     }
-    if (chunk_major_) {
+    if (chunk_major_ && has_feature_maps()) {
         uint64_t b_max = 1, chunks_max = 1;
         for (size_t d = 0; d < plan.size(); ++d) {
             b_max = std::max<uint64_t>(b_max, plan[d].b_prev);
@@ -1115,26 +1115,28 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
                                  cand_stride_q <= static_cast<uint64_t>(kQwNCap) && q.max_row_nnz <= kQwQCap;
         const bool query_warp = qw_eligible && !no_query_warp_ &&
                                 (force_query_warp_ || (lp.b_prev >= 16u && cand_stride_q <= 256u));
-        // EXPERIMENTAL (kernel mode 5): chunk-major scoring when the layer's chunks are narrow, small enough to stage in
-        // shared memory, and visited by many pairs each
-        const uint32_t cm_r = host_->layers[d].r_max, cm_e = layers_[d].e_max;
-        const bool chunk_major = chunk_major_ && lookup && L.c_max <= static_cast<uint32_t>(kCmCols) && L.n_chunks > 0 &&
-                                 static_cast<uint64_t>(cm_hash_slots(cm_r)) * 8 + (static_cast<uint64_t>(cm_r) + cm_e + 2) * 8 <= kCmChunkBytes &&
-                                 cm_smem_bytes(cm_r, cm_e) <= 200u * 1024u &&
-                                 static_cast<uint64_t>(rows) * lp.b_prev >= static_cast<uint64_t>(kCmMinReuse) * L.n_chunks;
+        // Chunk-major scoring (xlinear_cm_kernel.cuh) wherever the layer's feature map + largest chunk fit in shared memory
+        // and the chunks are visited by enough pairs to amortise the staging; otherwise the query-major kernels below.
+        const CmPlan cm = (chunk_major_ && lookup && cm_slot_pos_.capacity())
+                              ? cm_plan(L.fm_words, host_->layers[d].r_max, layers_[d].e_max, L.c_max, L.n_chunks,
+                                        static_cast<uint64_t>(rows) * lp.b_prev)
+                              : CmPlan{};
+        const bool chunk_major = cm.eligible;
         if (chunk_major) {
-            CmWork w{cm_slot_pos_.get(), cm_count_.get(), cm_bucket_ptr_.get(), cm_item_ptr_.get(), cm_pair_q_.get(), cm_pair_pos_.get()};
+            CmWork w{cm_slot_pos_.get(), cm_count_.get(), cm_bucket_ptr_.get(), cm_item_ptr_.get(), cm_pair_q_.get(), cm_pair_pos_.get(),
+                     cm.warps * 32u};
             PB200_CUDA(cudaMemsetAsync(w.count, 0, (static_cast<uint64_t>(L.n_chunks) + 1) * 4, stream_));
             const uint32_t warp_grid = (rows * 32u + 127u) / 128u;
             xl_cm_count_kernel<<<warp_grid, 128, 0, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w, stats);
             xl_cm_scan_kernel<<<1, 1024, 0, stream_>>>(L.n_chunks, w);
             xl_cm_scatter_kernel<<<warp_grid, 128, 0, stream_>>>(L, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w);
-            const uint64_t max_items = (static_cast<uint64_t>(rows) * lp.b_prev + kCmPairs - 1) / kCmPairs + L.n_chunks;
-            const size_t cm_smem = cm_smem_bytes(cm_r, cm_e);
+            const uint64_t max_items = (static_cast<uint64_t>(rows) * lp.b_prev + w.item_pairs - 1) / w.item_pairs + L.n_chunks;
             if (collect_stats)
-                xl_cm_scores_kernel<true><<<static_cast<uint32_t>(max_items), kCmWarps * 32, cm_smem, stream_>>>(L, q, w, cand_.get(), cand_stride_q, stats, cm_r, cm_e);
+                xl_cm_scores_kernel<true><<<static_cast<uint32_t>(max_items), cm.warps * 32, cm.smem, stream_>>>(
+                    L, q, w, cand_.get(), cand_stride_q, stats, cm.fm_words, cm.r_cap, cm.e_cap, cm.acc_cols);
             else
-                xl_cm_scores_kernel<false><<<static_cast<uint32_t>(max_items), kCmWarps * 32, cm_smem, stream_>>>(L, q, w, cand_.get(), cand_stride_q, stats, cm_r, cm_e);
+                xl_cm_scores_kernel<false><<<static_cast<uint32_t>(max_items), cm.warps * 32, cm.smem, stream_>>>(
+                    L, q, w, cand_.get(), cand_stride_q, stats, cm.fm_words, cm.r_cap, cm.e_cap, cm.acc_cols);
             launches_ += 3;  // + the score kernel counted below
         } else if (query_warp) {
             const uint32_t qw_qcap = std::max<uint32_t>(32u, (q.max_row_nnz + 31u) & ~31u);

@@ -10,9 +10,7 @@ Same names, argument meaning and error behaviour as the reference for the predic
 * ``MLModel.load / predict`` (one layer of the python chain, ``is_predict_only=False``) .. pecos/xmc/base.py:832-878, :890-949
 
 Training, pruning and ``predict_on_selected_outputs`` stay on the reference CPU library; they are outside this engine's
-scope and raise ``NotImplementedError`` here.  The python chain (``MLModel``, ``is_predict_only=False``) was written at the
-end of round 1 without GPU time left: its oracle is pinned on the CPU side, its GPU tests are opt-in
-(``PB200_UNVALIDATED=1``).
+scope and raise ``NotImplementedError`` here.
 """
 import copy
 import dataclasses as dc

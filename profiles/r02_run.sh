@@ -1,0 +1,30 @@
+#!/bin/bash
+# Round-2 GPU session script: GPU tests, E / S benches (default vs PB200_XL_KERNEL_MODE=6 = query-major kernels only),
+# optional ncu captures.  Usage (through gpurun, from the repo root): bash profiles/r02_run.sh <tag> [tests] [e] [s] [ncu_e] [ncu_s]
+tag=${1:-r02_x}; shift
+o=gpurun_out
+mkdir -p $o
+summ() { python - "$@" <<'PY'
+import json,sys
+for f in sys.argv[1:]:
+    try: d=json.loads(open(f).read().strip().splitlines()[-1])
+    except Exception as e: print(f, "unreadable", e); continue
+    print(f.split("/")[-1], "value", round(d["value"]), "ms", round(d.get("ms_per_step",0),4), "e2e", round((d.get("e2e") or {}).get("value",0)), "parity", (d.get("parity") or {}).get("ids_bit_equal"), "cpu", (d.get("cpu_baseline") or {}).get("value"))
+    r=d.get("roofline") or {}
+    print("   ", [(k["kernel"][3:].replace("_kernel",""), round(k["ms"],3)) for k in r.get("kernels",[])])
+PY
+}
+for what in "$@"; do
+case $what in
+tests) python -m pytest tests -x -q -m gpu > $o/${tag}_gpu_tests.log 2>&1; tail -4 $o/${tag}_gpu_tests.log;;
+e) python bench.py --steps 20 --warmup 5 > $o/${tag}_bench_eurlex4k.json 2> $o/${tag}_bench_eurlex4k.err || tail -5 $o/${tag}_bench_eurlex4k.err
+   PB200_XL_KERNEL_MODE=6 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $o/${tag}_bench_eurlex4k_mode6.json 2> $o/${tag}_bench_eurlex4k_mode6.err
+   summ $o/${tag}_bench_eurlex4k.json $o/${tag}_bench_eurlex4k_mode6.json;;
+s) python bench.py --workload synthetic-3m --steps 5 --warmup 3 --no-cpu-baseline > $o/${tag}_bench_synthetic3m.json 2> $o/${tag}_bench_synthetic3m.err || tail -5 $o/${tag}_bench_synthetic3m.err
+   summ $o/${tag}_bench_synthetic3m.json;;
+ref) python bench.py --impl reference --steps 5 --warmup 2 > $o/${tag}_bench_reference_arm.json 2> $o/${tag}_bench_reference_arm.err; cut -c1-600 $o/${tag}_bench_reference_arm.json;;
+ncu_e) ncu --set full --clock-control none --import-source on -k regex:xl_cm_scores -s 12 -c 1 -o $o/${tag}_ncu_cm_eurlex4k python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2> $o/${tag}_ncu_e.err;;
+ncu_s) ncu --set full --clock-control none --import-source on -k regex:xl_cm_scores -s 14 -c 1 -o $o/${tag}_ncu_cm_synthetic3m python bench.py --workload synthetic-3m --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2> $o/${tag}_ncu_s.err;;
+launches) ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/${tag}_launches_eurlex4k.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1;;
+esac
+done

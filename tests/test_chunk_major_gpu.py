@@ -1,8 +1,6 @@
-"""Opt-in GPU tests for the EXPERIMENTAL chunk-major score kernel (pecos_b200/csrc/xlinear_cm_kernel.cuh, kernel mode 5).
-
-STATUS: the kernel was written at the end of round 1 after the round's GPU budget was spent; it compiles for sm_100a but has
-not run on a GPU yet and is OFF by default.  Run with PB200_UNVALIDATED=1 python -m pytest tests -m gpu.
-"""
+"""GPU tests for the chunk-major score kernel (pecos_b200/csrc/xlinear_cm_kernel.cuh): the default scorer wherever a layer's
+feature map + largest chunk fit in shared memory.  It must return the same BITS as the query-major kernels (kernel mode 6
+switches it off) and match both oracles (ids bit-exact, scores 1e-5)."""
 import os
 from ctypes import c_int
 
@@ -14,11 +12,7 @@ from pecos_b200 import synth
 
 from .util import assert_csr_parity, csr_with_empty_rows, random_tree
 
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(os.environ.get("PB200_UNVALIDATED") != "1",
-                       reason="chunk-major kernel was written without GPU access (end of round 1); opt in with PB200_UNVALIDATED=1"),
-]
+pytestmark = pytest.mark.gpu
 
 
 def _oracles(folder, have_ref):
@@ -30,14 +24,16 @@ def _oracles(folder, have_ref):
     return out
 
 
-@pytest.mark.parametrize("permute,prune", [(False, 0.0), (True, 0.2)])
-def test_chunk_major_kernel_equals_default_kernels_and_oracles(tmp_path, gpu_clib, have_ref, permute, prune):
+@pytest.mark.parametrize("permute,prune,sizes,bias", [(False, 0.0, [8, 64, 512], 1.0), (True, 0.2, [8, 64, 512], 1.0),
+                                                      (False, 0.0, [4, 24, 1500], 1.0),   # wide chunks (~62 columns, eurlex-like)
+                                                      (True, 0.1, [6, 300], -1.0)])       # no bias row
+def test_chunk_major_kernel_equals_default_kernels_and_oracles(tmp_path, gpu_clib, have_ref, permute, prune, sizes, bias):
     from pecos_b200.xlinear import XLinearModel
 
     folder = str(tmp_path / "m")
-    # narrow chunks (8 children per node), enough queries that every chunk is visited by >= 32 pairs on average
-    layers = random_tree(131, [8, 64, 512], 400, 24, bias=1.0, permute=permute, prune=prune)
-    synth.save_xlinear_model(folder, layers, bias=1.0, only_topk=8)
+    # enough queries that every chunk is visited by >= 24 pairs on average
+    layers = random_tree(131, sizes, 400, 24, bias=bias, permute=permute, prune=prune)
+    synth.save_xlinear_model(folder, layers, bias=bias, only_topk=8)
     X = synth.make_queries(132, 3000, 400, 48)
     X = csr_with_empty_rows(X, [0, 7, 2999])
     # repeated column indices: only the first occurrence counts (inference.hpp:788-803)
@@ -53,13 +49,15 @@ def test_chunk_major_kernel_equals_default_kernels_and_oracles(tmp_path, gpu_cli
     h = m.model.model_chain
     for pp in ("l3-hinge", "noop", "log-sigmoid"):
         for Xq in (X, Xd):
-            c.pb200_xlinear_set_lookup(h, 1)
+            c.pb200_xlinear_set_lookup(h, 6)
             base = m.predict(Xq, beam_size=10, only_topk=8, post_processor=pp)
-            c.pb200_xlinear_set_lookup(h, 5)
-            got = m.predict(Xq, beam_size=10, only_topk=8, post_processor=pp)
             kid = (c_int * 6)()
             c.pb200_xlinear_get_kernel_ids(h, kid)
-            assert 4 in [kid[0], kid[2], kid[4]], "the chunk-major kernel did not run on any layer"
+            assert 4 not in [kid[2 * d] for d in range(len(sizes))], "kernel mode 6 must not use the chunk-major kernel"
+            c.pb200_xlinear_set_lookup(h, 1)
+            got = m.predict(Xq, beam_size=10, only_topk=8, post_processor=pp)
+            c.pb200_xlinear_get_kernel_ids(h, kid)
+            assert all(kid[2 * d] == 4 for d in range(len(sizes))), "the chunk-major kernel must serve every layer of this model"
             assert_csr_parity(got, base, rtol=0.0, what=f"chunk-major vs default {pp}")
             if Xq is X:
                 for name, o in oracles.items():
@@ -79,9 +77,9 @@ def test_chunk_major_tiles_and_small_batches(tmp_path, gpu_clib, have_ref):
     m = XLinearModel.load(folder, is_predict_only=True)
     c = gpu_clib.clib_float32
     h = m.model.model_chain
-    c.pb200_xlinear_set_lookup(h, 1)
+    c.pb200_xlinear_set_lookup(h, 6)
     base = m.predict(X, beam_size=8, only_topk=6)
-    c.pb200_xlinear_set_lookup(h, 5)
+    c.pb200_xlinear_set_lookup(h, 1)
     assert_csr_parity(m.predict(X, beam_size=8, only_topk=6, max_pred_chunk=1300), base, rtol=0.0, what="tiled")
     small = m.predict(X[:5], beam_size=8, only_topk=6)
     kid = (c_int * 6)()

@@ -73,6 +73,40 @@ def test_recall_against_brute_force(golden):
         assert recall == pytest.approx(1.0, abs=1e-2)
 
 
+MID = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hnsw_mid")
+
+
+def test_mid_size_golden_indices_from_the_reference(gpu_clib):
+    """Reference-built indices with d in {768, 128, 70, 20} (tests/golden/make_golden_hnsw.py): 16-lane main loop, permuted
+    layout, 4-wide remainder + scalar tail, real-sized TMA rows, six-fold exact ties, efS up to 600 -- ids, order and distance
+    BITS as recorded from the reference library (avx512f clone).  Needs no oracle/_ref at test time."""
+    E = np.load(os.path.join(MID, "expected.npz"))
+    index = json.load(open(os.path.join(MID, "expected_index.json")))
+    models = {}
+    for it in index:
+        folder = os.path.join(MID, it["model"])
+        m = models.get(it["model"]) or models.setdefault(it["model"], _load(folder))
+        Q = np.load(os.path.join(folder, "Q.npy"))
+        idx, dist = m.predict(Q, pred_params=_pp(it["efS"], it["topk"]), ret_csr=False)
+        assert np.array_equal(idx, E[it["key"] + "|idx"]), it["key"]
+        assert np.array_equal(dist.view(np.uint32), E[it["key"] + "|dist"].view(np.uint32)), it["key"]
+
+
+def test_mid_size_goldens_all_ring_depths(gpu_clib):
+    """The same goldens with direct loads (0) and both bulk-copy ring depths (4, 8)."""
+    E = np.load(os.path.join(MID, "expected.npz"))
+    c = gpu_clib.clib_float32
+    for name in ("ip_d768", "ip_d70", "l2_dup"):
+        folder = os.path.join(MID, name)
+        m = _load(folder)
+        Q = np.load(os.path.join(folder, "Q.npy"))
+        for stages in (0, 8, 4):
+            assert c.pb200_hnsw_set_stages(m.model_ptr, stages) == stages
+            idx, dist = m.predict(Q, pred_params=_pp(200, 10), ret_csr=False)
+            assert np.array_equal(idx, E[f"{name}|200|10|idx"]), (name, stages)
+            assert np.array_equal(dist.view(np.uint32), E[f"{name}|200|10|dist"].view(np.uint32)), (name, stages)
+
+
 def _save_index(tmp, X, M, efC, metric, threads=8):
     from oracle import ref
 
@@ -90,7 +124,8 @@ def _save_index(tmp, X, M, efC, metric, threads=8):
 def test_random_indices_match_reference_library(tmp_path, gpu_clib, have_ref, N, d, M, metric):
     """Indices built by the reference on this box; same saved index searched by the reference, the restatement and us."""
     if not have_ref:
-        pytest.skip("building an index needs oracle/_ref (c_ann_hnsw_train stays on the reference)")
+        pytest.fail("oracle/_ref/libpecos_float32.so did not travel to this box (built by __graft_entry__.build() where "
+                    "/root/reference exists); building an index needs the reference's c_ann_hnsw_train")
     from oracle import restatement
 
     rng = np.random.default_rng(N + d)
@@ -118,7 +153,7 @@ def test_random_indices_match_reference_library(tmp_path, gpu_clib, have_ref, N,
 def test_duplicate_points_and_ties(tmp_path, gpu_clib, have_ref):
     """Many exactly equal distances: the restated libstdc++ heap algorithms decide which duplicates survive."""
     if not have_ref:
-        pytest.skip("needs oracle/_ref to build the index")
+        pytest.fail("oracle/_ref/libpecos_float32.so did not travel to this box; needed to build the index")
     from oracle import restatement
 
     rng = np.random.default_rng(7)
@@ -141,7 +176,7 @@ def test_duplicate_points_and_ties(tmp_path, gpu_clib, have_ref):
 def test_bulk_copy_ring_depths_give_identical_results(tmp_path, gpu_clib, have_ref):
     """0 = direct loads, 4 / 8 = base vectors staged through the per-warp TMA bulk-copy ring: same bits."""
     if not have_ref:
-        pytest.skip("needs oracle/_ref to build the index")
+        pytest.fail("oracle/_ref/libpecos_float32.so did not travel to this box; needed to build the index")
     rng = np.random.default_rng(5)
     X = rng.standard_normal((5000, 200)).astype(np.float32)   # d = 200: permuted main part + 8-element tail
     X /= np.linalg.norm(X, axis=1, keepdims=True)

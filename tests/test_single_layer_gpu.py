@@ -1,10 +1,8 @@
 """GPU parity tests for the next scope row: c_xlinear_single_layer_predict_{csr,drm}_f32, the per-layer
 entry point of the reference's python prediction chain (pecos/core/libpecos.cpp:201-235, pecos/xmc/base.py:890-949).
 
-STATUS: the CUDA path behind these tests (XLinearEngine::predict_single_layer + the layer cache in c_api.cu) was written at
-the end of round 1 after the round's GPU budget was spent.  Its oracle IS pinned (tests/test_oracle_cpu.py::
-test_single_layer_restatement_equals_reference_library), the kernels it launches are the validated ones, but the new
-host code has not run on a GPU yet, so the tests are opt-in: PB200_UNVALIDATED=1 python -m pytest tests -m gpu.
+Validated on a B200 in round 2 (profiles/r02_a_gpu_tests_single_layer.log).  The oracle is pinned by
+tests/test_oracle_cpu.py::test_single_layer_restatement_equals_reference_library.
 """
 import os
 from ctypes import c_uint64
@@ -17,11 +15,7 @@ from pecos_b200 import synth
 
 from .util import assert_csr_parity, random_tree
 
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(os.environ.get("PB200_UNVALIDATED") != "1",
-                       reason="single-layer entry points were written without GPU access (end of round 1); opt in with PB200_UNVALIDATED=1"),
-]
+pytestmark = pytest.mark.gpu
 
 
 def _oracle_single(have_ref):
