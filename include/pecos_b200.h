@@ -174,6 +174,12 @@ void pb200_xlinear_get_kernel_ids(void* ptr, int* out);
 void pb200_xlinear_get_stats(void* ptr, uint64_t* out);
 uint64_t pb200_xlinear_launches(void* ptr);
 uint64_t pb200_xlinear_model_bytes(void* ptr);
+/* Replicas held by a handle: 1, or one per entry of PB200_DEVICES ("0,1,..." | "all", read at load time).  With replicas a
+ * c_xlinear_predict_* / c_ann_hnsw_predict_* call splits its rows over the devices (one host thread + stream each) and
+ * concatenates the results in row order -- the multi-GPU form of the reference's OpenMP loop over queries
+ * (pecos/core/xmc/inference.hpp:969-1005, pecos/core/libpecos.cpp:540-548). */
+uint32_t pb200_xlinear_replicas(void* ptr);
+uint32_t pb200_hnsw_replicas(void* model_ptr);
 
 /* HNSW: device-resident query batch, search-kernel time (ms, CUDA events), algorithmic counters of the last search
  *   counters out[4] = {distance evaluations, level-0 expansions, upper-level neighbourhood reads, queries}

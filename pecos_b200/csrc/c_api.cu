@@ -2,12 +2,16 @@
 // Signatures mirror pecos/core/libpecos.cpp:116-176 (see include/pecos_b200.h for the per-symbol citations).
 #include "../../include/pecos_b200.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <exception>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "hnsw_engine.h"
@@ -29,8 +33,54 @@ std::atomic<int> g_device{0};
     catch (const std::exception& e) { die(name, e.what()); } \
     catch (...) { die(name, "unknown exception"); }
 
+// In-library multi-GPU query fan-out (the reference's analogue is the OpenMP loop over work items,
+// pecos/core/xmc/inference.hpp:969-1005): PB200_DEVICES="0,1,2,3" | "all" at LOAD time puts a replica of the model on every
+// listed device; a predict call then splits its rows into contiguous blocks balanced by nnz, one host thread + stream per
+// device, and the per-device results are concatenated in row order into the single pred_alloc buffers.  A device may be
+// listed more than once (two engines on one GPU: how the single-GPU tests emulate a world of 2).  Unset: one engine on the
+// device chosen by pb200_set_device.
+std::vector<int> device_list() {
+    std::vector<int> out;
+    const char* env = std::getenv("PB200_DEVICES");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0)
+        throw std::runtime_error("no CUDA device visible: pecos_b200 has no CPU fallback");
+    if (!env || !*env) { out.push_back(g_device.load()); return out; }
+    const std::string v(env);
+    if (v == "all") { for (int i = 0; i < n; ++i) out.push_back(i); return out; }
+    size_t pos = 0;
+    while (pos <= v.size()) {
+        const size_t comma = v.find(',', pos);
+        const std::string tok = v.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos);
+        if (!tok.empty()) {
+            char* end = nullptr;
+            const long d = std::strtol(tok.c_str(), &end, 10);
+            if (*end != 0 || d < 0 || d >= n) throw std::runtime_error("PB200_DEVICES: bad device id '" + tok + "'");
+            out.push_back(static_cast<int>(d));
+        }
+        if (comma == std::string::npos) break;
+        pos = comma + 1;
+    }
+    if (out.empty()) out.push_back(g_device.load());
+    return out;
+}
+
+// runs fn(i) for i in [0, n) on n host threads (fn(0) on the caller); rethrows the first exception
+template <typename F>
+void fan_out(size_t n, F&& fn) {
+    if (n <= 1) { if (n == 1) fn(0); return; }
+    std::vector<std::exception_ptr> err(n);
+    std::vector<std::thread> th;
+    th.reserve(n - 1);
+    for (size_t i = 1; i < n; ++i)
+        th.emplace_back([&, i] { try { fn(i); } catch (...) { err[i] = std::current_exception(); } });
+    try { fn(0); } catch (...) { err[0] = std::current_exception(); }
+    for (auto& t : th) t.join();
+    for (auto& e : err) if (e) std::rethrow_exception(e);
+}
+
 struct XLinearHandle {
-    std::unique_ptr<pb200::XLinearEngine> engine;
+    std::vector<std::unique_ptr<pb200::XLinearEngine>> engines;  // [0] = primary; > 1: replicas for the query fan-out
     // The reference's handles are immutable after load and may be shared between threads (ctypes drops the GIL during a
     // call).  Ours own device workspaces, so calls on ONE handle are serialised; different handles run concurrently.
     std::mutex mu;
@@ -44,44 +94,85 @@ std::mutex& mutex_of(void* ptr) {
 
 pb200::XLinearEngine& engine_of(void* ptr) {
     if (!ptr) throw std::runtime_error("null model handle");
-    return *static_cast<XLinearHandle*>(ptr)->engine;
+    return *static_cast<XLinearHandle*>(ptr)->engines.at(0);
 }
 
-void emit_result(const pb200::XLinearEngine::Result& r, py_sparse_allocator_t pred_alloc) {
+void emit_results(const std::vector<pb200::XLinearEngine::Result>& parts, py_sparse_allocator_t pred_alloc) {
     // create_pycsr contract (pecos/core/utils/matrix.hpp:300-316): one allocator call, then fill the three arrays.
-    uint64_t nnz = 0;
-    for (uint32_t i = 0; i < r.rows; ++i) nnz += r.cnt[i];
+    uint64_t nnz = 0, rows = 0;
+    bool all_full = true;
+    for (const auto& r : parts) {
+        uint64_t part = 0;
+        for (uint32_t i = 0; i < r.rows; ++i) part += r.cnt[i];
+        all_full = all_full && (part == static_cast<uint64_t>(r.rows) * r.stride);
+        nnz += part;
+        rows += r.rows;
+    }
     uint32_t* indices = nullptr;
     uint64_t* indptr = nullptr;
     float* data = nullptr;
-    pred_alloc(false, r.rows, r.out_cols, nnz, &indices, &indptr, &data);
+    pred_alloc(false, rows, parts.empty() ? 0 : parts[0].out_cols, nnz, &indices, &indptr, &data);
     if (!indptr || (nnz && (!indices || !data))) throw std::runtime_error("result allocator returned null buffers");
-    uint64_t w = 0;
+    uint64_t w = 0, row = 0;
     indptr[0] = 0;
-    if (nnz == static_cast<uint64_t>(r.rows) * r.stride) {
-        // every row is full: the fixed-stride device layout already is the CSR payload
-        std::memcpy(indices, r.ids, nnz * sizeof(uint32_t));
-        std::memcpy(data, r.vals, nnz * sizeof(float));
-        for (uint32_t i = 0; i < r.rows; ++i) indptr[i + 1] = static_cast<uint64_t>(i + 1) * r.stride;
-        return;
-    }
-    for (uint32_t i = 0; i < r.rows; ++i) {
-        const uint32_t c = r.cnt[i];
-        std::memcpy(indices + w, r.ids + static_cast<uint64_t>(i) * r.stride, c * sizeof(uint32_t));
-        std::memcpy(data + w, r.vals + static_cast<uint64_t>(i) * r.stride, c * sizeof(float));
-        w += c;
-        indptr[i + 1] = w;
+    for (const auto& r : parts) {
+        if (all_full) {
+            // every row is full: the fixed-stride device layout already is the CSR payload
+            const uint64_t n = static_cast<uint64_t>(r.rows) * r.stride;
+            if (n) {
+                std::memcpy(indices + w, r.ids, n * sizeof(uint32_t));
+                std::memcpy(data + w, r.vals, n * sizeof(float));
+            }
+            for (uint32_t i = 0; i < r.rows; ++i) indptr[row + i + 1] = w + static_cast<uint64_t>(i + 1) * r.stride;
+            w += n;
+        } else {
+            for (uint32_t i = 0; i < r.rows; ++i) {
+                const uint32_t c = r.cnt[i];
+                std::memcpy(indices + w, r.ids + static_cast<uint64_t>(i) * r.stride, c * sizeof(uint32_t));
+                std::memcpy(data + w, r.vals + static_cast<uint64_t>(i) * r.stride, c * sizeof(float));
+                w += c;
+                indptr[row + i + 1] = w;
+            }
+        }
+        row += r.rows;
     }
 }
 
-void* make_engine(std::unique_ptr<pb200::XLinearHostModel> host) {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0)
-        throw std::runtime_error("no CUDA device visible: pecos_b200 has no CPU fallback");
-    auto h = new XLinearHandle();
-    h->engine = std::make_unique<pb200::XLinearEngine>(std::move(host), g_device.load());
-    return h;
+void emit_result(const pb200::XLinearEngine::Result& r, py_sparse_allocator_t pred_alloc) {
+    emit_results(std::vector<pb200::XLinearEngine::Result>{r}, pred_alloc);
 }
+
+void* make_engine(std::unique_ptr<pb200::XLinearHostModel> host, bool allow_replicas = true) {
+    std::vector<int> devs = device_list();
+    if (!allow_replicas || host->shard_world > 1) devs.resize(1);
+    auto h = std::make_unique<XLinearHandle>();
+    h->engines.resize(devs.size());
+    // the engine consumes (and frees) the host arrays while uploading: every replica gets its own copy
+    std::vector<std::unique_ptr<pb200::XLinearHostModel>> copies(devs.size());
+    for (size_t i = 1; i < devs.size(); ++i) copies[i] = std::make_unique<pb200::XLinearHostModel>(*host);
+    copies[0] = std::move(host);
+    fan_out(devs.size(), [&](size_t i) {
+        h->engines[i] = std::make_unique<pb200::XLinearEngine>(std::move(copies[i]), devs[i]);
+    });
+    return h.release();
+}
+
+// rows [0, rows) cut into n contiguous blocks of (nearly) equal nnz (pecos_b200.distributed.split_rows_by_nnz)
+std::vector<uint32_t> split_rows_by_nnz(const uint64_t* row_ptr, uint32_t rows, size_t n) {
+    std::vector<uint32_t> cut(n + 1, rows);
+    cut[0] = 0;
+    const uint64_t base = row_ptr[0], total = row_ptr[rows] - base;
+    for (size_t i = 1; i < n; ++i) {
+        const uint64_t target = base + total * i / n;
+        const uint64_t* p = std::lower_bound(row_ptr, row_ptr + rows + 1, target);
+        uint32_t r = static_cast<uint32_t>(p - row_ptr);
+        if (total == 0) r = static_cast<uint32_t>(static_cast<uint64_t>(rows) * i / n);
+        cut[i] = std::max(cut[i - 1], std::min(r, rows));
+    }
+    return cut;
+}
+
+constexpr uint32_t kFanOutMinRows = 256;  // below this many rows per device a single engine serves the call
 
 pb200::DeviceBuffer<unsigned char>* g_flush_buf = nullptr;
 std::mutex g_flush_mutex;
@@ -140,10 +231,16 @@ void c_xlinear_predict_csr_f32(void* ptr, const ScipyCsrF32* X, const uint32_t o
     (void)threads;
     PB200_API_BEGIN
     PB200_LOCK_XL(ptr)
-    auto& eng = engine_of(ptr);
-    auto r = eng.predict_csr(X->row_ptr, X->col_idx, X->val, X->rows, X->cols, overridden_beam_size,
-                             overridden_post_processor_str, overridden_only_topk);
-    emit_result(r, pred_alloc);
+    auto& H = *static_cast<XLinearHandle*>(ptr);
+    size_t n = H.engines.size();
+    if (static_cast<uint64_t>(X->rows) < static_cast<uint64_t>(kFanOutMinRows) * n) n = 1;
+    const auto cut = split_rows_by_nnz(X->row_ptr, X->rows, n);
+    std::vector<pb200::XLinearEngine::Result> parts(n);
+    fan_out(n, [&](size_t i) {
+        parts[i] = H.engines[i]->predict_csr(X->row_ptr + cut[i], X->col_idx, X->val, cut[i + 1] - cut[i], X->cols,
+                                             overridden_beam_size, overridden_post_processor_str, overridden_only_topk);
+    });
+    emit_results(parts, pred_alloc);
     PB200_API_END("c_xlinear_predict_csr_f32")
 }
 
@@ -153,11 +250,18 @@ void c_xlinear_predict_drm_f32(void* ptr, const ScipyDrmF32* X, const uint32_t o
     (void)threads;
     PB200_API_BEGIN
     PB200_LOCK_XL(ptr)
-    auto& eng = engine_of(ptr);
-    if (X->cols != eng.host().nr_features()) throw std::runtime_error("dense query width != nr_features");
-    auto r = eng.predict_drm(X->val, X->rows, X->cols, overridden_beam_size, overridden_post_processor_str,
-                             overridden_only_topk);
-    emit_result(r, pred_alloc);
+    auto& H = *static_cast<XLinearHandle*>(ptr);
+    if (X->cols != engine_of(ptr).host().nr_features()) throw std::runtime_error("dense query width != nr_features");
+    size_t n = H.engines.size();
+    if (static_cast<uint64_t>(X->rows) < static_cast<uint64_t>(kFanOutMinRows) * n) n = 1;
+    std::vector<pb200::XLinearEngine::Result> parts(n);
+    fan_out(n, [&](size_t i) {
+        const uint32_t r0 = static_cast<uint32_t>(static_cast<uint64_t>(X->rows) * i / n);
+        const uint32_t r1 = static_cast<uint32_t>(static_cast<uint64_t>(X->rows) * (i + 1) / n);
+        parts[i] = H.engines[i]->predict_drm(X->val + static_cast<uint64_t>(r0) * X->cols, r1 - r0, X->cols, overridden_beam_size,
+                                             overridden_post_processor_str, overridden_only_topk);
+    });
+    emit_results(parts, pred_alloc);
     PB200_API_END("c_xlinear_predict_drm_f32")
 }
 
@@ -251,7 +355,7 @@ std::shared_ptr<XLinearHandle> layer_engine(const ScipyCscF32* W, const ScipyCsc
     const pb200::CscRaw w{W->rows, W->cols, W->col_ptr, W->row_idx, W->val};
     const pb200::CscRaw c{C->rows, C->cols, C->col_ptr, C->row_idx, C->val};
     auto h = std::make_shared<XLinearHandle>();
-    h->engine = std::make_unique<pb200::XLinearEngine>(pb200::make_single_layer_model(w, c, bias), g_device.load());
+    h->engines.push_back(std::make_unique<pb200::XLinearEngine>(pb200::make_single_layer_model(w, c, bias), g_device.load()));
     g_layer_cache.push_back(CachedLayer{key, h, ++g_layer_clock});
     return h;
 }
@@ -263,7 +367,7 @@ void single_layer_predict(const ScipyCsrF32* Xs, const ScipyDrmF32* Xd, const Sc
     const uint32_t cols = Xs ? Xs->cols : Xd->cols;
     auto h = layer_engine(W, C, bias);
     std::lock_guard<std::mutex> lock(h->mu);
-    auto& eng = *h->engine;
+    auto& eng = *h->engines[0];
     // MLModel::predict_internal checks (inference.hpp:2041-2051)
     if (codes && codes->rows != rows) throw std::runtime_error("Instance dimension of query and prev_layer_pred matrix do not match");
     if (codes && codes->cols != C->cols) throw std::runtime_error("Label dimension of prev_layer_pred and C matrix do not match");
@@ -379,8 +483,8 @@ void pb200_xlinear_resident_fetch(void* ptr, py_sparse_allocator_t pred_alloc) {
 
 void* pb200_xlinear_load_sharded(const char* model_path, int weight_matrix_type, uint32_t shard_rank, uint32_t shard_world) {
     PB200_API_BEGIN
-    if (weight_matrix_type < 0) return make_engine(pb200::load_xlinear_mmap_model(model_path, false, shard_rank, shard_world));
-    return make_engine(pb200::load_xlinear_npz_model(model_path, weight_matrix_type, shard_rank, shard_world));
+    if (weight_matrix_type < 0) return make_engine(pb200::load_xlinear_mmap_model(model_path, false, shard_rank, shard_world), false);
+    return make_engine(pb200::load_xlinear_npz_model(model_path, weight_matrix_type, shard_rank, shard_world), false);
     PB200_API_END("pb200_xlinear_load_sharded")
 }
 
@@ -468,6 +572,13 @@ uint64_t pb200_xlinear_launches(void* ptr) {
     PB200_API_END("pb200_xlinear_launches")
 }
 
+uint32_t pb200_xlinear_replicas(void* ptr) {
+    PB200_API_BEGIN
+    if (!ptr) throw std::runtime_error("null model handle");
+    return static_cast<uint32_t>(static_cast<XLinearHandle*>(ptr)->engines.size());
+    PB200_API_END("pb200_xlinear_replicas")
+}
+
 uint64_t pb200_xlinear_model_bytes(void* ptr) {
     PB200_API_BEGIN
     return engine_of(ptr).model_bytes();
@@ -521,7 +632,7 @@ void pb200_xlinear_host_layer_export(void* hptr, uint32_t layer, void* chunks32,
 namespace {
 
 struct HnswHandle {
-    std::unique_ptr<pb200::HnswEngine> engine;
+    std::vector<std::unique_ptr<pb200::HnswEngine>> engines;  // [0] = primary; > 1: PB200_DEVICES replicas (query fan-out)
     std::mutex mu;  // per-warp search scratch lives with the engine: calls on one handle are serialised
 };
 
@@ -538,25 +649,36 @@ struct HnswSearchers {  // the reference hands out a vector<Searcher>; our scrat
 
 pb200::HnswEngine& hnsw_of(void* ptr) {
     if (!ptr) throw std::runtime_error("null HNSW handle");
-    return *static_cast<HnswHandle*>(ptr)->engine;
+    return *static_cast<HnswHandle*>(ptr)->engines.at(0);
 }
 
 void* hnsw_load(const char* model_dir, bool lazy_load, int metric) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0)
         throw std::runtime_error("no CUDA device visible: pecos_b200 has no CPU fallback");
-    auto host = pb200::load_hnsw_index(model_dir, metric, lazy_load);
-    auto h = new HnswHandle();
-    h->engine = std::make_unique<pb200::HnswEngine>(std::move(host), g_device.load());
-    return h;
+    const std::vector<int> devs = device_list();
+    auto h = std::make_unique<HnswHandle>();
+    h->engines.resize(devs.size());
+    // the host index is a view of the memory-mapped file: every replica maps it again (shared page cache)
+    std::vector<std::unique_ptr<pb200::HnswHostIndex>> views(devs.size());
+    for (size_t i = 0; i < devs.size(); ++i) views[i] = pb200::load_hnsw_index(model_dir, metric, lazy_load);
+    fan_out(devs.size(), [&](size_t i) { h->engines[i] = std::make_unique<pb200::HnswEngine>(std::move(views[i]), devs[i]); });
+    return h.release();
 }
 
 void hnsw_predict(void* model_ptr, const ScipyDrmF32* pX, uint32_t* ret_idx, float* ret_val, uint32_t efS, uint32_t topk,
                   int metric) {
     PB200_LOCK_HNSW(model_ptr)
-    auto& eng = hnsw_of(model_ptr);
-    if (eng.metric() != metric) throw std::runtime_error("HNSW handle was loaded with a different metric");
-    eng.predict(pX->val, pX->rows, pX->cols, efS, topk, ret_idx, ret_val);
+    auto& H = *static_cast<HnswHandle*>(model_ptr);
+    if (hnsw_of(model_ptr).metric() != metric) throw std::runtime_error("HNSW handle was loaded with a different metric");
+    size_t n = H.engines.size();  // replicas: contiguous row blocks, each engine writes its slice of the caller's arrays
+    if (static_cast<uint64_t>(pX->rows) < static_cast<uint64_t>(kFanOutMinRows) * n) n = 1;
+    fan_out(n, [&](size_t i) {
+        const uint32_t r0 = static_cast<uint32_t>(static_cast<uint64_t>(pX->rows) * i / n);
+        const uint32_t r1 = static_cast<uint32_t>(static_cast<uint64_t>(pX->rows) * (i + 1) / n);
+        H.engines[i]->predict(pX->val + static_cast<uint64_t>(r0) * pX->cols, r1 - r0, pX->cols, efS, topk,
+                              ret_idx + static_cast<uint64_t>(r0) * topk, ret_val + static_cast<uint64_t>(r0) * topk);
+    });
 }
 
 }  // namespace
@@ -628,6 +750,13 @@ void pb200_hnsw_get_counters(void* model_ptr, uint64_t* out) {
     auto c = hnsw_of(model_ptr).counters();
     out[0] = c.n_dist; out[1] = c.n_expand; out[2] = c.n_hops; out[3] = c.n_queries;
     PB200_API_END("pb200_hnsw_get_counters")
+}
+
+uint32_t pb200_hnsw_replicas(void* ptr) {
+    PB200_API_BEGIN
+    if (!ptr) throw std::runtime_error("null HNSW handle");
+    return static_cast<uint32_t>(static_cast<HnswHandle*>(ptr)->engines.size());
+    PB200_API_END("pb200_hnsw_replicas")
 }
 
 void pb200_hnsw_get_info(void* model_ptr, uint64_t* out) {

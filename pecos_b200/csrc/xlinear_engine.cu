@@ -956,8 +956,10 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     stats_dev_.reserve(8 * layers_.size());
@@ -981,7 +983,8 @@ void XLinearEngine::set_kernel_mode(int mode) {
     // 0: first generation (row-list streaming + block-wide sort); 1: default (query-warp / feature-map kernels + warp top-k);
     // 2: feature-map lookups with one warp per chunk (no query-warp kernel); 3: query-warp kernel wherever eligible;
     // 4: as 1 but the warp top-k evaluates the post-processor for every candidate (no estimate filter);
-    // 5: as 1 (kept for older scripts); 6: as 1 WITHOUT the chunk-major score kernel (query-major kernels only, for A/B tests)
+    // 5: as 1, and the chunk-major score kernel wherever it FITS (its reuse / occupancy heuristics ignored; tests);
+    // 6: as 1 WITHOUT the chunk-major score kernel (query-major kernels only, for A/B tests)
     const bool on = mode != 0;
     for (auto& l : layers_) l.view.featmap = (on && l.featmap.capacity()) ? l.featmap.get() : nullptr;
     force_block_topk_ = !on;
@@ -989,6 +992,7 @@ void XLinearEngine::set_kernel_mode(int mode) {
     force_query_warp_ = (mode == 3);
     no_topk_filter_ = (mode == 4);
     chunk_major_ = on && (mode != 6);
+    cm_force_ = (mode == 5);
 }
 
 bool XLinearEngine::has_feature_maps() const {
@@ -1118,8 +1122,8 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
         // Chunk-major scoring (xlinear_cm_kernel.cuh) wherever the layer's feature map + largest chunk fit in shared memory
         // and the chunks are visited by enough pairs to amortise the staging; otherwise the query-major kernels below.
         const CmPlan cm = (chunk_major_ && lookup && cm_slot_pos_.capacity())
-                              ? cm_plan(L.fm_words, host_->layers[d].r_max, layers_[d].e_max, L.c_max, L.n_chunks,
-                                        static_cast<uint64_t>(rows) * lp.b_prev)
+                              ? cm_plan(L.fm_words, L.w_rows, host_->layers[d].r_max, layers_[d].e_max, L.c_max, L.n_chunks,
+                                        static_cast<uint64_t>(rows) * lp.b_prev, cm_force_)
                               : CmPlan{};
         const bool chunk_major = cm.eligible;
         if (chunk_major) {
@@ -1131,12 +1135,12 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
             xl_cm_scan_kernel<<<1, 1024, 0, stream_>>>(L.n_chunks, w);
             xl_cm_scatter_kernel<<<warp_grid, 128, 0, stream_>>>(L, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w);
             const uint64_t max_items = (static_cast<uint64_t>(rows) * lp.b_prev + w.item_pairs - 1) / w.item_pairs + L.n_chunks;
-            if (collect_stats)
-                xl_cm_scores_kernel<true><<<static_cast<uint32_t>(max_items), cm.warps * 32, cm.smem, stream_>>>(
+            auto launch_cm = [&](auto kernel) {
+                kernel<<<static_cast<uint32_t>(max_items), cm.warps * 32, cm.smem, stream_>>>(
                     L, q, w, cand_.get(), cand_stride_q, stats, cm.fm_words, cm.r_cap, cm.e_cap, cm.acc_cols);
-            else
-                xl_cm_scores_kernel<false><<<static_cast<uint32_t>(max_items), cm.warps * 32, cm.smem, stream_>>>(
-                    L, q, w, cand_.get(), cand_stride_q, stats, cm.fm_words, cm.r_cap, cm.e_cap, cm.acc_cols);
+            };
+            if (collect_stats) { if (cm.direct) launch_cm(xl_cm_scores_kernel<true, true>); else launch_cm(xl_cm_scores_kernel<true, false>); }
+            else { if (cm.direct) launch_cm(xl_cm_scores_kernel<false, true>); else launch_cm(xl_cm_scores_kernel<false, false>); }
             launches_ += 3;  // + the score kernel counted below
         } else if (query_warp) {
             const uint32_t qw_qcap = std::max<uint32_t>(32u, (q.max_row_nnz + 31u) & ~31u);

@@ -54,7 +54,7 @@ def test_chunk_major_kernel_equals_default_kernels_and_oracles(tmp_path, gpu_cli
             kid = (c_int * 6)()
             c.pb200_xlinear_get_kernel_ids(h, kid)
             assert 4 not in [kid[2 * d] for d in range(len(sizes))], "kernel mode 6 must not use the chunk-major kernel"
-            c.pb200_xlinear_set_lookup(h, 1)
+            c.pb200_xlinear_set_lookup(h, 5)  # chunk-major wherever it fits (mode 1 also asks for >= 148 work items)
             got = m.predict(Xq, beam_size=10, only_topk=8, post_processor=pp)
             c.pb200_xlinear_get_kernel_ids(h, kid)
             assert all(kid[2 * d] == 4 for d in range(len(sizes))), "the chunk-major kernel must serve every layer of this model"
@@ -79,8 +79,9 @@ def test_chunk_major_tiles_and_small_batches(tmp_path, gpu_clib, have_ref):
     h = m.model.model_chain
     c.pb200_xlinear_set_lookup(h, 6)
     base = m.predict(X, beam_size=8, only_topk=6)
-    c.pb200_xlinear_set_lookup(h, 1)
+    c.pb200_xlinear_set_lookup(h, 5)
     assert_csr_parity(m.predict(X, beam_size=8, only_topk=6, max_pred_chunk=1300), base, rtol=0.0, what="tiled")
+    c.pb200_xlinear_set_lookup(h, 1)
     small = m.predict(X[:5], beam_size=8, only_topk=6)
     kid = (c_int * 6)()
     c.pb200_xlinear_get_kernel_ids(h, kid)
