@@ -78,6 +78,20 @@ void c_xlinear_predict_drm_f32(void* ptr, const ScipyDrmF32* input_x, const uint
                                const char* overridden_post_processor_str, const uint32_t overridden_only_topk,
                                const int threads, py_sparse_allocator_t pred_alloc);
 
+/* libpecos.cpp:179-198  predict_on_selected_outputs: scores of exactly the (query, label) pairs of the CSR pattern
+ * selected_outputs_csr (rows x nr_labels; values ignored), pushed through the hierarchy (transform + combine per layer), no
+ * top-k (HierarchicalMLModel::predict_on_selected_outputs, pecos/core/xmc/inference.hpp:2507-2571).  Result: CSR with the
+ * selected rows' lengths; a row's entries come in the reference's order (parents in the previous layer's order, children
+ * in C's column order); labels without a path to the root leave zero entries at the row's end, like the reference.
+ * The reference serves this from CSC layers only (inference.hpp:2143-2147; its Python gates on get_layer_type == CSC):
+ * here every handle can, and the arithmetic is the beam-search kernels' (bit-identical raw scores). */
+void c_xlinear_predict_on_selected_outputs_csr_f32(void* ptr, const ScipyCsrF32* X, const ScipyCsrF32* selected_outputs_csr,
+                                                   const char* overridden_post_processor_str, const int threads,
+                                                   py_sparse_allocator_t pred_alloc);
+void c_xlinear_predict_on_selected_outputs_drm_f32(void* ptr, const ScipyDrmF32* X, const ScipyCsrF32* selected_outputs_csr,
+                                                   const char* overridden_post_processor_str, const int threads,
+                                                   py_sparse_allocator_t pred_alloc);
+
 /* libpecos.cpp:201-235  One layer of the python prediction chain (pecos/xmc/base.py:890-949, is_predict_only=False
  * models): W ((nr_features [+1 bias row]) x nr_labels) and C (nr_labels x nr_codes) are handed over on every call;
  * csr_codes = the previous layer's prediction (rows x nr_codes, entries consumed in stored order) or NULL for the first
@@ -85,8 +99,7 @@ void c_xlinear_predict_drm_f32(void* ptr, const ScipyDrmF32* input_x, const uint
  * reference).  The chunked HBM layout of (W, C, bias) is built on first use and kept in a small LRU cache keyed by the
  * matrices' shapes, value pointer and a sampled content fingerprint (PB200_LAYER_CACHE entries, default 8): the
  * matrices are assumed immutable while cached (pb200_layer_cache_clear() drops them).
- * STATUS: written at the end of round 1 without GPU time left -- parity-pinned on the CPU side (oracle vs reference,
- * tests/test_oracle_cpu.py), GPU tests in tests/test_single_layer_gpu.py run only with PB200_UNVALIDATED=1. */
+ * Validated on a B200 (tests/test_single_layer_gpu.py); oracle pinned against the reference in tests/test_oracle_cpu.py. */
 void c_xlinear_single_layer_predict_csr_f32(const ScipyCsrF32* input_x, const ScipyCsrF32* csr_codes, ScipyCscF32* W,
                                             ScipyCscF32* C, const char* post_processor_str, const uint32_t only_topk,
                                             const int num_threads, const float bias, py_sparse_allocator_t pred_alloc);

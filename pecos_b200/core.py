@@ -203,6 +203,10 @@ class B200CoreLib(object):
         fp(c.c_xlinear_predict_csr_f32, None, [c_void_p, POINTER(ScipyCsrF32)] + pred_args)
         fp(c.c_xlinear_predict_drm_f32, None, [c_void_p, POINTER(ScipyDrmF32)] + pred_args)
 
+        sel_args = [POINTER(ScipyCsrF32), c_char_p, c_int, ScipyCompressedSparseAllocator.CFUNCTYPE]  # pecos/core/base.py:846-876
+        fp(c.c_xlinear_predict_on_selected_outputs_csr_f32, None, [c_void_p, POINTER(ScipyCsrF32)] + sel_args)
+        fp(c.c_xlinear_predict_on_selected_outputs_drm_f32, None, [c_void_p, POINTER(ScipyDrmF32)] + sel_args)
+
         single = [POINTER(ScipyCsrF32), POINTER(ScipyCscF32), POINTER(ScipyCscF32), c_char_p, c_uint32, c_int, c_float,
                   ScipyCompressedSparseAllocator.CFUNCTYPE]  # pecos/core/base.py:880-933
         fp(c.c_xlinear_single_layer_predict_csr_f32, None, [POINTER(ScipyCsrF32)] + single)
@@ -300,6 +304,33 @@ class B200CoreLib(object):
         )
 
     # ---------------------------------------------------------------- HNSW (base.py:1865-1964)
+    def xlinear_predict_on_selected_outputs(self, c_model, X, selected_outputs_csr, overriden_post_processor_str, threads, pred_alloc):
+        """Argument handling of corelib.xlinear_predict_on_selected_outputs (pecos/core/base.py:1097-1160)."""
+        clib = self.clib_float32
+        if isinstance(X, smat.csr_matrix):
+            if not X.has_sorted_indices:
+                raise ValueError("Query matrix does not have sorted indices!")
+            X = ScipyCsrF32.init_from(X)
+        elif isinstance(X, np.ndarray):
+            X = ScipyDrmF32.init_from(X)
+        if not isinstance(selected_outputs_csr, smat.csr_matrix):
+            raise ValueError("type(selected_outputs_csr) = {} not implemented".format(type(selected_outputs_csr)))
+        selected = ScipyCsrF32.init_from(selected_outputs_csr)
+        if isinstance(X, ScipyCsrF32):
+            c_predict = clib.c_xlinear_predict_on_selected_outputs_csr_f32
+        elif isinstance(X, ScipyDrmF32):
+            c_predict = clib.c_xlinear_predict_on_selected_outputs_drm_f32
+        else:
+            raise NotImplementedError("type(X) = {} not implemented".format(type(X)))
+        c_predict(
+            c_model,
+            byref(X),
+            byref(selected),
+            overriden_post_processor_str.encode("utf-8") if overriden_post_processor_str else None,
+            threads,
+            pred_alloc.cfunc,
+        )
+
     def link_ann_hnsw_methods(self):
         c = self.clib_float32
         fp = B200CoreLib.fillprototype

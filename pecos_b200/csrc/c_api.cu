@@ -265,6 +265,57 @@ void c_xlinear_predict_drm_f32(void* ptr, const ScipyDrmF32* X, const uint32_t o
     PB200_API_END("c_xlinear_predict_drm_f32")
 }
 
+// ------------------------------------------------ selected outputs -----------------------------------------------
+}  // extern "C"
+
+namespace {
+
+void predict_selected(void* ptr, const ScipyCsrF32* Xs, const ScipyDrmF32* Xd, const ScipyCsrF32* sel, const char* pp,
+                      py_sparse_allocator_t pred_alloc) {
+    PB200_LOCK_XL(ptr)
+    auto& eng = engine_of(ptr);
+    const uint32_t rows = Xs ? Xs->rows : Xd->rows;
+    const uint32_t cols = Xs ? Xs->cols : Xd->cols;
+    if (!sel) throw std::runtime_error("selected_outputs_csr is required");
+    if (sel->rows != rows) throw std::runtime_error("Instance dimension of query and selected output matrix do not match");
+    if (Xd && cols != eng.host().nr_features()) throw std::runtime_error("dense query width != nr_features");
+    auto r = eng.predict_selected(Xs ? Xs->row_ptr : nullptr, Xs ? Xs->col_idx : nullptr, Xs ? Xs->val : nullptr,
+                                  Xd ? Xd->val : nullptr, rows, cols, sel->row_ptr, sel->col_idx, sel->cols, pp);
+    uint32_t* indices = nullptr;
+    uint64_t* indptr = nullptr;
+    float* data = nullptr;
+    const uint64_t nnz = r.indptr.empty() ? 0 : r.indptr.back();
+    pred_alloc(false, r.rows, r.cols, nnz, &indices, &indptr, &data);
+    if (!indptr || (nnz && (!indices || !data))) throw std::runtime_error("result allocator returned null buffers");
+    std::memcpy(indptr, r.indptr.data(), r.indptr.size() * sizeof(uint64_t));
+    if (nnz) {
+        std::memcpy(indices, r.indices.data(), nnz * sizeof(uint32_t));
+        std::memcpy(data, r.data.data(), nnz * sizeof(float));
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+void c_xlinear_predict_on_selected_outputs_csr_f32(void* ptr, const ScipyCsrF32* X, const ScipyCsrF32* selected_outputs_csr,
+                                                   const char* overridden_post_processor_str, const int threads,
+                                                   py_sparse_allocator_t pred_alloc) {
+    (void)threads;
+    PB200_API_BEGIN
+    predict_selected(ptr, X, nullptr, selected_outputs_csr, overridden_post_processor_str, pred_alloc);
+    PB200_API_END("c_xlinear_predict_on_selected_outputs_csr_f32")
+}
+
+void c_xlinear_predict_on_selected_outputs_drm_f32(void* ptr, const ScipyDrmF32* X, const ScipyCsrF32* selected_outputs_csr,
+                                                   const char* overridden_post_processor_str, const int threads,
+                                                   py_sparse_allocator_t pred_alloc) {
+    (void)threads;
+    PB200_API_BEGIN
+    predict_selected(ptr, nullptr, X, selected_outputs_csr, overridden_post_processor_str, pred_alloc);
+    PB200_API_END("c_xlinear_predict_on_selected_outputs_drm_f32")
+}
+
 // ------------------------------------------------ single layer (python chain) ------------------------------------
 }  // extern "C"
 

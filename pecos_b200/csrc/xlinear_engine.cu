@@ -20,7 +20,10 @@
 #include "xlinear_engine.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <exception>
+#include <thread>
 
 namespace pb200 {
 
@@ -776,6 +779,10 @@ xl_topk_warp_kernel(const LayerDev L, const int pp_kind, const int pp_p, const i
 
 #include "xlinear_topk_filter.cuh"
 
+#define PB200_SELECTED_KERNELS
+#include "xlinear_selected.cuh"
+#undef PB200_SELECTED_KERNELS
+
 // K3 (index sharding): merge the per-GPU top-k lists gathered by ONE all-gather into the global top-k.
 // gathered layout: [world][rows][stride] for keys / ids / vals and [world][rows] for counts.  Keys are globally unique
 // (they embed the candidate's position in the full prolongated row), so the merge is an exact arg-max selection.
@@ -1074,6 +1081,88 @@ void XLinearEngine::ensure_workspace_(const std::vector<LayerPlan>& plan, uint32
     if (sort_max) sortbuf_.reserve(static_cast<uint64_t>(tile_rows) * sort_max);
 }
 
+// Launches the score kernel of layer d for the beam held in beam_*_[cur] (capacity b_prev slots per query): fills
+// cand_[q * b_prev * c_max + slot_base(j) + c] with the raw scores of every child of every beam node, in prolongation order.
+// Chooses between the chunk-major, query-warp, feature-map, row-list and dense kernels.  Returns the kernel id.
+int XLinearEngine::score_layer_(size_t d, const QueryDev& q, uint32_t b_prev, int cur, bool collect_stats) {
+    const LayerDev& L = layers_[d].view;
+    const uint32_t rows = q.rows;
+    const bool dense = (q.row_ptr == nullptr);
+    const uint32_t c_stride = std::max<uint32_t>(L.c_max, 1u);
+    const uint64_t cand_stride_q = static_cast<uint64_t>(b_prev) * c_stride;
+    unsigned long long* stats = collect_stats ? stats_dev_.get() + 8 * d : nullptr;
+    // spread the beam slots evenly: b = 10 -> 10 warps x 1 slot, b = 20 -> 10 warps x 2 slots
+    const uint32_t rounds = (b_prev + kWarpsMax - 1) / kWarpsMax;
+    const int warps = static_cast<int>(std::max<uint32_t>(1, (b_prev + rounds - 1) / std::max<uint32_t>(rounds, 1)));
+    const dim3 grid(rows), block(warps * 32);
+    const bool lookup = !dense && L.featmap != nullptr;
+    // query staging area: as small as the batch's longest row allows (occupancy), at most kQCap non-zeros
+    const uint32_t q_cap = dense ? 32u : std::min<uint32_t>(kQCap, std::max<uint32_t>(32u, (q.max_row_nnz + 31u) & ~31u));
+    const uint32_t sb_cap = (b_prev + 1u + 3u) & ~3u;
+    const uint32_t hdr_cap = b_prev <= 128u ? b_prev : 0u;  // beam chunk headers cached in shared memory
+    const size_t smem1 = chunk_kernel_smem(warps, lookup, q_cap, sb_cap, hdr_cap);
+    auto launch = [&](auto kernel) {
+        kernel<<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(),
+                                               cand_stride_q, c_stride, stats, q_cap, sb_cap, hdr_cap);
+    };
+    // One warp per query over the whole beam (feature-major).  Measured on B200: it wins when the beam consists of
+    // MANY NARROW chunks (per-chunk bookkeeping dominates: S layers 1-4, 20 x 8 columns: 2.1-2.9 ms vs 3.1 ms), and
+    // loses on wide chunks where one warp per chunk keeps more loads in flight (E leaf 2.2 vs 1.45 ms, S leaf 12.7 vs
+    // 8.4 ms).  force_query_warp_ (kernel mode 3) selects it whenever it is eligible, for tests.
+    const bool qw_eligible = lookup && b_prev <= static_cast<uint32_t>(kQwSlots) &&
+                             cand_stride_q <= static_cast<uint64_t>(kQwNCap) && q.max_row_nnz <= kQwQCap;
+    const bool query_warp = qw_eligible && !no_query_warp_ &&
+                            (force_query_warp_ || (b_prev >= 16u && cand_stride_q <= 256u));
+    // Chunk-major scoring (xlinear_cm_kernel.cuh) wherever the layer's feature map + largest chunk fit in shared memory
+    // and the chunks are visited by enough pairs to amortise the staging; otherwise the query-major kernels below.
+    const CmPlan cm = (chunk_major_ && lookup && cm_slot_pos_.capacity())
+                          ? cm_plan(L.fm_words, L.w_rows, host_->layers[d].r_max, layers_[d].e_max, L.c_max, L.n_chunks,
+                                    static_cast<uint64_t>(rows) * b_prev, cm_force_)
+                          : CmPlan{};
+    const bool chunk_major = cm.eligible;
+    if (chunk_major) {
+        CmWork w{cm_slot_pos_.get(), cm_count_.get(), cm_bucket_ptr_.get(), cm_item_ptr_.get(), cm_pair_q_.get(), cm_pair_pos_.get(),
+                 cm.warps * 32u};
+        PB200_CUDA(cudaMemsetAsync(w.count, 0, (static_cast<uint64_t>(L.n_chunks) + 1) * 4, stream_));
+        const uint32_t warp_grid = (rows * 32u + 127u) / 128u;
+        xl_cm_count_kernel<<<warp_grid, 128, 0, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w, stats);
+        xl_cm_scan_kernel<<<1, 1024, 0, stream_>>>(L.n_chunks, w);
+        xl_cm_scatter_kernel<<<warp_grid, 128, 0, stream_>>>(L, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w);
+        const uint64_t max_items = (static_cast<uint64_t>(rows) * b_prev + w.item_pairs - 1) / w.item_pairs + L.n_chunks;
+        auto launch_cm = [&](auto kernel) {
+            kernel<<<static_cast<uint32_t>(max_items), cm.warps * 32, cm.smem, stream_>>>(
+                L, q, w, cand_.get(), cand_stride_q, stats, cm.fm_words, cm.r_cap, cm.e_cap, cm.acc_cols);
+        };
+        if (collect_stats) { if (cm.direct) launch_cm(xl_cm_scores_kernel<true, true>); else launch_cm(xl_cm_scores_kernel<true, false>); }
+        else { if (cm.direct) launch_cm(xl_cm_scores_kernel<false, true>); else launch_cm(xl_cm_scores_kernel<false, false>); }
+        launches_ += 3;  // + the score kernel counted below
+    } else if (query_warp) {
+        const uint32_t qw_qcap = std::max<uint32_t>(32u, (q.max_row_nnz + 31u) & ~31u);
+        const uint32_t qw_ncap = static_cast<uint32_t>((cand_stride_q + 31) & ~static_cast<uint64_t>(31));
+        const size_t qw_smem = kQwWarps * ((qw_warp_bytes(qw_qcap, qw_ncap) + 15) & ~static_cast<size_t>(15));
+        const dim3 qw_grid((rows + kQwWarps - 1) / kQwWarps);
+        if (collect_stats)
+            xl_query_warp_scores_kernel<true><<<qw_grid, kQwWarps * 32, qw_smem, stream_>>>(
+                L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(), cand_stride_q, stats, qw_qcap, qw_ncap, rows);
+        else
+            xl_query_warp_scores_kernel<false><<<qw_grid, kQwWarps * 32, qw_smem, stream_>>>(
+                L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(), cand_stride_q, stats, qw_qcap, qw_ncap, rows);
+    } else if (dense) {
+        if (collect_stats) launch(xl_chunk_scores_kernel<true, true, false>);
+        else launch(xl_chunk_scores_kernel<true, false, false>);
+    } else if (lookup) {
+        if (collect_stats) launch(xl_chunk_scores_kernel<false, true, true>);
+        else launch(xl_chunk_scores_kernel<false, false, true>);
+    } else {
+        if (collect_stats) launch(xl_chunk_scores_kernel<false, true, false>);
+        else launch(xl_chunk_scores_kernel<false, false, false>);
+    }
+    PB200_CUDA(cudaGetLastError());
+    ++launches_;
+    layer_profile_[d].scores_kernel = chunk_major ? 4 : query_warp ? 3 : dense ? 2 : lookup ? 1 : 0;
+    return layer_profile_[d].scores_kernel;
+}
+
 // Runs every layer over one tile of queries.  The last layer writes into res_*_dev_ at row offset res_row0_.
 // ext_beam: beam_*_[0] already hold the beam entering the first layer (single-layer entry point); combine_first: that
 // layer combines its scores with the beam values (a previous prediction was given).
@@ -1095,77 +1184,11 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
         const int combine = (d == 0) ? combine_first : 1;
         const uint32_t c_stride = std::max<uint32_t>(L.c_max, 1u);
         const uint64_t cand_stride_q = static_cast<uint64_t>(lp.b_prev) * c_stride;
-        // spread the beam slots evenly: b = 10 -> 10 warps x 1 slot, b = 20 -> 10 warps x 2 slots
-        const uint32_t rounds = (lp.b_prev + kWarpsMax - 1) / kWarpsMax;
-        const int warps = static_cast<int>(std::max<uint32_t>(1, (lp.b_prev + rounds - 1) / std::max<uint32_t>(rounds, 1)));
         unsigned long long* stats = collect_stats ? stats_dev_.get() + 8 * d : nullptr;
         if (profile_) PB200_CUDA(cudaEventRecord(ev_[0], stream_));
-        const dim3 grid(rows), block(warps * 32);
-        const bool lookup = !dense && L.featmap != nullptr;
-        // query staging area: as small as the batch's longest row allows (occupancy), at most kQCap non-zeros
-        const uint32_t q_cap = dense ? 32u : std::min<uint32_t>(kQCap, std::max<uint32_t>(32u, (q.max_row_nnz + 31u) & ~31u));
-        const uint32_t sb_cap = (lp.b_prev + 1u + 3u) & ~3u;
-        const uint32_t hdr_cap = lp.b_prev <= 128u ? lp.b_prev : 0u;  // beam chunk headers cached in shared memory
-        const size_t smem1 = chunk_kernel_smem(warps, lookup, q_cap, sb_cap, hdr_cap);
-        auto launch = [&](auto kernel) {
-            kernel<<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(),
-                                                   cand_stride_q, c_stride, stats, q_cap, sb_cap, hdr_cap);
-        };
-        // One warp per query over the whole beam (feature-major).  Measured on B200: it wins when the beam consists of
-        // MANY NARROW chunks (per-chunk bookkeeping dominates: S layers 1-4, 20 x 8 columns: 2.1-2.9 ms vs 3.1 ms), and
-        // loses on wide chunks where one warp per chunk keeps more loads in flight (E leaf 2.2 vs 1.45 ms, S leaf 12.7 vs
-        // 8.4 ms).  force_query_warp_ (kernel mode 3) selects it whenever it is eligible, for tests.
-        const bool qw_eligible = lookup && lp.b_prev <= static_cast<uint32_t>(kQwSlots) &&
-                                 cand_stride_q <= static_cast<uint64_t>(kQwNCap) && q.max_row_nnz <= kQwQCap;
-        const bool query_warp = qw_eligible && !no_query_warp_ &&
-                                (force_query_warp_ || (lp.b_prev >= 16u && cand_stride_q <= 256u));
-        // Chunk-major scoring (xlinear_cm_kernel.cuh) wherever the layer's feature map + largest chunk fit in shared memory
-        // and the chunks are visited by enough pairs to amortise the staging; otherwise the query-major kernels below.
-        const CmPlan cm = (chunk_major_ && lookup && cm_slot_pos_.capacity())
-                              ? cm_plan(L.fm_words, L.w_rows, host_->layers[d].r_max, layers_[d].e_max, L.c_max, L.n_chunks,
-                                        static_cast<uint64_t>(rows) * lp.b_prev, cm_force_)
-                              : CmPlan{};
-        const bool chunk_major = cm.eligible;
-        if (chunk_major) {
-            CmWork w{cm_slot_pos_.get(), cm_count_.get(), cm_bucket_ptr_.get(), cm_item_ptr_.get(), cm_pair_q_.get(), cm_pair_pos_.get(),
-                     cm.warps * 32u};
-            PB200_CUDA(cudaMemsetAsync(w.count, 0, (static_cast<uint64_t>(L.n_chunks) + 1) * 4, stream_));
-            const uint32_t warp_grid = (rows * 32u + 127u) / 128u;
-            xl_cm_count_kernel<<<warp_grid, 128, 0, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w, stats);
-            xl_cm_scan_kernel<<<1, 1024, 0, stream_>>>(L.n_chunks, w);
-            xl_cm_scatter_kernel<<<warp_grid, 128, 0, stream_>>>(L, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w);
-            const uint64_t max_items = (static_cast<uint64_t>(rows) * lp.b_prev + w.item_pairs - 1) / w.item_pairs + L.n_chunks;
-            auto launch_cm = [&](auto kernel) {
-                kernel<<<static_cast<uint32_t>(max_items), cm.warps * 32, cm.smem, stream_>>>(
-                    L, q, w, cand_.get(), cand_stride_q, stats, cm.fm_words, cm.r_cap, cm.e_cap, cm.acc_cols);
-            };
-            if (collect_stats) { if (cm.direct) launch_cm(xl_cm_scores_kernel<true, true>); else launch_cm(xl_cm_scores_kernel<true, false>); }
-            else { if (cm.direct) launch_cm(xl_cm_scores_kernel<false, true>); else launch_cm(xl_cm_scores_kernel<false, false>); }
-            launches_ += 3;  // + the score kernel counted below
-        } else if (query_warp) {
-            const uint32_t qw_qcap = std::max<uint32_t>(32u, (q.max_row_nnz + 31u) & ~31u);
-            const uint32_t qw_ncap = static_cast<uint32_t>((cand_stride_q + 31) & ~static_cast<uint64_t>(31));
-            const size_t qw_smem = kQwWarps * ((qw_warp_bytes(qw_qcap, qw_ncap) + 15) & ~static_cast<size_t>(15));
-            const dim3 qw_grid((rows + kQwWarps - 1) / kQwWarps);
-            if (collect_stats)
-                xl_query_warp_scores_kernel<true><<<qw_grid, kQwWarps * 32, qw_smem, stream_>>>(
-                    L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(), cand_stride_q, stats, qw_qcap, qw_ncap, rows);
-            else
-                xl_query_warp_scores_kernel<false><<<qw_grid, kQwWarps * 32, qw_smem, stream_>>>(
-                    L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(), cand_stride_q, stats, qw_qcap, qw_ncap, rows);
-        } else if (dense) {
-            if (collect_stats) launch(xl_chunk_scores_kernel<true, true, false>);
-            else launch(xl_chunk_scores_kernel<true, false, false>);
-        } else if (lookup) {
-            if (collect_stats) launch(xl_chunk_scores_kernel<false, true, true>);
-            else launch(xl_chunk_scores_kernel<false, false, true>);
-        } else {
-            if (collect_stats) launch(xl_chunk_scores_kernel<false, true, false>);
-            else launch(xl_chunk_scores_kernel<false, false, false>);
-        }
-        PB200_CUDA(cudaGetLastError());
-        ++launches_;
-        layer_profile_[d].scores_kernel = chunk_major ? 4 : query_warp ? 3 : dense ? 2 : lookup ? 1 : 0;
+        const dim3 grid(rows);
+        const bool chunk_major = score_layer_(d, q, lp.b_prev, cur, collect_stats) == 4;
+        (void)chunk_major;
         if (profile_) PB200_CUDA(cudaEventRecord(ev_[1], stream_));
 
         const bool last = (d + 1 == depth);
@@ -1519,5 +1542,9 @@ XLinearEngine::Result XLinearEngine::resident_fetch() {
     PB200_CUDA(cudaSetDevice(device_));
     return finish_result_(resident_.rows, res_stride_);
 }
+
+#define PB200_SELECTED_ENGINE
+#include "xlinear_selected.cuh"
+#undef PB200_SELECTED_ENGINE
 
 }  // namespace pb200

@@ -94,6 +94,19 @@ public:
                                 uint32_t rows, uint32_t cols, const uint64_t* codes_row_ptr, const uint32_t* codes_col_idx,
                                 const float* codes_val, const char* post_processor, uint32_t only_topk);
 
+    // predict_on_selected_outputs (c_xlinear_predict_on_selected_outputs_*, pecos/core/libpecos.cpp:179-198): scores of exactly
+    // the (query, label) pairs of the CSR pattern `sel_*` (rows x nr_labels), pushed through the hierarchy, no top-k.
+    // Result rows have the selected rows' lengths; entry order = the reference's (see xlinear_selected.cuh).
+    struct SelectedResult {
+        uint32_t rows = 0, cols = 0;
+        std::vector<uint64_t> indptr;
+        std::vector<uint32_t> indices;
+        std::vector<float> data;
+    };
+    SelectedResult predict_selected(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, const float* dense,
+                                    uint32_t rows, uint32_t cols, const uint64_t* sel_ptr, const uint32_t* sel_idx,
+                                    uint32_t sel_cols, const char* post_processor);
+
     // Device-resident queries (bench "value" leg: inputs already in HBM when the timed region starts).
     void resident_upload_csr(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, uint32_t rows, uint32_t cols);
     // Runs all layers over the resident batch; results stay in HBM (fetch with resident_fetch). Returns device ms.
@@ -143,7 +156,13 @@ private:
     uint32_t pick_tile_rows_(const std::vector<LayerPlan>& plan, uint32_t rows) const;
     void run_tile_(const QueryDev& q, const std::vector<LayerPlan>& plan, bool collect_stats, bool ext_beam = false,
                    int combine_first = 0);
+    int score_layer_(size_t d, const QueryDev& q, uint32_t b_prev, int cur, bool collect_stats);
     Result finish_result_(uint32_t rows, uint32_t stride);
+
+    struct SelIndex {  // per layer: label -> (chunk, column offset); built on the first predict_selected call
+        std::vector<uint32_t> chunk_of_label, offset_of_label;
+    };
+    std::vector<SelIndex> sel_index_;
 
     std::unique_ptr<XLinearHostModel> host_;
     int device_ = 0;

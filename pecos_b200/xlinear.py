@@ -277,6 +277,47 @@ class HierarchicalMLModel(object):
         return pred_alloc.get()
 
 
+    def predict_on_selected_outputs(self, X, selected_outputs_csr, csr_codes=None, pred_params=None, **kwargs):
+        """Scores of exactly the (instance, label) pairs of ``selected_outputs_csr`` (pecos/xmc/base.py:1670-1771).  Unlike the
+        reference, which serves this from CSC-layout handles only, every pecos_b200 handle can."""
+        if X.dtype != np.float32:
+            raise ValueError("X.dtype = {} is not supported".format(X.dtype))
+        if not isinstance(X, smat.csr_matrix) and not (isinstance(X, np.ndarray) and X.flags["C_CONTIGUOUS"]):
+            raise ValueError("type(X) = {} is not supported".format(type(X)))
+        if X.shape[1] != self.nr_features:
+            raise ValueError("Feature dimension of query matrix does not match weight matrix")
+        if not isinstance(selected_outputs_csr, smat.csr_matrix):
+            raise ValueError("type(selected_outputs_csr) = {} is not supported".format(type(selected_outputs_csr)))
+        if selected_outputs_csr.shape[1] != self.nr_labels:
+            raise ValueError("Label dimension of selected output matrix does not match")
+        if X.shape[0] != selected_outputs_csr.shape[0]:
+            raise ValueError("Instance dimension of query and selected output matrix do not match")
+        if csr_codes is not None:
+            raise NotImplementedError("is_predict_only=True did not support csr_codes being not None")
+        if pred_params is None:
+            pred_params = self.get_pred_params()
+        elif isinstance(pred_params, self.PredParams):
+            pred_params = copy.deepcopy(pred_params)
+            if len(pred_params.model_chain) != self.depth:
+                raise ValueError("len(pred_params.model_chain) != depth")
+        else:
+            raise ValueError("unknown type(pred_params)!!")
+        pred_params.override_with_kwargs(kwargs)
+        old_chain = self.get_pred_params().model_chain
+        new_chain = pred_params.model_chain
+        if all(o.post_processor == n.post_processor for (o, n) in zip(old_chain, new_chain)):
+            overridden_post_processor = None
+        elif all(new_chain[0].post_processor == n.post_processor for n in new_chain):
+            overridden_post_processor = new_chain[0].post_processor
+        else:
+            raise NotImplementedError("when is_predict_only=True, post_processor is not supported for overriddng")
+        pred_alloc = ScipyCompressedSparseAllocator()
+        self._clib.xlinear_predict_on_selected_outputs(
+            self.model_chain, X, selected_outputs_csr, overridden_post_processor, kwargs.get("threads", -1), pred_alloc
+        )
+        return pred_alloc.get()
+
+
 class XLinearModel(object):
     """Predict-only ``XLinearModel`` (pecos/xmc/xlinear/model.py)."""
 
@@ -324,18 +365,22 @@ class XLinearModel(object):
     def predict(self, X, pred_params=None, selected_outputs_csr=None, **kwargs):
         if (pred_params is not None) and (not isinstance(pred_params, self.PredParams)):
             raise TypeError("type(pred_kwargs) is not supported")
-        if selected_outputs_csr is not None:
-            raise NotImplementedError("predict_on_selected_outputs is not served by pecos_b200")
+        if selected_outputs_csr is not None and not hasattr(self.model, "predict_on_selected_outputs"):
+            raise NotImplementedError("predict_on_selected_outputs needs a predict-only model (is_predict_only=True)")
         max_pred_chunk = kwargs.get("max_pred_chunk", 10**7)
         if max_pred_chunk is not None and not isinstance(max_pred_chunk, int):
             raise TypeError("type(max_pred_chunk) is not supported.")
+        hlm_args = None if pred_params is None else pred_params.hlm_args
         if max_pred_chunk is None or max_pred_chunk >= X.shape[0]:
-            return self.model.predict(X, pred_params=None if pred_params is None else pred_params.hlm_args, **kwargs)
+            if selected_outputs_csr is None:
+                return self.model.predict(X, pred_params=hlm_args, **kwargs)
+            return self.model.predict_on_selected_outputs(X, selected_outputs_csr, pred_params=hlm_args, **kwargs)
         Ys = []
         new_kwargs = kwargs.copy()
         new_kwargs.pop("max_pred_chunk", None)
         for i in range(0, X.shape[0], max_pred_chunk):
-            Ys.append(self.predict(X[i : i + max_pred_chunk, :], pred_params=pred_params, **new_kwargs))
+            sel = None if selected_outputs_csr is None else selected_outputs_csr[i : i + max_pred_chunk, :]
+            Ys.append(self.predict(X[i : i + max_pred_chunk, :], pred_params=pred_params, selected_outputs_csr=sel, **new_kwargs))
         return smat.vstack(Ys, format="csr")
 
     @staticmethod

@@ -1,0 +1,91 @@
+"""GPU parity tests for c_xlinear_predict_on_selected_outputs_{csr,drm}_f32 (pecos/core/libpecos.cpp:179-198).
+
+CUDA path (pecos_b200/csrc/xlinear_selected.cuh) vs the C restatement (pinned bit-for-bit against the reference library in
+tests/test_oracle_cpu.py) and, where oracle/_ref is present, vs the reference library itself (CSC handle).  Bar: same entry
+order and label ids, scores 1e-5 relative.  Mirrors test/pecos/xmc/xlinear/test_xlinear.py:1059-1137.
+"""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as smat
+
+from pecos_b200 import synth
+
+from .util import assert_csr_parity, random_tree
+
+pytestmark = pytest.mark.gpu
+
+
+def _selection(rng, rows, n_labels, max_per_row):
+    r, c = [], []
+    for q in range(rows):
+        k = int(rng.integers(0, max_per_row + 1))  # some rows select nothing
+        cols = rng.choice(n_labels, size=min(k, n_labels), replace=False)
+        r += [q] * len(cols)
+        c += list(cols)  # unsorted on purpose: the reference sorts the leaf set itself
+    return smat.csr_matrix((np.ones(len(r), dtype=np.float32), (r, c)), shape=(rows, n_labels))
+
+
+@pytest.mark.parametrize("permute,prune,sizes", [(False, 0.0, [6, 40, 300]), (True, 0.0, [6, 40, 300]), (True, 0.25, [5, 30, 400]),
+                                                 (False, 0.0, [50])])
+def test_selected_outputs_equal_the_oracles(tmp_path, gpu_clib, have_ref, permute, prune, sizes):
+    from oracle import restatement
+    from pecos_b200.xlinear import XLinearModel
+
+    folder = str(tmp_path / "m")
+    layers = random_tree(95, sizes, 200, 25, bias=1.0, permute=permute, prune=prune)
+    synth.save_xlinear_model(folder, layers, bias=1.0, only_topk=6)
+    X = synth.make_queries(96, 300, 200, 30)
+    S = _selection(np.random.default_rng(97), 300, sizes[-1], 12)
+    m = XLinearModel.load(folder, is_predict_only=True)
+    o = restatement.OracleXLinear(os.path.join(folder, "ranker"))
+    r = None
+    if have_ref:
+        from oracle import ref
+
+        r = ref.RefXLinear(os.path.join(folder, "ranker"), weight_matrix_type="CSC")
+    for pp in [None, "noop", "sigmoid", "log-sigmoid", "l2-hinge", "log-l3-hinge"]:
+        for Xq, Sq in ((X, S), (np.ascontiguousarray(X.toarray()[:40]), S[:40])):
+            kw = {"post_processor": pp} if pp else {}
+            got = m.predict(Xq, selected_outputs_csr=Sq, **kw)
+            assert got.nnz == Sq.nnz
+            assert_csr_parity(got, o.predict_on_selected_outputs(Xq, Sq, pp), what=f"vs restatement {pp}")
+            if r is not None:
+                from oracle import ref
+
+                assert_csr_parity(got, ref.predict_on_selected_outputs(r, Xq, Sq, pp), what=f"vs reference {pp}")
+    # chunked calls (max_pred_chunk) concatenate to the same matrix
+    assert_csr_parity(m.predict(X, selected_outputs_csr=S, max_pred_chunk=77), m.predict(X, selected_outputs_csr=S), rtol=0.0,
+                      what="max_pred_chunk")
+
+
+def test_selected_scores_equal_beam_search_scores(tmp_path, gpu_clib):
+    """A label returned by beam search has the same score BITS when it is selected explicitly (same kernels, same order)."""
+    from pecos_b200.xlinear import XLinearModel
+
+    folder = str(tmp_path / "m")
+    layers = random_tree(195, [6, 40, 300], 200, 25, bias=1.0)
+    synth.save_xlinear_model(folder, layers, bias=1.0, only_topk=6)
+    X = synth.make_queries(196, 500, 200, 30)
+    m = XLinearModel.load(folder, is_predict_only=True)
+    full = m.predict(X, beam_size=40, only_topk=5)  # beam 40 = exhaustive at the middle layer
+    sel = m.predict(X, selected_outputs_csr=smat.csr_matrix(full, dtype=np.float32))
+    assert np.array_equal(full.toarray().view(np.uint32), sel.toarray().view(np.uint32))
+
+
+def test_selected_outputs_argument_checks(tmp_path, gpu_clib):
+    from pecos_b200.xlinear import XLinearModel
+
+    folder = str(tmp_path / "m")
+    synth.save_xlinear_model(folder, random_tree(5, [4, 30], 50, 8, bias=1.0), bias=1.0, only_topk=3)
+    m = XLinearModel.load(folder, is_predict_only=True)
+    X = synth.make_queries(6, 10, 50, 5)
+    with pytest.raises(ValueError):
+        m.predict(X, selected_outputs_csr=smat.csr_matrix((10, 31), dtype=np.float32))
+    with pytest.raises(ValueError):
+        m.predict(X, selected_outputs_csr=smat.csr_matrix((9, 30), dtype=np.float32))
+    with pytest.raises(ValueError):
+        m.predict(X, selected_outputs_csr=np.zeros((10, 30), dtype=np.float32))
+    empty = m.predict(X, selected_outputs_csr=smat.csr_matrix((10, 30), dtype=np.float32))
+    assert empty.nnz == 0 and empty.shape == (10, 30)
