@@ -92,6 +92,28 @@ void c_xlinear_predict_on_selected_outputs_drm_f32(void* ptr, const ScipyDrmF32*
                                                    const char* overridden_post_processor_str, const int threads,
                                                    py_sparse_allocator_t pred_alloc);
 
+/* libpecos.cpp:37-113  Single-layer handles over ONE mmap-format MLModel folder (MLModel<csc_t>::save_mmap,
+ * pecos/core/xmc/inference.hpp:2274-2289: param.json with is_mmap = true + W.mmap_store + C.mmap_store in csc_t's mmap
+ * format, pecos/core/utils/matrix.hpp:386-407).  c_mlmodel_get_int_attr: nr_labels | nr_codes | nr_features.
+ * c_mlmodel_predict_*: csr_codes = previous layer's prediction or NULL (= ones(rows x nr_codes), no combine);
+ * overridden_post_processor NULL / overridden_only_topk 0 = the values stored with the layer.
+ * c_mlmodel_compile_mmap_model (the writer) stays on the reference library. */
+void* c_mlmodel_load_mmap_model(const char* model_path, const bool lazy_load);
+void c_mlmodel_destruct_model(void* ptr);
+uint32_t c_mlmodel_get_int_attr(void* ptr, const char* attr);
+void c_mlmodel_predict_csr_f32(void* ptr, const ScipyCsrF32* input_x, const ScipyCsrF32* csr_codes,
+                               const char* overridden_post_processor, const uint32_t overridden_only_topk, const int num_threads,
+                               py_sparse_allocator_t pred_alloc);
+void c_mlmodel_predict_drm_f32(void* ptr, const ScipyDrmF32* input_x, const ScipyCsrF32* csr_codes,
+                               const char* overridden_post_processor, const uint32_t overridden_only_topk, const int num_threads,
+                               py_sparse_allocator_t pred_alloc);
+void c_mlmodel_predict_on_selected_outputs_csr_f32(void* ptr, const ScipyCsrF32* input_x, const ScipyCsrF32* selected_outputs_csr,
+                                                   const ScipyCsrF32* csr_codes, const char* overridden_post_processor,
+                                                   const int num_threads, py_sparse_allocator_t pred_alloc);
+void c_mlmodel_predict_on_selected_outputs_drm_f32(void* ptr, const ScipyDrmF32* input_x, const ScipyCsrF32* selected_outputs_csr,
+                                                   const ScipyCsrF32* csr_codes, const char* overridden_post_processor,
+                                                   const int num_threads, py_sparse_allocator_t pred_alloc);
+
 /* libpecos.cpp:201-235  One layer of the python prediction chain (pecos/xmc/base.py:890-949, is_predict_only=False
  * models): W ((nr_features [+1 bias row]) x nr_labels) and C (nr_labels x nr_codes) are handed over on every call;
  * csr_codes = the previous layer's prediction (rows x nr_codes, entries consumed in stored order) or NULL for the first

@@ -55,6 +55,25 @@ def lib():
         L.c_xlinear_single_layer_predict_csr_f32.argtypes = [POINTER(ScipyCsrF32)] + single
         L.c_xlinear_single_layer_predict_drm_f32.restype = None
         L.c_xlinear_single_layer_predict_drm_f32.argtypes = [POINTER(ScipyDrmF32)] + single
+        # single-layer mmap handles (pecos/core/base.py:541-606)
+        L.c_mlmodel_compile_mmap_model.restype = None
+        L.c_mlmodel_compile_mmap_model.argtypes = [c_char_p, c_char_p]
+        L.c_mlmodel_load_mmap_model.restype = c_void_p
+        L.c_mlmodel_load_mmap_model.argtypes = [c_char_p, c_bool]
+        L.c_mlmodel_destruct_model.restype = None
+        L.c_mlmodel_destruct_model.argtypes = [c_void_p]
+        L.c_mlmodel_get_int_attr.restype = c_uint32
+        L.c_mlmodel_get_int_attr.argtypes = [c_void_p, c_char_p]
+        ml = [POINTER(ScipyCsrF32), c_char_p, c_uint32, c_int, ScipyCompressedSparseAllocator.CFUNCTYPE]
+        L.c_mlmodel_predict_csr_f32.restype = None
+        L.c_mlmodel_predict_csr_f32.argtypes = [c_void_p, POINTER(ScipyCsrF32)] + ml
+        L.c_mlmodel_predict_drm_f32.restype = None
+        L.c_mlmodel_predict_drm_f32.argtypes = [c_void_p, POINTER(ScipyDrmF32)] + ml
+        mls = [POINTER(ScipyCsrF32), POINTER(ScipyCsrF32), c_char_p, c_int, ScipyCompressedSparseAllocator.CFUNCTYPE]
+        L.c_mlmodel_predict_on_selected_outputs_csr_f32.restype = None
+        L.c_mlmodel_predict_on_selected_outputs_csr_f32.argtypes = [c_void_p, POINTER(ScipyCsrF32)] + mls
+        L.c_mlmodel_predict_on_selected_outputs_drm_f32.restype = None
+        L.c_mlmodel_predict_on_selected_outputs_drm_f32.argtypes = [c_void_p, POINTER(ScipyDrmF32)] + mls
         for metric in ("ip", "l2"):
             sfx = f"drm_{metric}_f32"
             f = getattr(L, "c_ann_hnsw_train_" + sfx)
@@ -155,6 +174,55 @@ def single_layer_predict(X, csr_codes, W, C, post_processor, only_topk, bias, th
         fn = L.c_xlinear_single_layer_predict_drm_f32
     fn(byref(cx), codes, byref(cw), byref(cc), post_processor.encode(), only_topk, threads, bias, alloc.cfunc)
     return alloc.get()
+
+
+class MLModelHandle(object):
+    """Drives the c_mlmodel_* entry points (pecos/core/libpecos.cpp:37-113) of ANY library exporting them: the reference
+    (default) or the CUDA library (`clib` = pecos_b200's ctypes handle) -- same prototypes, so the tests read the same."""
+
+    def __init__(self, folder, clib=None, lazy_load=False):
+        self.L = clib if clib is not None else lib()
+        self.h = c_void_p(self.L.c_mlmodel_load_mmap_model(folder.encode(), lazy_load))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.c_mlmodel_destruct_model(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def attr(self, name):
+        return self.L.c_mlmodel_get_int_attr(self.h, name.encode())
+
+    @staticmethod
+    def _x(X):
+        if isinstance(X, smat.csr_matrix):
+            assert X.has_sorted_indices
+            return ScipyCsrF32.init_from(X), "csr"
+        return ScipyDrmF32.init_from(np.ascontiguousarray(X, dtype=np.float32)), "drm"
+
+    def predict(self, X, csr_codes=None, post_processor=None, only_topk=0, threads=-1):
+        alloc = ScipyCompressedSparseAllocator()
+        cx, kind = self._x(X)
+        codes = byref(ScipyCsrF32.init_from(smat.csr_matrix(csr_codes, dtype=np.float32))) if csr_codes is not None else None
+        fn = getattr(self.L, f"c_mlmodel_predict_{kind}_f32")
+        fn(self.h, byref(cx), codes, post_processor.encode() if post_processor else None, only_topk or 0, threads, alloc.cfunc)
+        return alloc.get()
+
+    def predict_on_selected_outputs(self, X, selected_outputs_csr, csr_codes=None, post_processor=None, threads=-1):
+        alloc = ScipyCompressedSparseAllocator()
+        cx, kind = self._x(X)
+        cs = ScipyCsrF32.init_from(smat.csr_matrix(selected_outputs_csr, dtype=np.float32))
+        codes = byref(ScipyCsrF32.init_from(smat.csr_matrix(csr_codes, dtype=np.float32))) if csr_codes is not None else None
+        fn = getattr(self.L, f"c_mlmodel_predict_on_selected_outputs_{kind}_f32")
+        fn(self.h, byref(cx), byref(cs), codes, post_processor.encode() if post_processor else None, threads, alloc.cfunc)
+        return alloc.get()
+
+
+def compile_mlmodel_mmap(npz_layer_folder, mmap_folder):
+    """c_mlmodel_compile_mmap_model: one `<d>.model` folder (npz) -> single-layer mmap folder."""
+    lib().c_mlmodel_compile_mmap_model(npz_layer_folder.encode(), mmap_folder.encode())
 
 
 def compile_mmap_model(npz_ranker_folder, mmap_folder):

@@ -207,6 +207,17 @@ class B200CoreLib(object):
         fp(c.c_xlinear_predict_on_selected_outputs_csr_f32, None, [c_void_p, POINTER(ScipyCsrF32)] + sel_args)
         fp(c.c_xlinear_predict_on_selected_outputs_drm_f32, None, [c_void_p, POINTER(ScipyDrmF32)] + sel_args)
 
+        # single-layer mmap handles (pecos/core/base.py:541-606)
+        fp(c.c_mlmodel_load_mmap_model, c_void_p, [c_char_p, c_bool])
+        fp(c.c_mlmodel_destruct_model, None, [c_void_p])
+        fp(c.c_mlmodel_get_int_attr, c_uint32, [c_void_p, c_char_p])
+        ml_args = [POINTER(ScipyCsrF32), c_char_p, c_uint32, c_int, ScipyCompressedSparseAllocator.CFUNCTYPE]
+        fp(c.c_mlmodel_predict_csr_f32, None, [c_void_p, POINTER(ScipyCsrF32)] + ml_args)
+        fp(c.c_mlmodel_predict_drm_f32, None, [c_void_p, POINTER(ScipyDrmF32)] + ml_args)
+        ml_sel = [POINTER(ScipyCsrF32), POINTER(ScipyCsrF32), c_char_p, c_int, ScipyCompressedSparseAllocator.CFUNCTYPE]
+        fp(c.c_mlmodel_predict_on_selected_outputs_csr_f32, None, [c_void_p, POINTER(ScipyCsrF32)] + ml_sel)
+        fp(c.c_mlmodel_predict_on_selected_outputs_drm_f32, None, [c_void_p, POINTER(ScipyDrmF32)] + ml_sel)
+
         single = [POINTER(ScipyCsrF32), POINTER(ScipyCscF32), POINTER(ScipyCscF32), c_char_p, c_uint32, c_int, c_float,
                   ScipyCompressedSparseAllocator.CFUNCTYPE]  # pecos/core/base.py:880-933
         fp(c.c_xlinear_single_layer_predict_csr_f32, None, [POINTER(ScipyCsrF32)] + single)

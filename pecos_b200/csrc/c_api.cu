@@ -467,6 +467,120 @@ void pb200_layer_cache_info(uint64_t* out) {
     PB200_API_END("pb200_layer_cache_info")
 }
 
+// ------------------------------------------------ single-layer mmap handles (c_mlmodel_*) -------------------------
+// pecos/core/libpecos.cpp:37-113: MLModel<csc_t> saved by save_mmap, served here by a one-layer engine.
+void* c_mlmodel_load_mmap_model(const char* model_path, const bool lazy_load) {
+    PB200_API_BEGIN
+    return make_engine(pb200::load_mlmodel_mmap(model_path, lazy_load), false);
+    PB200_API_END("c_mlmodel_load_mmap_model")
+}
+
+void c_mlmodel_destruct_model(void* ptr) {
+    PB200_API_BEGIN
+    delete static_cast<XLinearHandle*>(ptr);
+    PB200_API_END("c_mlmodel_destruct_model")
+}
+
+uint32_t c_mlmodel_get_int_attr(void* ptr, const char* attr) {
+    PB200_API_BEGIN
+    const auto& m = engine_of(ptr).host();
+    if (std::strcmp(attr, "nr_labels") == 0) return m.nr_labels();
+    if (std::strcmp(attr, "nr_codes") == 0) return m.nr_codes();
+    if (std::strcmp(attr, "nr_features") == 0) return m.nr_features();
+    throw std::runtime_error(std::string(attr) + " is not implemented in get_int_attr.");
+    PB200_API_END("c_mlmodel_get_int_attr")
+}
+
+}  // extern "C"
+
+namespace {
+
+void mlmodel_predict(void* ptr, const ScipyCsrF32* Xs, const ScipyDrmF32* Xd, const ScipyCsrF32* codes, const char* pp,
+                     uint32_t only_topk, py_sparse_allocator_t pred_alloc) {
+    PB200_LOCK_XL(ptr)
+    auto& eng = engine_of(ptr);
+    const auto& L = eng.host().layers.at(0);
+    const uint32_t rows = Xs ? Xs->rows : Xd->rows;
+    const uint32_t cols = Xs ? Xs->cols : Xd->cols;
+    if (codes && codes->rows != rows) throw std::runtime_error("Instance dimension of query and prev_layer_pred matrix do not match");
+    if (codes && codes->cols != L.n_chunks) throw std::runtime_error("Label dimension of prev_layer_pred and C matrix do not match");
+    if (Xd && cols != eng.host().nr_features()) throw std::runtime_error("dense query width != nr_features");
+    // only_topk_to_use / post_processor_to_use (inference.hpp:2055-2058): the override if given, else the stored value
+    const uint32_t k = only_topk > 0 ? only_topk : static_cast<uint32_t>(L.only_topk);
+    auto r = eng.predict_single_layer(Xs ? Xs->row_ptr : nullptr, Xs ? Xs->col_idx : nullptr, Xs ? Xs->val : nullptr,
+                                      Xd ? Xd->val : nullptr, rows, cols, codes ? codes->row_ptr : nullptr,
+                                      codes ? codes->col_idx : nullptr, codes ? codes->val : nullptr, pp, k);
+    emit_result(r, pred_alloc);
+}
+
+void mlmodel_predict_selected(void* ptr, const ScipyCsrF32* Xs, const ScipyDrmF32* Xd, const ScipyCsrF32* sel,
+                              const ScipyCsrF32* codes, const char* pp, py_sparse_allocator_t pred_alloc) {
+    PB200_LOCK_XL(ptr)
+    auto& eng = engine_of(ptr);
+    const auto& L = eng.host().layers.at(0);
+    const uint32_t rows = Xs ? Xs->rows : Xd->rows;
+    const uint32_t cols = Xs ? Xs->cols : Xd->cols;
+    if (!sel) throw std::runtime_error("selected_outputs_csr is required");
+    if (sel->rows != rows) throw std::runtime_error("Instance dimension of query and selected output matrix do not match");
+    if (codes && codes->rows != rows) throw std::runtime_error("Instance dimension of query and prev_layer_pred matrix do not match");
+    if (codes && codes->cols != L.n_chunks) throw std::runtime_error("Label dimension of prev_layer_pred and C matrix do not match");
+    if (Xd && cols != eng.host().nr_features()) throw std::runtime_error("dense query width != nr_features");
+    auto r = eng.predict_selected(Xs ? Xs->row_ptr : nullptr, Xs ? Xs->col_idx : nullptr, Xs ? Xs->val : nullptr,
+                                  Xd ? Xd->val : nullptr, rows, cols, sel->row_ptr, sel->col_idx, sel->cols, pp,
+                                  codes ? codes->row_ptr : nullptr, codes ? codes->col_idx : nullptr, codes ? codes->val : nullptr);
+    uint32_t* indices = nullptr;
+    uint64_t* indptr = nullptr;
+    float* data = nullptr;
+    const uint64_t nnz = r.indptr.empty() ? 0 : r.indptr.back();
+    pred_alloc(false, r.rows, r.cols, nnz, &indices, &indptr, &data);
+    if (!indptr || (nnz && (!indices || !data))) throw std::runtime_error("result allocator returned null buffers");
+    std::memcpy(indptr, r.indptr.data(), r.indptr.size() * sizeof(uint64_t));
+    if (nnz) {
+        std::memcpy(indices, r.indices.data(), nnz * sizeof(uint32_t));
+        std::memcpy(data, r.data.data(), nnz * sizeof(float));
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+void c_mlmodel_predict_csr_f32(void* ptr, const ScipyCsrF32* input_x, const ScipyCsrF32* csr_codes,
+                               const char* overridden_post_processor, const uint32_t overridden_only_topk, const int num_threads,
+                               py_sparse_allocator_t pred_alloc) {
+    (void)num_threads;
+    PB200_API_BEGIN
+    mlmodel_predict(ptr, input_x, nullptr, csr_codes, overridden_post_processor, overridden_only_topk, pred_alloc);
+    PB200_API_END("c_mlmodel_predict_csr_f32")
+}
+
+void c_mlmodel_predict_drm_f32(void* ptr, const ScipyDrmF32* input_x, const ScipyCsrF32* csr_codes,
+                               const char* overridden_post_processor, const uint32_t overridden_only_topk, const int num_threads,
+                               py_sparse_allocator_t pred_alloc) {
+    (void)num_threads;
+    PB200_API_BEGIN
+    mlmodel_predict(ptr, nullptr, input_x, csr_codes, overridden_post_processor, overridden_only_topk, pred_alloc);
+    PB200_API_END("c_mlmodel_predict_drm_f32")
+}
+
+void c_mlmodel_predict_on_selected_outputs_csr_f32(void* ptr, const ScipyCsrF32* input_x, const ScipyCsrF32* selected_outputs_csr,
+                                                   const ScipyCsrF32* csr_codes, const char* overridden_post_processor,
+                                                   const int num_threads, py_sparse_allocator_t pred_alloc) {
+    (void)num_threads;
+    PB200_API_BEGIN
+    mlmodel_predict_selected(ptr, input_x, nullptr, selected_outputs_csr, csr_codes, overridden_post_processor, pred_alloc);
+    PB200_API_END("c_mlmodel_predict_on_selected_outputs_csr_f32")
+}
+
+void c_mlmodel_predict_on_selected_outputs_drm_f32(void* ptr, const ScipyDrmF32* input_x, const ScipyCsrF32* selected_outputs_csr,
+                                                   const ScipyCsrF32* csr_codes, const char* overridden_post_processor,
+                                                   const int num_threads, py_sparse_allocator_t pred_alloc) {
+    (void)num_threads;
+    PB200_API_BEGIN
+    mlmodel_predict_selected(ptr, nullptr, input_x, selected_outputs_csr, csr_codes, overridden_post_processor, pred_alloc);
+    PB200_API_END("c_mlmodel_predict_on_selected_outputs_drm_f32")
+}
+
 // ------------------------------------------------ additions ------------------------------------------------------
 const char* pb200_version(void) { return "pecos_b200 0.1 (sm_100a)"; }
 

@@ -105,7 +105,8 @@ public:
     };
     SelectedResult predict_selected(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, const float* dense,
                                     uint32_t rows, uint32_t cols, const uint64_t* sel_ptr, const uint32_t* sel_idx,
-                                    uint32_t sel_cols, const char* post_processor);
+                                    uint32_t sel_cols, const char* post_processor, const uint64_t* codes_ptr = nullptr,
+                                    const uint32_t* codes_idx = nullptr, const float* codes_val = nullptr);
 
     // Device-resident queries (bench "value" leg: inputs already in HBM when the timed region starts).
     void resident_upload_csr(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, uint32_t rows, uint32_t cols);

@@ -474,6 +474,41 @@ inline std::unique_ptr<XLinearHostModel> make_single_layer_model(const CscRaw& W
     return m;
 }
 
+// csc_t::load_from_mmap_store (pecos/core/utils/matrix.hpp:398-407): [rows u32][cols u32][nnz u64][col_ptr][row_idx][val]
+inline CscHost load_csc_mmap(const std::string& path, bool lazy_load) {
+    MmapStoreReader s(path, lazy_load);
+    CscHost m;
+    m.rows = s.get_one<uint32_t>();
+    m.cols = s.get_one<uint32_t>();
+    const uint64_t nnz = s.get_one<uint64_t>();
+    const uint64_t* cp = s.get_multiple<uint64_t>(static_cast<uint64_t>(m.cols) + 1);
+    const uint32_t* ri = s.get_multiple<uint32_t>(nnz);
+    const float* v = s.get_multiple<float>(nnz);
+    if (cp[m.cols] != nnz) throw std::runtime_error("mmap csc: col_ptr[-1] != nnz in " + path);
+    m.col_ptr.assign(cp, cp + m.cols + 1);
+    m.row_idx.assign(ri, ri + nnz);
+    m.val.assign(v, v + nnz);
+    return m;
+}
+
+// c_mlmodel_load_mmap_model (pecos/core/libpecos.cpp:37-40): ONE layer saved by MLModel<csc_t>::save_mmap
+// (inference.hpp:2274-2289: param.json with is_mmap = true, W.mmap_store and C.mmap_store in csc_t's mmap format).
+inline std::unique_ptr<XLinearHostModel> load_mlmodel_mmap(const std::string& folder, bool lazy_load) {
+    LayerMeta meta = load_layer_meta(folder + "/param.json");
+    if (!meta.is_mmap) throw std::runtime_error("This folder contains npz model. Cannot load in mmap format.");
+    auto m = std::make_unique<XLinearHostModel>();
+    m->layer_type = LT_CSC;
+    m->is_mmap = true;
+    m->layers.resize(1);
+    const CscHost W = load_csc_mmap(folder + "/W.mmap_store", lazy_load);
+    const CscHost C = load_csc_mmap(folder + "/C.mmap_store", lazy_load);
+    build_chunked_layer(W, C, meta.bias, m->layers[0]);
+    apply_meta(meta, m->layers[0]);
+    m->leaf_chunk_begin = 0;
+    m->leaf_chunk_end = m->layers[0].n_chunks;
+    return m;
+}
+
 // Compiled layer: W.mmap_store already holds the reference's chunked arrays; we only re-pack them.
 inline void load_mmap_layer(const std::string& folder, bool lazy_load, ChunkedLayerHost& L) {
     LayerMeta meta = load_layer_meta(folder + "/param.json");

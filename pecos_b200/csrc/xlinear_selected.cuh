@@ -66,8 +66,13 @@ SelLayerIndex build_sel_index(const ChunkedLayerHost& L) {
 XLinearEngine::SelectedResult XLinearEngine::predict_selected(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val,
                                                               const float* dense, uint32_t rows, uint32_t cols,
                                                               const uint64_t* sel_ptr, const uint32_t* sel_idx, uint32_t sel_cols,
-                                                              const char* post_processor) {
+                                                              const char* post_processor, const uint64_t* codes_ptr,
+                                                              const uint32_t* codes_idx, const float* codes_val) {
     PB200_CUDA(cudaSetDevice(device_));
+    // codes_* (single-layer handles only, c_mlmodel_predict_on_selected_outputs_*): the previous layer's prediction; its
+    // rows replace the root as the first layer's parent list and its values are combined with the first layer's scores
+    const bool have_codes = codes_ptr != nullptr;
+    if (have_codes && layers_.size() != 1) throw std::runtime_error("pecos_b200: csr_codes needs a one-layer model");
     const size_t depth = layers_.size();
     const auto& HL = host_->layers;
     if (sel_cols != HL.back().out_cols) throw std::runtime_error("pecos_b200: selected_outputs_csr.cols != nr_labels");
@@ -130,8 +135,11 @@ XLinearEngine::SelectedResult XLinearEngine::predict_selected(const uint64_t* ro
                             up.erase(std::unique(up.begin(), up.end()), up.end());
                         }
                         (void)n_leaf;
-                        // entry lists, root downwards
-                        std::vector<uint32_t> prev_id{0u};
+                        // entry lists, root downwards; first parent list: the given codes row, else every code of the first
+                        // layer (= the root for a hierarchical model; ones(rows x nr_codes) for a single layer, libpecos.cpp:96-99)
+                        std::vector<uint32_t> prev_id;
+                        if (have_codes) prev_id.assign(codes_idx + codes_ptr[q], codes_idx + codes_ptr[q + 1]);
+                        else { prev_id.resize(HL[0].n_chunks); for (uint32_t p = 0; p < HL[0].n_chunks; ++p) prev_id[p] = p; }
                         for (size_t d = 0; d < depth; ++d) {
                             auto& ids = q_id[static_cast<size_t>(q) * depth + d];
                             auto& pos = q_pos[static_cast<size_t>(q) * depth + d];
@@ -185,6 +193,10 @@ XLinearEngine::SelectedResult XLinearEngine::predict_selected(const uint64_t* ro
         uint32_t b = 1;
         if (d > 0)
             for (uint32_t q = 0; q < rows; ++q) b = std::max<uint32_t>(b, static_cast<uint32_t>(lists[d - 1].ptr[q + 1] - lists[d - 1].ptr[q]));
+        else if (have_codes)
+            for (uint32_t q = 0; q < rows; ++q) b = std::max<uint32_t>(b, static_cast<uint32_t>(codes_ptr[q + 1] - codes_ptr[q]));
+        else
+            b = std::max<uint32_t>(1u, HL[0].n_chunks);
         plan[d].b_prev = b;
         plan[d].k = 1;
         plan[d].k_cap = 1;
@@ -219,13 +231,25 @@ XLinearEngine::SelectedResult XLinearEngine::predict_selected(const uint64_t* ro
             qd = QueryDev{x_row_ptr_.get(), x_col_idx_.get(), x_val_.get(), base, tr, cols, max_row_nnz(row_ptr + r0, tr)};
         }
         int cur = 0;  // which d_ptr / d_val set holds the previous layer
+        if (have_codes) {  // the given previous prediction plays "layer -1"
+            const uint64_t c0 = codes_ptr[r0], c1 = codes_ptr[r0 + tr];
+            rel_ptr.resize(static_cast<size_t>(tr) + 1);
+            for (uint32_t r = 0; r <= tr; ++r) rel_ptr[r] = codes_ptr[r0 + r] - c0;
+            d_ptr[cur].upload(rel_ptr.data(), rel_ptr.size(), stream_);
+            d_val[cur].upload(codes_val + c0, c1 - c0, stream_);
+            PB200_CUDA(cudaStreamSynchronize(stream_));
+        }
         for (size_t d = 0; d < depth; ++d) {
             // beam = the previous layer's entry list (layer 0: the root)
             for (uint32_t r = 0; r < tr; ++r) {
                 uint32_t* ids = beam_id_host_.get() + static_cast<uint64_t>(r) * beam_stride_;
-                if (d == 0) {
-                    ids[0] = 0u;
-                    beam_cnt_host_.get()[r] = 1u;
+                if (d == 0 && have_codes) {
+                    const uint64_t b = codes_ptr[r0 + r], n = codes_ptr[r0 + r + 1] - b;
+                    std::memcpy(ids, codes_idx + b, n * 4);
+                    beam_cnt_host_.get()[r] = static_cast<uint32_t>(n);
+                } else if (d == 0) {
+                    for (uint32_t p = 0; p < HL[0].n_chunks; ++p) ids[p] = p;
+                    beam_cnt_host_.get()[r] = HL[0].n_chunks;
                 } else {
                     const auto& P = lists[d - 1];
                     const uint64_t b = P.ptr[r0 + r], n = P.ptr[r0 + r + 1] - b;
@@ -248,7 +272,7 @@ XLinearEngine::SelectedResult XLinearEngine::predict_selected(const uint64_t* ro
             const uint64_t cand_stride_q = static_cast<uint64_t>(plan[d].b_prev) * std::max<uint32_t>(layers_[d].view.c_max, 1u);
             xl_selected_gather_kernel<<<tr, 128, 0, stream_>>>(cand_.get(), cand_stride_q, d_ptr[nxt].get(), d_pos.get(), d_par.get(),
                                                              d_ptr[cur].get(), d_val[cur].get(), d_val[nxt].get(), plan[d].pp.kind,
-                                                             plan[d].pp.p, d > 0 ? 1 : 0);
+                                                             plan[d].pp.p, (d > 0 || have_codes) ? 1 : 0);
             PB200_CUDA(cudaGetLastError());
             ++launches_;
             PB200_CUDA(cudaStreamSynchronize(stream_));  // the pinned beam staging area and rel_ptr are refilled next
