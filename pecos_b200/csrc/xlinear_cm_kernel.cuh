@@ -6,21 +6,26 @@
 // Why (profiles/r02_*): the query-major kernels spend 600 - 3,900 warp-instructions per pair on match compaction, prefix
 // sums and on putting colliding entries of a 32-entry group back into feature order, and every probe / extent / entry
 // access is a scattered global load (one L1 line each).  Here
-//   * pairs are bucketed by chunk on the device (count -> scan -> scatter; the reference's b_sort_by_chunk,
+//   * at LOAD time every chunk of an eligible layer is packed into a self-contained IMAGE in HBM (xl_cm_build_images_kernel):
+//     header | lookup structure | entry weights (f32) | entry columns (u8).  Lookup structure: for feature spaces up to
+//     kCmDirectRows a direct table feature -> {first entry, end} (u16 | u16 << 16); else the chunk's feature map (one bit
+//     per feature + a 16-bit row prefix per 32 features: "is f a row, and which one" = one shared-memory word + popcount)
+//     and 16-bit row pointers;
+//   * per call the pairs are bucketed by chunk on the device (count -> scan -> scatter; the reference's b_sort_by_chunk,
 //     pecos/core/xmc/inference.hpp:985-993);
-//   * a work item = one chunk + up to W x 32 of its pairs.  The CTA stages the chunk's FEATURE MAP -- one bit per
-//     feature plus a 16-bit row prefix per 32 features: "is feature f a row of this chunk, and which one" is one
-//     shared-memory word + a popcount, no probing loop, no divergence -- and its row pointers (u16) and entries
-//     (u8 column + f32 weight, split arrays);
-//   * a lane walks its pair's query features in ascending order (staged through shared memory in coalesced rounds of 16),
-//     compacts the hits of a round in place, then adds the hit rows' entries to the lane's PRIVATE accumulators
-//     acc[column][lane] -- literally the reference's marching loop (inference.hpp:788-811): ascending feature order,
-//     separate multiply and add, bias row last.  No compaction across lanes, no conflict resolution: the order is right
-//     by construction, and a column is only ever touched by the lane that owns the pair.
+//   * the score kernel is PERSISTENT: one CTA per SM takes a contiguous 1/grid share of the chunk-sorted pair list, so it
+//     meets only a few chunks; a chunk's image arrives by ONE bulk asynchronous copy (cp.async.bulk + mbarrier, the TMA
+//     engine's non-tensor form) and serves every pair of the run; warps take 32-pair slices of the run;
+//   * a lane walks its pair's query features in ascending order (staged global -> shared by cp.async, two rounds of 8 in
+//     flight), compacts the hits of a round in place as {entry range, x}, then streams the hit rows' entries -- ONE entry
+//     per iteration, warp-uniform trip count, so rows of different lengths do not serialise -- into the lane's PRIVATE
+//     accumulators acc[column][lane].  That is the reference's marching loop (inference.hpp:788-811): ascending feature
+//     order, separate multiply and add, bias row last; the order is right by construction and a column is only ever
+//     touched by the lane that owns the pair: no compaction across lanes, no conflict resolution.
 //
-// Bit-identical to the query-major kernels (tests/test_chunk_major_gpu.py); eligibility is decided per layer on the
-// host (cm_plan): sparse queries, feature map + chunk fit in shared memory, chunk rows / entries < 65536, width <= 256,
-// enough pairs per chunk to amortise the staging.
+// Bit-identical to the query-major kernels (tests/test_chunk_major_gpu.py).  Eligibility: shape (cm_shape, at load: width
+// <= 256, rows / entries per chunk < 65535, image + 4 warps fit in shared memory, images within PB200_CMIMG_MB) and call
+// (cm_plan: sparse queries, enough pairs per chunk and per SM).
 #pragma once
 
 constexpr int kCmFeat = 8;                  // query features staged per pair and round (two rounds in flight per warp)
@@ -28,7 +33,7 @@ constexpr int kCmMaxWarps = 16;
 constexpr int kCmMinWarps = 4;
 constexpr uint32_t kCmSmemBudget = 224u << 10;  // dynamic shared memory a CTA may take (227 KB is the sm_100a maximum)
 constexpr uint32_t kCmMinReuse = 24;        // average pairs per chunk below which the per-chunk staging does not pay
-constexpr uint32_t kCmMinItems = 148;       // fewer work items than SMs: the query-major kernels fill the GPU better
+constexpr uint32_t kCmMinPairs = 148u * 48u; // fewer pairs than this: the query-major kernels fill the GPU better
 constexpr uint32_t kCmDirectRows = 16384;   // feature spaces up to this size get a direct feature -> entry-range table
 constexpr uint32_t kCmEmpty = 0xFFFFFFFFu;
 
@@ -36,63 +41,59 @@ struct CmWork {
     uint32_t* slot_pos;     // [rows x beam_stride] first candidate position of every beam slot
     uint32_t* count;        // [n_chunks] pairs per chunk, reused as the scatter cursor
     uint32_t* bucket_ptr;   // [n_chunks + 1]
-    uint32_t* item_ptr;     // [n_chunks + 1] work items (<= item_pairs pairs each) per chunk
+    uint32_t* item_ptr;     // [n_chunks + 1] (unused by the persistent score kernel; kept by the scan)
     uint32_t* pair_q;       // [pairs] query of a pair, grouped by chunk
     uint32_t* pair_pos;     // [pairs] candidate position of the pair's first column inside the query's row
-    uint32_t item_pairs;    // pairs per work item = 32 x warps of the score kernel
+    uint32_t item_pairs;
 };
 
-struct CmPlan {  // host-side launch plan of one layer
+struct CmPlan {  // per call
     bool eligible = false;
-    bool direct = false;     // feature -> {first entry, end} table (small feature spaces) instead of bits + prefix + row pointers
-    uint32_t warps = 0;
-    uint32_t fm_words = 0;   // feature-map cells staged (bits variant) / w_rows (direct variant)
-    uint32_t r_cap = 0;      // rows of the largest chunk
-    uint32_t e_cap = 0;      // entries of the largest chunk
-    uint32_t acc_cols = 0;   // accumulator rows per warp (= widest chunk)
+    uint32_t warps = 0, grid = 0;
     size_t smem = 0;
 };
 
-__host__ __device__ inline size_t cm_align16(size_t x) { return (x + 15) & ~static_cast<size_t>(15); }
-
-__host__ __device__ inline size_t cm_chunk_bytes(bool direct, uint32_t fm_words, uint32_t r_cap, uint32_t e_cap) {
-    const size_t lookup = direct ? cm_align16(static_cast<size_t>(fm_words) * 4)            // {u16 begin, u16 end} per feature
-                                 : cm_align16(static_cast<size_t>(fm_words) * 4)            // bits
-                                       + cm_align16(static_cast<size_t>(fm_words) * 2)      // row prefix per cell (u16)
-                                       + cm_align16(static_cast<size_t>(r_cap + 2) * 2);    // row pointers (u16)
-    return lookup + cm_align16(static_cast<size_t>(e_cap + 1) * 4)   // entry weights
-           + cm_align16(static_cast<size_t>(e_cap + 1));             // entry columns (u8)
-}
+__host__ __device__ inline uint32_t cm_align16(uint32_t x) { return (x + 15u) & ~15u; }
 
 __host__ __device__ inline size_t cm_warp_bytes(uint32_t acc_cols) {
     return static_cast<size_t>(2) * 32 * (kCmFeat + 1) * 8    // two staging buffers: query features / compacted hits, stride 9
            + static_cast<size_t>(acc_cols) * 32 * 4;          // accumulators [col][lane]
 }
 
-// force: take the kernel wherever it FITS, ignoring the reuse / occupancy heuristics (kernel mode 5, tests)
-inline CmPlan cm_plan(uint32_t fm_words, uint32_t w_rows, uint32_t r_max, uint32_t e_max, uint32_t c_max, uint32_t n_chunks,
-                      uint64_t pairs, bool force) {
+inline CmShape cm_shape(uint32_t fm_words, uint32_t w_rows, uint32_t r_max, uint32_t e_max, uint32_t c_max, uint32_t n_chunks) {
+    CmShape s;
+    if (fm_words == 0 || n_chunks == 0 || c_max == 0 || c_max > 256u || r_max >= 65535u || e_max >= 65535u) return s;
+    s.direct = w_rows <= kCmDirectRows;
+    s.words = s.direct ? w_rows : fm_words;
+    s.r_cap = r_max; s.e_cap = e_max; s.acc_cols = c_max;
+    uint32_t off = 16;  // header {bias range, n_cols, R, E}
+    s.off_lookup = off; off += cm_align16(s.words * 4u);
+    if (!s.direct) {
+        s.off_pre = off; off += cm_align16(s.words * 2u);
+        s.off_rp = off;  off += cm_align16((r_max + 2u) * 2u);
+    }
+    s.off_ew = off; off += cm_align16((e_max + 1u) * 4u);
+    s.off_ec = off; off += cm_align16(e_max + 1u);
+    s.img_bytes = (off + 127u) & ~127u;
+    if (s.img_bytes + kCmMinWarps * cm_warp_bytes(c_max) + 64 > kCmSmemBudget) return s;
+    s.ok = true;
+    return s;
+}
+
+// force: take the kernel wherever the layer has images, ignoring the reuse / occupancy heuristics (kernel mode 5, tests)
+inline CmPlan cm_plan(const CmShape& s, uint32_t n_chunks, uint64_t pairs, uint32_t n_sm, bool force) {
     CmPlan p;
-    if (fm_words == 0 || n_chunks == 0 || c_max == 0 || c_max > 256u || r_max >= 65535u || e_max >= 65535u || pairs == 0) return p;
-    if (!force && pairs < static_cast<uint64_t>(kCmMinReuse) * n_chunks) return p;
-    const bool direct = w_rows <= kCmDirectRows;
-    const uint32_t words = direct ? w_rows : fm_words;
-    const size_t chunk = cm_chunk_bytes(direct, words, r_max, e_max);
-    const size_t per_warp = cm_warp_bytes(c_max);
-    if (chunk + kCmMinWarps * per_warp + 64 > kCmSmemBudget) return p;
-    uint32_t warps = static_cast<uint32_t>(std::min<size_t>(kCmMaxWarps, (kCmSmemBudget - chunk - 64) / per_warp));
-    // no point in more lanes than the average bucket holds; and keep at least two waves of work items when possible
-    const uint64_t avg = pairs / n_chunks;
-    while (warps > kCmMinWarps && (static_cast<uint64_t>(warps - 1) * 32 >= avg || pairs / (32ull * warps) < 2ull * kCmMinItems)) --warps;
-    if (!force && pairs / (32ull * warps) < kCmMinItems) return p;
+    if (!s.ok || pairs == 0) return p;
+    if (!force && (pairs < static_cast<uint64_t>(kCmMinReuse) * n_chunks || pairs < kCmMinPairs)) return p;
+    const size_t per_warp = cm_warp_bytes(s.acc_cols);
+    uint32_t warps = static_cast<uint32_t>(std::min<size_t>(kCmMaxWarps, (kCmSmemBudget - s.img_bytes - 64) / per_warp));
+    // no point in more lanes than a CTA's share of the pair list holds
+    const uint64_t share = (pairs + n_sm - 1) / n_sm;
+    while (warps > kCmMinWarps && static_cast<uint64_t>(warps - 1) * 32 >= share) --warps;
     p.eligible = true;
-    p.direct = direct;
     p.warps = warps;
-    p.fm_words = words;
-    p.r_cap = r_max;
-    p.e_cap = e_max;
-    p.acc_cols = c_max;
-    p.smem = chunk + warps * per_warp + 64;
+    p.grid = n_sm;
+    p.smem = s.img_bytes + warps * per_warp + 64;
     return p;
 }
 
@@ -103,6 +104,71 @@ __device__ __forceinline__ void cm_cp_async4(void* smem_dst, const void* gmem_sr
 __device__ __forceinline__ void cm_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cm_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// bulk asynchronous copy global -> shared (TMA engine, non-tensor form; SASS UBLKCP) completing on an mbarrier
+__device__ __forceinline__ void cm_mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cm_bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void cm_mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t done = 0;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+    } while (!done);
+}
+
+// LOAD TIME: one CTA per chunk packs the chunk's image (see CmShape) from the layer's device arrays.
+__global__ void __launch_bounds__(256)
+xl_cm_build_images_kernel(const LayerDev L, const CmShape S, unsigned char* __restrict__ images) {
+    const uint32_t c = blockIdx.x;
+    const ChunkHeader h = L.chunks[c];
+    unsigned char* img = images + static_cast<uint64_t>(c) * S.img_bytes;
+    uint32_t* hdr = reinterpret_cast<uint32_t*>(img);
+    uint32_t* lookup = reinterpret_cast<uint32_t*>(img + S.off_lookup);
+    float* ew = reinterpret_cast<float*>(img + S.off_ew);
+    unsigned char* ec = img + S.off_ec;
+    for (uint32_t i = threadIdx.x; i < S.img_bytes / 4u; i += blockDim.x) reinterpret_cast<uint32_t*>(img)[i] = 0u;
+    __syncthreads();
+    if (h.has_bias & kChunkAbsent) return;
+    const uint32_t R = h.nnz_rows;
+    const uint32_t R4 = (R + 3u) & ~3u;
+    const uint32_t* ridx = L.meta + h.meta_off;
+    const uint32_t* rp = ridx + R4;
+    const uint2* ent = L.entries + h.ent_off;
+    const uint32_t E = R ? rp[R] : 0u;
+    if (threadIdx.x == 0) {
+        hdr[0] = (h.has_bias & 1u) ? (rp[R - 1u] | (E << 16)) : 0u;
+        hdr[1] = h.n_cols;
+        hdr[2] = R;
+        hdr[3] = E;
+    }
+    if (S.direct) {
+        for (uint32_t r = threadIdx.x; r < R; r += blockDim.x) {
+            const uint32_t f = ridx[r];
+            if (f < S.words) lookup[f] = rp[r] | (rp[r + 1] << 16);  // an empty row reads as "no row": nothing to add
+        }
+    } else {
+        unsigned short* pre = reinterpret_cast<unsigned short*>(img + S.off_pre);
+        unsigned short* rps = reinterpret_cast<unsigned short*>(img + S.off_rp);
+        const uint2* fm = L.featmap + static_cast<uint64_t>(c) * L.fm_words;
+        for (uint32_t i = threadIdx.x; i < S.words; i += blockDim.x) {
+            const uint2 cell = fm[i];
+            lookup[i] = cell.x;
+            pre[i] = static_cast<unsigned short>(cell.y);
+        }
+        for (uint32_t i = threadIdx.x; i <= R; i += blockDim.x) rps[i] = static_cast<unsigned short>(rp[i]);
+    }
+    for (uint32_t i = threadIdx.x; i < E; i += blockDim.x) {
+        const uint2 en = ent[i];
+        ec[i] = static_cast<unsigned char>(en.x);
+        ew[i] = __uint_as_float(en.y);
+    }
+}
 
 // one warp per query: candidate position of every beam slot (prefix of the chunk widths) and pairs per chunk
 __global__ void __launch_bounds__(128)
@@ -190,234 +256,216 @@ xl_cm_scatter_kernel(const LayerDev L, const uint32_t* __restrict__ beam_id, con
     }
 }
 
-template <bool STATS, bool DIRECT>
+template <bool STATS, bool DIRECT, bool FLAT>
 __global__ void __launch_bounds__(kCmMaxWarps * 32)
-xl_cm_scores_kernel(const LayerDev L, const QueryDev X, const CmWork w, float* __restrict__ cand,
-                    const uint64_t cand_stride_q, unsigned long long* stats, const uint32_t fm_words, const uint32_t r_cap,
-                    const uint32_t e_cap, const uint32_t acc_cols) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned char* sp = smem_raw;
-    // lookup structure: DIRECT: tab_s[f] = {first entry, end} (u16 | u16 << 16) of feature f's row, 0 = no row;
-    //                   else:   bits_s / pre_s = the chunk's feature map, rp_s = row pointers
-    uint32_t* bits_s = reinterpret_cast<uint32_t*>(sp);            sp += cm_align16(static_cast<size_t>(fm_words) * 4);
-    unsigned short* pre_s = reinterpret_cast<unsigned short*>(sp);
-    unsigned short* rp_s = nullptr;
-    if (!DIRECT) {
-        sp += cm_align16(static_cast<size_t>(fm_words) * 2);
-        rp_s = reinterpret_cast<unsigned short*>(sp);
-        sp += cm_align16(static_cast<size_t>(r_cap + 2) * 2);
-    }
-    float* ew_s = reinterpret_cast<float*>(sp);                    sp += cm_align16(static_cast<size_t>(e_cap + 1) * 4);
-    unsigned char* ec_s = sp;                                      sp += cm_align16(static_cast<size_t>(e_cap + 1));
+xl_cm_scores_kernel(const LayerDev L, const QueryDev X, const CmWork w, const CmShape S, const unsigned char* __restrict__ images,
+                    float* __restrict__ cand, const uint64_t cand_stride_q, unsigned long long* stats) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* img = smem_raw;                                   // the staged chunk image
+    const uint32_t* hdr_s = reinterpret_cast<const uint32_t*>(img);
+    const uint32_t* look_s = reinterpret_cast<const uint32_t*>(img + S.off_lookup);   // direct table, or feature-map bits
+    const unsigned short* pre_s = reinterpret_cast<const unsigned short*>(img + S.off_pre);
+    const unsigned short* rp_s = reinterpret_cast<const unsigned short*>(img + S.off_rp);
+    const float* ew_s = reinterpret_cast<const float*>(img + S.off_ew);
+    const unsigned char* ec_s = img + S.off_ec;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
     constexpr int kStride = kCmFeat + 1;
-    constexpr int kBuf = 32 * kStride;                             // words per staging array
-    unsigned char* mine = sp + static_cast<size_t>(warp) * cm_warp_bytes(acc_cols);
-    uint32_t* st_idx = reinterpret_cast<uint32_t*>(mine);          // [2][32][kStride]
-    float* st_val = reinterpret_cast<float*>(st_idx + 2 * kBuf);   // [2][32][kStride]
-    float* acc = st_val + 2 * kBuf;                                // [acc_cols][32]
+    constexpr int kBuf = 32 * kStride;                               // words per staging array
+    unsigned char* mine = smem_raw + S.img_bytes + static_cast<size_t>(warp) * cm_warp_bytes(S.acc_cols);
+    uint32_t* st_idx = reinterpret_cast<uint32_t*>(mine);            // [2][32][kStride]
+    float* st_val = reinterpret_cast<float*>(st_idx + 2 * kBuf);     // [2][32][kStride]
+    float* my_acc = st_val + 2 * kBuf + lane;                        // [acc_cols][32], this lane's column of it
 
-    // ---- which (chunk, slice) is this CTA's work item
-    __shared__ uint32_t s_chunk, s_first, s_last;
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const uint32_t mbar = static_cast<uint32_t>(__cvta_generic_to_shared(&s_mbar));
     if (threadIdx.x == 0) {
-        const uint32_t n_items = w.item_ptr[L.n_chunks];
-        uint32_t c = kCmEmpty;
-        if (blockIdx.x < n_items) {
-            uint32_t lo = 0, hi = L.n_chunks;  // largest c with item_ptr[c] <= blockIdx.x (empty chunks share offsets)
-            while (hi - lo > 1) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (w.item_ptr[mid] <= blockIdx.x) lo = mid; else hi = mid;
-            }
-            c = lo;
-            const uint32_t slice = blockIdx.x - w.item_ptr[c];
-            s_first = w.bucket_ptr[c] + slice * w.item_pairs;
-            s_last = min(s_first + w.item_pairs, w.bucket_ptr[c + 1]);
-        }
-        s_chunk = c;
+        cm_mbar_init(mbar, 1u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    const uint32_t c = s_chunk;
-    if (c == kCmEmpty) return;
 
-    // ---- this lane's pair
-    const uint32_t pidx = s_first + static_cast<uint32_t>(warp) * 32u + lane;
-    const bool have = pidx < s_last;
-    uint32_t q = 0, pos = 0;
-    uint64_t qb = 0;
-    uint32_t qn = 0;
-    if (have) {
-        q = w.pair_q[pidx];
-        pos = w.pair_pos[pidx];
-        qb = X.row_ptr[q] - X.nnz_base;
-        qn = static_cast<uint32_t>(X.row_ptr[q + 1] - X.nnz_base - qb);
+    // ---- this CTA's contiguous share of the chunk-sorted pair list
+    const uint32_t n_chunks = L.n_chunks;
+    const uint64_t P = w.bucket_ptr[n_chunks];
+    const uint32_t begin = static_cast<uint32_t>(P * blockIdx.x / gridDim.x);
+    const uint32_t end = static_cast<uint32_t>(P * (blockIdx.x + 1ull) / gridDim.x);
+    if (begin >= end) return;
+    uint32_t c;
+    {
+        uint32_t lo = 0, hi = n_chunks;  // largest c with bucket_ptr[c] <= begin (then skip empty chunks forward)
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (w.bucket_ptr[mid] <= begin) lo = mid; else hi = mid;
+        }
+        c = lo;
     }
-    uint32_t qn_max = qn;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) qn_max = max(qn_max, __shfl_xor_sync(kFull, qn_max, d));
-
-    // query features travel global -> shared memory by cp.async, two rounds in flight per warp: round r + 1 is copied while
-    // round r is processed.  Row i of a staging buffer = the next kCmFeat features of the warp's pair i (stride 9 words:
-    // the lane-per-row reads are bank-conflict free).
     constexpr int kPerIter = 32 / kCmFeat;  // pairs covered by one warp-wide copy instruction
     const int sub = lane / kCmFeat, fl = lane % kCmFeat;
-    auto stage_round = [&](uint32_t t0, int buf) {
-        uint32_t* di = st_idx + buf * kBuf;
-        float* dv = st_val + buf * kBuf;
-#pragma unroll
-        for (int i0 = 0; i0 < 32; i0 += kPerIter) {
-            const int i = i0 + sub;
-            const uint64_t b_i = __shfl_sync(kFull, qb, i);
-            const uint32_t n_i = __shfl_sync(kFull, qn, i);
-            if (t0 + fl < n_i) {
-                cm_cp_async4(di + i * kStride + fl, X.col_idx + b_i + t0 + fl);
-                cm_cp_async4(dv + i * kStride + fl, X.val + b_i + t0 + fl);
-            }
-        }
-        cm_cp_async_commit();
-    };
-    if (qn_max > 0) stage_round(0, 0);  // in flight during the chunk staging below
+    unsigned long long st_pairs = 0, st_rows = 0, st_cols = 0, st_match = 0, st_ent = 0;
+    uint32_t parity = 0;
 
-    // ---- stage the chunk
-    const ChunkHeader h = L.chunks[c];
-    const uint32_t R = h.nnz_rows;
-    const uint32_t R4 = (R + 3u) & ~3u;
-    const uint32_t* ridx_g = L.meta + h.meta_off;                  // sorted feature ids of the chunk's rows
-    const uint32_t* rp_g = ridx_g + R4;                            // row_ptr[R + 1], relative to the chunk's first entry
-    const uint2* ent_g = L.entries + h.ent_off;
-    const uint32_t nthreads = blockDim.x;
-    if (DIRECT) {
-        for (uint32_t i = threadIdx.x; i < fm_words; i += nthreads) bits_s[i] = 0u;
+    for (uint32_t i = begin; i < end;) {
+        while (w.bucket_ptr[c + 1] <= i) ++c;                        // chunk holding pair i
+        const uint32_t run_end = min(end, w.bucket_ptr[c + 1]);
+        // ---- stage chunk c: ONE bulk copy of its image (every warp has left the previous image: barrier first)
         __syncthreads();
-#pragma unroll 2
-        for (uint32_t r = threadIdx.x; r < R; r += nthreads) {
-            const uint32_t f = __ldg(ridx_g + r);
-            const uint32_t eb = __ldg(rp_g + r), ee = __ldg(rp_g + r + 1);
-            if (f < fm_words) bits_s[f] = eb | (ee << 16);           // empty rows (eb == ee) read as "no row": nothing to add
-        }
-    } else {
-        const uint2* fm_g = L.featmap + static_cast<uint64_t>(c) * L.fm_words;
-#pragma unroll 4
-        for (uint32_t i = threadIdx.x; i < fm_words; i += nthreads) {  // unrolled: four independent 8-byte loads per thread
-            const uint2 cell = __ldg(fm_g + i);
-            bits_s[i] = cell.x;
-            pre_s[i] = static_cast<unsigned short>(cell.y);
-        }
-        for (uint32_t i = threadIdx.x; i <= R; i += nthreads) rp_s[i] = static_cast<unsigned short>(__ldg(rp_g + i));
-    }
-    const uint32_t E = R ? __ldg(rp_g + R) : 0u;
-#pragma unroll 4
-    for (uint32_t i = threadIdx.x; i < E; i += nthreads) {
-        const uint2 en = __ldg(ent_g + i);
-        ec_s[i] = static_cast<unsigned char>(en.x);
-        ew_s[i] = __uint_as_float(en.y);
-    }
-    const uint32_t n_cols = h.n_cols;
-    float* my_acc = acc + lane;
-    for (uint32_t col = 0; col < n_cols; ++col) my_acc[col * 32] = 0.0f;
-    uint32_t bias_range = 0;  // {first entry, end} of the bias row
-    if (h.has_bias & 1u) bias_range = __ldg(rp_g + R - 1u) | (E << 16);
-    __syncthreads();
+        if (threadIdx.x == 0) cm_bulk_load(static_cast<uint32_t>(__cvta_generic_to_shared(img)), images + static_cast<uint64_t>(c) * S.img_bytes, S.img_bytes, mbar);
+        cm_mbar_wait(mbar, parity);
+        parity ^= 1u;
+        const uint32_t bias_range = hdr_s[0];
+        const uint32_t n_cols = hdr_s[1];
 
-    // ---- one pair per lane
-    if (__ballot_sync(kFull, have) == 0u) { cm_cp_async_wait<0>(); return; }
-    unsigned long long st_match = 0, st_ent = 0;
-    uint32_t prev_f = kCmEmpty;
-    // apply the entries [range & 0xFFFF, range >> 16) of one row to this lane's accumulators
-    auto apply_row = [&](uint32_t range, float x) {
-        const uint32_t ee = range >> 16;
-        for (uint32_t e = range & 0xFFFFu; e < ee; ++e) {
-            float* a = my_acc + static_cast<uint32_t>(ec_s[e]) * 32u;
-            *a = __fadd_rn(*a, __fmul_rn(x, ew_s[e]));
-        }
-    };
-    int buf = 0;
-    for (uint32_t t0 = 0; t0 < qn_max; t0 += kCmFeat, buf ^= 1) {
-        if (t0 + kCmFeat < qn_max) { stage_round(t0 + kCmFeat, buf ^ 1); cm_cp_async_wait<1>(); }
-        else cm_cp_async_wait<0>();
-        __syncwarp();
-        uint32_t* my_idx = st_idx + buf * kBuf + lane * kStride;
-        float* my_val = st_val + buf * kBuf + lane * kStride;
-        const uint32_t n_here = (qn > t0) ? min(static_cast<uint32_t>(kCmFeat), qn - t0) : 0u;
-        // phase 1: look the features up, compact the hits of this round IN PLACE as {entry range, x} (slot cnt <= k was
-        // already consumed)
-        uint32_t cnt = 0;
+        // ---- warps take 32-pair slices of the run
+        for (uint32_t s0 = i + static_cast<uint32_t>(warp) * 32u; s0 < run_end; s0 += static_cast<uint32_t>(nwarps) * 32u) {
+            const uint32_t pidx = s0 + lane;
+            const bool have = pidx < run_end;
+            uint32_t q = 0, pos = 0, qn = 0;
+            uint64_t qb = 0;
+            if (have) {
+                q = w.pair_q[pidx];
+                pos = w.pair_pos[pidx];
+                qb = X.row_ptr[q] - X.nnz_base;
+                qn = static_cast<uint32_t>(X.row_ptr[q + 1] - X.nnz_base - qb);
+            }
+            const uint32_t qn_max = __reduce_max_sync(kFull, qn);
+            // query features travel global -> shared by cp.async, two rounds in flight: round r + 1 is copied while round r
+            // is processed.  Row i of a staging buffer = the next kCmFeat features of the slice's pair i (stride 9 words:
+            // the lane-per-row reads are bank-conflict free).
+            auto stage_round = [&](uint32_t t0, int buf) {
+                uint32_t* di = st_idx + buf * kBuf;
+                float* dv = st_val + buf * kBuf;
 #pragma unroll
-        for (uint32_t k = 0; k < static_cast<uint32_t>(kCmFeat); ++k) {
-            if (k < n_here) {
-                const uint32_t f = my_idx[k];
-                const bool dup = (f == prev_f);  // a repeated column index only counts once (the first occurrence)
-                prev_f = f;
-                uint32_t range = 0;
-                if (!dup && f < L.w_rows) {
-                    if (DIRECT) {
-                        range = bits_s[f];
-                    } else {
-                        const uint32_t word = bits_s[f >> 5];
-                        const uint32_t bit = f & 31u;
-                        if ((word >> bit) & 1u) {
-                            const uint32_t row = static_cast<uint32_t>(pre_s[f >> 5]) + __popc(word & ((1u << bit) - 1u));
-                            range = static_cast<uint32_t>(rp_s[row]) | (static_cast<uint32_t>(rp_s[row + 1]) << 16);
+                for (int i0 = 0; i0 < 32; i0 += kPerIter) {
+                    const int pi = i0 + sub;
+                    const uint64_t b_i = __shfl_sync(kFull, qb, pi);
+                    const uint32_t n_i = __shfl_sync(kFull, qn, pi);
+                    if (t0 + fl < n_i) {
+                        cm_cp_async4(di + pi * kStride + fl, X.col_idx + b_i + t0 + fl);
+                        cm_cp_async4(dv + pi * kStride + fl, X.val + b_i + t0 + fl);
+                    }
+                }
+                cm_cp_async_commit();
+            };
+            __syncwarp();
+            if (qn_max > 0) stage_round(0, 0);
+            for (uint32_t col = 0; col < n_cols; ++col) my_acc[col * 32] = 0.0f;
+            uint32_t prev_f = kCmEmpty;
+            int buf = 0;
+            for (uint32_t t0 = 0; t0 < qn_max; t0 += kCmFeat, buf ^= 1) {
+                if (t0 + kCmFeat < qn_max) { stage_round(t0 + kCmFeat, buf ^ 1); cm_cp_async_wait<1>(); }
+                else cm_cp_async_wait<0>();
+                __syncwarp();
+                uint32_t* my_idx = st_idx + buf * kBuf + lane * kStride;
+                float* my_val = st_val + buf * kBuf + lane * kStride;
+                const uint32_t n_here = (qn > t0) ? min(static_cast<uint32_t>(kCmFeat), qn - t0) : 0u;
+                // phase 1: look the features up; compact the hits of this round IN PLACE as {entry range, x} (slot cnt <= k
+                // was already consumed); tot = entries this lane will add in this round
+                uint32_t cnt = 0, tot = 0;
+#pragma unroll
+                for (uint32_t k = 0; k < static_cast<uint32_t>(kCmFeat); ++k) {
+                    if (k < n_here) {
+                        const uint32_t f = my_idx[k];
+                        const bool dup = (f == prev_f);  // a repeated column index only counts once (the first occurrence)
+                        prev_f = f;
+                        uint32_t range = 0;
+                        if (!dup && f < L.w_rows) {
+                            if (DIRECT) {
+                                range = look_s[f];
+                            } else {
+                                const uint32_t word = look_s[f >> 5];
+                                const uint32_t bit = f & 31u;
+                                if ((word >> bit) & 1u) {
+                                    const uint32_t row = static_cast<uint32_t>(pre_s[f >> 5]) + __popc(word & ((1u << bit) - 1u));
+                                    range = static_cast<uint32_t>(rp_s[row]) | (static_cast<uint32_t>(rp_s[row + 1]) << 16);
+                                }
+                            }
+                        }
+                        const uint32_t len = (range >> 16) - (range & 0xFFFFu);
+                        if (static_cast<int>(len) > 0) {
+                            const float x = my_val[k];
+                            my_idx[cnt] = range;
+                            my_val[cnt] = x;
+                            ++cnt;
+                            tot += len;
                         }
                     }
                 }
-                if ((range >> 16) > (range & 0xFFFFu)) {
-                    const float x = my_val[k];
-                    my_idx[cnt] = range;
-                    my_val[cnt] = x;
-                    ++cnt;
+                // phase 2: the hit rows' entries, in feature order, into this lane's accumulators.
+                if (FLAT) {
+                    // ONE flat stream per lane, one entry per iteration; the trip count is the warp's maximum (uniform), lanes
+                    // with fewer entries idle at the end -- rows of different lengths do not serialise
+                    const uint32_t trips = __reduce_max_sync(kFull, tot);
+                    uint32_t hi = 0;
+                    const unsigned char* ecp = ec_s;
+                    const unsigned char* ece = ec_s;
+                    const float* ewp = ew_s;
+                    float x = 0.0f;
+                    for (uint32_t t = 0; t < trips; ++t) {
+                        if (t < tot) {
+                            if (ecp == ece) {  // next hit row
+                                const uint32_t range = my_idx[hi];
+                                x = my_val[hi];
+                                ++hi;
+                                ecp = ec_s + (range & 0xFFFFu);
+                                ece = ec_s + (range >> 16);
+                                ewp = ew_s + (range & 0xFFFFu);
+                            }
+                            float* a = my_acc + static_cast<uint32_t>(*ecp) * 32u;
+                            *a = __fadd_rn(*a, __fmul_rn(x, *ewp));
+                            ++ecp;
+                            ++ewp;
+                        }
+                    }
+                } else {
+                    for (uint32_t hi = 0; hi < cnt; ++hi) {
+                        const uint32_t range = my_idx[hi];
+                        const float x = my_val[hi];
+                        const unsigned char* ecp = ec_s + (range & 0xFFFFu);
+                        const unsigned char* ece = ec_s + (range >> 16);
+                        const float* ewp = ew_s + (range & 0xFFFFu);
+                        do {
+                            float* a = my_acc + static_cast<uint32_t>(*ecp) * 32u;
+                            *a = __fadd_rn(*a, __fmul_rn(x, *ewp));
+                            ++ewp;
+                        } while (++ecp != ece);
+                    }
                 }
+                if (STATS) { st_match += cnt; st_ent += tot; }
+                __syncwarp();
+            }
+            if (have && bias_range) {  // bias row last (inference.hpp:806-811)
+                const uint32_t ee = bias_range >> 16;
+                for (uint32_t e = bias_range & 0xFFFFu; e < ee; ++e) {
+                    float* a = my_acc + static_cast<uint32_t>(ec_s[e]) * 32u;
+                    *a = __fadd_rn(*a, __fmul_rn(L.bias, ew_s[e]));
+                }
+                if (STATS) { st_match += 1; st_ent += ee - (bias_range & 0xFFFFu); }
+            }
+            if (have) {
+                float* dst = cand + static_cast<uint64_t>(q) * cand_stride_q + pos;
+                for (uint32_t col = 0; col < n_cols; ++col) dst[col] = my_acc[col * 32];
+                if (STATS) { st_pairs += 1; st_rows += hdr_s[2]; st_cols += n_cols; }
             }
         }
-        // phase 2: ONE entry per iteration and lane (the hit rows of the round are walked as one flat entry stream, so lanes
-        // whose rows have different lengths stay busy), in feature order, into this lane's accumulators
-        if (cnt) {
-            uint32_t i = 1;
-            uint32_t range = my_idx[0];
-            float x = my_val[0];
-            uint32_t e = range & 0xFFFFu, ee = range >> 16;
-            if (STATS) st_ent += ee - e;
-            for (;;) {
-                float* a = my_acc + static_cast<uint32_t>(ec_s[e]) * 32u;
-                *a = __fadd_rn(*a, __fmul_rn(x, ew_s[e]));
-                if (++e == ee) {
-                    if (i == cnt) break;
-                    range = my_idx[i];
-                    x = my_val[i];
-                    ++i;
-                    e = range & 0xFFFFu;
-                    ee = range >> 16;
-                    if (STATS) st_ent += ee - e;
-                }
-            }
-        }
-        if (STATS) st_match += cnt;
-        __syncwarp();
-    }
-    if (have && (h.has_bias & 1u)) {  // bias row last (inference.hpp:806-811)
-        apply_row(bias_range, L.bias);
-        if (STATS) { st_match += 1; st_ent += (bias_range >> 16) - (bias_range & 0xFFFFu); }
-    }
-    if (have) {
-        float* dst = cand + static_cast<uint64_t>(q) * cand_stride_q + pos;
-        for (uint32_t col = 0; col < n_cols; ++col) dst[col] = my_acc[col * 32];
+        i = run_end;
     }
     if (STATS) {
-        unsigned long long pairs = have ? 1ull : 0ull, rows_sum = have ? R : 0ull, cols_sum = have ? n_cols : 0ull;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
-            pairs += __shfl_xor_sync(kFull, pairs, d);
-            rows_sum += __shfl_xor_sync(kFull, rows_sum, d);
-            cols_sum += __shfl_xor_sync(kFull, cols_sum, d);
+            st_pairs += __shfl_xor_sync(kFull, st_pairs, d);
+            st_rows += __shfl_xor_sync(kFull, st_rows, d);
+            st_cols += __shfl_xor_sync(kFull, st_cols, d);
             st_match += __shfl_xor_sync(kFull, st_match, d);
             st_ent += __shfl_xor_sync(kFull, st_ent, d);
         }
-        if (lane == 0) {
-            atomicAdd(&stats[0], pairs);
-            atomicAdd(&stats[1], rows_sum);
+        if (lane == 0 && st_pairs) {
+            atomicAdd(&stats[0], st_pairs);
+            atomicAdd(&stats[1], st_rows);
             atomicAdd(&stats[2], st_match);
             atomicAdd(&stats[3], st_ent);
-            atomicAdd(&stats[4], cols_sum);
+            atomicAdd(&stats[4], st_cols);
         }
     }
 }

@@ -901,6 +901,13 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
         if (v >= 2) pipeline_parts_ = static_cast<uint32_t>(std::min(v, 64));
     }
     layers_.resize(host_->layers.size());
+    uint64_t cmimg_budget = 8ull << 30;     // bytes of HBM the chunk images of the chunk-major kernel may take in total
+    if (const char* env = std::getenv("PB200_CMIMG_MB")) cmimg_budget = std::strtoull(env, nullptr, 10) << 20;
+    {
+        int sms = 0;
+        PB200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_));
+        n_sm_ = static_cast<uint32_t>(std::max(sms, 1));
+    }
     uint64_t featmap_budget = 32ull << 30;  // bytes of HBM the feature maps may take in total
     if (const char* env = std::getenv("PB200_FEATMAP_MB")) featmap_budget = std::strtoull(env, nullptr, 10) << 20;
     for (size_t d = 0; d < layers_.size(); ++d) {
@@ -944,6 +951,20 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
         dst.view.w_rows = src.w_rows;
         dst.view.bias = src.bias;
         dst.view.has_dup_cols = src.has_dup_cols ? 1 : 0;
+        // chunk images for the chunk-major score kernel (xlinear_cm_kernel.cuh), where the layer's shape allows it
+        dst.cm_shape = CmShape{};
+        if (dst.view.featmap) {
+            const CmShape shape = cm_shape(src.fm_words, src.w_rows, src.r_max, dst.e_max, src.c_max, src.n_chunks);
+            const uint64_t bytes = static_cast<uint64_t>(shape.img_bytes) * src.n_chunks;
+            if (shape.ok && bytes <= cmimg_budget) {
+                cmimg_budget -= bytes;
+                dst.cm_shape = shape;
+                dst.cm_images.reserve(bytes);
+                xl_cm_build_images_kernel<<<src.n_chunks, 256, 0, stream_>>>(dst.view, shape, dst.cm_images.get());
+                PB200_CUDA(cudaGetLastError());
+                model_bytes_ += bytes;
+            }
+        }
         model_bytes_ += src.chunks.size() * sizeof(ChunkHeader) + src.meta.size() * 4 + src.entries.size() * 8 +
                         src.label_of_col.size() * 4;
     }
@@ -963,10 +984,13 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    if (const char* env = std::getenv("PB200_CM_FLAT")) cm_flat_ = std::atoi(env) != 0;
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     stats_dev_.reserve(8 * layers_.size());
@@ -1115,9 +1139,8 @@ int XLinearEngine::score_layer_(size_t d, const QueryDev& q, uint32_t b_prev, in
                             (force_query_warp_ || (b_prev >= 16u && cand_stride_q <= 256u));
     // Chunk-major scoring (xlinear_cm_kernel.cuh) wherever the layer's feature map + largest chunk fit in shared memory
     // and the chunks are visited by enough pairs to amortise the staging; otherwise the query-major kernels below.
-    const CmPlan cm = (chunk_major_ && lookup && cm_slot_pos_.capacity())
-                          ? cm_plan(L.fm_words, L.w_rows, host_->layers[d].r_max, layers_[d].e_max, L.c_max, L.n_chunks,
-                                    static_cast<uint64_t>(rows) * b_prev, cm_force_)
+    const CmPlan cm = (chunk_major_ && lookup && cm_slot_pos_.capacity() && layers_[d].cm_images.capacity())
+                          ? cm_plan(layers_[d].cm_shape, L.n_chunks, static_cast<uint64_t>(rows) * b_prev, n_sm_, cm_force_)
                           : CmPlan{};
     const bool chunk_major = cm.eligible;
     if (chunk_major) {
@@ -1128,13 +1151,17 @@ int XLinearEngine::score_layer_(size_t d, const QueryDev& q, uint32_t b_prev, in
         xl_cm_count_kernel<<<warp_grid, 128, 0, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w, stats);
         xl_cm_scan_kernel<<<1, 1024, 0, stream_>>>(L.n_chunks, w);
         xl_cm_scatter_kernel<<<warp_grid, 128, 0, stream_>>>(L, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w);
-        const uint64_t max_items = (static_cast<uint64_t>(rows) * b_prev + w.item_pairs - 1) / w.item_pairs + L.n_chunks;
+        const CmShape& shape = layers_[d].cm_shape;
         auto launch_cm = [&](auto kernel) {
-            kernel<<<static_cast<uint32_t>(max_items), cm.warps * 32, cm.smem, stream_>>>(
-                L, q, w, cand_.get(), cand_stride_q, stats, cm.fm_words, cm.r_cap, cm.e_cap, cm.acc_cols);
+            kernel<<<cm.grid, cm.warps * 32, cm.smem, stream_>>>(L, q, w, shape, layers_[d].cm_images.get(), cand_.get(), cand_stride_q, stats);
         };
-        if (collect_stats) { if (cm.direct) launch_cm(xl_cm_scores_kernel<true, true>); else launch_cm(xl_cm_scores_kernel<true, false>); }
-        else { if (cm.direct) launch_cm(xl_cm_scores_kernel<false, true>); else launch_cm(xl_cm_scores_kernel<false, false>); }
+        if (collect_stats) {
+            if (shape.direct) launch_cm(xl_cm_scores_kernel<true, true, false>); else launch_cm(xl_cm_scores_kernel<true, false, false>);
+        } else if (cm_flat_) {
+            if (shape.direct) launch_cm(xl_cm_scores_kernel<false, true, true>); else launch_cm(xl_cm_scores_kernel<false, false, true>);
+        } else {
+            if (shape.direct) launch_cm(xl_cm_scores_kernel<false, true, false>); else launch_cm(xl_cm_scores_kernel<false, false, false>);
+        }
         launches_ += 3;  // + the score kernel counted below
     } else if (query_warp) {
         const uint32_t qw_qcap = std::max<uint32_t>(32u, (q.max_row_nnz + 31u) & ~31u);

@@ -35,6 +35,16 @@ struct LayerDev {
     int has_dup_cols;
 };
 
+// Chunk-major score kernel (xlinear_cm_kernel.cuh)
+struct CmShape {  // load-time, per layer: geometry of the chunk images
+    bool ok = false;
+    bool direct = false;
+    uint32_t words = 0;      // direct: w_rows (table entries); else fm_words (feature-map cells)
+    uint32_t r_cap = 0, e_cap = 0, acc_cols = 0;
+    uint32_t off_lookup = 16, off_pre = 0, off_rp = 0, off_ew = 0, off_ec = 0;  // byte offsets inside an image
+    uint32_t img_bytes = 0;  // image stride (multiple of 128)
+};
+
 // Device view of a batch of queries (either CSR or row-major dense).
 struct QueryDev {
     const uint64_t* row_ptr;  // CSR: absolute offsets (row_ptr[r] - nnz_base indexes col_idx/val); nullptr for dense
@@ -149,6 +159,8 @@ private:
         DeviceBuffer<uint32_t> label_of_col;
         DeviceBuffer<uint2> featmap;
         uint32_t e_max = 0;  // most entries of one chunk (sizes the chunk-major kernel's shared-memory staging)
+        DeviceBuffer<unsigned char> cm_images;  // packed chunk images of the chunk-major kernel (empty: layer not eligible)
+        CmShape cm_shape;
         LayerDev view{};
     };
 
@@ -219,6 +231,8 @@ private:
     bool no_topk_filter_ = false;
     bool chunk_major_ = true;   // chunk-major scoring wherever cm_plan() finds it eligible (kernel mode 6 switches it off)
     bool cm_force_ = false;     // kernel mode 5
+    uint32_t n_sm_ = 148;
+    bool cm_flat_ = false;      // PB200_CM_FLAT=1: flat entry stream in the chunk-major kernel (A/B)
     DeviceBuffer<uint32_t> cm_slot_pos_, cm_count_, cm_bucket_ptr_, cm_item_ptr_, cm_pair_q_, cm_pair_pos_;
     bool force_block_topk_ = false;  // A/B switch: first-generation kernels (row-list streaming + block-wide sort)
     std::vector<XLinearLayerProfile> layer_profile_;

@@ -22,9 +22,13 @@ e) python bench.py --steps 20 --warmup 5 > $o/${tag}_bench_eurlex4k.json 2> $o/$
    summ $o/${tag}_bench_eurlex4k.json $o/${tag}_bench_eurlex4k_mode6.json;;
 s) python bench.py --workload synthetic-3m --steps 5 --warmup 3 --no-cpu-baseline > $o/${tag}_bench_synthetic3m.json 2> $o/${tag}_bench_synthetic3m.err || tail -5 $o/${tag}_bench_synthetic3m.err
    summ $o/${tag}_bench_synthetic3m.json;;
+eflat) PB200_CM_FLAT=1 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $o/${tag}_bench_eurlex4k_flat.json 2> $o/${tag}_bench_eurlex4k_flat.err
+   summ $o/${tag}_bench_eurlex4k_flat.json;;
+sflat) PB200_CM_FLAT=1 python bench.py --workload synthetic-3m --steps 5 --warmup 3 --no-cpu-baseline > $o/${tag}_bench_synthetic3m_flat.json 2> $o/${tag}_bench_synthetic3m_flat.err
+   summ $o/${tag}_bench_synthetic3m_flat.json;;
 ref) python bench.py --impl reference --steps 5 --warmup 2 > $o/${tag}_bench_reference_arm.json 2> $o/${tag}_bench_reference_arm.err; cut -c1-600 $o/${tag}_bench_reference_arm.json;;
-ncu_e) ncu --set full --clock-control none --import-source on -k "regex:xl_cm_scores_kernel<0" -s ${NCU_SKIP_E:-5} -c 1 -o $o/${tag}_ncu_cm_eurlex4k python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2> $o/${tag}_ncu_e.err;;
-ncu_s) ncu --set full --clock-control none --import-source on -k "regex:xl_cm_scores_kernel<0" -s ${NCU_SKIP_S:-7} -c 1 -o $o/${tag}_ncu_cm_synthetic3m python bench.py --workload synthetic-3m --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2> $o/${tag}_ncu_s.err;;
+ncu_e) ncu --set full --clock-control none --import-source on -k regex:xl_cm_scores_kernel -s ${NCU_SKIP_E:-9} -c 1 -o $o/${tag}_ncu_cm_eurlex4k python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2> $o/${tag}_ncu_e.err;;
+ncu_s) ncu --set full --clock-control none --import-source on -k regex:xl_cm_scores_kernel -s ${NCU_SKIP_S:-13} -c 1 -o $o/${tag}_ncu_cm_synthetic3m python bench.py --workload synthetic-3m --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2> $o/${tag}_ncu_s.err;;
 launches) ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/${tag}_launches_eurlex4k.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1;;
 esac
 done
