@@ -189,6 +189,15 @@ void pb200_xlinear_sharded_merge(void* ptr, uint32_t world, uint32_t rows, uint3
                                  const void* g_keys, const void* g_ids, const void* g_vals, const void* g_cnt,
                                  py_sparse_allocator_t pred_alloc);
 
+/* Packed form of the exchange: rec_dev / g_rec hold 16-byte records {u64 key, u32 id, f32 value} ([rows][stride] locally,
+ * [world][rows][stride] gathered); key == 0 marks an empty slot, so no count array travels and the whole exchange is ONE
+ * ncclAllGather of one buffer (16 B x rows x stride per rank). */
+uint32_t pb200_xlinear_sharded_local_csr_packed(void* ptr, const ScipyCsrF32* input_x, uint32_t overridden_beam_size,
+                                                const char* overridden_post_processor_str, uint32_t overridden_only_topk,
+                                                uint32_t stride_capacity, void* rec_dev);
+void pb200_xlinear_sharded_merge_packed(void* ptr, uint32_t world, uint32_t rows, uint32_t stride, uint32_t overridden_only_topk,
+                                        const void* g_rec, py_sparse_allocator_t pred_alloc);
+
 /* Per-layer kernel timing (CUDA events) and algorithmic-byte counters.
  *   profile: out[2*d] = chunk-score kernel ms, out[2*d+1] = top-k kernel ms   (accumulated since reset)
  *   stats:   out[7*d + {0..6}] = chunks, sum R, sum m, sum e, sum c, sum nnz(x), sum beam-out   (last stats pass) */

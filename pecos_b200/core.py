@@ -396,6 +396,10 @@ class B200CoreLib(object):
                                                            c_void_p, c_void_p, c_void_p, c_void_p])
         fp(c.pb200_xlinear_sharded_merge, None, [c_void_p, c_uint32, c_uint32, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p,
                                                  c_void_p, ScipyCompressedSparseAllocator.CFUNCTYPE])
+        fp(c.pb200_xlinear_sharded_local_csr_packed, c_uint32, [c_void_p, POINTER(ScipyCsrF32), c_uint32, c_char_p, c_uint32, c_uint32,
+                                                                  c_void_p])
+        fp(c.pb200_xlinear_sharded_merge_packed, None, [c_void_p, c_uint32, c_uint32, c_uint32, c_uint32, c_void_p,
+                                                        ScipyCompressedSparseAllocator.CFUNCTYPE])
         fp(c.pb200_xlinear_set_profile, None, [c_void_p, c_int])
         fp(c.pb200_xlinear_reset_profile, None, [c_void_p])
         fp(c.pb200_xlinear_set_lookup, c_int, [c_void_p, c_int])

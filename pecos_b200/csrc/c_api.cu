@@ -681,6 +681,22 @@ void pb200_xlinear_sharded_merge(void* ptr, uint32_t world, uint32_t rows, uint3
     PB200_API_END("pb200_xlinear_sharded_merge")
 }
 
+uint32_t pb200_xlinear_sharded_local_csr_packed(void* ptr, const ScipyCsrF32* X, uint32_t beam, const char* pp, uint32_t topk,
+                                                uint32_t stride_capacity, void* rec_dev) {
+    PB200_API_BEGIN
+    PB200_LOCK_XL(ptr)
+    return engine_of(ptr).sharded_local_csr_packed(X->row_ptr, X->col_idx, X->val, X->rows, X->cols, beam, pp, topk, stride_capacity, rec_dev);
+    PB200_API_END("pb200_xlinear_sharded_local_csr_packed")
+}
+
+void pb200_xlinear_sharded_merge_packed(void* ptr, uint32_t world, uint32_t rows, uint32_t stride, uint32_t topk, const void* g_rec,
+                                        py_sparse_allocator_t pred_alloc) {
+    PB200_API_BEGIN
+    PB200_LOCK_XL(ptr)
+    emit_result(engine_of(ptr).sharded_merge_packed(world, rows, stride, topk, g_rec), pred_alloc);
+    PB200_API_END("pb200_xlinear_sharded_merge_packed")
+}
+
 void pb200_xlinear_set_profile(void* ptr, int on) {
     PB200_API_BEGIN
     PB200_LOCK_XL(ptr)

@@ -838,6 +838,76 @@ xl_merge_topk_kernel(const unsigned long long* __restrict__ g_keys, const uint32
     }
 }
 
+// Packed exchange records for index sharding: ONE 16-byte {key, id, value} record per (query, rank) slot, key == 0 marks an
+// empty slot (a valid key is never 0: its low word is ~position), so the per-query counts need not travel: the whole exchange
+// is a single all-gather of one buffer.
+struct __align__(16) ShardRecord {
+    unsigned long long key;
+    uint32_t id;
+    float val;
+};
+static_assert(sizeof(ShardRecord) == 16, "shard record must stay 16 bytes");
+
+__global__ void xl_shard_pack_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ ids,
+                                     const float* __restrict__ vals, const uint32_t* __restrict__ cnt, const uint32_t rows,
+                                     const uint32_t stride, ShardRecord* __restrict__ rec) {
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<uint64_t>(rows) * stride) return;
+    const uint32_t q = static_cast<uint32_t>(i / stride), r = static_cast<uint32_t>(i - static_cast<uint64_t>(q) * stride);
+    ShardRecord out{0ull, 0u, 0.0f};
+    if (r < cnt[q]) { out.key = keys[i]; out.id = ids[i]; out.val = vals[i]; }
+    rec[i] = out;
+}
+
+// merge of the gathered packed records [world][rows][stride]: same selection as xl_merge_topk_kernel
+__global__ void __launch_bounds__(kSelWarps * 32)
+xl_merge_packed_kernel(const ShardRecord* __restrict__ g_rec, const uint32_t world, const uint32_t rows, const uint32_t stride,
+                       const uint32_t k, uint32_t* __restrict__ out_id, float* __restrict__ out_val, uint32_t* __restrict__ out_cnt) {
+    __shared__ unsigned long long s_keys[kSelWarps][kSelKeys];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * kSelWarps + warp;
+    if (q >= rows) return;
+    unsigned long long* keys = s_keys[warp];
+    const uint32_t n = world * stride;
+    unsigned long long best = 0ull;
+    uint32_t total = 0;
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t g = i / stride, r = i - g * stride;
+        const unsigned long long key = g_rec[(static_cast<uint64_t>(g) * rows + q) * stride + r].key;
+        if (key) ++total;
+        keys[i] = key;
+        best = key > best ? key : best;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(kFull, total, d);
+    __syncwarp();
+    const uint32_t kk = min(k, total);
+    if (lane == 0) out_cnt[q] = kk;
+    for (uint32_t rnk = 0; rnk < kk; ++rnk) {
+        unsigned long long top = best;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(kFull, top, d);
+            top = o > top ? o : top;
+        }
+        uint32_t slot = 0xFFFFFFFFu;
+        if (best == top) {
+            for (uint32_t i = lane; i < n; i += 32) if (keys[i] == top) { slot = i; break; }
+        }
+        if (slot != 0xFFFFFFFFu) {
+            const uint32_t g = slot / stride, r = slot - g * stride;
+            const ShardRecord rc = g_rec[(static_cast<uint64_t>(g) * rows + q) * stride + r];
+            out_id[static_cast<uint64_t>(q) * k + rnk] = rc.id;
+            out_val[static_cast<uint64_t>(q) * k + rnk] = rc.val;
+            keys[slot] = 0ull;
+            best = 0ull;
+            for (uint32_t i = lane; i < n; i += 32) { const unsigned long long key = keys[i]; best = key > best ? key : best; }
+        }
+        __syncwarp();
+    }
+}
+
 // Row extents as one 8-byte record per chunk row, derived on the device from the row_ptr array of the chunk (the score
 // kernels then need ONE load per matched row).  The chunk's region of meta[] holds R4 + roundup4(R + 1) >= 2R words, so
 // rowext[] simply mirrors meta[]'s indexing.
@@ -1559,6 +1629,48 @@ XLinearEngine::Result XLinearEngine::sharded_merge(uint32_t world, uint32_t rows
     if (rows) {
         xl_merge_topk_kernel<<<(rows + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream_>>>(
             g_keys, g_ids, g_vals, g_cnt, world, rows, stride, k_out, res_ids_dev_.get(), res_vals_dev_.get(), res_cnt_dev_.get());
+        PB200_CUDA(cudaGetLastError());
+        ++launches_;
+    }
+    return finish_result_(rows, k_out);
+}
+
+uint32_t XLinearEngine::sharded_local_csr_packed(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, uint32_t rows,
+                                                 uint32_t cols, uint32_t beam_size, const char* post_processor, uint32_t only_topk,
+                                                 uint32_t stride_capacity, void* rec_dev) {
+    PB200_CUDA(cudaSetDevice(device_));
+    const uint64_t n = static_cast<uint64_t>(rows) * std::max<uint32_t>(stride_capacity, 1u);
+    shard_keys_.reserve(n + 1);
+    shard_ids_.reserve(n + 1);
+    shard_vals_.reserve(n + 1);
+    shard_cnt_.reserve(static_cast<uint64_t>(rows) + 1);
+    const uint32_t stride = sharded_local_csr(row_ptr, col_idx, val, rows, cols, beam_size, post_processor, only_topk, stride_capacity,
+                                              shard_keys_.get(), shard_ids_.get(), shard_vals_.get(), shard_cnt_.get());
+    const uint64_t total = static_cast<uint64_t>(rows) * stride;
+    if (total) {
+        xl_shard_pack_kernel<<<static_cast<uint32_t>((total + 255) / 256), 256, 0, stream_>>>(
+            shard_keys_.get(), shard_ids_.get(), shard_vals_.get(), shard_cnt_.get(), rows, stride, static_cast<ShardRecord*>(rec_dev));
+        PB200_CUDA(cudaGetLastError());
+        ++launches_;
+    }
+    PB200_CUDA(cudaStreamSynchronize(stream_));
+    return stride;
+}
+
+XLinearEngine::Result XLinearEngine::sharded_merge_packed(uint32_t world, uint32_t rows, uint32_t stride, uint32_t only_topk,
+                                                          const void* g_rec) {
+    PB200_CUDA(cudaSetDevice(device_));
+    if (static_cast<uint64_t>(world) * stride > static_cast<uint64_t>(kSelKeys))
+        throw std::runtime_error("pecos_b200: world * top-k exceeds the merge kernel's capacity");
+    const uint32_t k = only_topk ? only_topk : static_cast<uint32_t>(host_->layers.back().only_topk);
+    const uint32_t k_out = std::min<uint32_t>(k, world * stride);
+    res_stride_ = k_out;
+    res_ids_dev_.reserve(static_cast<uint64_t>(rows) * k_out + 1);
+    res_vals_dev_.reserve(static_cast<uint64_t>(rows) * k_out + 1);
+    res_cnt_dev_.reserve(static_cast<uint64_t>(rows) + 1);
+    if (rows) {
+        xl_merge_packed_kernel<<<(rows + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream_>>>(
+            static_cast<const ShardRecord*>(g_rec), world, rows, stride, k_out, res_ids_dev_.get(), res_vals_dev_.get(), res_cnt_dev_.get());
         PB200_CUDA(cudaGetLastError());
         ++launches_;
     }

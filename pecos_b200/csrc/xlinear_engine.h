@@ -134,6 +134,13 @@ public:
     Result sharded_merge(uint32_t world, uint32_t rows, uint32_t stride, uint32_t only_topk, const unsigned long long* g_keys,
                          const uint32_t* g_ids, const float* g_vals, const uint32_t* g_cnt);
 
+    // Packed form: ONE buffer of 16-byte {u64 key, u32 id, f32 value} records [rows][stride] (key == 0: empty slot), so the
+    // exchange is a single all-gather; sharded_merge_packed consumes the gathered [world][rows][stride] records.
+    uint32_t sharded_local_csr_packed(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, uint32_t rows, uint32_t cols,
+                                      uint32_t beam_size, const char* post_processor, uint32_t only_topk, uint32_t stride_capacity,
+                                      void* rec_dev);
+    Result sharded_merge_packed(uint32_t world, uint32_t rows, uint32_t stride, uint32_t only_topk, const void* g_rec);
+
     void set_profile(bool on) { profile_ = on; }
     // false = stream the chunk row lists (first-generation kernel) even when feature maps exist; for A/B tests
     void set_kernel_mode(int mode);
@@ -215,6 +222,9 @@ private:
     DeviceBuffer<float> res_vals_dev_;
     DeviceBuffer<uint32_t> res_cnt_dev_;
     uint32_t res_rows_ = 0, res_stride_ = 0;
+    DeviceBuffer<unsigned long long> shard_keys_;  // local top-k of an index-sharded run before packing
+    DeviceBuffer<uint32_t> shard_ids_, shard_cnt_;
+    DeviceBuffer<float> shard_vals_;
     unsigned long long* ext_keys_ = nullptr;  // caller-owned leaf outputs of an index-sharded run
     uint32_t* ext_ids_ = nullptr;
     float* ext_vals_ = nullptr;

@@ -105,21 +105,18 @@ class ShardedXLinearModel(object):
         k = int(only_topk or self.pred_params[-1]["only_topk"])
         rows = X.shape[0]
         dev = torch.device("cuda", c.pb200_get_device())
-        keys = torch.zeros((rows, k), dtype=torch.int64, device=dev)
-        ids = torch.zeros((rows, k), dtype=torch.int32, device=dev)
-        vals = torch.zeros((rows, k), dtype=torch.float32, device=dev)
-        cnt = torch.zeros((rows,), dtype=torch.int32, device=dev)
+        # send buffer of the exchange: 16-byte {u64 key, u32 id, f32 value} records, viewed as int64 pairs for torch
+        rec = torch.zeros((rows, k, 2), dtype=torch.int64, device=dev)
         torch.cuda.synchronize(dev)
         cx = ScipyCsrF32.init_from(X)
         pp = post_processor.encode("utf-8") if post_processor else None
-        stride = c.pb200_xlinear_sharded_local_csr(self.model_chain, byref(cx), beam_size or 0, pp, only_topk or 0, k,
-                                                   keys.data_ptr(), ids.data_ptr(), vals.data_ptr(), cnt.data_ptr())
+        stride = c.pb200_xlinear_sharded_local_csr_packed(self.model_chain, byref(cx), beam_size or 0, pp, only_topk or 0, k,
+                                                          rec.data_ptr())
         if stride != k:  # fewer candidates than k can exist at all: the engine used a narrower stride
-            keys, ids, vals = (t.view(-1)[: rows * stride].view(rows, stride) for t in (keys, ids, vals))
-        # ONE all-gather step (four tensors of the same step; key/id/value/count)
-        g_keys, g_ids, g_vals, g_cnt = (self.comm.all_gather(t.contiguous()) for t in (keys, ids, vals, cnt))
+            rec = rec.view(-1)[: rows * stride * 2].view(rows, stride, 2)
+        g_rec = self.comm.all_gather(rec.contiguous())  # THE exchange: one all-gather of one buffer
         torch.cuda.synchronize(dev)
+        self.last_exchange_bytes = int(rec.numel() * 8)
         alloc = ScipyCompressedSparseAllocator()
-        c.pb200_xlinear_sharded_merge(self.model_chain, self.world, rows, stride, only_topk or 0, g_keys.data_ptr(),
-                                      g_ids.data_ptr(), g_vals.data_ptr(), g_cnt.data_ptr(), alloc.cfunc)
+        c.pb200_xlinear_sharded_merge_packed(self.model_chain, self.world, rows, stride, only_topk or 0, g_rec.data_ptr(), alloc.cfunc)
         return alloc.get()

@@ -83,3 +83,47 @@ def test_saturated_ties_across_shards(tmp_path, gpu_clib):
     assert np.mean(want.data == 1.0) > 0.2
     got, _, _ = _sharded_predict(gpu_clib, os.path.join(folder, "ranker"), X, 4, 10, 10)
     assert_csr_parity(got, want, rtol=0.0, what="saturated, world=4")
+
+
+def _sharded_predict_packed(clib, ranker, X, world, beam, topk):
+    """The production exchange: every rank's local top-k as ONE buffer of 16-byte {key, id, value} records (key == 0: empty),
+    ONE all-gather (emulated by torch.stack), merge of the gathered records."""
+    import torch
+
+    from pecos_b200.core import ScipyCompressedSparseAllocator, ScipyCsrF32
+
+    c = clib.clib_float32
+    dev = torch.device("cuda", 0)
+    handles = [c_void_p(c.pb200_xlinear_load_sharded(ranker.encode(), 2, r, world)) for r in range(world)]
+    try:
+        rows = X.shape[0]
+        cx = ScipyCsrF32.init_from(X)
+        recs, stride = [], None
+        for h in handles:
+            rec = torch.zeros((rows, topk, 2), dtype=torch.int64, device=dev)
+            torch.cuda.synchronize()
+            s = c.pb200_xlinear_sharded_local_csr_packed(h, byref(cx), beam, None, topk, topk, rec.data_ptr())
+            assert stride in (None, s)
+            stride = s
+            recs.append(rec.view(-1)[: rows * s * 2].view(rows, s, 2))
+        g = torch.stack(recs).contiguous()
+        torch.cuda.synchronize()
+        alloc = ScipyCompressedSparseAllocator()
+        c.pb200_xlinear_sharded_merge_packed(handles[0], world, rows, stride, topk, g.data_ptr(), alloc.cfunc)
+        return alloc.get()
+    finally:
+        for h in handles:
+            c.c_xlinear_destruct_model(h)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_packed_single_allgather_exchange_is_bit_identical(tmp_path, gpu_clib, world):
+    from pecos_b200.xlinear import XLinearModel
+
+    folder = str(tmp_path / "m")
+    layers = random_tree(321, [8, 64, 900], 400, 30, bias=1.0, saturate=(world == 8))  # world 8: saturated hinge => ties decide
+    synth.save_xlinear_model(folder, layers, bias=1.0, only_topk=12)
+    X = synth.make_queries(322, 333, 400, 40)
+    want = XLinearModel.load(folder, is_predict_only=True).predict(X, beam_size=9, only_topk=12)
+    got = _sharded_predict_packed(gpu_clib, os.path.join(folder, "ranker"), X, world, 9, 12)
+    assert_csr_parity(got, want, rtol=0.0, what=f"packed exchange, world {world}")
