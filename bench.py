@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--workload", default="eurlex-4k")
     ap.add_argument("--cache-dir", default=os.environ.get("PB200_BENCH_CACHE", os.path.join(tempfile.gettempdir(), "pecos_b200_bench")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the other target configurations (synthetic-3m; at N > 1 also the index-sharded run) that the default "
+                         "eurlex-4k run reports under `secondary`")
     return ap.parse_args()
 
 
@@ -193,8 +196,9 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def prepare_workload(args, rank, world, barrier):
-    """Rank 0 writes the synthetic model folder once; every rank generates its own query batch from a seed."""
+def prepare_workload(args, rank, world, barrier, same_batch=False):
+    """Rank 0 writes the synthetic model folder once; every rank generates its own query batch from a seed (same_batch: the
+    SAME batch on every rank, for strong scaling)."""
     from pecos_b200 import synth
 
     folder = os.path.join(args.cache_dir, args.workload)
@@ -204,7 +208,7 @@ def prepare_workload(args, rank, world, barrier):
     barrier()
     cfg = dict(synth.WORKLOADS[args.workload])
     cdf = synth.zipf_cdf(cfg["D"]) if cfg["zipf"] else None
-    X = synth.make_queries(cfg["query_seed"] + 1000 * rank, cfg["Q"], cfg["D"], cfg["nnz_per_row"], cdf)
+    X = synth.make_queries(cfg["query_seed"] + (0 if same_batch else 1000 * rank), cfg["Q"], cfg["D"], cfg["nnz_per_row"], cdf)
     return folder, X, cfg
 
 
@@ -599,6 +603,255 @@ def parity_gate_xlinear(got, folder, X, cfg, rows=1024, what="resident batch"):
             "scores_bit_equal_frac": bits}
 
 
+def _max_over_ranks(dist, x):
+    if dist is None:
+        return float(x)
+    import torch
+
+    t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _ncu_notes(workload, kernel):
+    """What the committed ncu captures (profiles/ncu_traffic.json, written from `ncu --set full` runs) say about a kernel."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(workload, {}).get(kernel)
+    except Exception:
+        return None
+
+
+def measure_xlinear(args, workload, rank, n_gpus, local, dist, barrier, lib, steps, warmup, strong=False, with_cpu=True,
+                    with_clocks=True):
+    """One XR-Linear workload on this rank's GPU.  strong=False: every rank its own batch of the workload's shape (weak
+    scaling, replicas); strong=True: ONE batch of the workload's size, rows split over the ranks by nnz (strong scaling).
+    Returns the JSON-able record (rank 0) -- parity-gated: raises if the GPU result differs from the reference."""
+    from ctypes import byref, c_double, c_int, c_uint64
+
+    from pecos_b200.core import ScipyCompressedSparseAllocator, ScipyCsrF32
+    from pecos_b200.distributed import split_rows_by_nnz
+    from pecos_b200.xlinear import XLinearModel
+
+    c = lib.clib_float32
+    wargs = argparse.Namespace(**vars(args))
+    wargs.workload = workload
+    folder, X, cfg = prepare_workload(wargs, rank, n_gpus, barrier, same_batch=strong)
+    Q_total = X.shape[0] * (1 if strong else n_gpus)
+    if strong and n_gpus > 1:
+        cut = split_rows_by_nnz(X.indptr, n_gpus)
+        X = X[cut[rank]:cut[rank + 1]]
+        X.has_sorted_indices = True
+    model = XLinearModel.load(folder, is_predict_only=True)
+    h = model.model.model_chain
+    depth = model.depth
+    beam, topk = cfg["beam_size"], cfg["only_topk"]
+    Q = X.shape[0]
+
+    # ------------------------------------------------------------ resident batch + algorithmic-byte counters
+    cx = ScipyCsrF32.init_from(X)
+    c.pb200_xlinear_resident_upload_csr(h, byref(cx))
+    c.pb200_xlinear_resident_predict(h, beam, None, topk, 1)
+    stats = (c_uint64 * (7 * depth))()
+    c.pb200_xlinear_get_stats(h, stats)
+    st = np.array(list(stats), dtype=np.float64).reshape(depth, 7)  # chunks, sum R, sum m, sum e, sum c, sum nnz, beam out
+    # SURVEY.md 8(d) yardstick: per (query, chunk) 32 + 4R + 16m + 8e + 4c ; per query and layer 8 nnz(x) + 8 min(k, sum c)
+    survey_scores = 32 * st[:, 0] + 4 * st[:, 1] + 16 * st[:, 2] + 8 * st[:, 3] + 4 * st[:, 4] + 8 * st[:, 5]
+    # Bytes the IMPLEMENTED kernels must move: no 4R row-list term (they look features up instead of streaming the row
+    # list): one 32-byte sector per lookup (query-major kernels; the chunk-major kernel reads the query once per pair,
+    # 8 B x nnz, and its chunk images once per CTA and chunk), 8 B per matched row extent, 8 B per entry, 4 B per output.
+    topk_bytes = 4 * st[:, 4] + 8 * st[:, 6]
+
+    def one_step():
+        c.pb200_l2_flush()  # outside the event-timed region: every step starts with a cold L2
+        return c.pb200_xlinear_resident_predict(h, beam, None, topk, 0)
+
+    sampler = ClockSampler(local)
+    if rank == 0 and with_clocks:
+        sampler.start()  # started before the warm-up: nvidia-smi needs ~0.3 s before its first sample
+    for _ in range(max(3, warmup)):
+        one_step()
+    if rank == 0 and with_clocks:
+        sampler.mark()
+
+    # ------------------------------------------------------------ timed region: K steps, device time, max over ranks
+    c.pb200_xlinear_reset_profile(h)
+    barrier()
+    wall0 = time.perf_counter()
+    step_ms = [one_step() for _ in range(steps)]
+    wall1 = time.perf_counter()
+    launches = int(c.pb200_xlinear_launches(h))
+    barrier()
+    clocks = sampler.stop() if (rank == 0 and with_clocks) else None
+    total_ms = _max_over_ranks(dist, sum(step_ms))
+    ms_per_step = total_ms / steps
+    value = Q_total / (ms_per_step * 1e-3)
+
+    # ------------------------------------------------------------ parity gate on the result of the LAST timed step
+    fetch = ScipyCompressedSparseAllocator()
+    c.pb200_xlinear_resident_fetch(h, fetch.cfunc)
+    got_resident = fetch.get()
+    parity = parity_gate_xlinear(got_resident, folder, X, cfg, rows=(1024 if rank == 0 else 128), what=f"{workload} resident batch")
+
+    # ------------------------------------------------------------ per-kernel timing (CUDA events on the launch stream)
+    c.pb200_xlinear_set_profile(h, 1)
+    c.pb200_xlinear_reset_profile(h)
+    prof_steps = max(3, min(steps, 10))
+    for _ in range(prof_steps):
+        one_step()
+    prof = (c_double * (2 * depth))()
+    c.pb200_xlinear_get_profile(h, prof)
+    kid = (c_int * (2 * depth))()
+    c.pb200_xlinear_get_kernel_ids(h, kid)
+    c.pb200_xlinear_set_profile(h, 0)
+    pm = np.array(list(prof), dtype=np.float64).reshape(depth, 2) / prof_steps
+    peak, peak_src = measured_peak_gbs()
+    # per feature of a (query, chunk) pair: the chunk-major kernel (id 4) reads the query once per pair (8 B); the query-major
+    # lookup kernels read one 32-byte sector of the chunk's feature map per feature on top of the query (8 B, once per query)
+    probe = np.array([8.0 if kid[2 * d] == 4 else 32.0 for d in range(depth)])
+    pairs_per_query = st[:, 0] / np.maximum(st[:, 5] / np.maximum(X.nnz / max(Q, 1), 1e-9), 1.0)  # st5 = sum nnz over queries with a beam
+    impl_scores = (32 * st[:, 0] + probe * st[:, 5] * np.maximum(pairs_per_query, 1.0) + 8 * st[:, 2] + 8 * st[:, 3] + 4 * st[:, 4]
+                   + np.where(probe > 8, 8 * st[:, 5], 0.0))
+    kernels = []
+    for d in range(depth):
+        kernels.append({"kernel": f"{SCORE_KERNELS[kid[2 * d]]}[layer {d}]", "ms": pm[d, 0], "algorithmic_bytes": float(impl_scores[d]),
+                        "survey_formula_bytes": float(survey_scores[d]), "pairs": float(st[d, 0]), "matched_rows": float(st[d, 2]),
+                        "entries": float(st[d, 3])})
+        kernels.append({"kernel": f"{TOPK_KERNELS[kid[2 * d + 1]]}[layer {d}]", "ms": pm[d, 1], "algorithmic_bytes": float(topk_bytes[d])})
+    dom = max(kernels, key=lambda k: k["ms"])
+    achieved = dom["algorithmic_bytes"] / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
+    notes = _ncu_notes(workload, dom["kernel"].split("[")[0]) or {}
+    step_bytes = float(impl_scores.sum() + topk_bytes.sum())
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+        "traffic": notes.get("dram_bytes_per_launch") if isinstance(notes, dict) else notes,
+        "kernel": dom["kernel"], "kernel_ms": dom["ms"], "algorithmic_bytes_per_launch": dom["algorithmic_bytes"],
+        "algorithmic_bytes_definition": "bytes the implemented kernel must move per launch: per (query, chunk) pair 32 B chunk header + "
+                                        "nnz(query) x 8 B (chunk-major kernel: the query is read once per pair, lookups hit the staged "
+                                        "image) or x 32 B (query-major kernels: one feature-map sector per lookup) + 8 B per matched "
+                                        "row + 8 B per entry + 4 B per output column; NOT the 4R row list the SURVEY 8d yardstick "
+                                        "charges (kept per kernel as survey_formula_bytes)",
+        "peak_source": peak_src,
+        "ncu": notes if isinstance(notes, dict) else None,
+        "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                       "bytes_per_query": step_bytes / max(Q, 1), "survey_formula_bytes": float(survey_scores.sum() + 8 * st[:, 6].sum())},
+        "kernels": kernels,
+    }
+
+    # ------------------------------------------------------------ end to end through the C ABI with pinned host buffers
+    ip = lib.pinned_empty(Q + 1, np.uint64)
+    ix = lib.pinned_empty(max(X.nnz, 1), np.uint32)
+    dv = lib.pinned_empty(max(X.nnz, 1), np.float32)
+    ip.array[:] = X.indptr
+    ix.array[: X.nnz] = X.indices
+    dv.array[: X.nnz] = X.data
+    cx_pinned = ScipyCsrF32.init_from_arrays(X.shape[0], X.shape[1], ip.array, ix.array, dv.array)
+
+    def e2e_step():
+        alloc = ScipyCompressedSparseAllocator()
+        c.c_xlinear_predict_csr_f32(h, byref(cx_pinned), beam, None, topk, -1, alloc.cfunc)
+        return alloc
+
+    for _ in range(max(3, warmup)):
+        e2e_step()
+    barrier()
+    e2e_times = []
+    for _ in range(steps):
+        c.pb200_l2_flush()
+        t0 = time.perf_counter()
+        out = e2e_step()
+        e2e_times.append(time.perf_counter() - t0)
+    barrier()
+    e2e_total = _max_over_ranks(dist, sum(e2e_times))
+    e2e_value = Q_total * steps / e2e_total
+    h2d = int(ip.array.nbytes + X.nnz * 8)
+    d2h = int(out.indices.nbytes + out.data.nbytes + 4 * Q)
+    got_e2e = out.get()
+    if not (np.array_equal(got_e2e.indptr, got_resident.indptr) and np.array_equal(got_e2e.indices, got_resident.indices)
+            and np.array_equal(got_e2e.data.view(np.uint32), got_resident.data.view(np.uint32))):
+        raise RuntimeError("parity gate (e2e): the C-ABI result of the host-buffer call differs from the resident-batch result")
+    parity["e2e_equals_resident_bits"] = True
+    # the same call with PAGEABLE host memory (what scipy hands the reference's ctypes shim)
+    cx_pageable = ScipyCsrF32.init_from(X)
+    pg_times = []
+    for i in range(2 + min(steps, 10)):
+        c.pb200_l2_flush()
+        t0 = time.perf_counter()
+        alloc = ScipyCompressedSparseAllocator()
+        c.c_xlinear_predict_csr_f32(h, byref(cx_pageable), beam, None, topk, -1, alloc.cfunc)
+        if i >= 2:
+            pg_times.append(time.perf_counter() - t0)
+    e2e_pageable = Q / (sum(pg_times) / len(pg_times))
+
+    # ------------------------------------------------------------ CPU baseline beside it (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and n_gpus == 1 and with_cpu and not args.no_cpu_baseline:
+        try:
+            r = time_reference(folder, X, cfg, steps=5, warmup=2, budget_s=30.0)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                   "best": r["best"], "threads": r["threads"], "layout": r["layout"], "sweep": r["sweep"]}
+        except ReferenceUnavailable as e:  # never substitute the scalar port for the reference
+            print(f"bench.py: cpu_baseline unavailable: {e}", file=sys.stderr)
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)}
+
+    cfgd = workload_config(workload, cfg, X)
+    if strong:
+        cfgd["queries_total"] = int(Q_total)
+        cfgd["parallelism"] = "one batch, rows split over the ranks by nnz (strong scaling, no collective)"
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": max(3, warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": cfgd,
+        "l2": "flushed between timed iterations (512 MiB memset outside the event-timed region)",
+        "timing": "CUDA events on the engine stream per step, summed over steps, max over ranks",
+        "parity": parity,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_total / steps, "api": "c_xlinear_predict_csr_f32 (pinned host CSR in, scipy CSR out)",
+                "pageable_value_per_gpu": e2e_pageable},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "wall_s_timed_region": wall1 - wall0,
+    }, (model, folder, X, cfg)
+
+
+def measure_index_sharded(args, rank, n_gpus, local, dist, barrier, lib, whole, folder, X, cfg, rows=20000, calls=3):
+    """BASELINE.json configs[4]: the leaf layer of the 3M-label tree split over the ranks' GPUs (contiguous chunk ranges),
+    every rank scores the SAME queries on its shard, ONE NCCL all-gather of the packed per-rank top-k, merge.  The merged
+    result must be bit-identical to the unsharded model's (`whole`, loaded on every rank for the query-sharded line)."""
+    import torch
+
+    from pecos_b200.distributed import ShardedXLinearModel
+
+    Xs = X[: min(rows, X.shape[0])]
+    Xs.has_sorted_indices = True
+    beam, topk = cfg["beam_size"], cfg["only_topk"]
+    sharded = ShardedXLinearModel.load(folder, device=local)
+    got = sharded.predict(Xs, beam_size=beam, only_topk=topk)
+    want = whole.predict(Xs, beam_size=beam, only_topk=topk)
+    ok = bool(np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+              and np.array_equal(got.data.view(np.uint32), want.data.view(np.uint32)))
+    if not ok:
+        raise RuntimeError("parity gate (index sharding): merged result differs from the unsharded prediction")
+    barrier()
+    times = []
+    for _ in range(calls):
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        sharded.predict(Xs, beam_size=beam, only_topk=topk)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    dt = _max_over_ranks(dist, sum(times) / len(times))
+    return {"workload": "synthetic-3m-sharded", "value": Xs.shape[0] / dt, "unit": UNIT, "n_gpus": n_gpus,
+            "queries": int(Xs.shape[0]), "ms_per_call": 1e3 * dt, "bit_identical_to_unsharded": ok,
+            "exchange": "ONE ncclAllGather of %d bytes per rank (16-byte {key, id, value} records)" % sharded.last_exchange_bytes,
+            "shard_of_rank0": list(sharded.shard),
+            "timing": "wall clock around ShardedXLinearModel.predict (host CSR in, H2D + kernels + all-gather + merge + D2H), max over ranks"}
+
+
 def main():
     args = parse_args()
     if args.workload.startswith("hnsw"):
@@ -612,11 +865,8 @@ def main():
     n_gpus = max(world, 1)
 
     import __graft_entry__ as entry
-    from ctypes import byref, c_double, c_int, c_uint64
 
     from pecos_b200 import core
-    from pecos_b200.core import ScipyCompressedSparseAllocator, ScipyCsrF32
-    from pecos_b200.xlinear import XLinearModel
 
     if rank == 0 and not os.path.exists(core.LIB_PATH):
         entry.build()
@@ -638,178 +888,36 @@ def main():
     lib = core.get_clib()
     lib.require_gpu()
     lib.set_device(local)
-    c = lib.clib_float32
 
-    folder, X, cfg = prepare_workload(args, rank, n_gpus, barrier)
-    model = XLinearModel.load(folder, is_predict_only=True)
-    h = model.model.model_chain
-    depth = model.depth
-    beam, topk = cfg["beam_size"], cfg["only_topk"]
-    Q = X.shape[0]
+    line, keep = measure_xlinear(args, args.workload, rank, n_gpus, local, dist, barrier, lib, args.steps, args.warmup)
+    del keep
 
-    # ------------------------------------------------------------ resident batch + algorithmic-byte counters
-    cx = ScipyCsrF32.init_from(X)
-    c.pb200_xlinear_resident_upload_csr(h, byref(cx))
-    c.pb200_xlinear_resident_predict(h, beam, None, topk, 1)
-    stats = (c_uint64 * (7 * depth))()
-    c.pb200_xlinear_get_stats(h, stats)
-    st = np.array(list(stats), dtype=np.float64).reshape(depth, 7)
-    # per (query, chunk) 32 + 4R + 16m + 8e + 4c ; per query and layer 8 nnz(x) + 8 min(k, sum c)
-    scores_bytes = 32 * st[:, 0] + 4 * st[:, 1] + 16 * st[:, 2] + 8 * st[:, 3] + 4 * st[:, 4] + 8 * st[:, 5]
-    topk_bytes = 4 * st[:, 4] + 8 * st[:, 6]
-    bytes_per_step = float(scores_bytes.sum() + 8 * st[:, 6].sum())
-
-    def one_step():
-        c.pb200_l2_flush()  # outside the event-timed region: every step starts with a cold L2
-        return c.pb200_xlinear_resident_predict(h, beam, None, topk, 0)
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()  # started before the warm-up: nvidia-smi needs ~0.3 s before its first sample
-    for _ in range(max(3, args.warmup)):
-        one_step()
-    if rank == 0:
-        sampler.mark()
-
-    # ------------------------------------------------------------ timed region: K steps, device time, max over ranks
-    c.pb200_xlinear_reset_profile(h)
-    barrier()
-    wall0 = time.perf_counter()
-    step_ms = [one_step() for _ in range(args.steps)]
-    wall1 = time.perf_counter()
-    launches = int(c.pb200_xlinear_launches(h))
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    total_ms = float(sum(step_ms))
-    if dist is not None:
-        import torch
-
-        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = n_gpus * Q / (ms_per_step * 1e-3)
-
-    # ------------------------------------------------------------ parity gate on the result of the LAST timed step
-    fetch = ScipyCompressedSparseAllocator()
-    c.pb200_xlinear_resident_fetch(h, fetch.cfunc)
-    got_resident = fetch.get()
-    parity = parity_gate_xlinear(got_resident, folder, X, cfg, rows=(1024 if rank == 0 else 128), what="resident batch")
-
-    # ------------------------------------------------------------ per-kernel timing (CUDA events on the launch stream)
-    c.pb200_xlinear_set_profile(h, 1)
-    c.pb200_xlinear_reset_profile(h)
-    prof_steps = max(3, min(args.steps, 10))
-    for _ in range(prof_steps):
-        one_step()
-    prof = (c_double * (2 * depth))()
-    c.pb200_xlinear_get_profile(h, prof)
-    kid = (c_int * (2 * depth))()
-    c.pb200_xlinear_get_kernel_ids(h, kid)
-    c.pb200_xlinear_set_profile(h, 0)
-    pm = np.array(list(prof), dtype=np.float64).reshape(depth, 2) / prof_steps
-    peak, peak_src = measured_peak_gbs()
-    kernels = []
-    for d in range(depth):
-        kernels.append({"kernel": f"{SCORE_KERNELS[kid[2 * d]]}[layer {d}]", "ms": pm[d, 0], "algorithmic_bytes": float(scores_bytes[d])})
-        kernels.append({"kernel": f"{TOPK_KERNELS[kid[2 * d + 1]]}[layer {d}]", "ms": pm[d, 1], "algorithmic_bytes": float(topk_bytes[d])})
-    dom = max(kernels, key=lambda k: k["ms"])
-    achieved = dom["algorithmic_bytes"] / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
-    ncu_traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            ncu_traffic = json.load(f).get(args.workload, {}).get(dom["kernel"].split("[")[0])
-    except Exception:
-        pass
-    roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-        "traffic": ncu_traffic, "kernel": dom["kernel"], "kernel_ms": dom["ms"], "algorithmic_bytes_per_launch": dom["algorithmic_bytes"],
-        "peak_source": peak_src,
-        "whole_step": {"algorithmic_bytes": bytes_per_step, "achieved": bytes_per_step / (ms_per_step * 1e-3) / 1e9,
-                       "bytes_per_query": bytes_per_step / Q},
-        "kernels": kernels,
-    }
-
-    # ------------------------------------------------------------ end to end through the C ABI with pinned host buffers
-    ip = lib.pinned_empty(Q + 1, np.uint64)
-    ix = lib.pinned_empty(X.nnz, np.uint32)
-    dv = lib.pinned_empty(X.nnz, np.float32)
-    ip.array[:] = X.indptr
-    ix.array[:] = X.indices
-    dv.array[:] = X.data
-    cx_pinned = ScipyCsrF32.init_from_arrays(X.shape[0], X.shape[1], ip.array, ix.array, dv.array)
-
-    def e2e_step():
-        alloc = ScipyCompressedSparseAllocator()
-        c.c_xlinear_predict_csr_f32(h, byref(cx_pinned), beam, None, topk, -1, alloc.cfunc)
-        return alloc
-
-    for _ in range(max(3, args.warmup)):
-        e2e_step()
-    barrier()
-    e2e_times = []
-    for _ in range(args.steps):
-        c.pb200_l2_flush()
-        t0 = time.perf_counter()
-        out = e2e_step()
-        e2e_times.append(time.perf_counter() - t0)
-    barrier()
-    e2e_total = float(sum(e2e_times))
-    if dist is not None:
-        import torch
-
-        t = torch.tensor([e2e_total], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_total = float(t.item())
-    e2e_value = n_gpus * Q * args.steps / e2e_total
-    h2d = int(ip.array.nbytes + ix.array.nbytes + dv.array.nbytes)
-    d2h = int(out.indices.nbytes + out.data.nbytes + 4 * Q)
-    got_e2e = out.get()
-    if not (np.array_equal(got_e2e.indptr, got_resident.indptr) and np.array_equal(got_e2e.indices, got_resident.indices)
-            and np.array_equal(got_e2e.data.view(np.uint32), got_resident.data.view(np.uint32))):
-        raise RuntimeError("parity gate (e2e): the C-ABI result of the host-buffer call differs from the resident-batch result")
-    parity["e2e_equals_resident_bits"] = True
-    # the same call with PAGEABLE host memory (what scipy hands the reference's ctypes shim)
-    cx_pageable = ScipyCsrF32.init_from(X)
-    pg_times = []
-    for i in range(2 + min(args.steps, 10)):
-        c.pb200_l2_flush()
-        t0 = time.perf_counter()
-        alloc = ScipyCompressedSparseAllocator()
-        c.c_xlinear_predict_csr_f32(h, byref(cx_pageable), beam, None, topk, -1, alloc.cfunc)
-        if i >= 2:
-            pg_times.append(time.perf_counter() - t0)
-    e2e_pageable = Q / (sum(pg_times) / len(pg_times))
-
-    # ------------------------------------------------------------ CPU baseline beside it (rank 0, N=1 only)
-    cpu = None
-    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+    # ------------------------------------------------------------ the other target configurations, in the same run
+    # (BASELINE.json configs[2..4]; each parity-gated like the headline; a failure is recorded, not fatal for the headline)
+    secondary = {}
+    if not args.no_secondary and args.workload == "eurlex-4k":
+        t_sec = time.perf_counter()
         try:
-            r = time_reference(folder, X, cfg, steps=5, warmup=2, budget_s=30.0)
-            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
-                   "best": r["best"], "threads": r["threads"], "layout": r["layout"], "sweep": r["sweep"]}
-        except ReferenceUnavailable as e:  # never substitute the scalar port for the reference
-            print(f"bench.py: cpu_baseline unavailable: {e}", file=sys.stderr)
-            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)}
+            s_line, (whole, s_folder, s_X, s_cfg) = measure_xlinear(args, "synthetic-3m", rank, n_gpus, local, dist, barrier, lib,
+                                                                    steps=5, warmup=3, strong=(n_gpus > 1), with_cpu=False, with_clocks=False)
+            secondary["synthetic-3m"] = {k: s_line[k] for k in ("value", "unit", "n_gpus", "steps", "ms_per_step", "scaling", "config",
+                                                                "parity", "e2e", "gpu_launches", "roofline")}
+            if n_gpus > 1:
+                # the batch of the strong-scaled line is per-rank; the index-sharded line needs the SAME queries on every rank
+                from pecos_b200 import synth
 
+                wcfg = dict(synth.WORKLOADS["synthetic-3m"])
+                Xall = synth.make_queries(wcfg["query_seed"] + 77, 20000, wcfg["D"], wcfg["nnz_per_row"], synth.zipf_cdf(wcfg["D"]))
+                secondary["synthetic-3m-sharded"] = measure_index_sharded(args, rank, n_gpus, local, dist, barrier, lib, whole, s_folder,
+                                                                          Xall, s_cfg)
+            del whole
+        except Exception as e:  # noqa: BLE001
+            secondary["error"] = f"{type(e).__name__}: {e}"
+            print(f"bench.py: secondary workloads failed: {e}", file=sys.stderr)
+        secondary["wall_s"] = time.perf_counter() - t_sec
     if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, cfg, X),
-            "l2": "flushed between timed iterations (512 MiB memset outside the event-timed region)",
-            "timing": "CUDA events on the engine stream per step, summed over steps, max over ranks",
-            "parity": parity,
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_total / args.steps, "api": "c_xlinear_predict_csr_f32 (pinned host CSR in, scipy CSR out)",
-                    "pageable_value_per_gpu": e2e_pageable},
-            "gpu_launches": launches,
-            "roofline": roofline,
-            "cpu_baseline": cpu,
-            "wall_s_timed_region": wall1 - wall0,
-        }
+        if secondary:
+            line["secondary"] = secondary
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

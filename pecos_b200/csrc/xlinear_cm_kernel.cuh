@@ -55,9 +55,9 @@ struct CmPlan {  // per call
 
 __host__ __device__ inline uint32_t cm_align16(uint32_t x) { return (x + 15u) & ~15u; }
 
-__host__ __device__ inline size_t cm_warp_bytes(uint32_t acc_cols) {
-    return static_cast<size_t>(2) * 32 * (kCmFeat + 1) * 8    // two staging buffers: query features / compacted hits, stride 9
-           + static_cast<size_t>(acc_cols) * 32 * 4;          // accumulators [col][lane]
+__host__ __device__ inline size_t cm_warp_bytes(uint32_t acc_cols, uint32_t stages) {
+    return static_cast<size_t>(stages) * 32 * (kCmFeat + 1) * 8   // staging ring: query features / compacted hits, stride 9
+           + static_cast<size_t>(acc_cols) * 32 * 4;              // accumulators [col][lane]
 }
 
 inline CmShape cm_shape(uint32_t fm_words, uint32_t w_rows, uint32_t r_max, uint32_t e_max, uint32_t c_max, uint32_t n_chunks) {
@@ -66,6 +66,9 @@ inline CmShape cm_shape(uint32_t fm_words, uint32_t w_rows, uint32_t r_max, uint
     s.direct = w_rows <= kCmDirectRows;
     s.words = s.direct ? w_rows : fm_words;
     s.r_cap = r_max; s.e_cap = e_max; s.acc_cols = c_max;
+    // narrow chunks do little arithmetic per round of query features: keep four rounds of cp.async in flight per warp to
+    // cover the global-memory latency; wide chunks (long accumulate phases) get by with two
+    s.stages = c_max <= 16u ? 4u : 2u;
     uint32_t off = 16;  // header {bias range, n_cols, R, E}
     s.off_lookup = off; off += cm_align16(s.words * 4u);
     if (!s.direct) {
@@ -75,7 +78,7 @@ inline CmShape cm_shape(uint32_t fm_words, uint32_t w_rows, uint32_t r_max, uint
     s.off_ew = off; off += cm_align16((e_max + 1u) * 4u);
     s.off_ec = off; off += cm_align16(e_max + 1u);
     s.img_bytes = (off + 127u) & ~127u;
-    if (s.img_bytes + kCmMinWarps * cm_warp_bytes(c_max) + 64 > kCmSmemBudget) return s;
+    if (s.img_bytes + kCmMinWarps * cm_warp_bytes(c_max, s.stages) + 64 > kCmSmemBudget) return s;
     s.ok = true;
     return s;
 }
@@ -85,7 +88,7 @@ inline CmPlan cm_plan(const CmShape& s, uint32_t n_chunks, uint64_t pairs, uint3
     CmPlan p;
     if (!s.ok || pairs == 0) return p;
     if (!force && (pairs < static_cast<uint64_t>(kCmMinReuse) * n_chunks || pairs < kCmMinPairs)) return p;
-    const size_t per_warp = cm_warp_bytes(s.acc_cols);
+    const size_t per_warp = cm_warp_bytes(s.acc_cols, s.stages);
     uint32_t warps = static_cast<uint32_t>(std::min<size_t>(kCmMaxWarps, (kCmSmemBudget - s.img_bytes - 64) / per_warp));
     // no point in more lanes than a CTA's share of the pair list holds
     const uint64_t share = (pairs + n_sm - 1) / n_sm;
@@ -256,27 +259,29 @@ xl_cm_scatter_kernel(const LayerDev L, const uint32_t* __restrict__ beam_id, con
     }
 }
 
-template <bool STATS, bool DIRECT, bool FLAT>
+template <bool STATS, bool DIRECT, bool FLAT, int STAGES>
 __global__ void __launch_bounds__(kCmMaxWarps * 32)
 xl_cm_scores_kernel(const LayerDev L, const QueryDev X, const CmWork w, const CmShape S, const unsigned char* __restrict__ images,
                     float* __restrict__ cand, const uint64_t cand_stride_q, unsigned long long* stats) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* img = smem_raw;                                   // the staged chunk image
-    const uint32_t* hdr_s = reinterpret_cast<const uint32_t*>(img);
-    const uint32_t* look_s = reinterpret_cast<const uint32_t*>(img + S.off_lookup);   // direct table, or feature-map bits
-    const unsigned short* pre_s = reinterpret_cast<const unsigned short*>(img + S.off_pre);
-    const unsigned short* rp_s = reinterpret_cast<const unsigned short*>(img + S.off_rp);
-    const float* ew_s = reinterpret_cast<const float*>(img + S.off_ew);
-    const unsigned char* ec_s = img + S.off_ec;
+    // the image is only ever written by the bulk copy (async proxy), never by this kernel's stores: __restrict__ lets the
+    // compiler hoist its loads above the accumulator stores
+    const uint32_t* __restrict__ hdr_s = reinterpret_cast<const uint32_t*>(img);
+    const uint32_t* __restrict__ look_s = reinterpret_cast<const uint32_t*>(img + S.off_lookup);   // direct table, or feature-map bits
+    const unsigned short* __restrict__ pre_s = reinterpret_cast<const unsigned short*>(img + S.off_pre);
+    const unsigned short* __restrict__ rp_s = reinterpret_cast<const unsigned short*>(img + S.off_rp);
+    const float* __restrict__ ew_s = reinterpret_cast<const float*>(img + S.off_ew);
+    const unsigned char* __restrict__ ec_s = img + S.off_ec;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
     constexpr int kStride = kCmFeat + 1;
     constexpr int kBuf = 32 * kStride;                               // words per staging array
-    unsigned char* mine = smem_raw + S.img_bytes + static_cast<size_t>(warp) * cm_warp_bytes(S.acc_cols);
-    uint32_t* st_idx = reinterpret_cast<uint32_t*>(mine);            // [2][32][kStride]
-    float* st_val = reinterpret_cast<float*>(st_idx + 2 * kBuf);     // [2][32][kStride]
-    float* my_acc = st_val + 2 * kBuf + lane;                        // [acc_cols][32], this lane's column of it
+    unsigned char* mine = smem_raw + S.img_bytes + static_cast<size_t>(warp) * cm_warp_bytes(S.acc_cols, STAGES);
+    uint32_t* st_idx = reinterpret_cast<uint32_t*>(mine);            // [STAGES][32][kStride]
+    float* st_val = reinterpret_cast<float*>(st_idx + STAGES * kBuf); // [STAGES][32][kStride]
+    float* my_acc = st_val + STAGES * kBuf + lane;                   // [acc_cols][32], this lane's column of it
 
     __shared__ __align__(8) unsigned long long s_mbar;
     const uint32_t mbar = static_cast<uint32_t>(__cvta_generic_to_shared(&s_mbar));
@@ -330,66 +335,78 @@ xl_cm_scores_kernel(const LayerDev L, const QueryDev X, const CmWork w, const Cm
                 qn = static_cast<uint32_t>(X.row_ptr[q + 1] - X.nnz_base - qb);
             }
             const uint32_t qn_max = __reduce_max_sync(kFull, qn);
-            // query features travel global -> shared by cp.async, two rounds in flight: round r + 1 is copied while round r
-            // is processed.  Row i of a staging buffer = the next kCmFeat features of the slice's pair i (stride 9 words:
-            // the lane-per-row reads are bank-conflict free).
+            // query features travel global -> shared by cp.async through a ring of STAGES buffers: rounds r + 1 .. r + STAGES - 1
+            // are in flight while round r is processed.  Row i of a buffer = the next kCmFeat features of the slice's pair i
+            // (stride 9 words: the lane-per-row reads are bank-conflict free).  A (possibly empty) group is committed for every
+            // round slot, so "all but the newest STAGES - 1 groups are complete" always means "round r has landed".
             auto stage_round = [&](uint32_t t0, int buf) {
-                uint32_t* di = st_idx + buf * kBuf;
-                float* dv = st_val + buf * kBuf;
+                if (t0 < qn_max) {
+                    uint32_t* di = st_idx + buf * kBuf;
+                    float* dv = st_val + buf * kBuf;
 #pragma unroll
-                for (int i0 = 0; i0 < 32; i0 += kPerIter) {
-                    const int pi = i0 + sub;
-                    const uint64_t b_i = __shfl_sync(kFull, qb, pi);
-                    const uint32_t n_i = __shfl_sync(kFull, qn, pi);
-                    if (t0 + fl < n_i) {
-                        cm_cp_async4(di + pi * kStride + fl, X.col_idx + b_i + t0 + fl);
-                        cm_cp_async4(dv + pi * kStride + fl, X.val + b_i + t0 + fl);
+                    for (int i0 = 0; i0 < 32; i0 += kPerIter) {
+                        const int pi = i0 + sub;
+                        const uint64_t b_i = __shfl_sync(kFull, qb, pi);
+                        const uint32_t n_i = __shfl_sync(kFull, qn, pi);
+                        if (t0 + fl < n_i) {
+                            cm_cp_async4(di + pi * kStride + fl, X.col_idx + b_i + t0 + fl);
+                            cm_cp_async4(dv + pi * kStride + fl, X.val + b_i + t0 + fl);
+                        }
                     }
                 }
                 cm_cp_async_commit();
             };
             __syncwarp();
-            if (qn_max > 0) stage_round(0, 0);
+#pragma unroll
+            for (int st = 0; st < STAGES - 1; ++st) stage_round(static_cast<uint32_t>(st) * kCmFeat, st);
             for (uint32_t col = 0; col < n_cols; ++col) my_acc[col * 32] = 0.0f;
             uint32_t prev_f = kCmEmpty;
             int buf = 0;
-            for (uint32_t t0 = 0; t0 < qn_max; t0 += kCmFeat, buf ^= 1) {
-                if (t0 + kCmFeat < qn_max) { stage_round(t0 + kCmFeat, buf ^ 1); cm_cp_async_wait<1>(); }
-                else cm_cp_async_wait<0>();
+            for (uint32_t t0 = 0; t0 < qn_max; t0 += kCmFeat, buf = (buf + 1 == STAGES) ? 0 : buf + 1) {
+                stage_round(t0 + (STAGES - 1) * kCmFeat, (buf + STAGES - 1) % STAGES);  // refills the buffer consumed last round
+                cm_cp_async_wait<STAGES - 1>();
                 __syncwarp();
                 uint32_t* my_idx = st_idx + buf * kBuf + lane * kStride;
                 float* my_val = st_val + buf * kBuf + lane * kStride;
                 const uint32_t n_here = (qn > t0) ? min(static_cast<uint32_t>(kCmFeat), qn - t0) : 0u;
-                // phase 1: look the features up; compact the hits of this round IN PLACE as {entry range, x} (slot cnt <= k
-                // was already consumed); tot = entries this lane will add in this round
-                uint32_t cnt = 0, tot = 0;
+                // phase 1: look the features up -- all loads of the round are issued before the first store (eight independent
+                // feature / lookup / value loads in flight per lane) -- then compact the hits IN PLACE as {entry range, x}
+                uint32_t fq[kCmFeat], rq[kCmFeat];
+                float xq[kCmFeat];
 #pragma unroll
-                for (uint32_t k = 0; k < static_cast<uint32_t>(kCmFeat); ++k) {
-                    if (k < n_here) {
-                        const uint32_t f = my_idx[k];
-                        const bool dup = (f == prev_f);  // a repeated column index only counts once (the first occurrence)
-                        prev_f = f;
-                        uint32_t range = 0;
-                        if (!dup && f < L.w_rows) {
-                            if (DIRECT) {
-                                range = look_s[f];
-                            } else {
-                                const uint32_t word = look_s[f >> 5];
-                                const uint32_t bit = f & 31u;
-                                if ((word >> bit) & 1u) {
-                                    const uint32_t row = static_cast<uint32_t>(pre_s[f >> 5]) + __popc(word & ((1u << bit) - 1u));
-                                    range = static_cast<uint32_t>(rp_s[row]) | (static_cast<uint32_t>(rp_s[row + 1]) << 16);
-                                }
+                for (int k = 0; k < kCmFeat; ++k) {
+                    fq[k] = (static_cast<uint32_t>(k) < n_here) ? my_idx[k] : kCmEmpty;
+                    xq[k] = my_val[k];
+                }
+#pragma unroll
+                for (int k = 0; k < kCmFeat; ++k) {
+                    const uint32_t f = fq[k];
+                    const bool dup = (f == prev_f);  // a repeated column index only counts once (the first occurrence)
+                    if (static_cast<uint32_t>(k) < n_here) prev_f = f;
+                    uint32_t range = 0;
+                    if (static_cast<uint32_t>(k) < n_here && !dup && f < L.w_rows) {
+                        if (DIRECT) {
+                            range = look_s[f];
+                        } else {
+                            const uint32_t word = look_s[f >> 5];
+                            const uint32_t bit = f & 31u;
+                            if ((word >> bit) & 1u) {
+                                const uint32_t row = static_cast<uint32_t>(pre_s[f >> 5]) + __popc(word & ((1u << bit) - 1u));
+                                range = static_cast<uint32_t>(rp_s[row]) | (static_cast<uint32_t>(rp_s[row + 1]) << 16);
                             }
                         }
-                        const uint32_t len = (range >> 16) - (range & 0xFFFFu);
-                        if (static_cast<int>(len) > 0) {
-                            const float x = my_val[k];
-                            my_idx[cnt] = range;
-                            my_val[cnt] = x;
-                            ++cnt;
-                            tot += len;
-                        }
+                    }
+                    rq[k] = range;
+                }
+                uint32_t cnt = 0, tot = 0;
+#pragma unroll
+                for (int k = 0; k < kCmFeat; ++k) {
+                    const int len = static_cast<int>(rq[k] >> 16) - static_cast<int>(rq[k] & 0xFFFFu);
+                    if (len > 0) {
+                        my_idx[cnt] = rq[k];
+                        my_val[cnt] = xq[k];
+                        ++cnt;
+                        tot += static_cast<uint32_t>(len);
                     }
                 }
                 // phase 2: the hit rows' entries, in feature order, into this lane's accumulators.
@@ -418,23 +435,51 @@ xl_cm_scores_kernel(const LayerDev L, const QueryDev X, const CmWork w, const Cm
                             ++ewp;
                         }
                     }
-                } else {
+                } else if (L.has_dup_cols) {
+                    // a row may repeat a column (non-canonical W): strictly one entry at a time
                     for (uint32_t hi = 0; hi < cnt; ++hi) {
                         const uint32_t range = my_idx[hi];
                         const float x = my_val[hi];
-                        const unsigned char* ecp = ec_s + (range & 0xFFFFu);
-                        const unsigned char* ece = ec_s + (range >> 16);
-                        const float* ewp = ew_s + (range & 0xFFFFu);
-                        do {
-                            float* a = my_acc + static_cast<uint32_t>(*ecp) * 32u;
-                            *a = __fadd_rn(*a, __fmul_rn(x, *ewp));
-                            ++ewp;
-                        } while (++ecp != ece);
+                        const uint32_t ee = range >> 16;
+                        for (uint32_t e = range & 0xFFFFu; e < ee; ++e) {
+                            float* a = my_acc + static_cast<uint32_t>(ec_s[e]) * 32u;
+                            *a = __fadd_rn(*a, __fmul_rn(x, ew_s[e]));
+                        }
+                    }
+                } else {
+                    // the columns of ONE row are distinct, so its entries are independent: four at a time -- their column /
+                    // weight loads, accumulator loads, multiply-adds and stores overlap instead of forming one dependent chain
+                    // per entry.  Rows stay in feature order (program order of the accumulator accesses).
+                    for (uint32_t hi = 0; hi < cnt; ++hi) {
+                        const uint32_t range = my_idx[hi];
+                        const float x = my_val[hi];
+                        const uint32_t ee = range >> 16;
+                        for (uint32_t e = range & 0xFFFFu; e < ee; e += 4u) {
+                            const uint32_t n = ee - e;  // >= 1
+                            const uint32_t c0 = ec_s[e];
+                            const uint32_t c1 = ec_s[e + (n > 1u ? 1u : 0u)];
+                            const uint32_t c2 = ec_s[e + (n > 2u ? 2u : 0u)];
+                            const uint32_t c3 = ec_s[e + (n > 3u ? 3u : 0u)];
+                            const float w0 = ew_s[e];
+                            const float w1 = ew_s[e + (n > 1u ? 1u : 0u)];
+                            const float w2 = ew_s[e + (n > 2u ? 2u : 0u)];
+                            const float w3 = ew_s[e + (n > 3u ? 3u : 0u)];
+                            float* a0 = my_acc + c0 * 32u;
+                            float* a1 = my_acc + c1 * 32u;
+                            float* a2 = my_acc + c2 * 32u;
+                            float* a3 = my_acc + c3 * 32u;
+                            const float v0 = *a0, v1 = *a1, v2 = *a2, v3 = *a3;
+                            *a0 = __fadd_rn(v0, __fmul_rn(x, w0));
+                            if (n > 1u) *a1 = __fadd_rn(v1, __fmul_rn(x, w1));
+                            if (n > 2u) *a2 = __fadd_rn(v2, __fmul_rn(x, w2));
+                            if (n > 3u) *a3 = __fadd_rn(v3, __fmul_rn(x, w3));
+                        }
                     }
                 }
                 if (STATS) { st_match += cnt; st_ent += tot; }
                 __syncwarp();
             }
+            cm_cp_async_wait<0>();
             if (have && bias_range) {  // bias row last (inference.hpp:806-811)
                 const uint32_t ee = bias_range >> 16;
                 for (uint32_t e = bias_range & 0xFFFFu; e < ee; ++e) {

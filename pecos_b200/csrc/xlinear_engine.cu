@@ -1054,12 +1054,18 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, false, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
     if (const char* env = std::getenv("PB200_CM_FLAT")) cm_flat_ = std::atoi(env) != 0;
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -1225,12 +1231,16 @@ int XLinearEngine::score_layer_(size_t d, const QueryDev& q, uint32_t b_prev, in
         auto launch_cm = [&](auto kernel) {
             kernel<<<cm.grid, cm.warps * 32, cm.smem, stream_>>>(L, q, w, shape, layers_[d].cm_images.get(), cand_.get(), cand_stride_q, stats);
         };
+        auto pick = [&](auto st4, auto st2) { if (shape.stages == 4) launch_cm(st4); else launch_cm(st2); };
         if (collect_stats) {
-            if (shape.direct) launch_cm(xl_cm_scores_kernel<true, true, false>); else launch_cm(xl_cm_scores_kernel<true, false, false>);
+            if (shape.direct) pick(xl_cm_scores_kernel<true, true, false, 4>, xl_cm_scores_kernel<true, true, false, 2>);
+            else pick(xl_cm_scores_kernel<true, false, false, 4>, xl_cm_scores_kernel<true, false, false, 2>);
         } else if (cm_flat_) {
-            if (shape.direct) launch_cm(xl_cm_scores_kernel<false, true, true>); else launch_cm(xl_cm_scores_kernel<false, false, true>);
+            if (shape.direct) pick(xl_cm_scores_kernel<false, true, true, 4>, xl_cm_scores_kernel<false, true, true, 2>);
+            else pick(xl_cm_scores_kernel<false, false, true, 4>, xl_cm_scores_kernel<false, false, true, 2>);
         } else {
-            if (shape.direct) launch_cm(xl_cm_scores_kernel<false, true, false>); else launch_cm(xl_cm_scores_kernel<false, false, false>);
+            if (shape.direct) pick(xl_cm_scores_kernel<false, true, false, 4>, xl_cm_scores_kernel<false, true, false, 2>);
+            else pick(xl_cm_scores_kernel<false, false, false, 4>, xl_cm_scores_kernel<false, false, false, 2>);
         }
         launches_ += 3;  // + the score kernel counted below
     } else if (query_warp) {

@@ -41,6 +41,7 @@ struct CmShape {  // load-time, per layer: geometry of the chunk images
     bool direct = false;
     uint32_t words = 0;      // direct: w_rows (table entries); else fm_words (feature-map cells)
     uint32_t r_cap = 0, e_cap = 0, acc_cols = 0;
+    uint32_t stages = 2;     // depth of the per-warp cp.async ring of query-feature rounds
     uint32_t off_lookup = 16, off_pre = 0, off_rp = 0, off_ew = 0, off_ec = 0;  // byte offsets inside an image
     uint32_t img_bytes = 0;  // image stride (multiple of 128)
 };

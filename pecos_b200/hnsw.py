@@ -1,16 +1,20 @@
-"""``HNSW`` -- search-only mirror of ``pecos.ann.hnsw.HNSW`` running on a B200.
+"""``HNSW`` -- search-only B200 counterpart of ``pecos.ann.hnsw.HNSW``.
 
-Same names, argument meaning and error behaviour as the reference for the load / search path:
+The class keeps the reference's public surface for the load / search path, so code written against
+``pecos.ann.hnsw.HNSW`` (pecos/ann/hnsw/model.py) runs unchanged:
 
-* ``HNSW.load(model_folder, lazy_load=False)`` ........... pecos/ann/hnsw/model.py:152-175
-* ``HNSW.predict(X, pred_params, searchers, ret_csr)`` ... pecos/ann/hnsw/model.py:219-269
-* ``HNSW.searchers_create`` / ``HNSW.Searchers`` ......... pecos/ann/hnsw/model.py:65-78, :198-209
-* ``HNSW.PredParams(efS, topk, threads)`` ................ pecos/ann/hnsw/model.py:51-63
+=============================================  =======================================================
+``HNSW.load(model_folder, lazy_load=False)``   reads ``param.json`` + ``c_model/`` written by the reference
+``HNSW.predict(X, pred_params, searchers,      top-k neighbours per row of ``X``; CSR (distances as values) or a pair of
+ret_csr=True)``                                ``(indices, distances)`` arrays
+``HNSW.PredParams(efS, topk, threads)``        search parameters (``threads`` is accepted and ignored: the GPU kernel
+                                               assigns one warp per query)
+``HNSW.searchers_create(n)`` / ``Searchers``   opaque scratch token (the per-warp scratch lives with the engine)
+=============================================  =======================================================
 
-Index construction (``train``) and ``save`` stay on the reference CPU library; only dense (``drm``) float32 indices with
-the ``ip`` or ``l2`` metric are served (sparse ``csr`` indices raise ``NotImplementedError``).
+Index construction and ``save`` stay on the reference CPU library.  Served index kinds: dense ``drm`` float32 with the
+``ip`` or ``l2`` metric.  There is no CPU fallback: loading without a visible CUDA device raises ``RuntimeError``.
 """
-import copy
 import dataclasses as dc
 import json
 import os
@@ -20,6 +24,21 @@ import numpy as np
 import scipy.sparse as smat
 
 from .core import ScipyDrmF32, get_clib
+
+_REQUIRED_KEYS = ("model", "data_type", "metric_type", "num_item", "feat_dim")
+
+
+def _read_index_meta(model_folder):
+    """``param.json`` of a saved index -> dict; validates what the loader relies on."""
+    path = os.path.join(model_folder, "param.json")
+    with open(path, "r", encoding="utf-8") as f:
+        meta = json.load(f)
+    missing = [k for k in _REQUIRED_KEYS if k not in meta]
+    if missing:
+        raise ValueError(f"{path}: missing field(s) {missing}")
+    if meta["model"] != "HNSW":
+        raise ValueError(f"{path}: model = {meta['model']!r}, expected 'HNSW'")
+    return meta
 
 
 class HNSW(object):
@@ -31,109 +50,95 @@ class HNSW(object):
 
         @classmethod
         def from_dict(cls, d):
-            d = d or {}
-            return cls(efS=int(d.get("efS", 100)), topk=int(d.get("topk", 10)), threads=int(d.get("threads", 1)))
+            known = {f.name for f in dc.fields(cls)}
+            return cls(**{k: int(v) for k, v in (d or {}).items() if k in known})
 
     class Searchers(object):
-        def __init__(self, model, num_searcher=1):
-            self.searchers_ptr = c_void_p(model.fn_dict["searchers_create"](model.model_ptr, num_searcher))
-            self.destruct_fn = model.fn_dict["searchers_destruct"]
+        """Owner of the native searcher token; released with the object."""
 
-        def __del__(self):
-            try:
-                if self.searchers_ptr is not None:
-                    self.destruct_fn(self.searchers_ptr)
-                    self.searchers_ptr = None
-            except Exception:
-                pass
+        def __init__(self, model, num_searcher=1):
+            self._release = model.fn_dict["searchers_destruct"]
+            self.searchers_ptr = c_void_p(model.fn_dict["searchers_create"](model.model_ptr, int(num_searcher)))
 
         def ctypes(self):
             return self.searchers_ptr
 
+        def __del__(self):
+            ptr, self.searchers_ptr = getattr(self, "searchers_ptr", None), None
+            if ptr:
+                try:
+                    self._release(ptr)
+                except Exception:
+                    pass
+
     def __init__(self, model_ptr, num_item, feat_dim, fn_dict, pred_params=None, data_type="drm", metric_type="ip"):
-        self.model_ptr = model_ptr
-        self.num_item = num_item
-        self.feat_dim = feat_dim
-        self.fn_dict = fn_dict
-        self.pred_params = self.PredParams() if pred_params is None else pred_params
-        self.data_type_ = data_type
-        self.metric_type_ = metric_type
+        self.model_ptr, self.fn_dict = model_ptr, fn_dict
+        self.num_item, self.feat_dim = int(num_item), int(feat_dim)
+        self.pred_params = pred_params if pred_params is not None else self.PredParams()
+        self._data_type, self._metric_type = data_type, metric_type
+
+    data_type = property(lambda self: self._data_type)
+    metric_type = property(lambda self: self._metric_type)
 
     def __del__(self):
-        try:
-            if self.model_ptr and self.fn_dict:
-                self.fn_dict["destruct"](self.model_ptr)
-                self.model_ptr = None
-        except Exception:
-            pass
+        ptr, self.model_ptr = getattr(self, "model_ptr", None), None
+        if ptr and getattr(self, "fn_dict", None):
+            try:
+                self.fn_dict["destruct"](ptr)
+            except Exception:
+                pass
 
-    @property
-    def data_type(self):
-        return self.data_type_
+    # ------------------------------------------------------------------ load
+    @classmethod
+    def load(cls, model_folder, lazy_load=False):
+        meta = _read_index_meta(model_folder)
+        native_dir = os.path.join(model_folder, "c_model")
+        if not os.path.isdir(native_dir):
+            raise ValueError(f"{native_dir} is not a directory: not a saved HNSW index")
+        lib = get_clib()
+        symbols = lib.ann_hnsw_init(meta["data_type"], meta["metric_type"])  # raises for index kinds this engine does not serve
+        lib.require_gpu()
+        handle = symbols["load"](c_char_p(native_dir.encode("utf-8")), c_bool(bool(lazy_load)))
+        return cls(c_void_p(handle), meta["num_item"], meta["feat_dim"], symbols,
+                   cls.PredParams.from_dict(meta.get("pred_kwargs")), meta["data_type"], meta["metric_type"])
 
-    @property
-    def metric_type(self):
-        return self.metric_type_
+    def get_pred_params(self):
+        return dc.replace(self.pred_params)
 
+    def searchers_create(self, num_searcher=1):
+        if not self.model_ptr:
+            raise ValueError("the index is not loaded")
+        if int(num_searcher) < 1:
+            raise ValueError(f"num_searcher must be >= 1, got {num_searcher}")
+        return HNSW.Searchers(self, num_searcher)
+
+    # ------------------------------------------------------------------ search
     @staticmethod
     def create_pymat(X):
-        """Wrap the query matrix (pecos/ann/hnsw/model.py:100-121); sparse queries are outside this engine's scope."""
+        """Query matrix -> (ctypes view, kind).  Dense float32 row-major queries only."""
         if isinstance(X, ScipyDrmF32):
             return X, "drm"
         if isinstance(X, np.ndarray):
             return ScipyDrmF32.init_from(np.ascontiguousarray(X, dtype=np.float32)), "drm"
-        if isinstance(X, smat.csr_matrix):
+        if smat.issparse(X):
             return None, "csr"
-        raise ValueError("type(X)={} is NOT supported!".format(type(X)))
-
-    @classmethod
-    def load(cls, model_folder, lazy_load=False):
-        with open("{}/param.json".format(model_folder), "r") as fin:
-            param = json.loads(fin.read())
-        if param["model"] != cls.__name__:
-            raise ValueError("param[model] != cls.__name__")
-        if not ("data_type" in param and "metric_type" in param):
-            raise ValueError("param.json did not have data_type or metric_type!")
-        clib = get_clib()
-        fn_dict = clib.ann_hnsw_init(param["data_type"], param["metric_type"])
-        c_model_dir = f"{model_folder}/c_model"
-        if not os.path.isdir(c_model_dir):
-            raise ValueError(f"c_model_dir did not exist: {c_model_dir}")
-        clib.require_gpu()
-        model_ptr = c_void_p(fn_dict["load"](c_char_p(c_model_dir.encode("utf-8")), c_bool(lazy_load)))
-        pred_params = cls.PredParams.from_dict(param.get("pred_kwargs"))
-        return cls(model_ptr, param["num_item"], param["feat_dim"], fn_dict, pred_params, param["data_type"], param["metric_type"])
-
-    def searchers_create(self, num_searcher=1):
-        if not self.model_ptr:
-            raise ValueError("self.model_ptr must exist before using self.create_searcher()")
-        if num_searcher <= 0:
-            raise ValueError("num_searcher={} <= 0 is NOT valid".format(num_searcher))
-        return HNSW.Searchers(self, num_searcher)
-
-    def get_pred_params(self):
-        return copy.deepcopy(self.pred_params)
+        raise ValueError(f"queries of type {type(X)} are not supported")
 
     def predict(self, X, pred_params=None, searchers=None, ret_csr=True):
-        pred_params = self.get_pred_params() if pred_params is None else pred_params
-        pX, data_type = self.create_pymat(X)
-        if data_type != self.data_type:
-            raise ValueError("data_type={} is NOT consistent with self.data_type={}".format(data_type, self.data_type))
-        if pX.cols != self.feat_dim:
-            raise ValueError("pX.cols={} is NOT consistent with self.feat_dim={}".format(pX.cols, self.feat_dim))
-        indices = np.zeros(pX.rows * pred_params.topk, dtype=np.uint32)
-        distances = np.zeros(pX.rows * pred_params.topk, dtype=np.float32)
-        self.fn_dict["predict"](
-            self.model_ptr,
-            byref(pX),
-            indices.ctypes.data_as(POINTER(c_uint32)),
-            distances.ctypes.data_as(POINTER(c_float)),
-            pred_params.efS,
-            pred_params.topk,
-            pred_params.threads,
-            None if searchers is None else searchers.ctypes(),
-        )
+        params = pred_params if pred_params is not None else self.get_pred_params()
+        view, kind = self.create_pymat(X)
+        if kind != self.data_type:
+            raise ValueError(f"{kind} queries cannot be searched in a {self.data_type} index")
+        if view.cols != self.feat_dim:
+            raise ValueError(f"query dimension {view.cols} != index dimension {self.feat_dim}")
+        n, k = int(view.rows), int(params.topk)
+        # the native call only fills the slots it found neighbours for; the rest must read as zeros (reference contract)
+        idx = np.zeros((n, k), dtype=np.uint32)
+        dist = np.zeros((n, k), dtype=np.float32)
+        token = searchers.ctypes() if searchers is not None else None
+        self.fn_dict["predict"](self.model_ptr, byref(view), idx.ctypes.data_as(POINTER(c_uint32)),
+                                dist.ctypes.data_as(POINTER(c_float)), int(params.efS), k, int(params.threads), token)
         if not ret_csr:
-            return indices.reshape(pX.rows, pred_params.topk), distances.reshape(pX.rows, pred_params.topk)
-        indptr = np.arange(0, pred_params.topk * (pX.rows + 1), pred_params.topk, dtype=np.int64)
-        return smat.csr_matrix((distances, indices.astype(np.int64), indptr), shape=(pX.rows, self.num_item), dtype=np.float32)
+            return idx, dist
+        row_starts = np.arange(n + 1, dtype=np.int64) * k
+        return smat.csr_matrix((dist.ravel(), idx.ravel().astype(np.int64), row_starts), shape=(n, self.num_item), dtype=np.float32)

@@ -30,8 +30,14 @@ def main():
     Xt.sort_indices()
     nr_codes, nr_labels = m.attr("nr_codes"), m.attr("nr_labels")
     rng = np.random.default_rng(3)
-    codes = smat.csr_matrix((rng.random((Xt.shape[0], nr_codes)) * (rng.random((Xt.shape[0], nr_codes)) < 0.7)).astype(np.float32))
     sel = smat.csr_matrix((rng.random((Xt.shape[0], nr_labels)) < 0.4).astype(np.float32))
+    # csr_codes as the reference's own callers build it (pecos/xmc/base.py:1771-1780): the parents of the selected labels
+    # (selected x C) -- a selected label whose parent is missing from csr_codes is outside the reference's contract -- plus a
+    # few extra codes, with random positive values
+    C = smat.load_npz(os.path.join(toy, "model", "ranker", f"{depth - 1}.model", "C.npz")).tocsr()
+    pattern = ((sel @ C) + smat.csr_matrix((rng.random((Xt.shape[0], nr_codes)) < 0.3).astype(np.float32))).tocsr()
+    pattern.sort_indices()
+    codes = smat.csr_matrix((0.05 + rng.random(pattern.nnz).astype(np.float32), pattern.indices, pattern.indptr), shape=pattern.shape)
     smat.save_npz(os.path.join(out, "codes.npz"), codes, compressed=False)
     smat.save_npz(os.path.join(out, "selected.npz"), sel, compressed=False)
     E, index = {}, []

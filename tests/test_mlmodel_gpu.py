@@ -71,8 +71,14 @@ def test_random_layers_equal_the_reference_library(tmp_path, gpu_clib, have_ref,
         g = ref.MLModelHandle(mm, clib=gpu_clib.clib_float32)
         n_codes, n_labels = r.attr("nr_codes"), r.attr("nr_labels")
         assert (g.attr("nr_codes"), g.attr("nr_labels"), g.attr("nr_features")) == (n_codes, n_labels, r.attr("nr_features"))
-        codes = smat.csr_matrix((rng.random((400, n_codes)) * (rng.random((400, n_codes)) < 0.2)).astype(np.float32))
-        sel = smat.csr_matrix((rng.random((400, n_labels)) < 0.03).astype(np.float32))
+        C = smat.load_npz(os.path.join(folder, "ranker", f"{d}.model", "C.npz")).tocsr()
+        has_parent = np.asarray(C.sum(axis=1)).ravel() > 0   # pruned trees: a parentless label is outside the reference's contract
+        sel = smat.csr_matrix(((rng.random((400, n_labels)) < 0.03) & has_parent[None, :]).astype(np.float32))
+        # csr_codes = parents of the selected labels (what the reference's callers pass: selected x C, pecos/xmc/base.py:1771-1780;
+        # the reference reads out of bounds when a selected label's parent is missing) + some extra codes
+        pattern = ((sel @ C) + smat.csr_matrix((rng.random((400, n_codes)) < 0.1).astype(np.float32))).tocsr()
+        pattern.sort_indices()
+        codes = smat.csr_matrix((0.05 + rng.random(pattern.nnz).astype(np.float32), pattern.indices, pattern.indptr), shape=pattern.shape)
         for pp in (None, "sigmoid", "log-l3-hinge"):
             for cc in (codes, None) if d == 1 else (codes,):  # "no codes" on the 600-label layer = 40 x 600 candidates: covered at d = 1
                 for Xq in (X, np.ascontiguousarray(X.toarray()[:50])):

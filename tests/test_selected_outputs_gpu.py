@@ -12,16 +12,17 @@ import scipy.sparse as smat
 
 from pecos_b200 import synth
 
-from .util import assert_csr_parity, random_tree
+from .util import assert_csr_parity, random_tree, reachable_labels
 
 pytestmark = pytest.mark.gpu
 
 
-def _selection(rng, rows, n_labels, max_per_row):
+def _selection(rng, rows, n_labels, max_per_row, allowed=None):
+    allowed = np.arange(n_labels) if allowed is None else np.asarray(allowed)
     r, c = [], []
     for q in range(rows):
         k = int(rng.integers(0, max_per_row + 1))  # some rows select nothing
-        cols = rng.choice(n_labels, size=min(k, n_labels), replace=False)
+        cols = rng.choice(allowed, size=min(k, allowed.size), replace=False)
         r += [q] * len(cols)
         c += list(cols)  # unsorted on purpose: the reference sorts the leaf set itself
     return smat.csr_matrix((np.ones(len(r), dtype=np.float32), (r, c)), shape=(rows, n_labels))
@@ -37,7 +38,8 @@ def test_selected_outputs_equal_the_oracles(tmp_path, gpu_clib, have_ref, permut
     layers = random_tree(95, sizes, 200, 25, bias=1.0, permute=permute, prune=prune)
     synth.save_xlinear_model(folder, layers, bias=1.0, only_topk=6)
     X = synth.make_queries(96, 300, 200, 30)
-    S = _selection(np.random.default_rng(97), 300, sizes[-1], 12)
+    # pruned trees: only labels with a path to the root (the reference indexes with uninitialised memory otherwise)
+    S = _selection(np.random.default_rng(97), 300, sizes[-1], 12, allowed=reachable_labels(layers))
     m = XLinearModel.load(folder, is_predict_only=True)
     o = restatement.OracleXLinear(os.path.join(folder, "ranker"))
     r = None
@@ -58,6 +60,23 @@ def test_selected_outputs_equal_the_oracles(tmp_path, gpu_clib, have_ref, permut
     # chunked calls (max_pred_chunk) concatenate to the same matrix
     assert_csr_parity(m.predict(X, selected_outputs_csr=S, max_pred_chunk=77), m.predict(X, selected_outputs_csr=S), rtol=0.0,
                       what="max_pred_chunk")
+
+
+def test_unreachable_selected_labels_leave_zero_entries(tmp_path, gpu_clib):
+    """Pruned tree, selection includes labels WITHOUT a path to the root: out of the reference's contract (it reads
+    uninitialised memory); the CUDA path and the restatement both leave zero entries at the end of such rows."""
+    from oracle import restatement
+    from pecos_b200.xlinear import XLinearModel
+
+    folder = str(tmp_path / "m")
+    layers = random_tree(395, [5, 30, 400], 200, 25, bias=1.0, permute=True, prune=0.3)
+    synth.save_xlinear_model(folder, layers, bias=1.0, only_topk=6)
+    X = synth.make_queries(396, 120, 200, 30)
+    S = _selection(np.random.default_rng(397), 120, 400, 15)
+    assert np.setdiff1d(np.unique(S.indices), reachable_labels(layers)).size > 0
+    m = XLinearModel.load(folder, is_predict_only=True)
+    o = restatement.OracleXLinear(os.path.join(folder, "ranker"))
+    assert_csr_parity(m.predict(X, selected_outputs_csr=S), o.predict_on_selected_outputs(X, S, None), what="unreachable labels")
 
 
 def test_selected_scores_equal_beam_search_scores(tmp_path, gpu_clib):

@@ -80,3 +80,14 @@ def merge_topk_numpy(g_keys, g_ids, g_vals, g_cnt, k):
         for r in range(kk):
             out_ids[q, r], out_vals[q, r] = cand[r][1], cand[r][2]
     return out_ids, out_vals, out_cnt
+
+
+def reachable_labels(layers):
+    """Labels of the last layer with a complete path to the root (pruned trees drop rows of C at every layer).  The reference's
+    predict_on_selected_outputs leaves the entry of an unreachable selected label UNINITIALISED and then indexes with it
+    (pecos/core/xmc/inference.hpp:1302-1358), so in-contract selections only contain reachable labels."""
+    reach = np.ones(1, dtype=bool)
+    for _, C in layers:
+        C = smat.csr_matrix(C)
+        reach = np.asarray((C.astype(np.float32) @ reach.astype(np.float32)) > 0).ravel()
+    return np.nonzero(reach)[0]
