@@ -23,82 +23,87 @@ from . import REF_LIB
 _lib = None
 
 
+def bind(L):
+    """Declares the prototypes of the reference symbols used by the tests on a ctypes library object (the reference library,
+    or -- tests/test_overlay_gpu.py -- a stand-in for ``pecos.core.clib.clib_float32`` that gets overlaid)."""
+    L.c_xlinear_load_model_from_disk_ext.restype = c_void_p
+    L.c_xlinear_load_model_from_disk_ext.argtypes = [c_char_p, c_int]
+    L.c_xlinear_load_mmap_model_from_disk.restype = c_void_p
+    L.c_xlinear_load_mmap_model_from_disk.argtypes = [c_char_p, c_bool]
+    L.c_xlinear_compile_mmap_model.restype = None
+    L.c_xlinear_compile_mmap_model.argtypes = [c_char_p, c_char_p]
+    L.c_xlinear_destruct_model.restype = None
+    L.c_xlinear_destruct_model.argtypes = [c_void_p]
+    L.c_xlinear_get_int_attr.restype = c_uint32
+    L.c_xlinear_get_int_attr.argtypes = [c_void_p, c_char_p]
+    pred = [c_uint32, c_char_p, c_uint32, c_int, ScipyCompressedSparseAllocator.CFUNCTYPE]
+    L.c_xlinear_predict_csr_f32.restype = None
+    L.c_xlinear_predict_csr_f32.argtypes = [c_void_p, POINTER(ScipyCsrF32)] + pred
+    L.c_xlinear_predict_drm_f32.restype = None
+    L.c_xlinear_predict_drm_f32.argtypes = [c_void_p, POINTER(ScipyDrmF32)] + pred
+    sel = [POINTER(ScipyCsrF32), c_char_p, c_int, ScipyCompressedSparseAllocator.CFUNCTYPE]  # pecos/core/base.py:846-876
+    L.c_xlinear_predict_on_selected_outputs_csr_f32.restype = None
+    L.c_xlinear_predict_on_selected_outputs_csr_f32.argtypes = [c_void_p, POINTER(ScipyCsrF32)] + sel
+    L.c_xlinear_predict_on_selected_outputs_drm_f32.restype = None
+    L.c_xlinear_predict_on_selected_outputs_drm_f32.argtypes = [c_void_p, POINTER(ScipyDrmF32)] + sel
+    single = [POINTER(ScipyCsrF32), POINTER(ScipyCscF32), POINTER(ScipyCscF32), c_char_p, c_uint32, c_int, c_float,
+              ScipyCompressedSparseAllocator.CFUNCTYPE]  # pecos/core/base.py:880-905
+    L.c_xlinear_single_layer_predict_csr_f32.restype = None
+    L.c_xlinear_single_layer_predict_csr_f32.argtypes = [POINTER(ScipyCsrF32)] + single
+    L.c_xlinear_single_layer_predict_drm_f32.restype = None
+    L.c_xlinear_single_layer_predict_drm_f32.argtypes = [POINTER(ScipyDrmF32)] + single
+    # single-layer mmap handles (pecos/core/base.py:541-606)
+    L.c_mlmodel_compile_mmap_model.restype = None
+    L.c_mlmodel_compile_mmap_model.argtypes = [c_char_p, c_char_p]
+    L.c_mlmodel_load_mmap_model.restype = c_void_p
+    L.c_mlmodel_load_mmap_model.argtypes = [c_char_p, c_bool]
+    L.c_mlmodel_destruct_model.restype = None
+    L.c_mlmodel_destruct_model.argtypes = [c_void_p]
+    L.c_mlmodel_get_int_attr.restype = c_uint32
+    L.c_mlmodel_get_int_attr.argtypes = [c_void_p, c_char_p]
+    ml = [POINTER(ScipyCsrF32), c_char_p, c_uint32, c_int, ScipyCompressedSparseAllocator.CFUNCTYPE]
+    L.c_mlmodel_predict_csr_f32.restype = None
+    L.c_mlmodel_predict_csr_f32.argtypes = [c_void_p, POINTER(ScipyCsrF32)] + ml
+    L.c_mlmodel_predict_drm_f32.restype = None
+    L.c_mlmodel_predict_drm_f32.argtypes = [c_void_p, POINTER(ScipyDrmF32)] + ml
+    mls = [POINTER(ScipyCsrF32), POINTER(ScipyCsrF32), c_char_p, c_int, ScipyCompressedSparseAllocator.CFUNCTYPE]
+    L.c_mlmodel_predict_on_selected_outputs_csr_f32.restype = None
+    L.c_mlmodel_predict_on_selected_outputs_csr_f32.argtypes = [c_void_p, POINTER(ScipyCsrF32)] + mls
+    L.c_mlmodel_predict_on_selected_outputs_drm_f32.restype = None
+    L.c_mlmodel_predict_on_selected_outputs_drm_f32.argtypes = [c_void_p, POINTER(ScipyDrmF32)] + mls
+    for metric in ("ip", "l2"):
+        sfx = f"drm_{metric}_f32"
+        f = getattr(L, "c_ann_hnsw_train_" + sfx)
+        f.restype = c_void_p
+        f.argtypes = [POINTER(ScipyDrmF32), c_uint32, c_uint32, c_int, c_int]
+        f = getattr(L, "c_ann_hnsw_load_" + sfx)
+        f.restype = c_void_p
+        f.argtypes = [c_char_p, c_bool]
+        f = getattr(L, "c_ann_hnsw_save_" + sfx)
+        f.restype = None
+        f.argtypes = [c_void_p, c_char_p]
+        f = getattr(L, "c_ann_hnsw_destruct_" + sfx)
+        f.restype = None
+        f.argtypes = [c_void_p]
+        f = getattr(L, "c_ann_hnsw_searchers_create_" + sfx)
+        f.restype = c_void_p
+        f.argtypes = [c_void_p, c_uint32]
+        f = getattr(L, "c_ann_hnsw_searchers_destruct_" + sfx)
+        f.restype = None
+        f.argtypes = [c_void_p]
+        f = getattr(L, "c_ann_hnsw_predict_" + sfx)
+        f.restype = None
+        f.argtypes = [c_void_p, POINTER(ScipyDrmF32), POINTER(c_uint32), POINTER(c_float), c_uint32, c_uint32,
+                      c_int32, c_void_p]
+    return L
+
+
 def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(REF_LIB):
             raise RuntimeError(f"{REF_LIB} missing: run `make -C oracle` where /root/reference is available")
-        L = ctypes.CDLL(REF_LIB)
-        L.c_xlinear_load_model_from_disk_ext.restype = c_void_p
-        L.c_xlinear_load_model_from_disk_ext.argtypes = [c_char_p, c_int]
-        L.c_xlinear_load_mmap_model_from_disk.restype = c_void_p
-        L.c_xlinear_load_mmap_model_from_disk.argtypes = [c_char_p, c_bool]
-        L.c_xlinear_compile_mmap_model.restype = None
-        L.c_xlinear_compile_mmap_model.argtypes = [c_char_p, c_char_p]
-        L.c_xlinear_destruct_model.restype = None
-        L.c_xlinear_destruct_model.argtypes = [c_void_p]
-        L.c_xlinear_get_int_attr.restype = c_uint32
-        L.c_xlinear_get_int_attr.argtypes = [c_void_p, c_char_p]
-        pred = [c_uint32, c_char_p, c_uint32, c_int, ScipyCompressedSparseAllocator.CFUNCTYPE]
-        L.c_xlinear_predict_csr_f32.restype = None
-        L.c_xlinear_predict_csr_f32.argtypes = [c_void_p, POINTER(ScipyCsrF32)] + pred
-        L.c_xlinear_predict_drm_f32.restype = None
-        L.c_xlinear_predict_drm_f32.argtypes = [c_void_p, POINTER(ScipyDrmF32)] + pred
-        sel = [POINTER(ScipyCsrF32), c_char_p, c_int, ScipyCompressedSparseAllocator.CFUNCTYPE]  # pecos/core/base.py:846-876
-        L.c_xlinear_predict_on_selected_outputs_csr_f32.restype = None
-        L.c_xlinear_predict_on_selected_outputs_csr_f32.argtypes = [c_void_p, POINTER(ScipyCsrF32)] + sel
-        L.c_xlinear_predict_on_selected_outputs_drm_f32.restype = None
-        L.c_xlinear_predict_on_selected_outputs_drm_f32.argtypes = [c_void_p, POINTER(ScipyDrmF32)] + sel
-        single = [POINTER(ScipyCsrF32), POINTER(ScipyCscF32), POINTER(ScipyCscF32), c_char_p, c_uint32, c_int, c_float,
-                  ScipyCompressedSparseAllocator.CFUNCTYPE]  # pecos/core/base.py:880-905
-        L.c_xlinear_single_layer_predict_csr_f32.restype = None
-        L.c_xlinear_single_layer_predict_csr_f32.argtypes = [POINTER(ScipyCsrF32)] + single
-        L.c_xlinear_single_layer_predict_drm_f32.restype = None
-        L.c_xlinear_single_layer_predict_drm_f32.argtypes = [POINTER(ScipyDrmF32)] + single
-        # single-layer mmap handles (pecos/core/base.py:541-606)
-        L.c_mlmodel_compile_mmap_model.restype = None
-        L.c_mlmodel_compile_mmap_model.argtypes = [c_char_p, c_char_p]
-        L.c_mlmodel_load_mmap_model.restype = c_void_p
-        L.c_mlmodel_load_mmap_model.argtypes = [c_char_p, c_bool]
-        L.c_mlmodel_destruct_model.restype = None
-        L.c_mlmodel_destruct_model.argtypes = [c_void_p]
-        L.c_mlmodel_get_int_attr.restype = c_uint32
-        L.c_mlmodel_get_int_attr.argtypes = [c_void_p, c_char_p]
-        ml = [POINTER(ScipyCsrF32), c_char_p, c_uint32, c_int, ScipyCompressedSparseAllocator.CFUNCTYPE]
-        L.c_mlmodel_predict_csr_f32.restype = None
-        L.c_mlmodel_predict_csr_f32.argtypes = [c_void_p, POINTER(ScipyCsrF32)] + ml
-        L.c_mlmodel_predict_drm_f32.restype = None
-        L.c_mlmodel_predict_drm_f32.argtypes = [c_void_p, POINTER(ScipyDrmF32)] + ml
-        mls = [POINTER(ScipyCsrF32), POINTER(ScipyCsrF32), c_char_p, c_int, ScipyCompressedSparseAllocator.CFUNCTYPE]
-        L.c_mlmodel_predict_on_selected_outputs_csr_f32.restype = None
-        L.c_mlmodel_predict_on_selected_outputs_csr_f32.argtypes = [c_void_p, POINTER(ScipyCsrF32)] + mls
-        L.c_mlmodel_predict_on_selected_outputs_drm_f32.restype = None
-        L.c_mlmodel_predict_on_selected_outputs_drm_f32.argtypes = [c_void_p, POINTER(ScipyDrmF32)] + mls
-        for metric in ("ip", "l2"):
-            sfx = f"drm_{metric}_f32"
-            f = getattr(L, "c_ann_hnsw_train_" + sfx)
-            f.restype = c_void_p
-            f.argtypes = [POINTER(ScipyDrmF32), c_uint32, c_uint32, c_int, c_int]
-            f = getattr(L, "c_ann_hnsw_load_" + sfx)
-            f.restype = c_void_p
-            f.argtypes = [c_char_p, c_bool]
-            f = getattr(L, "c_ann_hnsw_save_" + sfx)
-            f.restype = None
-            f.argtypes = [c_void_p, c_char_p]
-            f = getattr(L, "c_ann_hnsw_destruct_" + sfx)
-            f.restype = None
-            f.argtypes = [c_void_p]
-            f = getattr(L, "c_ann_hnsw_searchers_create_" + sfx)
-            f.restype = c_void_p
-            f.argtypes = [c_void_p, c_uint32]
-            f = getattr(L, "c_ann_hnsw_searchers_destruct_" + sfx)
-            f.restype = None
-            f.argtypes = [c_void_p]
-            f = getattr(L, "c_ann_hnsw_predict_" + sfx)
-            f.restype = None
-            f.argtypes = [c_void_p, POINTER(ScipyDrmF32), POINTER(c_uint32), POINTER(c_float), c_uint32, c_uint32,
-                          c_int32, c_void_p]
-        _lib = L
+        _lib = bind(ctypes.CDLL(REF_LIB))
     return _lib
 
 

@@ -17,14 +17,29 @@ XLINEAR_SYMBOLS = (
     "c_xlinear_get_layer_type",
     "c_xlinear_predict_csr_f32",
     "c_xlinear_predict_drm_f32",
+    # predict_on_selected_outputs (the reference serves it from CSC handles; every pecos_b200 handle can)
+    "c_xlinear_predict_on_selected_outputs_csr_f32",
+    "c_xlinear_predict_on_selected_outputs_drm_f32",
+    # python prediction chain (is_predict_only=False models): one layer per call, W / C handed over by the caller
+    "c_xlinear_single_layer_predict_csr_f32",
+    "c_xlinear_single_layer_predict_drm_f32",
+    # single-layer mmap handles (load / attrs / predict / destruct swapped together: handles are library-specific)
+    "c_mlmodel_load_mmap_model",
+    "c_mlmodel_destruct_model",
+    "c_mlmodel_get_int_attr",
+    "c_mlmodel_predict_csr_f32",
+    "c_mlmodel_predict_drm_f32",
+    "c_mlmodel_predict_on_selected_outputs_csr_f32",
+    "c_mlmodel_predict_on_selected_outputs_drm_f32",
 )
 HNSW_SLOTS = ("load", "destruct", "searchers_create", "searchers_destruct", "predict")
 
 
-def overlay(clib, lib_path=LIB_PATH):
-    """Returns the list of symbols that were re-pointed."""
+def overlay(clib, lib_path=LIB_PATH, require_gpu=True):
+    """Returns the list of symbols that were re-pointed.  require_gpu=False only re-points (binding tests on a box without a
+    GPU); any call into the re-pointed symbols then aborts with "no CUDA device visible" -- there is no CPU fallback."""
     b200 = ctypes.CDLL(lib_path)
-    if b200.pb200_device_count() <= 0:
+    if require_gpu and b200.pb200_device_count() <= 0:
         raise RuntimeError("pecos_b200: no CUDA device visible and there is no CPU fallback")
     swapped = []
     for name in XLINEAR_SYMBOLS:
