@@ -59,6 +59,7 @@ def overlay(clib, lib_path=LIB_PATH, require_gpu=True):
             fn = getattr(b200, name)
             fn.restype, fn.argtypes = ref.restype, ref.argtypes
             fn_dict[key][slot] = fn
+            setattr(clib.clib_float32, name, fn)  # direct attribute users see the same function as fn_dict users
             swapped.append(name)
     clib.clib_b200 = b200
     return swapped
