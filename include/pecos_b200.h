@@ -236,6 +236,9 @@ void pb200_hnsw_get_counters(void* model_ptr, uint64_t* out);
  * value in effect.  Results are identical for every setting. */
 int pb200_hnsw_set_stages(void* model_ptr, int stages);
 void pb200_hnsw_get_info(void* model_ptr, uint64_t* out);
+/* A query whose candidate queue outgrows the per-warp scratch (PB200_HNSW_VCAP entries, default 32768) makes the engine re-run
+ * the batch with twice the capacity (up to num_node + 1, which cannot overflow) -- this counts those re-runs. */
+uint32_t pb200_hnsw_vcap_retries(void* model_ptr);
 
 /* Host-only model ingest (no GPU needed): loads + builds the chunk layout, for layout tests.
  *   kind: 0 = npz folder, 1 = mmap folder.  dims out[8] = {w_rows, n_cols, out_cols, n_chunks, c_max, meta_len,

@@ -410,6 +410,7 @@ class B200CoreLib(object):
         fp(c.pb200_xlinear_model_bytes, c_uint64, [c_void_p])
         fp(c.pb200_xlinear_replicas, c_uint32, [c_void_p])
         fp(c.pb200_hnsw_replicas, c_uint32, [c_void_p])
+        fp(c.pb200_hnsw_vcap_retries, c_uint32, [c_void_p])
         fp(c.pb200_hnsw_resident_upload, None, [c_void_p, POINTER(ScipyDrmF32)])
         fp(c.pb200_hnsw_resident_predict, c_double, [c_void_p, c_uint32, c_uint32])
         fp(c.pb200_hnsw_resident_fetch, None, [c_void_p, POINTER(c_uint32), POINTER(c_float)])

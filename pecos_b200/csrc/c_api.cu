@@ -484,7 +484,9 @@ void c_mlmodel_destruct_model(void* ptr) {
 uint32_t c_mlmodel_get_int_attr(void* ptr, const char* attr) {
     PB200_API_BEGIN
     const auto& m = engine_of(ptr).host();
-    if (std::strcmp(attr, "nr_labels") == 0) return m.nr_labels();
+    // MLModel<csc_t>::label_count() = W.cols: the csc layout is never rearranged, so pruned / permuted trees report every
+    // column of W (our chunked layout scores nnz(C) columns; out_cols keeps the reference's count)
+    if (std::strcmp(attr, "nr_labels") == 0) return m.layers.back().out_cols;
     if (std::strcmp(attr, "nr_codes") == 0) return m.nr_codes();
     if (std::strcmp(attr, "nr_features") == 0) return m.nr_features();
     throw std::runtime_error(std::string(attr) + " is not implemented in get_int_attr.");
@@ -931,6 +933,12 @@ void pb200_hnsw_get_counters(void* model_ptr, uint64_t* out) {
     auto c = hnsw_of(model_ptr).counters();
     out[0] = c.n_dist; out[1] = c.n_expand; out[2] = c.n_hops; out[3] = c.n_queries;
     PB200_API_END("pb200_hnsw_get_counters")
+}
+
+uint32_t pb200_hnsw_vcap_retries(void* ptr) {
+    PB200_API_BEGIN
+    return hnsw_of(ptr).vcap_retries();
+    PB200_API_END("pb200_hnsw_vcap_retries")
 }
 
 uint32_t pb200_hnsw_replicas(void* ptr) {

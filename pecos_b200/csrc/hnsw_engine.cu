@@ -528,7 +528,8 @@ void HnswEngine::ensure_scratch_(uint32_t ef) {
     // bound the scratch footprint (bitmap N/8 bytes per warp)
     const uint64_t words = (static_cast<uint64_t>(H.num_node) + 31) / 32;
     uint32_t vcap = 32768;
-    if (const char* env = std::getenv("PB200_HNSW_VCAP")) vcap = static_cast<uint32_t>(std::max<uint64_t>(1024, std::strtoull(env, nullptr, 10)));
+    if (const char* env = std::getenv("PB200_HNSW_VCAP")) vcap = static_cast<uint32_t>(std::max<uint64_t>(64, std::strtoull(env, nullptr, 10)));
+    vcap = std::max(vcap, vcap_floor_);  // raised by launch_ after a candidate-queue overflow
     vcap = static_cast<uint32_t>(std::min<uint64_t>(vcap, static_cast<uint64_t>(H.num_node) + 1));
     const uint64_t per_warp_scratch = words * 4 + static_cast<uint64_t>(vcap) * 12 + (top_in_smem ? 0 : static_cast<uint64_t>(ef + 1) * 8);
     while (n_ctas > static_cast<uint32_t>(sms) && static_cast<uint64_t>(n_ctas) * warps * per_warp_scratch > (24ull << 30)) n_ctas -= sms;
@@ -543,7 +544,7 @@ void HnswEngine::ensure_scratch_(uint32_t ef) {
     }
 }
 
-double HnswEngine::launch_(const float* q_dev, uint32_t nq, uint32_t efS, uint32_t topk) {
+double HnswEngine::launch_once_(const float* q_dev, uint32_t nq, uint32_t efS, uint32_t topk, bool* overflow) {
     const HnswHostIndex& H = *host_;
     const uint32_t ef = std::max(efS, topk);
     if (ef == 0) throw std::runtime_error("pecos_b200: efS and topk are both zero");
@@ -575,11 +576,26 @@ double HnswEngine::launch_(const float* q_dev, uint32_t nq, uint32_t efS, uint32
     PB200_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
     unsigned long long flag[2] = {0, 0};
     PB200_CUDA(cudaMemcpy(flag, ctrl_.get(), sizeof(flag), cudaMemcpyDeviceToHost));
-    if (flag[1])
-        throw std::runtime_error("pecos_b200: HNSW candidate queue overflow (raise PB200_HNSW_VCAP above " + std::to_string(vcap_) + ")");
+    *overflow = flag[1] != 0;
     last_ms_ = ms;
     return ms;
 }
+
+// A query whose candidate queue outgrows the per-warp scratch (vcap entries) flags an overflow; the batch is then re-run with
+// twice the capacity (at most num_node + 1 entries, which can never overflow: a node enters the queue at most once), instead
+// of aborting the host process.
+double HnswEngine::launch_(const float* q_dev, uint32_t nq, uint32_t efS, uint32_t topk) {
+    for (;;) {
+        bool overflow = false;
+        const double ms = launch_once_(q_dev, nq, efS, topk, &overflow);
+        if (!overflow) return ms;
+        const uint64_t cap_max = static_cast<uint64_t>(host_->num_node) + 1;
+        if (vcap_ >= cap_max) throw std::runtime_error("pecos_b200: HNSW candidate queue overflow at full capacity (internal error)");
+        vcap_floor_ = static_cast<uint32_t>(std::min<uint64_t>(cap_max, static_cast<uint64_t>(vcap_) * 2));
+        ++vcap_retries_;
+    }
+}
+
 
 void HnswEngine::predict(const float* X, uint32_t nq, uint32_t d, uint32_t efS, uint32_t topk, uint32_t* ret_idx, float* ret_val) {
     PB200_CUDA(cudaSetDevice(device_));

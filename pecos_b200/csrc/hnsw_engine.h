@@ -51,6 +51,7 @@ public:
 
     HnswCounters counters();
     uint64_t launches() const { return launches_; }
+    uint32_t vcap_retries() const { return vcap_retries_; }  // batches re-run after a candidate-queue overflow
     uint64_t index_bytes() const { return index_bytes_; }
     double last_kernel_ms() const { return last_ms_; }
     // rows kept in flight per warp by the bulk-copy ring: 0 (direct loads), 4 or 8
@@ -61,6 +62,7 @@ private:
     void ensure_scratch_(uint32_t ef);
     uint32_t per_warp_smem_(uint32_t ef, uint32_t* nbmax_out) const;
     double launch_(const float* q_dev, uint32_t nq, uint32_t efS, uint32_t topk);
+    double launch_once_(const float* q_dev, uint32_t nq, uint32_t efS, uint32_t topk, bool* overflow);
 
     std::unique_ptr<HnswHostIndex> host_;
     int device_ = 0;
@@ -75,6 +77,8 @@ private:
     // per-warp scratch
     uint32_t n_warps_ = 0, warps_per_cta_ = 0, n_ctas_ = 0;
     uint32_t vcap_ = 0, scratch_ef_ = 0;
+    uint32_t vcap_floor_ = 0;    // minimum candidate-queue capacity (doubled after an overflow)
+    uint32_t vcap_retries_ = 0;
     DeviceBuffer<uint32_t> bitmap_;
     DeviceBuffer<uint32_t> vlist_;
     DeviceBuffer<uint2> cand_;

@@ -60,15 +60,21 @@ __host__ __device__ inline size_t cm_warp_bytes(uint32_t acc_cols, uint32_t stag
            + static_cast<size_t>(acc_cols) * 32 * 4;              // accumulators [col][lane]
 }
 
-inline CmShape cm_shape(uint32_t fm_words, uint32_t w_rows, uint32_t r_max, uint32_t e_max, uint32_t c_max, uint32_t n_chunks) {
+// split: the chunk's columns are cut into `split` ranges of ceil(n_cols / split) columns, each with its OWN image (only its
+// entries) -- a "virtual chunk"; a (query, chunk) pair is then scored once per range.  The lookups are repeated, the
+// accumulate work is not, and both the image and the per-warp accumulators shrink, so more warps fit (occupancy is what the
+// kernel is short of on wide chunks: profiles/r02_e).  e_max = most entries of one virtual chunk.
+inline CmShape cm_shape(uint32_t fm_words, uint32_t w_rows, uint32_t r_max, uint32_t e_max, uint32_t c_max, uint32_t n_chunks,
+                        uint32_t split = 1) {
     CmShape s;
-    if (fm_words == 0 || n_chunks == 0 || c_max == 0 || c_max > 256u || r_max >= 65535u || e_max >= 65535u) return s;
+    if (fm_words == 0 || n_chunks == 0 || c_max == 0 || split == 0 || (c_max + split - 1) / split > 256u || r_max >= 65535u || e_max >= 65535u) return s;
     s.direct = w_rows <= kCmDirectRows;
     s.words = s.direct ? w_rows : fm_words;
-    s.r_cap = r_max; s.e_cap = e_max; s.acc_cols = c_max;
+    s.split = split;
+    s.r_cap = r_max; s.e_cap = e_max; s.acc_cols = (c_max + split - 1) / split;
     // narrow chunks do little arithmetic per round of query features: keep four rounds of cp.async in flight per warp to
     // cover the global-memory latency; wide chunks (long accumulate phases) get by with two
-    s.stages = c_max <= 16u ? 4u : 2u;
+    s.stages = s.acc_cols <= 16u ? 4u : 2u;
     uint32_t off = 16;  // header {bias range, n_cols, R, E}
     s.off_lookup = off; off += cm_align16(s.words * 4u);
     if (!s.direct) {
@@ -78,7 +84,8 @@ inline CmShape cm_shape(uint32_t fm_words, uint32_t w_rows, uint32_t r_max, uint
     s.off_ew = off; off += cm_align16((e_max + 1u) * 4u);
     s.off_ec = off; off += cm_align16(e_max + 1u);
     s.img_bytes = (off + 127u) & ~127u;
-    if (s.img_bytes + kCmMinWarps * cm_warp_bytes(c_max, s.stages) + 64 > kCmSmemBudget) return s;
+    if (s.img_bytes + kCmMinWarps * cm_warp_bytes(s.acc_cols, s.stages) + 64 > kCmSmemBudget) return s;
+    s.warps_fit = static_cast<uint32_t>(std::min<size_t>(kCmMaxWarps, (kCmSmemBudget - s.img_bytes - 64) / cm_warp_bytes(s.acc_cols, s.stages)));
     s.ok = true;
     return s;
 }
@@ -87,6 +94,11 @@ inline CmShape cm_shape(uint32_t fm_words, uint32_t w_rows, uint32_t r_max, uint
 inline CmPlan cm_plan(const CmShape& s, uint32_t n_chunks, uint64_t pairs, uint32_t n_sm, bool force) {
     CmPlan p;
     if (!s.ok || pairs == 0) return p;
+    // measured (profiles/r02_d, r02_e): with the 94 KB feature-map image of a large feature space the kernel does not beat the
+    // query-major kernels (S layers 1-4: 2.0 / 2.4 / 6.3 ms vs 1.9 / 1.9 / 2.0 ms) -- only direct-table layers take it by default
+    if (!force && !s.direct) return p;
+    pairs *= s.split;
+    n_chunks *= s.split;
     if (!force && (pairs < static_cast<uint64_t>(kCmMinReuse) * n_chunks || pairs < kCmMinPairs)) return p;
     const size_t per_warp = cm_warp_bytes(s.acc_cols, s.stages);
     uint32_t warps = static_cast<uint32_t>(std::min<size_t>(kCmMaxWarps, (kCmSmemBudget - s.img_bytes - 64) / per_warp));
@@ -125,12 +137,15 @@ __device__ __forceinline__ void cm_mbar_wait(uint32_t mbar, uint32_t parity) {
     } while (!done);
 }
 
-// LOAD TIME: one CTA per chunk packs the chunk's image (see CmShape) from the layer's device arrays.
+// LOAD TIME: one CTA per VIRTUAL chunk (chunk p, column range h of S.split) packs its image (see CmShape) from the layer's
+// device arrays: the rows' entries whose column falls into the range (contiguous inside a row: entries are stored in
+// ascending column order), columns re-based to the range.
 __global__ void __launch_bounds__(256)
 xl_cm_build_images_kernel(const LayerDev L, const CmShape S, unsigned char* __restrict__ images) {
-    const uint32_t c = blockIdx.x;
+    const uint32_t vc = blockIdx.x;
+    const uint32_t c = vc / S.split, hh = vc - c * S.split;
     const ChunkHeader h = L.chunks[c];
-    unsigned char* img = images + static_cast<uint64_t>(c) * S.img_bytes;
+    unsigned char* img = images + static_cast<uint64_t>(vc) * S.img_bytes;
     uint32_t* hdr = reinterpret_cast<uint32_t*>(img);
     uint32_t* lookup = reinterpret_cast<uint32_t*>(img + S.off_lookup);
     float* ew = reinterpret_cast<float*>(img + S.off_ew);
@@ -138,38 +153,76 @@ xl_cm_build_images_kernel(const LayerDev L, const CmShape S, unsigned char* __re
     for (uint32_t i = threadIdx.x; i < S.img_bytes / 4u; i += blockDim.x) reinterpret_cast<uint32_t*>(img)[i] = 0u;
     __syncthreads();
     if (h.has_bias & kChunkAbsent) return;
+    const uint32_t width = (h.n_cols + S.split - 1u) / S.split;   // columns per range of THIS chunk
+    const uint32_t lo = hh * width;
+    if (lo >= h.n_cols) return;                                    // empty range: no pair is ever bucketed here
+    const uint32_t hi = min(h.n_cols, lo + width);
     const uint32_t R = h.nnz_rows;
     const uint32_t R4 = (R + 3u) & ~3u;
     const uint32_t* ridx = L.meta + h.meta_off;
     const uint32_t* rp = ridx + R4;
     const uint2* ent = L.entries + h.ent_off;
-    const uint32_t E = R ? rp[R] : 0u;
-    if (threadIdx.x == 0) {
-        hdr[0] = (h.has_bias & 1u) ? (rp[R - 1u] | (E << 16)) : 0u;
-        hdr[1] = h.n_cols;
-        hdr[2] = R;
-        hdr[3] = E;
-    }
-    if (S.direct) {
-        for (uint32_t r = threadIdx.x; r < R; r += blockDim.x) {
-            const uint32_t f = ridx[r];
-            if (f < S.words) lookup[f] = rp[r] | (rp[r + 1] << 16);  // an empty row reads as "no row": nothing to add
-        }
-    } else {
+    unsigned short* rps = S.direct ? nullptr : reinterpret_cast<unsigned short*>(img + S.off_rp);
+    if (!S.direct) {
         unsigned short* pre = reinterpret_cast<unsigned short*>(img + S.off_pre);
-        unsigned short* rps = reinterpret_cast<unsigned short*>(img + S.off_rp);
         const uint2* fm = L.featmap + static_cast<uint64_t>(c) * L.fm_words;
         for (uint32_t i = threadIdx.x; i < S.words; i += blockDim.x) {
             const uint2 cell = fm[i];
             lookup[i] = cell.x;
             pre[i] = static_cast<unsigned short>(cell.y);
         }
-        for (uint32_t i = threadIdx.x; i <= R; i += blockDim.x) rps[i] = static_cast<unsigned short>(rp[i]);
     }
-    for (uint32_t i = threadIdx.x; i < E; i += blockDim.x) {
-        const uint2 en = ent[i];
-        ec[i] = static_cast<unsigned char>(en.x);
-        ew[i] = __uint_as_float(en.y);
+    // rows in blocks of 256: sub-range of the row inside [lo, hi), exclusive scan of the lengths, copy
+    __shared__ uint32_t s_scan[256];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t r0 = 0; r0 < R; r0 += 256u) {
+        const uint32_t r = r0 + threadIdx.x;
+        uint32_t b = 0, e = 0;
+        if (r < R) {
+            b = rp[r];
+            e = rp[r + 1];
+            while (b < e && ent[b].x < lo) ++b;
+            uint32_t t = b;
+            while (t < e && ent[t].x < hi) ++t;
+            e = t;
+        }
+        const uint32_t len = e - b;
+        s_scan[threadIdx.x] = len;
+        __syncthreads();
+        for (uint32_t d = 1; d < 256u; d <<= 1) {  // Hillis-Steele inclusive scan
+            const uint32_t v = (threadIdx.x >= d) ? s_scan[threadIdx.x - d] : 0u;
+            __syncthreads();
+            s_scan[threadIdx.x] += v;
+            __syncthreads();
+        }
+        const uint32_t base = s_carry + s_scan[threadIdx.x] - len;
+        if (r < R) {
+            for (uint32_t i = 0; i < len; ++i) {
+                const uint2 en = ent[b + i];
+                ec[base + i] = static_cast<unsigned char>(en.x - lo);
+                ew[base + i] = __uint_as_float(en.y);
+            }
+            if (S.direct) {
+                const uint32_t f = ridx[r];
+                if (f < S.words) lookup[f] = base | ((base + len) << 16);  // an empty row reads as "no row": nothing to add
+            } else {
+                rps[r] = static_cast<unsigned short>(base);
+            }
+            if (r + 1u == R) {
+                if (!S.direct) rps[R] = static_cast<unsigned short>(base + len);
+                hdr[0] = (h.has_bias & 1u) ? (base | ((base + len) << 16)) : 0u;  // the bias row is the chunk's last row
+                hdr[3] = base + len;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 255u) s_carry += s_scan[255];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        hdr[1] = hi - lo;
+        hdr[2] = R;
     }
 }
 
@@ -177,12 +230,11 @@ xl_cm_build_images_kernel(const LayerDev L, const CmShape S, unsigned char* __re
 __global__ void __launch_bounds__(128)
 xl_cm_count_kernel(const LayerDev L, const QueryDev X, const uint32_t* __restrict__ beam_id,
                    const uint32_t* __restrict__ beam_cnt, const uint32_t beam_stride, const uint32_t rows, CmWork w,
-                   unsigned long long* stats) {
+                   const uint32_t split) {
     const int lane = threadIdx.x & 31;
     const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= rows) return;
     const uint32_t cnt = beam_cnt[q];
-    if (stats && lane == 0 && cnt > 0) atomicAdd(&stats[5], static_cast<unsigned long long>(X.row_ptr[q + 1] - X.row_ptr[q]));
     uint32_t run = 0;
     for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
         const uint32_t j = j0 + lane;
@@ -197,7 +249,10 @@ xl_cm_count_kernel(const LayerDev L, const QueryDev X, const uint32_t* __restric
         const uint32_t incl = warp_incl_scan(width, lane);
         if (j < cnt) {
             w.slot_pos[static_cast<uint64_t>(q) * beam_stride + j] = run + incl - width;
-            if (scored) atomicAdd(&w.count[p], 1u);
+            if (scored) {  // one pair per non-empty column range of the chunk
+                const uint32_t cw = (width + split - 1u) / split;
+                for (uint32_t hh = 0; hh * cw < width; ++hh) atomicAdd(&w.count[p * split + hh], 1u);
+            }
         }
         run += __shfl_sync(kFull, incl, 31);
     }
@@ -244,7 +299,7 @@ xl_cm_scan_kernel(const uint32_t n_chunks, CmWork w) {
 // irrelevant: a pair's result location is fixed by its query and position)
 __global__ void __launch_bounds__(128)
 xl_cm_scatter_kernel(const LayerDev L, const uint32_t* __restrict__ beam_id, const uint32_t* __restrict__ beam_cnt,
-                     const uint32_t beam_stride, const uint32_t rows, CmWork w) {
+                     const uint32_t beam_stride, const uint32_t rows, CmWork w, const uint32_t split) {
     const int lane = threadIdx.x & 31;
     const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= rows) return;
@@ -253,18 +308,22 @@ xl_cm_scatter_kernel(const LayerDev L, const uint32_t* __restrict__ beam_id, con
         const uint32_t p = beam_id[static_cast<uint64_t>(q) * beam_stride + j];
         const uint4 h = *reinterpret_cast<const uint4*>(&L.chunks[p]);
         if ((h.w & kChunkAbsent) || h.y == 0) continue;
-        const uint32_t at = atomicAdd(&w.count[p], 1u);
-        w.pair_q[at] = q;
-        w.pair_pos[at] = w.slot_pos[static_cast<uint64_t>(q) * beam_stride + j];
+        const uint32_t pos = w.slot_pos[static_cast<uint64_t>(q) * beam_stride + j];
+        const uint32_t cw = (h.y + split - 1u) / split;
+        for (uint32_t hh = 0; hh * cw < h.y; ++hh) {
+            const uint32_t at = atomicAdd(&w.count[p * split + hh], 1u);
+            w.pair_q[at] = q;
+            w.pair_pos[at] = pos + hh * cw;  // first candidate of this column range
+        }
     }
 }
 
-template <bool STATS, bool DIRECT, bool FLAT, int STAGES>
+template <bool DIRECT, int STAGES>
 __global__ void __launch_bounds__(kCmMaxWarps * 32)
 xl_cm_scores_kernel(const LayerDev L, const QueryDev X, const CmWork w, const CmShape S, const unsigned char* __restrict__ images,
-                    float* __restrict__ cand, const uint64_t cand_stride_q, unsigned long long* stats) {
+                    float* __restrict__ cand, const uint64_t cand_stride_q) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* img = smem_raw;                                   // the staged chunk image
+    unsigned char* img = smem_raw;                                   // the staged image of one virtual chunk
     // the image is only ever written by the bulk copy (async proxy), never by this kernel's stores: __restrict__ lets the
     // compiler hoist its loads above the accumulator stores
     const uint32_t* __restrict__ hdr_s = reinterpret_cast<const uint32_t*>(img);
@@ -291,30 +350,32 @@ xl_cm_scores_kernel(const LayerDev L, const QueryDev X, const CmWork w, const Cm
     }
     __syncthreads();
 
-    // ---- this CTA's contiguous share of the chunk-sorted pair list
-    const uint32_t n_chunks = L.n_chunks;
-    const uint64_t P = w.bucket_ptr[n_chunks];
+    // ---- this CTA's contiguous share of the (virtual-)chunk-sorted pair list
+    const uint32_t n_vc = L.n_chunks * S.split;
+    const uint64_t P = w.bucket_ptr[n_vc];
     const uint32_t begin = static_cast<uint32_t>(P * blockIdx.x / gridDim.x);
     const uint32_t end = static_cast<uint32_t>(P * (blockIdx.x + 1ull) / gridDim.x);
     if (begin >= end) return;
     uint32_t c;
     {
-        uint32_t lo = 0, hi = n_chunks;  // largest c with bucket_ptr[c] <= begin (then skip empty chunks forward)
+        uint32_t lo = 0, hi = n_vc;  // largest c with bucket_ptr[c] <= begin (then skip empty buckets forward)
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
             if (w.bucket_ptr[mid] <= begin) lo = mid; else hi = mid;
         }
         c = lo;
     }
-    constexpr int kPerIter = 32 / kCmFeat;  // pairs covered by one warp-wide copy instruction
+    // staging geometry: one warp-wide cp.async instruction copies kCmFeat consecutive features of kPerIter pairs; this lane
+    // always serves feature fl of the pairs sub, sub + kPerIter, ...
+    constexpr int kPerIter = 32 / kCmFeat;
+    constexpr int kIters = 32 / kPerIter;
     const int sub = lane / kCmFeat, fl = lane % kCmFeat;
-    unsigned long long st_pairs = 0, st_rows = 0, st_cols = 0, st_match = 0, st_ent = 0;
     uint32_t parity = 0;
 
     for (uint32_t i = begin; i < end;) {
-        while (w.bucket_ptr[c + 1] <= i) ++c;                        // chunk holding pair i
+        while (w.bucket_ptr[c + 1] <= i) ++c;                        // virtual chunk holding pair i
         const uint32_t run_end = min(end, w.bucket_ptr[c + 1]);
-        // ---- stage chunk c: ONE bulk copy of its image (every warp has left the previous image: barrier first)
+        // ---- stage the image: ONE bulk copy (every warp has left the previous image: barrier first)
         __syncthreads();
         if (threadIdx.x == 0) cm_bulk_load(static_cast<uint32_t>(__cvta_generic_to_shared(img)), images + static_cast<uint64_t>(c) * S.img_bytes, S.img_bytes, mbar);
         cm_mbar_wait(mbar, parity);
@@ -335,22 +396,27 @@ xl_cm_scores_kernel(const LayerDev L, const QueryDev X, const CmWork w, const Cm
                 qn = static_cast<uint32_t>(X.row_ptr[q + 1] - X.nnz_base - qb);
             }
             const uint32_t qn_max = __reduce_max_sync(kFull, qn);
+            // the pairs this lane copies for: source pointers (feature fl of the pair's row) and row lengths, once per slice
+            uint32_t src_o[kIters], src_n[kIters];  // offsets fit 32 bits: a tile of queries holds < 2^32 non-zeros
+#pragma unroll
+            for (int it = 0; it < kIters; ++it) {
+                const int pi = it * kPerIter + sub;
+                src_o[it] = static_cast<uint32_t>(__shfl_sync(kFull, qb, pi)) + fl;
+                src_n[it] = __shfl_sync(kFull, qn, pi);
+            }
             // query features travel global -> shared by cp.async through a ring of STAGES buffers: rounds r + 1 .. r + STAGES - 1
             // are in flight while round r is processed.  Row i of a buffer = the next kCmFeat features of the slice's pair i
             // (stride 9 words: the lane-per-row reads are bank-conflict free).  A (possibly empty) group is committed for every
             // round slot, so "all but the newest STAGES - 1 groups are complete" always means "round r has landed".
             auto stage_round = [&](uint32_t t0, int buf) {
                 if (t0 < qn_max) {
-                    uint32_t* di = st_idx + buf * kBuf;
-                    float* dv = st_val + buf * kBuf;
+                    uint32_t* di = st_idx + buf * kBuf + sub * kStride + fl;
+                    float* dv = st_val + buf * kBuf + sub * kStride + fl;
 #pragma unroll
-                    for (int i0 = 0; i0 < 32; i0 += kPerIter) {
-                        const int pi = i0 + sub;
-                        const uint64_t b_i = __shfl_sync(kFull, qb, pi);
-                        const uint32_t n_i = __shfl_sync(kFull, qn, pi);
-                        if (t0 + fl < n_i) {
-                            cm_cp_async4(di + pi * kStride + fl, X.col_idx + b_i + t0 + fl);
-                            cm_cp_async4(dv + pi * kStride + fl, X.val + b_i + t0 + fl);
+                    for (int it = 0; it < kIters; ++it) {
+                        if (t0 + fl < src_n[it]) {
+                            cm_cp_async4(di + it * kPerIter * kStride, X.col_idx + src_o[it] + t0);
+                            cm_cp_async4(dv + it * kPerIter * kStride, X.val + src_o[it] + t0);
                         }
                     }
                 }
@@ -398,44 +464,17 @@ xl_cm_scores_kernel(const LayerDev L, const QueryDev X, const CmWork w, const Cm
                     }
                     rq[k] = range;
                 }
-                uint32_t cnt = 0, tot = 0;
+                uint32_t cnt = 0;
 #pragma unroll
                 for (int k = 0; k < kCmFeat; ++k) {
-                    const int len = static_cast<int>(rq[k] >> 16) - static_cast<int>(rq[k] & 0xFFFFu);
-                    if (len > 0) {
+                    if (static_cast<int>(rq[k] >> 16) > static_cast<int>(rq[k] & 0xFFFFu)) {
                         my_idx[cnt] = rq[k];
                         my_val[cnt] = xq[k];
                         ++cnt;
-                        tot += static_cast<uint32_t>(len);
                     }
                 }
-                // phase 2: the hit rows' entries, in feature order, into this lane's accumulators.
-                if (FLAT) {
-                    // ONE flat stream per lane, one entry per iteration; the trip count is the warp's maximum (uniform), lanes
-                    // with fewer entries idle at the end -- rows of different lengths do not serialise
-                    const uint32_t trips = __reduce_max_sync(kFull, tot);
-                    uint32_t hi = 0;
-                    const unsigned char* ecp = ec_s;
-                    const unsigned char* ece = ec_s;
-                    const float* ewp = ew_s;
-                    float x = 0.0f;
-                    for (uint32_t t = 0; t < trips; ++t) {
-                        if (t < tot) {
-                            if (ecp == ece) {  // next hit row
-                                const uint32_t range = my_idx[hi];
-                                x = my_val[hi];
-                                ++hi;
-                                ecp = ec_s + (range & 0xFFFFu);
-                                ece = ec_s + (range >> 16);
-                                ewp = ew_s + (range & 0xFFFFu);
-                            }
-                            float* a = my_acc + static_cast<uint32_t>(*ecp) * 32u;
-                            *a = __fadd_rn(*a, __fmul_rn(x, *ewp));
-                            ++ecp;
-                            ++ewp;
-                        }
-                    }
-                } else if (L.has_dup_cols) {
+                // phase 2: the hit rows' entries, in feature order, into this lane's accumulators
+                if (L.has_dup_cols) {
                     // a row may repeat a column (non-canonical W): strictly one entry at a time
                     for (uint32_t hi = 0; hi < cnt; ++hi) {
                         const uint32_t range = my_idx[hi];
@@ -476,7 +515,6 @@ xl_cm_scores_kernel(const LayerDev L, const QueryDev X, const CmWork w, const Cm
                         }
                     }
                 }
-                if (STATS) { st_match += cnt; st_ent += tot; }
                 __syncwarp();
             }
             cm_cp_async_wait<0>();
@@ -486,31 +524,12 @@ xl_cm_scores_kernel(const LayerDev L, const QueryDev X, const CmWork w, const Cm
                     float* a = my_acc + static_cast<uint32_t>(ec_s[e]) * 32u;
                     *a = __fadd_rn(*a, __fmul_rn(L.bias, ew_s[e]));
                 }
-                if (STATS) { st_match += 1; st_ent += ee - (bias_range & 0xFFFFu); }
             }
             if (have) {
                 float* dst = cand + static_cast<uint64_t>(q) * cand_stride_q + pos;
                 for (uint32_t col = 0; col < n_cols; ++col) dst[col] = my_acc[col * 32];
-                if (STATS) { st_pairs += 1; st_rows += hdr_s[2]; st_cols += n_cols; }
             }
         }
         i = run_end;
-    }
-    if (STATS) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            st_pairs += __shfl_xor_sync(kFull, st_pairs, d);
-            st_rows += __shfl_xor_sync(kFull, st_rows, d);
-            st_cols += __shfl_xor_sync(kFull, st_cols, d);
-            st_match += __shfl_xor_sync(kFull, st_match, d);
-            st_ent += __shfl_xor_sync(kFull, st_ent, d);
-        }
-        if (lane == 0 && st_pairs) {
-            atomicAdd(&stats[0], st_pairs);
-            atomicAdd(&stats[1], st_rows);
-            atomicAdd(&stats[2], st_match);
-            atomicAdd(&stats[3], st_ent);
-            atomicAdd(&stats[4], st_cols);
-        }
     }
 }

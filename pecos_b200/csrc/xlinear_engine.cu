@@ -1021,16 +1021,38 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
         dst.view.w_rows = src.w_rows;
         dst.view.bias = src.bias;
         dst.view.has_dup_cols = src.has_dup_cols ? 1 : 0;
-        // chunk images for the chunk-major score kernel (xlinear_cm_kernel.cuh), where the layer's shape allows it
+        // chunk images for the chunk-major score kernel (xlinear_cm_kernel.cuh), where the layer's shape allows it.  Wide chunks
+        // are cut into 2..4 column ranges ("virtual chunks") when that is what lets >= 12 warps share an SM with an image.
         dst.cm_shape = CmShape{};
         if (dst.view.featmap) {
-            const CmShape shape = cm_shape(src.fm_words, src.w_rows, src.r_max, dst.e_max, src.c_max, src.n_chunks);
-            const uint64_t bytes = static_cast<uint64_t>(shape.img_bytes) * src.n_chunks;
+            auto emax_for_split = [&](uint32_t split) {  // most entries of one virtual chunk
+                uint32_t best = 0;
+                std::vector<uint32_t> cnt(split);
+                for (const ChunkHeader& ch : src.chunks) {
+                    if ((ch.has_bias & kChunkAbsent) || ch.nnz_rows == 0 || ch.n_cols == 0) continue;
+                    const uint32_t* rp = src.meta.data() + ch.meta_off + round_up4(ch.nnz_rows);
+                    const uint32_t width = (ch.n_cols + split - 1) / split;
+                    std::fill(cnt.begin(), cnt.end(), 0u);
+                    const ChunkEntry* en = src.entries.data() + ch.ent_off;
+                    for (uint32_t i = 0; i < rp[ch.nnz_rows]; ++i) ++cnt[std::min(en[i].col_offset / width, split - 1)];
+                    for (uint32_t v : cnt) best = std::max(best, v);
+                }
+                return best;
+            };
+            CmShape shape;
+            for (uint32_t split = 1; split <= 4; ++split) {
+                const CmShape cand = cm_shape(src.fm_words, src.w_rows, src.r_max, split == 1 ? dst.e_max : emax_for_split(split),
+                                              src.c_max, src.n_chunks, split);
+                if (cand.ok && (!shape.ok || cand.warps_fit > shape.warps_fit)) shape = cand;
+                if (shape.ok && shape.warps_fit >= 12u) break;
+                if (src.c_max < 2u * (split + 1)) break;  // nothing left to cut
+            }
+            const uint64_t bytes = static_cast<uint64_t>(shape.img_bytes) * src.n_chunks * std::max<uint32_t>(shape.split, 1u);
             if (shape.ok && bytes <= cmimg_budget) {
                 cmimg_budget -= bytes;
                 dst.cm_shape = shape;
                 dst.cm_images.reserve(bytes);
-                xl_cm_build_images_kernel<<<src.n_chunks, 256, 0, stream_>>>(dst.view, shape, dst.cm_images.get());
+                xl_cm_build_images_kernel<<<src.n_chunks * shape.split, 256, 0, stream_>>>(dst.view, shape, dst.cm_images.get());
                 PB200_CUDA(cudaGetLastError());
                 model_bytes_ += bytes;
             }
@@ -1054,19 +1076,10 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_topk_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, false, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    if (const char* env = std::getenv("PB200_CM_FLAT")) cm_flat_ = std::atoi(env) != 0;
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     stats_dev_.reserve(8 * layers_.size());
@@ -1171,11 +1184,11 @@ void XLinearEngine::ensure_workspace_(const std::vector<LayerPlan>& plan, uint32
             chunks_max = std::max<uint64_t>(chunks_max, host_->layers[d].n_chunks);
         }
         cm_slot_pos_.reserve(static_cast<uint64_t>(tile_rows) * beam_stride);
-        cm_pair_q_.reserve(static_cast<uint64_t>(tile_rows) * b_max);
-        cm_pair_pos_.reserve(static_cast<uint64_t>(tile_rows) * b_max);
-        cm_count_.reserve(chunks_max + 1);
-        cm_bucket_ptr_.reserve(chunks_max + 1);
-        cm_item_ptr_.reserve(chunks_max + 1);
+        cm_pair_q_.reserve(static_cast<uint64_t>(tile_rows) * b_max * 4);   // up to 4 column ranges per chunk
+        cm_pair_pos_.reserve(static_cast<uint64_t>(tile_rows) * b_max * 4);
+        cm_count_.reserve(chunks_max * 4 + 1);
+        cm_bucket_ptr_.reserve(chunks_max * 4 + 1);
+        cm_item_ptr_.reserve(chunks_max * 4 + 1);
     }
     cand_.reserve(static_cast<uint64_t>(tile_rows) * cand_max);
     if (sort_max) sortbuf_.reserve(static_cast<uint64_t>(tile_rows) * sort_max);
@@ -1215,33 +1228,27 @@ int XLinearEngine::score_layer_(size_t d, const QueryDev& q, uint32_t b_prev, in
                             (force_query_warp_ || (b_prev >= 16u && cand_stride_q <= 256u));
     // Chunk-major scoring (xlinear_cm_kernel.cuh) wherever the layer's feature map + largest chunk fit in shared memory
     // and the chunks are visited by enough pairs to amortise the staging; otherwise the query-major kernels below.
-    const CmPlan cm = (chunk_major_ && lookup && cm_slot_pos_.capacity() && layers_[d].cm_images.capacity())
+    // (the statistics pass always runs the query-major kernels: their counters are the canonical ones)
+    const bool cm_offsets_fit = static_cast<uint64_t>(rows) * std::max<uint32_t>(q.max_row_nnz, 1u) < (1ull << 32);  // 32-bit feature offsets
+    const CmPlan cm = (chunk_major_ && lookup && !collect_stats && cm_offsets_fit && cm_slot_pos_.capacity() && layers_[d].cm_images.capacity())
                           ? cm_plan(layers_[d].cm_shape, L.n_chunks, static_cast<uint64_t>(rows) * b_prev, n_sm_, cm_force_)
                           : CmPlan{};
     const bool chunk_major = cm.eligible;
     if (chunk_major) {
+        const CmShape& shape = layers_[d].cm_shape;
+        const uint32_t n_vc = L.n_chunks * shape.split;
         CmWork w{cm_slot_pos_.get(), cm_count_.get(), cm_bucket_ptr_.get(), cm_item_ptr_.get(), cm_pair_q_.get(), cm_pair_pos_.get(),
                  cm.warps * 32u};
-        PB200_CUDA(cudaMemsetAsync(w.count, 0, (static_cast<uint64_t>(L.n_chunks) + 1) * 4, stream_));
+        PB200_CUDA(cudaMemsetAsync(w.count, 0, (static_cast<uint64_t>(n_vc) + 1) * 4, stream_));
         const uint32_t warp_grid = (rows * 32u + 127u) / 128u;
-        xl_cm_count_kernel<<<warp_grid, 128, 0, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w, stats);
-        xl_cm_scan_kernel<<<1, 1024, 0, stream_>>>(L.n_chunks, w);
-        xl_cm_scatter_kernel<<<warp_grid, 128, 0, stream_>>>(L, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w);
-        const CmShape& shape = layers_[d].cm_shape;
+        xl_cm_count_kernel<<<warp_grid, 128, 0, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w, shape.split);
+        xl_cm_scan_kernel<<<1, 1024, 0, stream_>>>(n_vc, w);
+        xl_cm_scatter_kernel<<<warp_grid, 128, 0, stream_>>>(L, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w, shape.split);
         auto launch_cm = [&](auto kernel) {
-            kernel<<<cm.grid, cm.warps * 32, cm.smem, stream_>>>(L, q, w, shape, layers_[d].cm_images.get(), cand_.get(), cand_stride_q, stats);
+            kernel<<<cm.grid, cm.warps * 32, cm.smem, stream_>>>(L, q, w, shape, layers_[d].cm_images.get(), cand_.get(), cand_stride_q);
         };
-        auto pick = [&](auto st4, auto st2) { if (shape.stages == 4) launch_cm(st4); else launch_cm(st2); };
-        if (collect_stats) {
-            if (shape.direct) pick(xl_cm_scores_kernel<true, true, false, 4>, xl_cm_scores_kernel<true, true, false, 2>);
-            else pick(xl_cm_scores_kernel<true, false, false, 4>, xl_cm_scores_kernel<true, false, false, 2>);
-        } else if (cm_flat_) {
-            if (shape.direct) pick(xl_cm_scores_kernel<false, true, true, 4>, xl_cm_scores_kernel<false, true, true, 2>);
-            else pick(xl_cm_scores_kernel<false, false, true, 4>, xl_cm_scores_kernel<false, false, true, 2>);
-        } else {
-            if (shape.direct) pick(xl_cm_scores_kernel<false, true, false, 4>, xl_cm_scores_kernel<false, true, false, 2>);
-            else pick(xl_cm_scores_kernel<false, false, false, 4>, xl_cm_scores_kernel<false, false, false, 2>);
-        }
+        if (shape.direct) { if (shape.stages == 4) launch_cm(xl_cm_scores_kernel<true, 4>); else launch_cm(xl_cm_scores_kernel<true, 2>); }
+        else { if (shape.stages == 4) launch_cm(xl_cm_scores_kernel<false, 4>); else launch_cm(xl_cm_scores_kernel<false, 2>); }
         launches_ += 3;  // + the score kernel counted below
     } else if (query_warp) {
         const uint32_t qw_qcap = std::max<uint32_t>(32u, (q.max_row_nnz + 31u) & ~31u);

@@ -42,6 +42,8 @@ struct CmShape {  // load-time, per layer: geometry of the chunk images
     uint32_t words = 0;      // direct: w_rows (table entries); else fm_words (feature-map cells)
     uint32_t r_cap = 0, e_cap = 0, acc_cols = 0;
     uint32_t stages = 2;     // depth of the per-warp cp.async ring of query-feature rounds
+    uint32_t split = 1;      // column ranges per chunk ("virtual chunks"), each with its own image
+    uint32_t warps_fit = 0;  // warps of the score kernel that fit next to one image in shared memory
     uint32_t off_lookup = 16, off_pre = 0, off_rp = 0, off_ew = 0, off_ec = 0;  // byte offsets inside an image
     uint32_t img_bytes = 0;  // image stride (multiple of 128)
 };
@@ -243,7 +245,6 @@ private:
     bool chunk_major_ = true;   // chunk-major scoring wherever cm_plan() finds it eligible (kernel mode 6 switches it off)
     bool cm_force_ = false;     // kernel mode 5
     uint32_t n_sm_ = 148;
-    bool cm_flat_ = false;      // PB200_CM_FLAT=1: flat entry stream in the chunk-major kernel (A/B)
     DeviceBuffer<uint32_t> cm_slot_pos_, cm_count_, cm_bucket_ptr_, cm_item_ptr_, cm_pair_q_, cm_pair_pos_;
     bool force_block_topk_ = false;  // A/B switch: first-generation kernels (row-list streaming + block-wide sort)
     std::vector<XLinearLayerProfile> layer_profile_;

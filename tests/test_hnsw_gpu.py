@@ -215,3 +215,21 @@ def test_resident_batch_and_counters(golden, gpu_clib):
     c.pb200_hnsw_get_counters(m.model_ptr, cnt)
     oi, od, oc = restatement.OracleHNSW(os.path.join(GOLD, "model_l2"), isa=0).predict(Xt, 50, 10, return_counters=True)
     assert [int(x) for x in cnt] == [int(oc[:, 0].sum()), int(oc[:, 1].sum()), int(oc[:, 2].sum()), Xt.shape[0]]
+
+
+def test_candidate_queue_overflow_is_retried_not_fatal(gpu_clib):
+    """PB200_HNSW_VCAP=64 cannot hold the candidate queue of an efS = 600 search: the engine must re-run the batch with a larger
+    queue (no abort) and return the recorded reference results."""
+    import subprocess
+    import sys
+
+    code = ("import os, sys, numpy as np; sys.path.insert(0, %r); os.environ['PB200_HNSW_VCAP'] = '64'\n"
+            "from pecos_b200.hnsw import HNSW; from pecos_b200 import core\n"
+            "m = HNSW.load(%r); Q = np.load(%r); E = np.load(%r)\n"
+            "idx, dist = m.predict(Q, pred_params=HNSW.PredParams(efS=600, topk=10, threads=1), ret_csr=False)\n"
+            "assert np.array_equal(idx, E['ip_d70|600|10|idx']) and np.array_equal(dist.view(np.uint32), E['ip_d70|600|10|dist'].view(np.uint32))\n"
+            "r = core.get_clib().clib_float32.pb200_hnsw_vcap_retries(m.model_ptr); assert r >= 1, r; print('retries', r)"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(MID, "ip_d70"),
+               os.path.join(MID, "ip_d70", "Q.npy"), os.path.join(MID, "expected.npz")))
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and "retries" in r.stdout, r.stderr[-1500:]
