@@ -347,7 +347,7 @@ def workload_config(name, cfg, X, extra=None):
 
 
 SCORE_KERNELS = ["xl_chunk_scores_kernel<stream>", "xl_chunk_scores_kernel", "xl_chunk_scores_kernel<dense>", "xl_query_warp_scores_kernel",
-                 "xl_cm_scores_kernel"]
+                 "xl_cm_scores_kernel", "xl_pair_scores_kernel"]
 TOPK_KERNELS = ["xl_topk_kernel", "xl_topk_warp_kernel", "xl_topk_filter_kernel"]
 
 HNSW_WORKLOADS = {
