@@ -232,6 +232,18 @@ void pb200_hnsw_resident_upload(void* model_ptr, const ScipyDrmF32* pX);
 double pb200_hnsw_resident_predict(void* model_ptr, uint32_t efS, uint32_t topk);
 void pb200_hnsw_resident_fetch(void* model_ptr, uint32_t* ret_idx, float* ret_val);
 void pb200_hnsw_get_counters(void* model_ptr, uint64_t* out);
+/* libpecos.cpp:482-490  c_ann_hnsw_save_drm_{ip,l2}_f32(model_ptr, model_dir): for an index loaded by THIS library the saved
+ * form is what it was loaded from (config.json + index.mmap_store are copied to model_dir).
+ *
+ * Handles are library-specific: an index TRAINED by the reference (c_ann_hnsw_train_* is not served here) is a reference
+ * handle, but after the overlay the reference's Python passes it to this library's destruct / searchers / predict / save.
+ * pb200_hnsw_set_foreign registers the reference's own functions for one metric (0 = ip, 1 = l2); handles and searcher tokens
+ * that were not created here are forwarded to them (pecos_b200.integration.overlay does this).  Without the registration a
+ * foreign handle is a fatal error with a clear message. */
+void c_ann_hnsw_save_drm_ip_f32(void* model_ptr, const char* model_dir);
+void c_ann_hnsw_save_drm_l2_f32(void* model_ptr, const char* model_dir);
+void pb200_hnsw_set_foreign(int metric, void* destruct, void* searchers_create, void* searchers_destruct, void* predict, void* save);
+
 /* base-vector rows kept in flight per warp by the bulk-copy (TMA) ring: 0 = direct loads, 4 (default) or 8; returns the
  * value in effect.  Results are identical for every setting. */
 int pb200_hnsw_set_stages(void* model_ptr, int stages);

@@ -12,6 +12,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_set>
 #include <vector>
 
 #include "hnsw_engine.h"
@@ -815,6 +816,7 @@ void pb200_xlinear_host_layer_export(void* hptr, uint32_t layer, void* chunks32,
 namespace {
 
 struct HnswHandle {
+    std::string model_dir;                                     // <model>/c_model the index was loaded from (c_ann_hnsw_save copies it)
     std::vector<std::unique_ptr<pb200::HnswEngine>> engines;  // [0] = primary; > 1: PB200_DEVICES replicas (query fan-out)
     std::mutex mu;  // per-warp search scratch lives with the engine: calls on one handle are serialised
 };
@@ -846,6 +848,7 @@ void* hnsw_load(const char* model_dir, bool lazy_load, int metric) {
     std::vector<std::unique_ptr<pb200::HnswHostIndex>> views(devs.size());
     for (size_t i = 0; i < devs.size(); ++i) views[i] = pb200::load_hnsw_index(model_dir, metric, lazy_load);
     fan_out(devs.size(), [&](size_t i) { h->engines[i] = std::make_unique<pb200::HnswEngine>(std::move(views[i]), devs[i]); });
+    h->model_dir = model_dir;
     return h.release();
 }
 
@@ -868,31 +871,136 @@ void hnsw_predict(void* model_ptr, const ScipyDrmF32* pX, uint32_t* ret_idx, flo
 
 extern "C" {
 
+// Handles are library-specific.  Indices TRAINED by the reference (c_ann_hnsw_train_* stays on the reference library) are
+// reference handles, yet once the overlay has re-pointed destruct / predict / searchers_* / save at this library the reference's
+// Python hands them to us.  Live handles and searcher tokens created HERE are therefore registered; anything else is forwarded
+// to the reference's own function, which the overlay registers through pb200_hnsw_set_foreign (without it: a clear fatal error
+// instead of undefined behaviour).
+typedef void (*hnsw_destruct_fn)(void*);
+typedef void* (*hnsw_searchers_create_fn)(void*, uint32_t);
+typedef void (*hnsw_predict_fn)(void*, const ScipyDrmF32*, uint32_t*, float*, uint32_t, uint32_t, int32_t, void*);
+typedef void (*hnsw_save_fn)(void*, const char*);
+struct HnswForeign {
+    hnsw_destruct_fn destruct = nullptr;
+    hnsw_searchers_create_fn searchers_create = nullptr;
+    hnsw_destruct_fn searchers_destruct = nullptr;
+    hnsw_predict_fn predict = nullptr;
+    hnsw_save_fn save = nullptr;
+};
+}  // extern "C"
+
+namespace {
+std::mutex g_hnsw_reg_mutex;
+std::unordered_set<void*>& g_hnsw_models = *new std::unordered_set<void*>();
+std::unordered_set<void*>& g_hnsw_tokens = *new std::unordered_set<void*>();
+HnswForeign g_hnsw_foreign[2];
+
+bool hnsw_is_ours(void* p, bool token = false) {
+    std::lock_guard<std::mutex> lock(g_hnsw_reg_mutex);
+    return (token ? g_hnsw_tokens : g_hnsw_models).count(p) != 0;
+}
+void hnsw_register(void* p, bool token, bool add) {
+    std::lock_guard<std::mutex> lock(g_hnsw_reg_mutex);
+    auto& s = token ? g_hnsw_tokens : g_hnsw_models;
+    if (add) s.insert(p); else s.erase(p);
+}
+[[noreturn]] void hnsw_foreign_missing(const char* what) {
+    throw std::runtime_error(std::string(what) + ": the handle was not created by pecos_b200 (an index trained by the reference "
+                             "library?) and no reference functions were registered with pb200_hnsw_set_foreign");
+}
+void hnsw_save_copy(void* model_ptr, const char* model_dir) {
+    // an index loaded here is a view of <dir>/index.mmap_store + config.json written by the reference: saving = copying them
+    const std::string src = static_cast<HnswHandle*>(model_ptr)->model_dir, dst(model_dir);
+    if (system(("mkdir -p '" + dst + "'").c_str()) != 0) throw std::runtime_error("cannot create " + dst);
+    for (const char* f : {"/config.json", "/index.mmap_store"}) {
+        std::FILE* in = std::fopen((src + f).c_str(), "rb");
+        if (!in) throw std::runtime_error("cannot read " + src + f);
+        std::FILE* out = std::fopen((dst + f).c_str(), "wb");
+        if (!out) { std::fclose(in); throw std::runtime_error("cannot write " + dst + f); }
+        std::vector<char> buf(1 << 20);
+        size_t n;
+        while ((n = std::fread(buf.data(), 1, buf.size(), in)) > 0) std::fwrite(buf.data(), 1, n, out);
+        std::fclose(in);
+        std::fclose(out);
+    }
+}
+}  // namespace
+
+extern "C" {
+
+void pb200_hnsw_set_foreign(int metric, void* destruct, void* searchers_create, void* searchers_destruct, void* predict, void* save) {
+    if (metric < 0 || metric > 1) return;
+    HnswForeign& f = g_hnsw_foreign[metric];
+    f.destruct = reinterpret_cast<hnsw_destruct_fn>(destruct);
+    f.searchers_create = reinterpret_cast<hnsw_searchers_create_fn>(searchers_create);
+    f.searchers_destruct = reinterpret_cast<hnsw_destruct_fn>(searchers_destruct);
+    f.predict = reinterpret_cast<hnsw_predict_fn>(predict);
+    f.save = reinterpret_cast<hnsw_save_fn>(save);
+}
+
 #define PB200_HNSW_API(SUFFIX, METRIC)                                                                                  \
     void* c_ann_hnsw_load##SUFFIX(const char* model_dir, const bool lazy_load) {                                        \
         PB200_API_BEGIN                                                                                                 \
-        return hnsw_load(model_dir, lazy_load, METRIC);                                                                 \
+        void* h = hnsw_load(model_dir, lazy_load, METRIC);                                                              \
+        hnsw_register(h, false, true);                                                                                  \
+        return h;                                                                                                       \
         PB200_API_END("c_ann_hnsw_load" #SUFFIX)                                                                        \
     }                                                                                                                   \
     void c_ann_hnsw_destruct##SUFFIX(void* model_ptr) {                                                                 \
         PB200_API_BEGIN                                                                                                 \
+        if (!model_ptr) return;                                                                                         \
+        if (!hnsw_is_ours(model_ptr)) {                                                                                 \
+            if (!g_hnsw_foreign[METRIC].destruct) hnsw_foreign_missing("c_ann_hnsw_destruct" #SUFFIX);                  \
+            g_hnsw_foreign[METRIC].destruct(model_ptr);                                                                 \
+            return;                                                                                                     \
+        }                                                                                                               \
+        hnsw_register(model_ptr, false, false);                                                                         \
         delete static_cast<HnswHandle*>(model_ptr);                                                                     \
         PB200_API_END("c_ann_hnsw_destruct" #SUFFIX)                                                                    \
     }                                                                                                                   \
     void* c_ann_hnsw_searchers_create##SUFFIX(void* model_ptr, uint32_t num_searcher) {                                 \
         PB200_API_BEGIN                                                                                                 \
-        (void)hnsw_of(model_ptr);                                                                                       \
-        return new HnswSearchers{static_cast<HnswHandle*>(model_ptr), num_searcher};                                    \
+        if (!hnsw_is_ours(model_ptr)) {                                                                                 \
+            if (!g_hnsw_foreign[METRIC].searchers_create) hnsw_foreign_missing("c_ann_hnsw_searchers_create" #SUFFIX);  \
+            return g_hnsw_foreign[METRIC].searchers_create(model_ptr, num_searcher);                                    \
+        }                                                                                                               \
+        void* t = new HnswSearchers{static_cast<HnswHandle*>(model_ptr), num_searcher};                                 \
+        hnsw_register(t, true, true);                                                                                   \
+        return t;                                                                                                       \
         PB200_API_END("c_ann_hnsw_searchers_create" #SUFFIX)                                                            \
     }                                                                                                                   \
-    void c_ann_hnsw_searchers_destruct##SUFFIX(void* searchers_ptr) { delete static_cast<HnswSearchers*>(searchers_ptr); } \
+    void c_ann_hnsw_searchers_destruct##SUFFIX(void* searchers_ptr) {                                                   \
+        PB200_API_BEGIN                                                                                                 \
+        if (!searchers_ptr) return;                                                                                     \
+        if (!hnsw_is_ours(searchers_ptr, true)) {                                                                       \
+            if (!g_hnsw_foreign[METRIC].searchers_destruct) hnsw_foreign_missing("c_ann_hnsw_searchers_destruct" #SUFFIX); \
+            g_hnsw_foreign[METRIC].searchers_destruct(searchers_ptr);                                                   \
+            return;                                                                                                     \
+        }                                                                                                               \
+        hnsw_register(searchers_ptr, true, false);                                                                      \
+        delete static_cast<HnswSearchers*>(searchers_ptr);                                                              \
+        PB200_API_END("c_ann_hnsw_searchers_destruct" #SUFFIX)                                                          \
+    }                                                                                                                   \
     void c_ann_hnsw_predict##SUFFIX(void* model_ptr, const ScipyDrmF32* pX, uint32_t* ret_idx, float* ret_val,          \
                                     uint32_t efS, uint32_t topk, int32_t threads, void* searchers_ptr) {                \
-        (void)threads;                                                                                                  \
-        (void)searchers_ptr;                                                                                            \
         PB200_API_BEGIN                                                                                                 \
+        if (!hnsw_is_ours(model_ptr)) {                                                                                 \
+            if (!g_hnsw_foreign[METRIC].predict) hnsw_foreign_missing("c_ann_hnsw_predict" #SUFFIX);                    \
+            g_hnsw_foreign[METRIC].predict(model_ptr, pX, ret_idx, ret_val, efS, topk, threads, searchers_ptr);         \
+            return;                                                                                                     \
+        }                                                                                                               \
         hnsw_predict(model_ptr, pX, ret_idx, ret_val, efS, topk, METRIC);                                               \
         PB200_API_END("c_ann_hnsw_predict" #SUFFIX)                                                                     \
+    }                                                                                                                   \
+    void c_ann_hnsw_save##SUFFIX(void* model_ptr, const char* model_dir) {                                              \
+        PB200_API_BEGIN                                                                                                 \
+        if (!hnsw_is_ours(model_ptr)) {                                                                                 \
+            if (!g_hnsw_foreign[METRIC].save) hnsw_foreign_missing("c_ann_hnsw_save" #SUFFIX);                          \
+            g_hnsw_foreign[METRIC].save(model_ptr, model_dir);                                                          \
+            return;                                                                                                     \
+        }                                                                                                               \
+        hnsw_save_copy(model_ptr, model_dir);                                                                           \
+        PB200_API_END("c_ann_hnsw_save" #SUFFIX)                                                                        \
     }
 
 PB200_HNSW_API(_drm_ip_f32, pb200::HNSW_IP)

@@ -31,6 +31,7 @@
 constexpr int kCmFeat = 8;                  // query features staged per pair and round (two rounds in flight per warp)
 constexpr int kCmMaxWarps = 16;
 constexpr int kCmMinWarps = 4;
+constexpr uint32_t kCmGoodWarps = 6;        // column ranges are only introduced when fewer warps than this fit unsplit
 constexpr uint32_t kCmSmemBudget = 224u << 10;  // dynamic shared memory a CTA may take (227 KB is the sm_100a maximum)
 constexpr uint32_t kCmMinReuse = 24;        // average pairs per chunk below which the per-chunk staging does not pay
 constexpr uint32_t kCmMinPairs = 148u * 48u; // fewer pairs than this: the query-major kernels fill the GPU better

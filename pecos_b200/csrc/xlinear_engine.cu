@@ -1022,8 +1022,10 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
         dst.view.w_rows = src.w_rows;
         dst.view.bias = src.bias;
         dst.view.has_dup_cols = src.has_dup_cols ? 1 : 0;
-        // chunk images for the chunk-major score kernel (xlinear_cm_kernel.cuh), where the layer's shape allows it.  Wide chunks
-        // are cut into 2..4 column ranges ("virtual chunks") when that is what lets >= 12 warps share an SM with an image.
+        // chunk images for the chunk-major score kernel (xlinear_cm_kernel.cuh), where the layer's shape allows it.  Chunks too
+        // wide for kCmGoodWarps warps to share an SM with an image are cut into 2..4 column ranges ("virtual chunks").  Measured
+        // on the eurlex-4k leaf (85-column chunks): 6 warps unsplit 0.94 ms vs 14 warps with 2 ranges 1.04 ms (the repeated
+        // lookups and the shared-memory pipe eat the occupancy gain: profiles/r02_e, r02_f), hence the low threshold.
         dst.cm_shape = CmShape{};
         if (dst.view.featmap) {
             auto emax_for_split = [&](uint32_t split) {  // most entries of one virtual chunk
@@ -1045,7 +1047,7 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
                 const CmShape cand = cm_shape(src.fm_words, src.w_rows, src.r_max, split == 1 ? dst.e_max : emax_for_split(split),
                                               src.c_max, src.n_chunks, split);
                 if (cand.ok && (!shape.ok || cand.warps_fit > shape.warps_fit)) shape = cand;
-                if (shape.ok && shape.warps_fit >= 12u) break;
+                if (shape.ok && shape.warps_fit >= kCmGoodWarps) break;
                 if (src.c_max < 2u * (split + 1)) break;  // nothing left to cut
             }
             const uint64_t bytes = static_cast<uint64_t>(shape.img_bytes) * src.n_chunks * std::max<uint32_t>(shape.split, 1u);

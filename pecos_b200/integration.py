@@ -32,7 +32,7 @@ XLINEAR_SYMBOLS = (
     "c_mlmodel_predict_on_selected_outputs_csr_f32",
     "c_mlmodel_predict_on_selected_outputs_drm_f32",
 )
-HNSW_SLOTS = ("load", "destruct", "searchers_create", "searchers_destruct", "predict")
+HNSW_SLOTS = ("load", "destruct", "searchers_create", "searchers_destruct", "predict", "save")
 
 
 def overlay(clib, lib_path=LIB_PATH, require_gpu=True):
@@ -49,11 +49,19 @@ def overlay(clib, lib_path=LIB_PATH, require_gpu=True):
         setattr(clib.clib_float32, name, fn)
         swapped.append(name)
     fn_dict = getattr(clib, "ann_hnsw_fn_dict", {})
-    for metric in ("ip", "l2"):
+    b200.pb200_hnsw_set_foreign.restype = None
+    b200.pb200_hnsw_set_foreign.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 5
+    for metric_id, metric in enumerate(("ip", "l2")):
         key = ("drm", metric)
         if key not in fn_dict:
             continue
+        # Indices trained by the reference are REFERENCE handles: hand the reference's own functions to the library, which
+        # forwards every handle / searcher token it did not create itself (train stays on the reference).
+        ref_fns = [fn_dict[key].get(slot) for slot in ("destruct", "searchers_create", "searchers_destruct", "predict", "save")]
+        b200.pb200_hnsw_set_foreign(metric_id, *[ctypes.cast(f, ctypes.c_void_p) if f is not None else None for f in ref_fns])
         for slot in HNSW_SLOTS:
+            if slot not in fn_dict[key]:
+                continue
             name = "c_ann_hnsw_{}_drm_{}_f32".format(slot, metric)
             ref = fn_dict[key][slot]
             fn = getattr(b200, name)

@@ -17,8 +17,8 @@ PY
 for what in "$@"; do
 case $what in
 tests) python -m pytest tests -x -q -m gpu > $o/${tag}_gpu_tests.log 2>&1; tail -4 $o/${tag}_gpu_tests.log;;
-e) python bench.py --steps 20 --warmup 5 > $o/${tag}_bench_eurlex4k.json 2> $o/${tag}_bench_eurlex4k.err || tail -5 $o/${tag}_bench_eurlex4k.err
-   PB200_XL_KERNEL_MODE=6 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $o/${tag}_bench_eurlex4k_mode6.json 2> $o/${tag}_bench_eurlex4k_mode6.err
+e) python bench.py --steps 20 --warmup 5 --no-secondary > $o/${tag}_bench_eurlex4k.json 2> $o/${tag}_bench_eurlex4k.err || tail -5 $o/${tag}_bench_eurlex4k.err
+   PB200_XL_KERNEL_MODE=6 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-secondary > $o/${tag}_bench_eurlex4k_mode6.json 2> $o/${tag}_bench_eurlex4k_mode6.err
    summ $o/${tag}_bench_eurlex4k.json $o/${tag}_bench_eurlex4k_mode6.json;;
 s) python bench.py --workload synthetic-3m --steps 5 --warmup 3 --no-cpu-baseline > $o/${tag}_bench_synthetic3m.json 2> $o/${tag}_bench_synthetic3m.err || tail -5 $o/${tag}_bench_synthetic3m.err
    summ $o/${tag}_bench_synthetic3m.json;;
@@ -26,6 +26,9 @@ eflat) PB200_CM_FLAT=1 python bench.py --steps 20 --warmup 5 --no-cpu-baseline >
    summ $o/${tag}_bench_eurlex4k_flat.json;;
 sflat) PB200_CM_FLAT=1 python bench.py --workload synthetic-3m --steps 5 --warmup 3 --no-cpu-baseline > $o/${tag}_bench_synthetic3m_flat.json 2> $o/${tag}_bench_synthetic3m_flat.err
    summ $o/${tag}_bench_synthetic3m_flat.json;;
+s7) PB200_XL_KERNEL_MODE=6 python bench.py --workload synthetic-3m --steps 5 --warmup 3 --no-cpu-baseline > $o/${tag}_bench_synthetic3m_mode6.json 2> $o/${tag}_bench_synthetic3m_mode6.err
+   summ $o/${tag}_bench_synthetic3m_mode6.json;;
+ncu_pw) ncu --set full --clock-control none --import-source on -k regex:xl_pair_scores -s 3 -c 1 -o $o/${tag}_ncu_pw_synthetic3m python bench.py --workload synthetic-3m --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2> $o/${tag}_ncu_pw.err;;
 ref) python bench.py --impl reference --steps 5 --warmup 2 > $o/${tag}_bench_reference_arm.json 2> $o/${tag}_bench_reference_arm.err; cut -c1-600 $o/${tag}_bench_reference_arm.json;;
 ncu_e) ncu --set full --clock-control none --import-source on -k regex:xl_cm_scores_kernel -s ${NCU_SKIP_E:-9} -c 1 -o $o/${tag}_ncu_cm_eurlex4k python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2> $o/${tag}_ncu_e.err;;
 ncu_s) ncu --set full --clock-control none --import-source on -k regex:xl_cm_scores_kernel -s ${NCU_SKIP_S:-13} -c 1 -o $o/${tag}_ncu_cm_synthetic3m python bench.py --workload synthetic-3m --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2> $o/${tag}_ncu_s.err;;

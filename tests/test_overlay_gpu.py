@@ -48,6 +48,14 @@ def _run_through_the_overlay(tmp_path, gpu_clib, ref, restatement, folder, X, wa
     gi, gd = loaded.predict(Q, 60, 10, threads=1)
     oi, od = restatement.OracleHNSW(idx, isa=0).predict(Q, 60, 10)
     assert np.array_equal(gi, oi) and np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    # the TRAINED index is a reference handle: predict / searchers / destruct on it are forwarded to the reference library
+    ti, td = trained.predict(Q, 60, 10, threads=1)
+    assert np.array_equal(ti, oi)
+    # save of an index loaded HERE = copy of the files it was loaded from; the copy loads and searches identically
+    loaded.save(os.path.join(str(tmp_path / "idx2"), "c_model"))
+    again = ref.RefHNSW.load(os.path.join(str(tmp_path / "idx2"), "c_model"), "l2")
+    ai, ad = again.predict(Q, 60, 10, threads=1)
+    assert np.array_equal(ai, oi) and np.array_equal(ad.view(np.uint32), od.view(np.uint32))
 
 
 def test_overlay_end_to_end_on_a_stand_in_corelib(tmp_path, gpu_clib, have_ref, monkeypatch):
@@ -70,7 +78,7 @@ def test_overlay_end_to_end_on_a_stand_in_corelib(tmp_path, gpu_clib, have_ref, 
                                                                    "searchers_destruct", "predict")}
     swapped = integration.overlay(stand_in)
     assert "c_xlinear_predict_csr_f32" in swapped and "c_ann_hnsw_predict_drm_ip_f32" in swapped
-    assert "c_xlinear_compile_mmap_model" not in swapped
+    assert "c_xlinear_compile_mmap_model" not in swapped and "c_ann_hnsw_train_drm_l2_f32" not in swapped
 
     folder = str(tmp_path / "m")
     synth.save_xlinear_model(folder, random_tree(411, [5, 30, 300], 200, 20, bias=1.0, permute=True), bias=1.0, only_topk=6)
