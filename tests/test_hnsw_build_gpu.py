@@ -1,0 +1,47 @@
+"""GPU index construction (pecos_b200/hnsw_build.py): the index is BUILT on the GPU (exact kNN by tiled GEMMs + the reference's
+neighbour-selection heuristic), written in the reference's index.mmap_store format and then searched by the CUDA engine, the
+restatement and -- where oracle/_ref travelled -- the reference library ON THE SAME FILE: bit-level search parity, recall-level
+build parity (reference build: pecos/core/ann/hnsw.hpp:677-846)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _unit(rng, n, d):
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    return X / np.linalg.norm(X, axis=1, keepdims=True)
+
+
+@pytest.mark.parametrize("N,d,M,efC,metric", [(20000, 96, 16, 80, "ip"), (8000, 200, 12, 60, "l2")])
+def test_gpu_built_index_search_parity_and_recall(tmp_path, gpu_clib, have_ref, N, d, M, efC, metric):
+    from oracle import restatement
+    from pecos_b200.hnsw import HNSW
+    from pecos_b200.hnsw_build import build_hnsw_index
+
+    rng = np.random.default_rng(N)
+    X, Q = _unit(rng, N, d), _unit(rng, 256, d)
+    folder = str(tmp_path / "idx")
+    build_hnsw_index(X, folder, M=M, efC=efC, metric=metric, seed=5, device="cuda:0")
+    m = HNSW.load(folder)
+    o = restatement.OracleHNSW(folder, isa=0)
+    exact = np.argsort((1 - Q @ X.T) if metric == "ip" else (-2 * Q @ X.T + (X * X).sum(1)[None, :]), axis=1)[:, :10]
+    for efS in (20, 100, 300):
+        gi, gd = m.predict(Q, pred_params=HNSW.PredParams(efS=efS, topk=10, threads=1), ret_csr=False)
+        oi, od = o.predict(Q, efS, 10)
+        assert np.array_equal(gi, oi) and np.array_equal(gd.view(np.uint32), od.view(np.uint32)), f"efS={efS}"
+    recall = float(np.mean([len(set(gi[i]) & set(exact[i])) / 10 for i in range(Q.shape[0])]))
+    assert recall >= 0.97
+    if have_ref:
+        from oracle import ref
+
+        r = ref.RefHNSW.load(os.path.join(folder, "c_model"), metric)  # the reference loads the GPU-built file
+        ri, rd = r.predict(Q, 300, 10, threads=8)
+        if restatement.host_isa() == 0:
+            assert np.array_equal(ri, gi) and np.array_equal(rd.view(np.uint32), gd.view(np.uint32))
+        trained = ref.RefHNSW.train(X, M=M, efC=efC, metric=metric, threads=8)
+        ti, _ = trained.predict(Q, 300, 10, threads=8)
+        recall_ref = float(np.mean([len(set(ti[i]) & set(exact[i])) / 10 for i in range(Q.shape[0])]))
+        assert recall >= recall_ref - 0.02
