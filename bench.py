@@ -347,7 +347,7 @@ def workload_config(name, cfg, X, extra=None):
 
 
 SCORE_KERNELS = ["xl_chunk_scores_kernel<stream>", "xl_chunk_scores_kernel", "xl_chunk_scores_kernel<dense>", "xl_query_warp_scores_kernel",
-                 "xl_cm_scores_kernel", "xl_pair_scores_kernel"]
+                 "xl_cm_scores_kernel"]
 TOPK_KERNELS = ["xl_topk_kernel", "xl_topk_warp_kernel", "xl_topk_filter_kernel"]
 
 HNSW_WORKLOADS = {
@@ -359,37 +359,55 @@ HNSW_WORKLOADS = {
 }
 
 
-def hnsw_prepare(args, rank, barrier):
+def hnsw_prepare(args, rank, barrier, local=0):
+    """Rank 0 builds the index once per box ON THE GPU (pecos_b200.hnsw_build: exact kNN by tiled GEMMs + the reference's
+    neighbour-selection heuristic) and writes it in the reference's index.mmap_store format -- the same file is then searched by
+    the CUDA engine and by the reference library (cpu_baseline / parity gate).  PB200_BENCH_HNSW_BUILDER=reference uses the
+    reference's own (CPU, minutes to hours) HNSW.train instead."""
     cfg = dict(HNSW_WORKLOADS[args.workload])
     folder = os.path.join(args.cache_dir, args.workload)
     if rank == 0 and not os.path.exists(os.path.join(folder, "c_model", "index.mmap_store")):
-        import oracle
-        from oracle import ref
-
-        oracle.build()
         os.makedirs(folder, exist_ok=True)
         rng = np.random.default_rng(30)
         X = rng.standard_normal((cfg["N"], cfg["d"]), dtype=np.float32)
         X /= np.linalg.norm(X, axis=1, keepdims=True)
         t0 = time.perf_counter()
-        r = ref.RefHNSW.train(X, M=cfg["M"], efC=cfg["efC"], metric=cfg["metric"], threads=-1)
-        r.save(os.path.join(folder, "c_model"))
-        with open(os.path.join(folder, "param.json"), "w") as f:
-            json.dump({"model": "HNSW", "data_type": "drm", "metric_type": cfg["metric"], "num_item": cfg["N"],
-                       "feat_dim": cfg["d"], "pred_kwargs": {"efS": cfg["efS"], "topk": cfg["topk"], "threads": 1},
-                       "build_seconds": time.perf_counter() - t0}, f)
-        del r, X
+        if os.environ.get("PB200_BENCH_HNSW_BUILDER", "gpu") == "reference":
+            import oracle
+            from oracle import ref
+
+            oracle.build()
+            r = ref.RefHNSW.train(X, M=cfg["M"], efC=cfg["efC"], metric=cfg["metric"], threads=-1)
+            r.save(os.path.join(folder, "c_model"))
+            del r
+            builder = "reference HNSW.train (all host threads)"
+            with open(os.path.join(folder, "param.json"), "w") as f:
+                json.dump({"model": "HNSW", "data_type": "drm", "metric_type": cfg["metric"], "num_item": cfg["N"],
+                           "feat_dim": cfg["d"], "pred_kwargs": {"efS": cfg["efS"], "topk": cfg["topk"], "threads": 1}}, f)
+        else:
+            from pecos_b200.hnsw_build import build_hnsw_index
+
+            build_hnsw_index(X, folder, M=cfg["M"], efC=cfg["efC"], metric=cfg["metric"], seed=30, device=f"cuda:{local}",
+                             pred_kwargs={"efS": cfg["efS"], "topk": cfg["topk"], "threads": 1}, allow_tf32=cfg["N"] > 2_000_000)
+            builder = "pecos_b200.hnsw_build on the GPU"
+        with open(os.path.join(folder, "build.json"), "w") as f:
+            json.dump({"builder": builder, "build_seconds": time.perf_counter() - t0}, f)
+        del X
     barrier()
     rng = np.random.default_rng(31 + 1000 * rank)
     Q = rng.standard_normal((cfg["Q"], cfg["d"]), dtype=np.float32)
     Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+    try:
+        cfg["index_build"] = json.load(open(os.path.join(folder, "build.json")))
+    except Exception:
+        cfg["index_build"] = None
     return folder, np.ascontiguousarray(Q), cfg
 
 
 def hnsw_config(name, cfg, extra=None):
     c = {"workload": name, "base_vectors": cfg["N"], "dim": cfg["d"], "M": cfg["M"], "efC": cfg["efC"], "efS": cfg["efS"],
          "topk": cfg["topk"], "metric": cfg["metric"], "queries_per_step_per_gpu": cfg["Q"],
-         "parallelism": "query-sharded replicas (no collective)"}
+         "parallelism": "query-sharded replicas (no collective)", "index_build": cfg.get("index_build")}
     if extra:
         c.update(extra)
     return c
@@ -460,7 +478,7 @@ def main_hnsw(args):
     lib.require_gpu()
     lib.set_device(local)
     c = lib.clib_float32
-    folder, Q, cfg = hnsw_prepare(args, rank, barrier)
+    folder, Q, cfg = hnsw_prepare(args, rank, barrier, local)
     model = HNSW.load(folder)
     h = model.model_ptr
     nq, d, efS, topk = Q.shape[0], Q.shape[1], cfg["efS"], cfg["topk"]
@@ -514,6 +532,26 @@ def main_hnsw(args):
                 "peak_source": peak_src, "per_query": {"distance_evals": n_dist / nq, "expansions": n_expand / nq,
                                                        "upper_level_reads": n_hops / nq, "bytes": bytes_per_step / nq}}
 
+    # parity gate: the first queries of the timed batch, searched by the reference library ON THE SAME index file
+    gi = np.zeros((nq, topk), dtype=np.uint32)
+    gd = np.zeros((nq, topk), dtype=np.float32)
+    c.pb200_hnsw_resident_fetch(h, gi.ctypes.data_as(POINTER(c_uint32)), gd.ctypes.data_as(POINTER(c_float)))
+    parity = {"checked_queries": 0, "checker": "unavailable (oracle/_ref absent)"}
+    import oracle
+
+    if oracle.have_ref():
+        from oracle import ref, restatement
+
+        n_chk = min(512, nq)
+        ri, rd = ref.RefHNSW.load(os.path.join(folder, "c_model"), cfg["metric"]).predict(Q[:n_chk], efS, topk, threads=os.cpu_count() or 1)
+        if not np.array_equal(ri, gi[:n_chk]):
+            raise RuntimeError("parity gate (hnsw): neighbour ids / ranks differ from the reference library on the same index file")
+        bits = bool(np.array_equal(rd.view(np.uint32), gd[:n_chk].view(np.uint32)))
+        if not bits and (restatement.host_isa() == 0 or not np.allclose(rd, gd[:n_chk], rtol=1e-5, atol=1e-7)):
+            raise RuntimeError("parity gate (hnsw): distances differ from the reference library")
+        parity = {"checked_queries": n_chk, "checker": "reference library (oracle/_ref), same index file", "ids_bit_equal": True,
+                  "distance_bits_equal": bits}
+
     # end to end through the C ABI with pinned host buffers
     qp = lib.pinned_empty(Q.size, np.float32)
     qp.array[:] = Q.ravel()
@@ -557,8 +595,10 @@ def main_hnsw(args):
             "metric": metric_name, "value": value, "unit": unit, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": hnsw_config(args.workload, cfg, {"l2": "flushed between timed iterations; index (%.1f GB) >> L2" % (int(info[6]) / 1e9),
-                                                       "timing": "CUDA events around the search kernel per step, summed, max over ranks"}),
+            "config": hnsw_config(args.workload, cfg),
+            "l2": "flushed between timed iterations; index (%.1f GB) >> L2" % (int(info[6]) / 1e9),
+            "timing": "CUDA events around the search kernel per step, summed, max over ranks",
+            "parity": parity,
             "clocks": clocks,
             "e2e": {"value": n_gpus * nq * args.steps / e2e_total, "unit": unit, "h2d_bytes_per_step": int(Q.nbytes),
                     "d2h_bytes_per_step": int(nq * topk * 8), "ms_per_step": 1e3 * e2e_total / args.steps,

@@ -46,7 +46,6 @@ struct CmWork {
     uint32_t* pair_q;       // [pairs] query of a pair, grouped by chunk
     uint32_t* pair_pos;     // [pairs] candidate position of the pair's first column inside the query's row
     uint32_t item_pairs;
-    uint32_t* pair_chunk;   // [pairs] (virtual) chunk of the pair; nullptr when the consumer finds it from bucket_ptr
 };
 
 struct CmPlan {  // per call
@@ -316,7 +315,6 @@ xl_cm_scatter_kernel(const LayerDev L, const uint32_t* __restrict__ beam_id, con
             const uint32_t at = atomicAdd(&w.count[p * split + hh], 1u);
             w.pair_q[at] = q;
             w.pair_pos[at] = pos + hh * cw;  // first candidate of this column range
-            if (w.pair_chunk) w.pair_chunk[at] = p * split + hh;
         }
     }
 }

@@ -496,7 +496,6 @@ __device__ __forceinline__ unsigned long long xl_make_key(float v, uint32_t pos)
 
 #include "xlinear_qw_kernel.cuh"
 #include "xlinear_cm_kernel.cuh"
-#include "xlinear_pw_kernel.cuh"
 
 // descending bitonic sort of n (power of two) keys; a may live in shared or global memory
 __device__ void xl_bitonic_desc(unsigned long long* a, uint32_t n) {
@@ -1083,7 +1082,6 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
     PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
     PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
     PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
-    PB200_CUDA(cudaFuncSetAttribute(xl_pair_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     stats_dev_.reserve(8 * layers_.size());
@@ -1117,8 +1115,6 @@ void XLinearEngine::set_kernel_mode(int mode) {
     no_topk_filter_ = (mode == 4);
     chunk_major_ = on && (mode != 6);
     cm_force_ = (mode == 5);
-    pair_sorted_ = on && (mode != 6);   // 7: pair-sorted kernel wherever it applies (tests); 6: neither chunk-major nor pair-sorted
-    pw_force_ = (mode == 7);
 }
 
 bool XLinearEngine::has_feature_maps() const {
@@ -1192,7 +1188,6 @@ void XLinearEngine::ensure_workspace_(const std::vector<LayerPlan>& plan, uint32
         cm_slot_pos_.reserve(static_cast<uint64_t>(tile_rows) * beam_stride);
         cm_pair_q_.reserve(static_cast<uint64_t>(tile_rows) * b_max * 4);   // up to 4 column ranges per chunk
         cm_pair_pos_.reserve(static_cast<uint64_t>(tile_rows) * b_max * 4);
-        cm_pair_chunk_.reserve(static_cast<uint64_t>(tile_rows) * b_max);
         cm_count_.reserve(chunks_max * 4 + 1);
         cm_bucket_ptr_.reserve(chunks_max * 4 + 1);
         cm_item_ptr_.reserve(chunks_max * 4 + 1);
@@ -1241,17 +1236,11 @@ int XLinearEngine::score_layer_(size_t d, const QueryDev& q, uint32_t b_prev, in
                           ? cm_plan(layers_[d].cm_shape, L.n_chunks, static_cast<uint64_t>(rows) * b_prev, n_sm_, cm_force_)
                           : CmPlan{};
     const bool chunk_major = cm.eligible;
-    // Pair-sorted scoring for WIDE layers whose feature maps cannot live in L2 (the 3M-label leaf: 4.1 GB): same per-pair
-    // algorithm as the feature-map chunk kernel, but the pairs run in chunk order so that a chunk's map, extents and entries are
-    // fetched from DRAM once (prefetched into L2 by the chunk's first pair) instead of once per probe.
-    const uint64_t fm_bytes = static_cast<uint64_t>(L.n_chunks) * L.fm_words * 8ull;
-    const bool pair_sorted = !chunk_major && lookup && !collect_stats && !query_warp && cm_pair_chunk_.capacity() && pair_sorted_ &&
-                             (pw_force_ || (fm_bytes > (96ull << 20) && static_cast<uint64_t>(rows) * b_prev >= 4ull * L.n_chunks));
     if (chunk_major) {
         const CmShape& shape = layers_[d].cm_shape;
         const uint32_t n_vc = L.n_chunks * shape.split;
         CmWork w{cm_slot_pos_.get(), cm_count_.get(), cm_bucket_ptr_.get(), cm_item_ptr_.get(), cm_pair_q_.get(), cm_pair_pos_.get(),
-                 cm.warps * 32u, nullptr};
+                 cm.warps * 32u};
         PB200_CUDA(cudaMemsetAsync(w.count, 0, (static_cast<uint64_t>(n_vc) + 1) * 4, stream_));
         const uint32_t warp_grid = (rows * 32u + 127u) / 128u;
         xl_cm_count_kernel<<<warp_grid, 128, 0, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w, shape.split);
@@ -1263,21 +1252,6 @@ int XLinearEngine::score_layer_(size_t d, const QueryDev& q, uint32_t b_prev, in
         if (shape.direct) { if (shape.stages == 4) launch_cm(xl_cm_scores_kernel<true, 4>); else launch_cm(xl_cm_scores_kernel<true, 2>); }
         else { if (shape.stages == 4) launch_cm(xl_cm_scores_kernel<false, 4>); else launch_cm(xl_cm_scores_kernel<false, 2>); }
         launches_ += 3;  // + the score kernel counted below
-    } else if (pair_sorted) {
-        // chunk-sorted pairs, one warp per pair (xlinear_pw_kernel.cuh)
-        CmWork w{cm_slot_pos_.get(), cm_count_.get(), cm_bucket_ptr_.get(), cm_item_ptr_.get(), cm_pair_q_.get(), cm_pair_pos_.get(),
-                 32u, cm_pair_chunk_.get()};
-        PB200_CUDA(cudaMemsetAsync(w.count, 0, (static_cast<uint64_t>(L.n_chunks) + 1) * 4, stream_));
-        const uint32_t warp_grid = (rows * 32u + 127u) / 128u;
-        xl_cm_count_kernel<<<warp_grid, 128, 0, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w, 1u);
-        xl_cm_scan_kernel<<<1, 1024, 0, stream_>>>(L.n_chunks, w);
-        xl_cm_scatter_kernel<<<warp_grid, 128, 0, stream_>>>(L, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w, 1u);
-        const uint32_t pw_qcap = std::min<uint32_t>(kQCap, std::max<uint32_t>(32u, (q.max_row_nnz + 31u) & ~31u));
-        const size_t pw_smem = kPwWarps * ((pw_warp_bytes(pw_qcap) + 15) & ~static_cast<size_t>(15));
-        const uint64_t max_pairs = static_cast<uint64_t>(rows) * b_prev;
-        xl_pair_scores_kernel<<<static_cast<uint32_t>((max_pairs + kPwWarps - 1) / kPwWarps), kPwWarps * 32, pw_smem, stream_>>>(
-            L, q, w, cm_pair_chunk_.get(), cand_.get(), cand_stride_q, pw_qcap);
-        launches_ += 3;
     } else if (query_warp) {
         const uint32_t qw_qcap = std::max<uint32_t>(32u, (q.max_row_nnz + 31u) & ~31u);
         const uint32_t qw_ncap = static_cast<uint32_t>((cand_stride_q + 31) & ~static_cast<uint64_t>(31));
@@ -1301,7 +1275,7 @@ int XLinearEngine::score_layer_(size_t d, const QueryDev& q, uint32_t b_prev, in
     }
     PB200_CUDA(cudaGetLastError());
     ++launches_;
-    layer_profile_[d].scores_kernel = chunk_major ? 4 : pair_sorted ? 5 : query_warp ? 3 : dense ? 2 : lookup ? 1 : 0;
+    layer_profile_[d].scores_kernel = chunk_major ? 4 : query_warp ? 3 : dense ? 2 : lookup ? 1 : 0;
     return layer_profile_[d].scores_kernel;
 }
 

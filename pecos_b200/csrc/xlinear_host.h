@@ -122,7 +122,9 @@ struct XLinearHostModel {
         const auto& l = layers.back();
         return l.bias > 0.0f ? l.w_rows - 1 : l.w_rows;
     }
-    uint32_t nr_labels() const { return layers.back().n_cols; }
+    // label_count() of the last layer: the chunked layouts report the columns of the (possibly rearranged / pruned) chunked
+    // matrix, MLModel<csc_t> reports W.cols (inference.hpp:2367-2379) -- handles requested as CSC follow the latter
+    uint32_t nr_labels() const { return layer_type == LT_CSC ? layers.back().out_cols : layers.back().n_cols; }
     uint32_t nr_codes() const { return layers.back().n_chunks; }
 };
 

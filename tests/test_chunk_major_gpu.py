@@ -89,33 +89,3 @@ def test_chunk_major_tiles_and_small_batches(tmp_path, gpu_clib, have_ref):
     assert kid[4] != 4, "5 queries x beam 8 must not pay for staging 512 chunks"
     assert_csr_parity(small, base[:5], rtol=0.0, what="small batch")
     c.pb200_xlinear_set_lookup(h, 1)
-
-
-@pytest.mark.parametrize("permute,prune,sizes", [(False, 0.0, [4, 24, 1500]), (True, 0.2, [8, 64, 512])])
-def test_pair_sorted_kernel_equals_query_major_kernels_and_oracles(tmp_path, gpu_clib, have_ref, permute, prune, sizes):
-    """Kernel mode 7: the pair-sorted scorer (pecos_b200/csrc/xlinear_pw_kernel.cuh; by default only for layers whose feature
-    maps exceed L2, e.g. the 3M-label leaf) on every layer it applies to -- same bits as the query-major kernels (mode 6)."""
-    from pecos_b200.xlinear import XLinearModel
-
-    folder = str(tmp_path / "m")
-    layers = random_tree(531, sizes, 400, 24, bias=1.0, permute=permute, prune=prune)
-    synth.save_xlinear_model(folder, layers, bias=1.0, only_topk=8)
-    X = synth.make_queries(532, 1200, 400, 48)
-    X = csr_with_empty_rows(X, [0, 5, 1199])
-    Xl = synth.make_queries(533, 64, 400, 300)  # long rows: more than one 128-feature block, several flushes
-    m, oracles = XLinearModel.load(folder, is_predict_only=True), _oracles(folder, have_ref)
-    c = gpu_clib.clib_float32
-    h = m.model.model_chain
-    kid = (c_int * 6)()
-    for Xq in (X, Xl):
-        for pp in ("l3-hinge", "noop"):
-            c.pb200_xlinear_set_lookup(h, 6)
-            base = m.predict(Xq, beam_size=6, only_topk=8, post_processor=pp)  # beam < 16: the chunk kernel's territory
-            c.pb200_xlinear_set_lookup(h, 7)
-            got = m.predict(Xq, beam_size=6, only_topk=8, post_processor=pp)
-            c.pb200_xlinear_get_kernel_ids(h, kid)
-            assert 5 in [kid[2 * d] for d in range(len(sizes))], "the pair-sorted kernel did not run on any layer"
-            assert_csr_parity(got, base, rtol=0.0, what=f"pair-sorted vs query-major {pp}")
-            for name, o in oracles.items():
-                assert_csr_parity(got[:100], o.predict(Xq[:100], 6, pp, 8), what=f"pair-sorted vs {name} {pp}")
-    c.pb200_xlinear_set_lookup(h, 1)

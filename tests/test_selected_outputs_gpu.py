@@ -40,7 +40,9 @@ def test_selected_outputs_equal_the_oracles(tmp_path, gpu_clib, have_ref, permut
     X = synth.make_queries(96, 300, 200, 30)
     # pruned trees: only labels with a path to the root (the reference indexes with uninitialised memory otherwise)
     S = _selection(np.random.default_rng(97), 300, sizes[-1], 12, allowed=reachable_labels(layers))
-    m = XLinearModel.load(folder, is_predict_only=True)
+    # the reference serves selected outputs from CSC handles (whose nr_labels = W.cols also on pruned trees): load the same way
+    m = XLinearModel.load(folder, is_predict_only=True, weight_matrix_type="CSC")
+    assert m.nr_labels == sizes[-1]
     o = restatement.OracleXLinear(os.path.join(folder, "ranker"))
     r = None
     if have_ref:
@@ -74,7 +76,7 @@ def test_unreachable_selected_labels_leave_zero_entries(tmp_path, gpu_clib):
     X = synth.make_queries(396, 120, 200, 30)
     S = _selection(np.random.default_rng(397), 120, 400, 15)
     assert np.setdiff1d(np.unique(S.indices), reachable_labels(layers)).size > 0
-    m = XLinearModel.load(folder, is_predict_only=True)
+    m = XLinearModel.load(folder, is_predict_only=True, weight_matrix_type="CSC")
     o = restatement.OracleXLinear(os.path.join(folder, "ranker"))
     assert_csr_parity(m.predict(X, selected_outputs_csr=S), o.predict_on_selected_outputs(X, S, None), what="unreachable labels")
 
