@@ -29,6 +29,19 @@ sflat) PB200_CM_FLAT=1 python bench.py --workload synthetic-3m --steps 5 --warmu
 s7) PB200_XL_KERNEL_MODE=6 python bench.py --workload synthetic-3m --steps 5 --warmup 3 --no-cpu-baseline > $o/${tag}_bench_synthetic3m_mode6.json 2> $o/${tag}_bench_synthetic3m_mode6.err
    summ $o/${tag}_bench_synthetic3m_mode6.json;;
 ncu_pw) ncu --set full --clock-control none --import-source on -k regex:xl_pair_scores -s 3 -c 1 -o $o/${tag}_ncu_pw_synthetic3m python bench.py --workload synthetic-3m --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2> $o/${tag}_ncu_pw.err;;
+h100k) python bench.py --workload hnsw-100k --steps 5 --warmup 3 > $o/${tag}_bench_hnsw100k.json 2> $o/${tag}_bench_hnsw100k.err || tail -5 $o/${tag}_bench_hnsw100k.err
+   summ $o/${tag}_bench_hnsw100k.json;;
+h1m) python bench.py --workload hnsw-1m --steps 3 --warmup 3 > $o/${tag}_bench_hnsw1m.json 2> $o/${tag}_bench_hnsw1m.err || tail -5 $o/${tag}_bench_hnsw1m.err
+   summ $o/${tag}_bench_hnsw1m.json;;
+full) python bench.py --steps 20 --warmup 5 > $o/${tag}_bench_default.json 2> $o/${tag}_bench_default.err || tail -5 $o/${tag}_bench_default.err
+   summ $o/${tag}_bench_default.json
+   python - <<PY
+import json
+d=json.loads(open("$o/${tag}_bench_default.json").read().strip().splitlines()[-1])
+s=d.get("secondary",{})
+print("secondary:", {k:(round(v.get("value",0)) if isinstance(v,dict) else v) for k,v in s.items()})
+PY
+   ;;
 ref) python bench.py --impl reference --steps 5 --warmup 2 > $o/${tag}_bench_reference_arm.json 2> $o/${tag}_bench_reference_arm.err; cut -c1-600 $o/${tag}_bench_reference_arm.json;;
 ncu_e) ncu --set full --clock-control none --import-source on -k regex:xl_cm_scores_kernel -s ${NCU_SKIP_E:-9} -c 1 -o $o/${tag}_ncu_cm_eurlex4k python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2> $o/${tag}_ncu_e.err;;
 ncu_s) ncu --set full --clock-control none --import-source on -k regex:xl_cm_scores_kernel -s ${NCU_SKIP_S:-13} -c 1 -o $o/${tag}_ncu_cm_synthetic3m python bench.py --workload synthetic-3m --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2> $o/${tag}_ncu_s.err;;
