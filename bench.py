@@ -552,6 +552,26 @@ def main_hnsw(args):
         parity = {"checked_queries": n_chk, "checker": "reference library (oracle/_ref), same index file", "ids_bit_equal": True,
                   "distance_bits_equal": bits}
 
+    # recall@topk of the timed results against brute force (a sample of the batch; exact distances by a GEMM on the GPU)
+    recall = None
+    try:
+        import torch
+
+        from oracle import restatement as _rs
+
+        n_rc = min(256, nq)
+        base = torch.from_numpy(_rs.OracleHNSW(folder, isa=0).vectors()).to(f"cuda:{local}")
+        qs = torch.from_numpy(Q[:n_rc]).to(base.device)
+        sc = qs @ base.T
+        dist_all = (1.0 - sc) if cfg["metric"] == "ip" else ((base * base).sum(1)[None, :] - 2.0 * sc)
+        exact = torch.topk(dist_all, topk, dim=1, largest=False).indices.cpu().numpy()
+        recall = float(np.mean([len(set(gi[i].tolist()) & set(exact[i].tolist())) / topk for i in range(n_rc)]))
+        del base, sc, dist_all
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        print(f"bench.py: recall check skipped: {e}", file=sys.stderr)
+    parity["recall_at_topk_vs_brute_force"] = recall
+
     # end to end through the C ABI with pinned host buffers
     qp = lib.pinned_empty(Q.size, np.float32)
     qp.array[:] = Q.ravel()

@@ -1217,7 +1217,7 @@ int XLinearEngine::score_layer_(size_t d, const QueryDev& q, uint32_t b_prev, in
     const uint32_t hdr_cap = b_prev <= 128u ? b_prev : 0u;  // beam chunk headers cached in shared memory
     const size_t smem1 = chunk_kernel_smem(warps, lookup, q_cap, sb_cap, hdr_cap);
     auto launch = [&](auto kernel) {
-        kernel<<<grid, block, smem1, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(),
+        kernel<<<grid, block, smem1, stream_>>>(L, q, bid_(cur), bcnt_(cur), beam_stride_, cand_at_(cand_stride_q),
                                                cand_stride_q, c_stride, stats, q_cap, sb_cap, hdr_cap);
     };
     // One warp per query over the whole beam (feature-major).  Measured on B200: it wins when the beam consists of
@@ -1243,11 +1243,11 @@ int XLinearEngine::score_layer_(size_t d, const QueryDev& q, uint32_t b_prev, in
                  cm.warps * 32u};
         PB200_CUDA(cudaMemsetAsync(w.count, 0, (static_cast<uint64_t>(n_vc) + 1) * 4, stream_));
         const uint32_t warp_grid = (rows * 32u + 127u) / 128u;
-        xl_cm_count_kernel<<<warp_grid, 128, 0, stream_>>>(L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w, shape.split);
+        xl_cm_count_kernel<<<warp_grid, 128, 0, stream_>>>(L, q, bid_(cur), bcnt_(cur), beam_stride_, rows, w, shape.split);
         xl_cm_scan_kernel<<<1, 1024, 0, stream_>>>(n_vc, w);
-        xl_cm_scatter_kernel<<<warp_grid, 128, 0, stream_>>>(L, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, rows, w, shape.split);
+        xl_cm_scatter_kernel<<<warp_grid, 128, 0, stream_>>>(L, bid_(cur), bcnt_(cur), beam_stride_, rows, w, shape.split);
         auto launch_cm = [&](auto kernel) {
-            kernel<<<cm.grid, cm.warps * 32, cm.smem, stream_>>>(L, q, w, shape, layers_[d].cm_images.get(), cand_.get(), cand_stride_q);
+            kernel<<<cm.grid, cm.warps * 32, cm.smem, stream_>>>(L, q, w, shape, layers_[d].cm_images.get(), cand_at_(cand_stride_q), cand_stride_q);
         };
         if (shape.direct) { if (shape.stages == 4) launch_cm(xl_cm_scores_kernel<true, 4>); else launch_cm(xl_cm_scores_kernel<true, 2>); }
         else { if (shape.stages == 4) launch_cm(xl_cm_scores_kernel<false, 4>); else launch_cm(xl_cm_scores_kernel<false, 2>); }
@@ -1259,10 +1259,10 @@ int XLinearEngine::score_layer_(size_t d, const QueryDev& q, uint32_t b_prev, in
         const dim3 qw_grid((rows + kQwWarps - 1) / kQwWarps);
         if (collect_stats)
             xl_query_warp_scores_kernel<true><<<qw_grid, kQwWarps * 32, qw_smem, stream_>>>(
-                L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(), cand_stride_q, stats, qw_qcap, qw_ncap, rows);
+                L, q, bid_(cur), bcnt_(cur), beam_stride_, cand_at_(cand_stride_q), cand_stride_q, stats, qw_qcap, qw_ncap, rows);
         else
             xl_query_warp_scores_kernel<false><<<qw_grid, kQwWarps * 32, qw_smem, stream_>>>(
-                L, q, beam_id_[cur].get(), beam_cnt_[cur].get(), beam_stride_, cand_.get(), cand_stride_q, stats, qw_qcap, qw_ncap, rows);
+                L, q, bid_(cur), bcnt_(cur), beam_stride_, cand_at_(cand_stride_q), cand_stride_q, stats, qw_qcap, qw_ncap, rows);
     } else if (dense) {
         if (collect_stats) launch(xl_chunk_scores_kernel<true, true, false>);
         else launch(xl_chunk_scores_kernel<true, false, false>);
@@ -1283,18 +1283,19 @@ int XLinearEngine::score_layer_(size_t d, const QueryDev& q, uint32_t b_prev, in
 // ext_beam: beam_*_[0] already hold the beam entering the first layer (single-layer entry point); combine_first: that
 // layer combines its scores with the beam values (a previous prediction was given).
 void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& plan, bool collect_stats, bool ext_beam,
-                              int combine_first) {
+                              int combine_first, size_t d_begin, size_t d_end) {
     const uint32_t rows = q.rows;
     if (rows == 0) return;
     const bool dense = (q.row_ptr == nullptr);
-    int cur = 0;
-    if (!ext_beam) {
-        xl_init_beam_kernel<<<(rows + 255) / 256, 256, 0, stream_>>>(beam_id_[cur].get(), beam_val_[cur].get(),
-                                                                     beam_cnt_[cur].get(), beam_stride_, rows);
+    int cur = static_cast<int>(d_begin & 1);  // every layer flips the ping-pong beam buffers once
+    if (!ext_beam && d_begin == 0) {
+        xl_init_beam_kernel<<<(rows + 255) / 256, 256, 0, stream_>>>(bid_(cur), bval_(cur),
+                                                                     bcnt_(cur), beam_stride_, rows);
         ++launches_;
     }
     const size_t depth = plan.size();
-    for (size_t d = 0; d < depth; ++d) {
+    d_end = std::min(d_end, depth);
+    for (size_t d = d_begin; d < d_end; ++d) {
         const LayerDev& L = layers_[d].view;
         const LayerPlan& lp = plan[d];
         const int combine = (d == 0) ? combine_first : 1;
@@ -1322,7 +1323,7 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
             o_cnt = res_cnt_dev_.get() + res_rows_;
             o_stride = res_stride_;
         } else {
-            o_id = beam_id_[cur ^ 1].get(); o_val = beam_val_[cur ^ 1].get(); o_cnt = beam_cnt_[cur ^ 1].get();
+            o_id = bid_(cur ^ 1); o_val = bval_(cur ^ 1); o_cnt = bcnt_(cur ^ 1);
             o_stride = beam_stride_;
         }
         const uint64_t sort_stride = next_pow2_host(cand_stride_q);
@@ -1337,18 +1338,18 @@ void XLinearEngine::run_tile_(const QueryDev& q, const std::vector<LayerPlan>& p
             const uint32_t key_cap = static_cast<uint32_t>((cand_stride_q + 127) & ~static_cast<uint64_t>(127));
             const size_t flt_smem = kFltWarps * flt_warp_bytes(key_cap);
             xl_topk_filter_kernel<<<(rows + kFltWarps - 1) / kFltWarps, kFltWarps * 32, flt_smem, stream_>>>(
-                L, lp.pp.kind, lp.pp.p, combine, lp.k, beam_id_[cur].get(), beam_val_[cur].get(), beam_cnt_[cur].get(),
-                beam_stride_, cand_.get(), cand_stride_q, o_id, o_val, o_cnt, o_stride, rows, stats, o_key, key_cap);
+                L, lp.pp.kind, lp.pp.p, combine, lp.k, bid_(cur), bval_(cur), bcnt_(cur),
+                beam_stride_, cand_at_(cand_stride_q), cand_stride_q, o_id, o_val, o_cnt, o_stride, rows, stats, o_key, key_cap);
         } else if (warp_select) {
             const uint32_t key_cap = static_cast<uint32_t>((cand_stride_q + 31) & ~static_cast<uint64_t>(31));
             const size_t sel_smem = kSelWarps * ((sel_warp_bytes(key_cap) + 15) & ~static_cast<size_t>(15));
             xl_topk_warp_kernel<<<(rows + kSelWarps - 1) / kSelWarps, kSelWarps * 32, sel_smem, stream_>>>(
-                L, lp.pp.kind, lp.pp.p, combine, lp.k, beam_id_[cur].get(), beam_val_[cur].get(), beam_cnt_[cur].get(),
-                beam_stride_, cand_.get(), cand_stride_q, c_stride, o_id, o_val, o_cnt, o_stride, rows, stats, o_key, key_cap);
+                L, lp.pp.kind, lp.pp.p, combine, lp.k, bid_(cur), bval_(cur), bcnt_(cur),
+                beam_stride_, cand_at_(cand_stride_q), cand_stride_q, c_stride, o_id, o_val, o_cnt, o_stride, rows, stats, o_key, key_cap);
         } else {
             xl_topk_kernel<<<grid, kTopkThreads, topk_kernel_smem(lp.b_prev), stream_>>>(
-                L, lp.pp.kind, lp.pp.p, combine, lp.k, beam_id_[cur].get(), beam_val_[cur].get(), beam_cnt_[cur].get(),
-                beam_stride_, cand_.get(), cand_stride_q, c_stride, o_id, o_val, o_cnt, o_stride, sortbuf_.get(), sort_stride,
+                L, lp.pp.kind, lp.pp.p, combine, lp.k, bid_(cur), bval_(cur), bcnt_(cur),
+                beam_stride_, cand_at_(cand_stride_q), cand_stride_q, c_stride, o_id, o_val, o_cnt, o_stride, sortbuf_.get(), sort_stride,
                 lp.b_prev, stats, o_key);
         }
         PB200_CUDA(cudaGetLastError());
@@ -1400,6 +1401,48 @@ XLinearEngine::Result XLinearEngine::predict_csr(const uint64_t* row_ptr, const 
     res_ids_dev_.reserve(static_cast<uint64_t>(rows) * stride + 1);
     res_vals_dev_.reserve(static_cast<uint64_t>(rows) * stride + 1);
     res_cnt_dev_.reserve(static_cast<uint64_t>(rows) + 1);
+    // Whole batch fits the workspace (the common case): the rows are uploaded in `parts` chunks on the copy stream into ONE
+    // staging set; the UPPER layers (cheap) run per chunk as it lands, overlapping the rest of the upload, and the LAST layer
+    // -- where the time goes, and where the chunk-major kernel wants as many pairs per launch as it can get -- runs once over
+    // the whole batch.
+    if (pipeline_uploads_ && rows >= 4096u && tile >= rows) {
+        const size_t depth = plan.size();
+        const uint64_t nnz0 = row_ptr[0], nnz = row_ptr[rows] - nnz0;
+        x_row_ptr_.reserve(static_cast<uint64_t>(rows) + 1);
+        x_col_idx_.reserve(nnz);
+        x_val_.reserve(nnz);
+        const uint32_t part = ((rows + pipeline_parts_ - 1u) / pipeline_parts_ + 31u) & ~31u;
+        std::vector<cudaEvent_t> evs;
+        for (uint32_t r0 = 0; r0 < rows; r0 += part) {
+            const uint32_t tr = std::min(part, rows - r0);
+            const uint64_t b = row_ptr[r0] - nnz0, e = row_ptr[r0 + tr] - nnz0;
+            PB200_CUDA(cudaMemcpyAsync(x_row_ptr_.get() + r0, row_ptr + r0, (static_cast<uint64_t>(tr) + 1) * 8, cudaMemcpyHostToDevice, copy_stream_));
+            PB200_CUDA(cudaMemcpyAsync(x_col_idx_.get() + b, col_idx + nnz0 + b, (e - b) * 4, cudaMemcpyHostToDevice, copy_stream_));
+            PB200_CUDA(cudaMemcpyAsync(x_val_.get() + b, val + nnz0 + b, (e - b) * 4, cudaMemcpyHostToDevice, copy_stream_));
+            cudaEvent_t ev;
+            PB200_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            PB200_CUDA(cudaEventRecord(ev, copy_stream_));
+            evs.push_back(ev);
+        }
+        size_t t = 0;
+        for (uint32_t r0 = 0; r0 < rows; r0 += part, ++t) {
+            const uint32_t tr = std::min(part, rows - r0);
+            PB200_CUDA(cudaStreamWaitEvent(stream_, evs[t], 0));
+            if (depth > 1) {
+                QueryDev q{x_row_ptr_.get() + r0, x_col_idx_.get(), x_val_.get(), nnz0, tr, cols, max_row_nnz(row_ptr + r0, tr)};
+                row_off_ = r0;
+                res_rows_ = r0;
+                run_tile_(q, plan, false, false, 0, 0, depth - 1);
+            }
+        }
+        row_off_ = 0;
+        res_rows_ = 0;
+        QueryDev q{x_row_ptr_.get(), x_col_idx_.get(), x_val_.get(), nnz0, rows, cols, max_row_nnz(row_ptr, rows)};
+        run_tile_(q, plan, false, false, 0, depth - 1, depth);
+        Result r = finish_result_(rows, stride);
+        for (auto ev : evs) cudaEventDestroy(ev);
+        return r;
+    }
     // Host buffers: the batch is cut into sub-tiles whose uploads (copy stream, two staging sets) overlap the scoring of
     // the previous sub-tile; results stay on the device until the last sub-tile is done.
     uint32_t sub = tile;

@@ -177,8 +177,14 @@ private:
     std::vector<LayerPlan> make_plan_(uint32_t beam_size, const char* post_processor, uint32_t only_topk) const;
     void ensure_workspace_(const std::vector<LayerPlan>& plan, uint32_t tile_rows);
     uint32_t pick_tile_rows_(const std::vector<LayerPlan>& plan, uint32_t rows) const;
+    // layers [d_begin, d_end) over one tile of queries; the tile's beam / candidate rows start at row_off_ of the workspace
     void run_tile_(const QueryDev& q, const std::vector<LayerPlan>& plan, bool collect_stats, bool ext_beam = false,
-                   int combine_first = 0);
+                   int combine_first = 0, size_t d_begin = 0, size_t d_end = static_cast<size_t>(-1));
+    uint32_t* bid_(int b) const { return beam_id_[b].get() + static_cast<uint64_t>(row_off_) * beam_stride_; }
+    float* bval_(int b) const { return beam_val_[b].get() + static_cast<uint64_t>(row_off_) * beam_stride_; }
+    uint32_t* bcnt_(int b) const { return beam_cnt_[b].get() + row_off_; }
+    float* cand_at_(uint64_t stride_q) const { return cand_.get() + static_cast<uint64_t>(row_off_) * stride_q; }
+    uint32_t row_off_ = 0;
     int score_layer_(size_t d, const QueryDev& q, uint32_t b_prev, int cur, bool collect_stats);
     Result finish_result_(uint32_t rows, uint32_t stride);
 
