@@ -64,6 +64,10 @@ void* c_xlinear_load_model_from_disk_ext(const char* model_path, int weight_matr
 /* libpecos.cpp:128  folder written by c_xlinear_compile_mmap_model (W/C/perm.mmap_store per layer). */
 void* c_xlinear_load_mmap_model_from_disk(const char* model_path, const bool lazy_load);
 /* libpecos.cpp:140 */
+/* libpecos.cpp:133-138  npz model folder (ranker/) -> the reference's mmap format (param.json with is_mmap = true; per layer
+ * W.mmap_store = chunked matrix, C.mmap_store, perm.mmap_store when the tree is not contiguously ordered; formats: SURVEY.md
+ * Appendix B).  Host-only: needs no GPU.  The output loads in the reference library and here. */
+void c_xlinear_compile_mmap_model(const char* model_path, const char* mmap_model_path);
 void c_xlinear_destruct_model(void* ptr);
 /* libpecos.cpp:147  attr in {"depth","nr_features","nr_labels","nr_codes"} (inference.hpp:2367-2379). */
 uint32_t c_xlinear_get_int_attr(void* ptr, const char* attr);

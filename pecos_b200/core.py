@@ -196,6 +196,7 @@ class B200CoreLib(object):
         fp(c.c_xlinear_load_model_from_disk, c_void_p, [c_char_p])
         fp(c.c_xlinear_load_model_from_disk_ext, c_void_p, [c_char_p, c_int])
         fp(c.c_xlinear_load_mmap_model_from_disk, c_void_p, [c_char_p, c_bool])
+        fp(c.c_xlinear_compile_mmap_model, None, [c_char_p, c_char_p])
         fp(c.c_xlinear_destruct_model, None, [c_void_p])
         fp(c.c_xlinear_get_int_attr, c_uint32, [c_void_p, c_char_p])
         fp(c.c_xlinear_get_layer_type, c_int, [c_void_p, c_int])

@@ -201,6 +201,14 @@ void* c_xlinear_load_mmap_model_from_disk(const char* model_path, const bool laz
     PB200_API_END("c_xlinear_load_mmap_model_from_disk")
 }
 
+void c_xlinear_compile_mmap_model(const char* model_path, const char* mmap_model_path) {
+    // host-only (no CUDA calls): npz model folder -> the reference's mmap format (libpecos.cpp:133-138)
+    PB200_API_BEGIN
+    auto host = pb200::load_xlinear_npz_model(model_path, pb200::LT_BINARY_SEARCH_CHUNKED);
+    pb200::write_xlinear_mmap_model(*host, mmap_model_path);
+    PB200_API_END("c_xlinear_compile_mmap_model")
+}
+
 void c_xlinear_destruct_model(void* ptr) {
     PB200_API_BEGIN
     delete static_cast<XLinearHandle*>(ptr);

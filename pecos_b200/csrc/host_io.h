@@ -514,6 +514,55 @@ private:
 };
 
 // ----------------------------------------------------------------------------------------------
+// PECOS mmap_store container (write side; pecos/core/utils/mmap_util.hpp:54-140, :304-317)
+// ----------------------------------------------------------------------------------------------
+class MmapStoreWriter {
+public:
+    explicit MmapStoreWriter(const std::string& path) : path_(path) {
+        f_ = std::fopen(path.c_str(), "wb");
+        if (!f_) throw std::runtime_error("mmap_store: cannot open " + path + " for writing");
+    }
+    ~MmapStoreWriter() { if (f_) std::fclose(f_); }
+    MmapStoreWriter(const MmapStoreWriter&) = delete;
+    MmapStoreWriter& operator=(const MmapStoreWriter&) = delete;
+
+    template <typename T>
+    void put_multiple(const T* data, uint64_t n) {  // one block, padded to 16-byte alignment
+        const uint64_t bytes = n * sizeof(T);
+        blocks_.emplace_back(off_, bytes);
+        if (bytes && std::fwrite(data, 1, bytes, f_) != bytes) throw std::runtime_error("mmap_store: short write to " + path_);
+        off_ += bytes;
+        static const char zeros[16] = {0};
+        const uint64_t pad = (16 - off_ % 16) % 16;
+        if (pad && std::fwrite(zeros, 1, pad, f_) != pad) throw std::runtime_error("mmap_store: short write to " + path_);
+        off_ += pad;
+    }
+    template <typename T>
+    void put_one(const T& v) { put_multiple<T>(&v, 1); }
+    template <typename T>
+    void put_vector(const T* data, uint64_t n) {  // MmapableVector<T>: size block + data block
+        put_one<uint64_t>(n);
+        put_multiple<T>(data, n);
+    }
+    void close() {  // metadata [n][(offset, size) x n] + 16-byte signature
+        const uint64_t meta_off = off_, n = blocks_.size();
+        std::fwrite(&n, 8, 1, f_);
+        for (auto& b : blocks_) { std::fwrite(&b.first, 8, 1, f_); std::fwrite(&b.second, 8, 1, f_); }
+        const uint8_t sig[8] = {0x93, 'P', 'E', 'C', 'O', 'S', '<', 1};
+        std::fwrite(sig, 1, 8, f_);
+        std::fwrite(&meta_off, 8, 1, f_);
+        if (std::fclose(f_) != 0) { f_ = nullptr; throw std::runtime_error("mmap_store: cannot finish " + path_); }
+        f_ = nullptr;
+    }
+
+private:
+    std::string path_;
+    std::FILE* f_ = nullptr;
+    uint64_t off_ = 0;
+    std::vector<std::pair<uint64_t, uint64_t>> blocks_;
+};
+
+// ----------------------------------------------------------------------------------------------
 // tiny host thread pool for load-time work
 // ----------------------------------------------------------------------------------------------
 template <typename F>

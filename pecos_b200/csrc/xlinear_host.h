@@ -601,6 +601,89 @@ inline void load_mmap_layer(const std::string& folder, bool lazy_load, ChunkedLa
     apply_meta(meta, L);
 }
 
+// c_xlinear_compile_mmap_model (pecos/core/libpecos.cpp:133-138; HierarchicalMLModel::save_mmap inference.hpp:2575-2595, layer
+// :1907-1916, chunked matrix :413-423, csc_t matrix.hpp:386-396, rearrangement :1716-1728): writes a model in the reference's
+// mmap format from our host layout -- the same arrays, u64 row pointers global to the layer's entry array.  Needs the host
+// arrays, i.e. a model that has not been handed to an engine yet.
+inline void write_json_text(const std::string& path, const std::string& text) {
+    std::FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("could not open " + path);
+    std::fwrite(text.data(), 1, text.size(), f);
+    std::fclose(f);
+}
+
+inline void write_xlinear_mmap_model(const XLinearHostModel& m, const std::string& folder) {
+    if (system(("mkdir -p '" + folder + "'").c_str()) != 0) throw std::runtime_error("Cannot create folder: " + folder);
+    write_json_text(folder + "/param.json",
+                    "{\n\"model\": \"HierarchicalMLModel\",\n\"depth\": " + std::to_string(m.depth()) + ",\n\"is_mmap\": true\n}\n");
+    for (uint32_t d = 0; d < m.depth(); ++d) {
+        const ChunkedLayerHost& L = m.layers[d];
+        if (L.meta.empty() && !L.chunks.empty() && L.n_cols > 0 && L.entries.empty())
+            throw std::runtime_error("write_xlinear_mmap_model: the host arrays of this model were already released");
+        const std::string lf = folder + "/" + std::to_string(d) + ".model";
+        if (system(("mkdir -p '" + lf + "'").c_str()) != 0) throw std::runtime_error("Cannot create folder: " + lf);
+        char bias_txt[64];
+        std::snprintf(bias_txt, sizeof(bias_txt), "%.9g", static_cast<double>(L.bias));
+        write_json_text(lf + "/param.json",
+                        std::string("{\n\"model\": \"MLModel\",\n\"bias\": ") + bias_txt + ",\n\"pred_kwargs\": {\n\t\"only_topk\": " +
+                            std::to_string(L.only_topk) + ",\n\t\"post_processor\": \"" + L.post_processor_name +
+                            "\"\n\t},\n\"is_mmap\": true\n}\n");
+        {   // W.mmap_store
+            struct RefChunk { uint32_t col_begin, col_end, nnz_rows, has_bias; uint64_t p0, p1; };
+            std::vector<RefChunk> rc(L.n_chunks);
+            std::vector<uint32_t> ridx;
+            std::vector<uint64_t> rptr;
+            uint64_t ent_total = 0;
+            for (uint32_t p = 0; p < L.n_chunks; ++p) {
+                const ChunkHeader& h = L.chunks[p];
+                if (h.has_bias & kChunkAbsent) throw std::runtime_error("write_xlinear_mmap_model: index-sharded models cannot be written");
+                rc[p] = RefChunk{h.col_begin, h.col_begin + h.n_cols, h.nnz_rows, (h.has_bias & 1u) ? 1u : 0u, 0, 0};
+                if (h.nnz_rows == 0) continue;
+                const uint32_t* mi = L.meta.data() + h.meta_off;
+                const uint32_t* rp = mi + round_up4(h.nnz_rows);
+                ridx.insert(ridx.end(), mi, mi + h.nnz_rows);
+                for (uint32_t r = 0; r <= h.nnz_rows; ++r) rptr.push_back(h.ent_off + rp[r]);
+                ent_total = std::max<uint64_t>(ent_total, h.ent_off + rp[h.nnz_rows]);
+            }
+            MmapStoreWriter w(lf + "/W.mmap_store");
+            w.put_one<uint32_t>(L.n_chunks);
+            w.put_one<uint32_t>(L.w_rows);
+            w.put_one<uint32_t>(L.n_cols);
+            w.put_vector<RefChunk>(rc.data(), rc.size());
+            w.put_vector<uint32_t>(ridx.data(), ridx.size());
+            w.put_vector<uint64_t>(rptr.data(), rptr.size());
+            w.put_vector<ChunkEntry>(L.entries.data(), L.entries.size());
+            w.close();
+        }
+        {   // C.mmap_store: the (rearranged) code matrix -- column p holds the contiguous rows [col_begin, col_end) of chunk p
+            std::vector<uint64_t> col_ptr(static_cast<size_t>(L.n_chunks) + 1, 0);
+            for (uint32_t p = 0; p < L.n_chunks; ++p) col_ptr[p + 1] = col_ptr[p] + L.chunks[p].n_cols;
+            const uint64_t nnz = col_ptr[L.n_chunks];
+            std::vector<uint32_t> row_idx(nnz);
+            for (uint32_t p = 0; p < L.n_chunks; ++p)
+                for (uint32_t j = 0; j < L.chunks[p].n_cols; ++j) row_idx[col_ptr[p] + j] = L.chunks[p].col_begin + j;
+            std::vector<float> val(nnz, 1.0f);
+            MmapStoreWriter w(lf + "/C.mmap_store");
+            w.put_one<uint32_t>(L.n_cols);
+            w.put_one<uint32_t>(L.n_chunks);
+            w.put_one<uint64_t>(nnz);
+            w.put_multiple<uint64_t>(col_ptr.data(), col_ptr.size());
+            w.put_multiple<uint32_t>(row_idx.data(), nnz);
+            w.put_multiple<float>(val.data(), nnz);
+            w.close();
+        }
+        if (L.reordered) {  // perm[label] = rearranged position (nnz(C) for labels without a parent), perm_inv = its inverse
+            std::vector<uint32_t> perm(L.out_cols, static_cast<uint32_t>(L.label_of_col.size()));
+            for (uint32_t i = 0; i < L.label_of_col.size(); ++i)
+                if (L.label_of_col[i] < L.out_cols) perm[L.label_of_col[i]] = i;
+            MmapStoreWriter w(lf + "/perm.mmap_store");
+            w.put_vector<uint32_t>(perm.data(), perm.size());
+            w.put_vector<uint32_t>(L.label_of_col.data(), L.label_of_col.size());
+            w.close();
+        }
+    }
+}
+
 struct HierMeta { int depth = 0; bool is_mmap = false; };
 
 inline HierMeta load_hier_meta(const std::string& path) {

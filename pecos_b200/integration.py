@@ -12,6 +12,7 @@ XLINEAR_SYMBOLS = (
     "c_xlinear_load_model_from_disk",
     "c_xlinear_load_model_from_disk_ext",
     "c_xlinear_load_mmap_model_from_disk",
+    "c_xlinear_compile_mmap_model",  # host-only writer of the reference's mmap format
     "c_xlinear_destruct_model",
     "c_xlinear_get_int_attr",
     "c_xlinear_get_layer_type",

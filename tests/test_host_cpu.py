@@ -191,3 +191,38 @@ def test_single_layer_model_from_in_memory_csc_equals_the_folder_loader(clib, tm
         for k in ("chunks", "meta", "entries", "label_of_col"):
             assert np.array_equal(got[0][k], from_folder[d][k]), k
     _check_layout([clib.host_layer_layout_from_csc(*layers[-1], bias)[0]], [layers[-1][0]], [layers[-1][1]], bias)
+
+
+@pytest.mark.parametrize("permute,prune,bias", [(False, 0.0, 1.0), (True, 0.25, 1.0), (False, 0.0, -1.0)])
+def test_mmap_writer_output_loads_in_the_reference_library(tmp_path, clib, have_ref, permute, prune, bias):
+    """c_xlinear_compile_mmap_model of THIS library (host-only writer, pecos_b200/csrc/xlinear_host.h write_xlinear_mmap_model):
+    the folder it writes must load in the REFERENCE library and predict exactly what the reference predicts from the npz model
+    (and from its own compiled copy); our own mmap loader must read it back to the same chunked layout."""
+    from .util import assert_csr_parity, random_tree
+
+    folder = str(tmp_path / "m")
+    layers = random_tree(77, [5, 30, 400], 300, 20, bias=bias, permute=permute, prune=prune)
+    synth.save_xlinear_model(folder, layers, bias=bias, only_topk=7, post_processor="l2-hinge")
+    ours = str(tmp_path / "ours")
+    clib.clib_float32.c_xlinear_compile_mmap_model(os.path.join(folder, "ranker").encode(), os.path.join(ours, "ranker").encode())
+    a = clib.host_model_layout(os.path.join(folder, "ranker"))
+    b = clib.host_model_layout(os.path.join(ours, "ranker"), is_mmap=True)
+    assert len(a) == len(b)
+    for la, lb in zip(a, b):
+        for key in la:
+            assert np.array_equal(np.asarray(la[key]), np.asarray(lb[key])), key
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from oracle import ref
+
+    X = synth.make_queries(78, 60, 300, 25)
+    want = ref.RefXLinear(os.path.join(folder, "ranker")).predict(X, 6, None, 5)
+    got = ref.RefXLinear(os.path.join(ours, "ranker"), is_mmap=True).predict(X, 6, None, 5)
+    assert_csr_parity(got, want, rtol=0.0, what="reference library on the folder written by pecos_b200")
+    theirs = str(tmp_path / "theirs")
+    os.makedirs(theirs)
+    ref.compile_mmap_model(os.path.join(folder, "ranker"), os.path.join(theirs, "ranker"))
+    c = clib.host_model_layout(os.path.join(theirs, "ranker"), is_mmap=True)
+    for lb, lc in zip(b, c):
+        for key in lb:
+            assert np.array_equal(np.asarray(lb[key]), np.asarray(lc[key])), key
