@@ -31,7 +31,7 @@
 constexpr int kCmFeat = 8;                  // query features staged per pair and round (two rounds in flight per warp)
 constexpr int kCmMaxWarps = 16;
 constexpr int kCmMinWarps = 4;
-constexpr uint32_t kCmGoodWarps = 6;        // column ranges are only introduced when fewer warps than this fit unsplit
+constexpr uint32_t kCmMaxDup = 200;         // a column cap may at most double the (virtual) chunks of a layer
 constexpr uint32_t kCmSmemBudget = 224u << 10;  // dynamic shared memory a CTA may take (227 KB is the sm_100a maximum)
 constexpr uint32_t kCmMinReuse = 24;        // average pairs per chunk below which the per-chunk staging does not pay
 constexpr uint32_t kCmMinPairs = 148u * 48u; // fewer pairs than this: the query-major kernels fill the GPU better
@@ -61,18 +61,21 @@ __host__ __device__ inline size_t cm_warp_bytes(uint32_t acc_cols, uint32_t stag
            + static_cast<size_t>(acc_cols) * 32 * 4;              // accumulators [col][lane]
 }
 
-// split: the chunk's columns are cut into `split` ranges of ceil(n_cols / split) columns, each with its OWN image (only its
-// entries) -- a "virtual chunk"; a (query, chunk) pair is then scored once per range.  The lookups are repeated, the
-// accumulate work is not, and both the image and the per-warp accumulators shrink, so more warps fit (occupancy is what the
-// kernel is short of on wide chunks: profiles/r02_e).  e_max = most entries of one virtual chunk.
-inline CmShape cm_shape(uint32_t fm_words, uint32_t w_rows, uint32_t r_max, uint32_t e_max, uint32_t c_max, uint32_t n_chunks,
-                        uint32_t split = 1) {
+// col_cap: a chunk wider than col_cap columns is cut into ceil(n_cols / col_cap) column ranges of (nearly) equal width, each
+// with its OWN image (only its entries) -- a "virtual chunk"; a (query, chunk) pair is then scored once per range.  The lookups
+// are repeated for the cut chunks, the accumulate work is not, and both the image and the per-warp accumulators shrink to the
+// cap, so more warps fit (occupancy is what the kernel is short of on wide chunks: profiles/r02_e, r02_i).  The cap is chosen
+// at load so that only the few widest chunks of a layer are cut (cm_choose_cap).  e_max = most entries of one virtual chunk,
+// n_vc = number of virtual chunks.
+inline CmShape cm_shape(uint32_t fm_words, uint32_t w_rows, uint32_t r_max, uint32_t e_max, uint32_t col_cap, uint32_t n_chunks,
+                        uint32_t n_vc) {
     CmShape s;
-    if (fm_words == 0 || n_chunks == 0 || c_max == 0 || split == 0 || (c_max + split - 1) / split > 256u || r_max >= 65535u || e_max >= 65535u) return s;
+    if (fm_words == 0 || n_chunks == 0 || col_cap == 0 || col_cap > 256u || r_max >= 65535u || e_max >= 65535u) return s;
     s.direct = w_rows <= kCmDirectRows;
     s.words = s.direct ? w_rows : fm_words;
-    s.split = split;
-    s.r_cap = r_max; s.e_cap = e_max; s.acc_cols = (c_max + split - 1) / split;
+    s.col_cap = col_cap;
+    s.n_vc = n_vc;
+    s.r_cap = r_max; s.e_cap = e_max; s.acc_cols = col_cap;
     // narrow chunks do little arithmetic per round of query features: keep four rounds of cp.async in flight per warp to
     // cover the global-memory latency; wide chunks (long accumulate phases) get by with two
     s.stages = s.acc_cols <= 16u ? 4u : 2u;
@@ -98,8 +101,8 @@ inline CmPlan cm_plan(const CmShape& s, uint32_t n_chunks, uint64_t pairs, uint3
     // measured (profiles/r02_d, r02_e): with the 94 KB feature-map image of a large feature space the kernel does not beat the
     // query-major kernels (S layers 1-4: 2.0 / 2.4 / 6.3 ms vs 1.9 / 1.9 / 2.0 ms) -- only direct-table layers take it by default
     if (!force && !s.direct) return p;
-    pairs *= s.split;
-    n_chunks *= s.split;
+    pairs = pairs * s.n_vc / std::max<uint32_t>(n_chunks, 1u);  // cut chunks are visited once per column range
+    n_chunks = s.n_vc;
     if (!force && (pairs < static_cast<uint64_t>(kCmMinReuse) * n_chunks || pairs < kCmMinPairs)) return p;
     const size_t per_warp = cm_warp_bytes(s.acc_cols, s.stages);
     uint32_t warps = static_cast<uint32_t>(std::min<size_t>(kCmMaxWarps, (kCmSmemBudget - s.img_bytes - 64) / per_warp));
@@ -138,13 +141,23 @@ __device__ __forceinline__ void cm_mbar_wait(uint32_t mbar, uint32_t parity) {
     } while (!done);
 }
 
-// LOAD TIME: one CTA per VIRTUAL chunk (chunk p, column range h of S.split) packs its image (see CmShape) from the layer's
+// LOAD TIME: one CTA per VIRTUAL chunk (chunk p, column range h; S.vc_ptr[p] = first virtual chunk of chunk p) packs its image (see CmShape) from the layer's
 // device arrays: the rows' entries whose column falls into the range (contiguous inside a row: entries are stored in
 // ascending column order), columns re-based to the range.
 __global__ void __launch_bounds__(256)
 xl_cm_build_images_kernel(const LayerDev L, const CmShape S, unsigned char* __restrict__ images) {
     const uint32_t vc = blockIdx.x;
-    const uint32_t c = vc / S.split, hh = vc - c * S.split;
+    uint32_t c;
+    {
+        uint32_t lo = 0, hi = L.n_chunks;  // largest c with vc_ptr[c] <= vc
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (S.vc_ptr[mid] <= vc) lo = mid; else hi = mid;
+        }
+        c = lo;
+    }
+    const uint32_t hh = vc - S.vc_ptr[c];
+    const uint32_t n_ranges = S.vc_ptr[c + 1] - S.vc_ptr[c];
     const ChunkHeader h = L.chunks[c];
     unsigned char* img = images + static_cast<uint64_t>(vc) * S.img_bytes;
     uint32_t* hdr = reinterpret_cast<uint32_t*>(img);
@@ -154,7 +167,8 @@ xl_cm_build_images_kernel(const LayerDev L, const CmShape S, unsigned char* __re
     for (uint32_t i = threadIdx.x; i < S.img_bytes / 4u; i += blockDim.x) reinterpret_cast<uint32_t*>(img)[i] = 0u;
     __syncthreads();
     if (h.has_bias & kChunkAbsent) return;
-    const uint32_t width = (h.n_cols + S.split - 1u) / S.split;   // columns per range of THIS chunk
+    if (n_ranges == 0) return;
+    const uint32_t width = (h.n_cols + n_ranges - 1u) / n_ranges;  // columns per range of THIS chunk
     const uint32_t lo = hh * width;
     if (lo >= h.n_cols) return;                                    // empty range: no pair is ever bucketed here
     const uint32_t hi = min(h.n_cols, lo + width);
@@ -231,7 +245,7 @@ xl_cm_build_images_kernel(const LayerDev L, const CmShape S, unsigned char* __re
 __global__ void __launch_bounds__(128)
 xl_cm_count_kernel(const LayerDev L, const QueryDev X, const uint32_t* __restrict__ beam_id,
                    const uint32_t* __restrict__ beam_cnt, const uint32_t beam_stride, const uint32_t rows, CmWork w,
-                   const uint32_t split) {
+                   const uint32_t* __restrict__ vc_ptr) {
     const int lane = threadIdx.x & 31;
     const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= rows) return;
@@ -251,8 +265,9 @@ xl_cm_count_kernel(const LayerDev L, const QueryDev X, const uint32_t* __restric
         if (j < cnt) {
             w.slot_pos[static_cast<uint64_t>(q) * beam_stride + j] = run + incl - width;
             if (scored) {  // one pair per non-empty column range of the chunk
-                const uint32_t cw = (width + split - 1u) / split;
-                for (uint32_t hh = 0; hh * cw < width; ++hh) atomicAdd(&w.count[p * split + hh], 1u);
+                const uint32_t v0 = vc_ptr[p], nr = vc_ptr[p + 1] - v0;
+                const uint32_t cw = (width + nr - 1u) / max(nr, 1u);
+                for (uint32_t hh = 0; hh < nr && hh * cw < width; ++hh) atomicAdd(&w.count[v0 + hh], 1u);
             }
         }
         run += __shfl_sync(kFull, incl, 31);
@@ -300,7 +315,7 @@ xl_cm_scan_kernel(const uint32_t n_chunks, CmWork w) {
 // irrelevant: a pair's result location is fixed by its query and position)
 __global__ void __launch_bounds__(128)
 xl_cm_scatter_kernel(const LayerDev L, const uint32_t* __restrict__ beam_id, const uint32_t* __restrict__ beam_cnt,
-                     const uint32_t beam_stride, const uint32_t rows, CmWork w, const uint32_t split) {
+                     const uint32_t beam_stride, const uint32_t rows, CmWork w, const uint32_t* __restrict__ vc_ptr) {
     const int lane = threadIdx.x & 31;
     const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= rows) return;
@@ -310,9 +325,10 @@ xl_cm_scatter_kernel(const LayerDev L, const uint32_t* __restrict__ beam_id, con
         const uint4 h = *reinterpret_cast<const uint4*>(&L.chunks[p]);
         if ((h.w & kChunkAbsent) || h.y == 0) continue;
         const uint32_t pos = w.slot_pos[static_cast<uint64_t>(q) * beam_stride + j];
-        const uint32_t cw = (h.y + split - 1u) / split;
-        for (uint32_t hh = 0; hh * cw < h.y; ++hh) {
-            const uint32_t at = atomicAdd(&w.count[p * split + hh], 1u);
+        const uint32_t v0 = vc_ptr[p], nr = vc_ptr[p + 1] - v0;
+        const uint32_t cw = (h.y + nr - 1u) / max(nr, 1u);
+        for (uint32_t hh = 0; hh < nr && hh * cw < h.y; ++hh) {
+            const uint32_t at = atomicAdd(&w.count[v0 + hh], 1u);
             w.pair_q[at] = q;
             w.pair_pos[at] = pos + hh * cw;  // first candidate of this column range
         }
@@ -352,7 +368,7 @@ xl_cm_scores_kernel(const LayerDev L, const QueryDev X, const CmWork w, const Cm
     __syncthreads();
 
     // ---- this CTA's contiguous share of the (virtual-)chunk-sorted pair list
-    const uint32_t n_vc = L.n_chunks * S.split;
+    const uint32_t n_vc = S.n_vc;
     const uint64_t P = w.bucket_ptr[n_vc];
     const uint32_t begin = static_cast<uint32_t>(P * blockIdx.x / gridDim.x);
     const uint32_t end = static_cast<uint32_t>(P * (blockIdx.x + 1ull) / gridDim.x);

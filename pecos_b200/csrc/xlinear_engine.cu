@@ -1021,40 +1021,62 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
         dst.view.w_rows = src.w_rows;
         dst.view.bias = src.bias;
         dst.view.has_dup_cols = src.has_dup_cols ? 1 : 0;
-        // chunk images for the chunk-major score kernel (xlinear_cm_kernel.cuh), where the layer's shape allows it.  Chunks too
-        // wide for kCmGoodWarps warps to share an SM with an image are cut into 2..4 column ranges ("virtual chunks").  Measured
-        // on the eurlex-4k leaf (85-column chunks): 6 warps unsplit 0.94 ms vs 14 warps with 2 ranges 1.04 ms (the repeated
-        // lookups and the shared-memory pipe eat the occupancy gain: profiles/r02_e, r02_f), hence the low threshold.
+        // chunk images for the chunk-major score kernel (xlinear_cm_kernel.cuh), where the layer's shape allows it.  A column
+        // cap cuts the widest chunks of the layer into column ranges ("virtual chunks") when that lets more warps share an SM
+        // with an image: candidates are tried from "no cut" downwards, a cap may add at most 25 % virtual chunks, the cap with
+        // the most warps wins (the larger cap on ties).  Measured on the eurlex-4k leaf (chunks of 62 +- 8 columns, widest 85):
+        // no cut 6 warps 0.78 ms; every chunk in two ranges 14 warps 1.04 ms (the doubled lookups eat the gain).
         dst.cm_shape = CmShape{};
         if (dst.view.featmap) {
-            auto emax_for_split = [&](uint32_t split) {  // most entries of one virtual chunk
-                uint32_t best = 0;
-                std::vector<uint32_t> cnt(split);
-                for (const ChunkHeader& ch : src.chunks) {
-                    if ((ch.has_bias & kChunkAbsent) || ch.nnz_rows == 0 || ch.n_cols == 0) continue;
+            auto layout_for_cap = [&](uint32_t cap, std::vector<uint32_t>* vc_ptr_out, uint32_t* e_max_out) {
+                uint32_t n_vc = 0, best = 0;
+                std::vector<uint32_t> cnt;
+                if (vc_ptr_out) vc_ptr_out->assign(static_cast<size_t>(src.n_chunks) + 1, 0u);
+                for (uint32_t p = 0; p < src.n_chunks; ++p) {
+                    const ChunkHeader& ch = src.chunks[p];
+                    if (vc_ptr_out) (*vc_ptr_out)[p] = n_vc;
+                    if ((ch.has_bias & kChunkAbsent) || ch.n_cols == 0) continue;
+                    const uint32_t nr = (ch.n_cols + cap - 1) / cap;
+                    n_vc += nr;
+                    if (!e_max_out || ch.nnz_rows == 0) continue;
                     const uint32_t* rp = src.meta.data() + ch.meta_off + round_up4(ch.nnz_rows);
-                    const uint32_t width = (ch.n_cols + split - 1) / split;
-                    std::fill(cnt.begin(), cnt.end(), 0u);
+                    const uint32_t width = (ch.n_cols + nr - 1) / nr;
+                    cnt.assign(nr, 0u);
                     const ChunkEntry* en = src.entries.data() + ch.ent_off;
-                    for (uint32_t i = 0; i < rp[ch.nnz_rows]; ++i) ++cnt[std::min(en[i].col_offset / width, split - 1)];
+                    for (uint32_t i = 0; i < rp[ch.nnz_rows]; ++i) ++cnt[std::min(en[i].col_offset / width, nr - 1)];
                     for (uint32_t v : cnt) best = std::max(best, v);
                 }
-                return best;
+                if (vc_ptr_out) (*vc_ptr_out)[src.n_chunks] = n_vc;
+                if (e_max_out) *e_max_out = best;
+                return n_vc;
             };
             CmShape shape;
-            for (uint32_t split = 1; split <= 4; ++split) {
-                const CmShape cand = cm_shape(src.fm_words, src.w_rows, src.r_max, split == 1 ? dst.e_max : emax_for_split(split),
-                                              src.c_max, src.n_chunks, split);
-                if (cand.ok && (!shape.ok || cand.warps_fit > shape.warps_fit)) shape = cand;
-                if (shape.ok && shape.warps_fit >= kCmGoodWarps) break;
-                if (src.c_max < 2u * (split + 1)) break;  // nothing left to cut
+            double best_score = 0.0;
+            const uint32_t n_real = layout_for_cap(std::max<uint32_t>(src.c_max, 1u), nullptr, nullptr);
+            for (uint32_t cap = src.c_max; cap >= 4u && n_real > 0; cap = cap * 7 / 8) {
+                const uint32_t n_vc = layout_for_cap(cap, nullptr, nullptr);
+                if (static_cast<uint64_t>(n_vc) * 100u > static_cast<uint64_t>(n_real) * kCmMaxDup) break;
+                uint32_t e_cap = dst.e_max;
+                if (cap < src.c_max) layout_for_cap(cap, nullptr, &e_cap);
+                const CmShape cand = cm_shape(src.fm_words, src.w_rows, src.r_max, e_cap, cap, src.n_chunks, n_vc);
+                // expected throughput ~ warps (up to ~10: beyond that the shared-memory pipe saturates, 42 % busy at 6 warps)
+                // over the work, of which the lookups (~30 %) are repeated once per extra column range
+                const double dup = static_cast<double>(n_vc) / n_real;
+                const double score = cand.ok ? std::min<double>(cand.warps_fit, 10.0) / (0.3 * dup + 0.7) : 0.0;
+                if (score > best_score * 1.02) { best_score = score; shape = cand; }
+                if (cap * 7 / 8 == cap) break;
             }
-            const uint64_t bytes = static_cast<uint64_t>(shape.img_bytes) * src.n_chunks * std::max<uint32_t>(shape.split, 1u);
+            const uint64_t bytes = static_cast<uint64_t>(shape.img_bytes) * shape.n_vc;
             if (shape.ok && bytes <= cmimg_budget) {
                 cmimg_budget -= bytes;
+                std::vector<uint32_t> vc_ptr;
+                layout_for_cap(shape.col_cap, &vc_ptr, nullptr);
+                dst.cm_vc_ptr.upload(vc_ptr.data(), vc_ptr.size(), stream_);
+                PB200_CUDA(cudaStreamSynchronize(stream_));
+                shape.vc_ptr = dst.cm_vc_ptr.get();
                 dst.cm_shape = shape;
-                dst.cm_images.reserve(bytes);
-                xl_cm_build_images_kernel<<<src.n_chunks * shape.split, 256, 0, stream_>>>(dst.view, shape, dst.cm_images.get());
+                dst.cm_images.reserve(std::max<uint64_t>(bytes, 1));
+                xl_cm_build_images_kernel<<<shape.n_vc, 256, 0, stream_>>>(dst.view, shape, dst.cm_images.get());
                 PB200_CUDA(cudaGetLastError());
                 model_bytes_ += bytes;
             }
@@ -1238,14 +1260,14 @@ int XLinearEngine::score_layer_(size_t d, const QueryDev& q, uint32_t b_prev, in
     const bool chunk_major = cm.eligible;
     if (chunk_major) {
         const CmShape& shape = layers_[d].cm_shape;
-        const uint32_t n_vc = L.n_chunks * shape.split;
+        const uint32_t n_vc = shape.n_vc;
         CmWork w{cm_slot_pos_.get(), cm_count_.get(), cm_bucket_ptr_.get(), cm_item_ptr_.get(), cm_pair_q_.get(), cm_pair_pos_.get(),
                  cm.warps * 32u};
         PB200_CUDA(cudaMemsetAsync(w.count, 0, (static_cast<uint64_t>(n_vc) + 1) * 4, stream_));
         const uint32_t warp_grid = (rows * 32u + 127u) / 128u;
-        xl_cm_count_kernel<<<warp_grid, 128, 0, stream_>>>(L, q, bid_(cur), bcnt_(cur), beam_stride_, rows, w, shape.split);
+        xl_cm_count_kernel<<<warp_grid, 128, 0, stream_>>>(L, q, bid_(cur), bcnt_(cur), beam_stride_, rows, w, shape.vc_ptr);
         xl_cm_scan_kernel<<<1, 1024, 0, stream_>>>(n_vc, w);
-        xl_cm_scatter_kernel<<<warp_grid, 128, 0, stream_>>>(L, bid_(cur), bcnt_(cur), beam_stride_, rows, w, shape.split);
+        xl_cm_scatter_kernel<<<warp_grid, 128, 0, stream_>>>(L, bid_(cur), bcnt_(cur), beam_stride_, rows, w, shape.vc_ptr);
         auto launch_cm = [&](auto kernel) {
             kernel<<<cm.grid, cm.warps * 32, cm.smem, stream_>>>(L, q, w, shape, layers_[d].cm_images.get(), cand_at_(cand_stride_q), cand_stride_q);
         };

@@ -42,7 +42,9 @@ struct CmShape {  // load-time, per layer: geometry of the chunk images
     uint32_t words = 0;      // direct: w_rows (table entries); else fm_words (feature-map cells)
     uint32_t r_cap = 0, e_cap = 0, acc_cols = 0;
     uint32_t stages = 2;     // depth of the per-warp cp.async ring of query-feature rounds
-    uint32_t split = 1;      // column ranges per chunk ("virtual chunks"), each with its own image
+    uint32_t col_cap = 0;    // widest column range: wider chunks are cut into ranges ("virtual chunks"), each with its own image
+    uint32_t n_vc = 0;       // virtual chunks of the layer
+    const uint32_t* vc_ptr = nullptr;  // DEVICE [n_chunks + 1]: first virtual chunk of every chunk
     uint32_t warps_fit = 0;  // warps of the score kernel that fit next to one image in shared memory
     uint32_t off_lookup = 16, off_pre = 0, off_rp = 0, off_ew = 0, off_ec = 0;  // byte offsets inside an image
     uint32_t img_bytes = 0;  // image stride (multiple of 128)
@@ -170,6 +172,7 @@ private:
         DeviceBuffer<uint2> featmap;
         uint32_t e_max = 0;  // most entries of one chunk (sizes the chunk-major kernel's shared-memory staging)
         DeviceBuffer<unsigned char> cm_images;  // packed chunk images of the chunk-major kernel (empty: layer not eligible)
+        DeviceBuffer<uint32_t> cm_vc_ptr;
         CmShape cm_shape;
         LayerDev view{};
     };

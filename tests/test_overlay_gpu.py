@@ -5,8 +5,8 @@ attributes the overlay touches (`clib_float32`: a ctypes handle of the REFERENCE
 prototypes; `ann_hnsw_fn_dict`).  After `pecos_b200.integration.overlay(stand_in)`:
   * loading / predicting through the stand-in's function pointers runs on the GPU (handles are pecos_b200 handles) and returns
     the oracle's results,
-  * symbols that are not part of the hot path (c_xlinear_compile_mmap_model, HNSW train / save) still run in the reference
-    library -- a model compiled by the reference is then loaded by the overlaid loader.
+  * symbols that are not served (HNSW train, ...) still run in the reference library, and the handles they create are forwarded
+    back to it (pb200_hnsw_set_foreign).
 tests/test_overlay_cpu.py checks the same overlay against the real reference Python package (binding only, no GPU there)."""
 import ctypes
 import gc
@@ -28,7 +28,7 @@ def _run_through_the_overlay(tmp_path, gpu_clib, ref, restatement, folder, X, wa
     assert gpu_clib.clib_float32.pb200_xlinear_replicas(m.h) == 1, "the handle must come from the CUDA library"
     assert_csr_parity(m.predict(X, 8, None, 5), want, what="overlaid c_xlinear_predict_csr_f32")
     assert_csr_parity(m.predict(X.toarray(), 8, None, 5), want, what="overlaid c_xlinear_predict_drm_f32")
-    # compile with the REFERENCE (not swapped), load + predict through the overlaid mmap loader
+    # compile (overlaid: this library's host-only writer of the reference's mmap format), load + predict through the overlay
     mm = str(tmp_path / "mm")
     os.makedirs(mm)
     ref.compile_mmap_model(os.path.join(folder, "ranker"), os.path.join(mm, "ranker"))
@@ -78,7 +78,7 @@ def test_overlay_end_to_end_on_a_stand_in_corelib(tmp_path, gpu_clib, have_ref, 
                                                                    "searchers_destruct", "predict")}
     swapped = integration.overlay(stand_in)
     assert "c_xlinear_predict_csr_f32" in swapped and "c_ann_hnsw_predict_drm_ip_f32" in swapped
-    assert "c_xlinear_compile_mmap_model" not in swapped and "c_ann_hnsw_train_drm_l2_f32" not in swapped
+    assert "c_ann_hnsw_train_drm_l2_f32" not in swapped and "c_xlinear_compile_mmap_model" in swapped
 
     folder = str(tmp_path / "m")
     synth.save_xlinear_model(folder, random_tree(411, [5, 30, 300], 200, 20, bias=1.0, permute=True), bias=1.0, only_topk=6)

@@ -358,3 +358,23 @@ def test_reference_compiled_mmap_model_through_the_cuda_path(gpu_clib):
             assert_csr_parity(m.predict(Xt, **kw), want, what=f"mmap lazy={lazy} {key}")
     gold = np.load(os.path.join(GOLD, "Yt_pred_reference_golden.npy"))  # the reference repo's own Yt_pred.npz
     assert np.abs(_load(os.path.join(GOLD, "model_mmap")).predict(Xt).toarray() - gold).max() <= 1e-6
+
+
+def test_synthetic_3m_slice_matches_the_recorded_reference_result(gpu_clib, tmp_path_factory):
+    """BASELINE.json configs[2] at FULL size (3M labels, 500k features, depth 6, beam 20, top-10): the first 2,000 queries of the
+    benchmark batch against the result RECORDED FROM THE REFERENCE LIBRARY (tests/golden/make_golden_s_slice.py; no oracle/_ref
+    needed here).  The model is regenerated from the same seeds (pecos_b200/synth.py) -- reusing bench.py's cache folder when it
+    exists on this box (~1.5 min otherwise).  ids / ranks bit-exact, scores 1e-5."""
+    import tempfile
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "synthetic3m_slice", "expected.npz")
+    E = np.load(gold)
+    folder = os.path.join(os.environ.get("PB200_BENCH_CACHE", os.path.join(tempfile.gettempdir(), "pecos_b200_bench")), "synthetic-3m")
+    synth.build_workload("synthetic-3m", folder, scale_queries=8)  # writes the model if absent
+    cfg = synth.WORKLOADS["synthetic-3m"]
+    assert int(E["query_seed"]) == cfg["query_seed"]
+    X = synth.make_queries(cfg["query_seed"], int(E["query_rows"]), cfg["D"], cfg["nnz_per_row"], synth.zipf_cdf(cfg["D"]))
+    m = _load(folder)
+    got = m.predict(X, beam_size=cfg["beam_size"], only_topk=cfg["only_topk"])
+    want = smat.csr_matrix((E["data"], E["indices"].astype(np.int64), E["indptr"]), shape=(X.shape[0], cfg["layer_sizes"][-1]))
+    assert_csr_parity(got, want, what="synthetic-3m slice vs recorded reference")
