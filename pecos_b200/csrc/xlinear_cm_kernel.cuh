@@ -31,7 +31,7 @@
 constexpr int kCmFeat = 8;                  // query features staged per pair and round (two rounds in flight per warp)
 constexpr int kCmMaxWarps = 16;
 constexpr int kCmMinWarps = 4;
-constexpr uint32_t kCmMaxDup = 200;         // a column cap may at most double the (virtual) chunks of a layer
+constexpr uint32_t kCmMaxDup = 400;         // a column cap may at most quadruple the (virtual) chunks of a layer
 constexpr uint32_t kCmSmemBudget = 224u << 10;  // dynamic shared memory a CTA may take (227 KB is the sm_100a maximum)
 constexpr uint32_t kCmMinReuse = 24;        // average pairs per chunk below which the per-chunk staging does not pay
 constexpr uint32_t kCmMinPairs = 148u * 48u; // fewer pairs than this: the query-major kernels fill the GPU better

@@ -1022,10 +1022,7 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
         dst.view.bias = src.bias;
         dst.view.has_dup_cols = src.has_dup_cols ? 1 : 0;
         // chunk images for the chunk-major score kernel (xlinear_cm_kernel.cuh), where the layer's shape allows it.  A column
-        // cap cuts the widest chunks of the layer into column ranges ("virtual chunks") when that lets more warps share an SM
-        // with an image: candidates are tried from "no cut" downwards, a cap may add at most 25 % virtual chunks, the cap with
-        // the most warps wins (the larger cap on ties).  Measured on the eurlex-4k leaf (chunks of 62 +- 8 columns, widest 85):
-        // no cut 6 warps 0.78 ms; every chunk in two ranges 14 warps 1.04 ms (the doubled lookups eat the gain).
+        // cap cuts the widest chunks of the layer into column ranges ("virtual chunks") when the layer does not fit uncut.
         dst.cm_shape = CmShape{};
         if (dst.view.featmap) {
             auto layout_for_cap = [&](uint32_t cap, std::vector<uint32_t>* vc_ptr_out, uint32_t* e_max_out) {
@@ -1050,21 +1047,20 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
                 if (e_max_out) *e_max_out = best;
                 return n_vc;
             };
+            // Policy (measured, eurlex-4k leaf: chunks of 62 +- 8 columns, widest 85): uncut 6 warps 0.78 ms; cap 64 (a third of
+            // the chunks cut) 10 warps 0.94 ms; every chunk in two ranges 14 warps 1.04 ms -- more warps raise the issue rate
+            // (32 -> 43 %) but the repeated lookups (+21 % instructions) and the uneven cost of cut / uncut pairs inside the
+            // equal-count CTA shares cost more.  So: the LARGEST cap that fits at all (no cut whenever the layer fits uncut).
             CmShape shape;
-            double best_score = 0.0;
             const uint32_t n_real = layout_for_cap(std::max<uint32_t>(src.c_max, 1u), nullptr, nullptr);
-            for (uint32_t cap = src.c_max; cap >= 4u && n_real > 0; cap = cap * 7 / 8) {
+            for (uint32_t cap = std::max<uint32_t>(src.c_max, 1u); n_real > 0; cap = cap * 7 / 8) {
                 const uint32_t n_vc = layout_for_cap(cap, nullptr, nullptr);
                 if (static_cast<uint64_t>(n_vc) * 100u > static_cast<uint64_t>(n_real) * kCmMaxDup) break;
                 uint32_t e_cap = dst.e_max;
                 if (cap < src.c_max) layout_for_cap(cap, nullptr, &e_cap);
                 const CmShape cand = cm_shape(src.fm_words, src.w_rows, src.r_max, e_cap, cap, src.n_chunks, n_vc);
-                // expected throughput ~ warps (up to ~10: beyond that the shared-memory pipe saturates, 42 % busy at 6 warps)
-                // over the work, of which the lookups (~30 %) are repeated once per extra column range
-                const double dup = static_cast<double>(n_vc) / n_real;
-                const double score = cand.ok ? std::min<double>(cand.warps_fit, 10.0) / (0.3 * dup + 0.7) : 0.0;
-                if (score > best_score * 1.02) { best_score = score; shape = cand; }
-                if (cap * 7 / 8 == cap) break;
+                if (cand.ok) { shape = cand; break; }
+                if (cap < 8u) break;
             }
             const uint64_t bytes = static_cast<uint64_t>(shape.img_bytes) * shape.n_vc;
             if (shape.ok && bytes <= cmimg_budget) {

@@ -27,7 +27,7 @@ def _oracles(folder, have_ref):
 @pytest.mark.parametrize("permute,prune,sizes,bias", [(False, 0.0, [8, 64, 512], 1.0), (True, 0.2, [8, 64, 512], 1.0),
                                                       (False, 0.0, [4, 24, 1500], 1.0),   # wide chunks (~62 columns, eurlex-like)
                                                       (True, 0.1, [6, 300], -1.0),        # no bias row
-                                                      (False, 0.0, [3, 9, 1800], 1.0)])   # ~200-column chunks: cut into column ranges
+                                                      (False, 0.0, [2, 4, 1800], 1.0)])   # 450-column chunks (> 256): cut into column ranges
 def test_chunk_major_kernel_equals_default_kernels_and_oracles(tmp_path, gpu_clib, have_ref, permute, prune, sizes, bias):
     from pecos_b200.xlinear import XLinearModel
 
