@@ -525,6 +525,8 @@ def main_hnsw(args):
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             ncu_traffic = json.load(f).get(args.workload, {}).get("hnsw_search_kernel")
+            if isinstance(ncu_traffic, dict):
+                ncu_traffic = ncu_traffic.get("dram_bytes_per_launch")
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic,
