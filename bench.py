@@ -75,6 +75,7 @@ class ClockSampler(object):
         self.nvml_max = None
         self.nvml_thread = None
         self.stop_flag = False
+        self.active = True       # NVML samples are only kept while a timed region runs (pause / resume)
         self.mark_at = 0
         self.nvml_mark_at = 0
 
@@ -106,10 +107,11 @@ class ClockSampler(object):
                         bits = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
                     except Exception:
                         bits = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                    self.nvml_samples.append((mhz, bits))
+                    if self.active:
+                        self.nvml_samples.append((mhz, bits))
                 except Exception:
                     break
-                time.sleep(0.002)
+                time.sleep(0.001)
         except Exception:
             pass
 
@@ -140,6 +142,12 @@ class ClockSampler(object):
         self.mark_at = len(self.lines)
         self.nvml_mark_at = len(self.nvml_samples)
 
+    def pause(self):
+        self.active = False
+
+    def resume(self):
+        self.active = True
+
     def stop(self):
         self.stop_flag = True
         if self.nvml_thread is not None:
@@ -159,7 +167,7 @@ class ClockSampler(object):
             sm = [m for m, _ in timed]
             reasons = sorted({name for _, bits in timed for name, mask in self.NVML_REASONS if bits & mask})
             return {"sm_mhz": statistics.median(sm), "sm_max_mhz": self.nvml_max if self.nvml_max else max(sm),
-                    "reasons": reasons, "samples": len(sm), "source": "nvml, ~2 ms period, timed region only"}
+                    "reasons": reasons, "samples": len(sm), "source": "nvml, ~1 ms period, both timed regions (resident steps + end-to-end calls)"}
         if self.proc is None and not self.nvml_samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi and NVML unavailable"], "samples": 0}
         lines = self.lines[self.mark_at:]
@@ -743,8 +751,8 @@ def measure_xlinear(args, workload, rank, n_gpus, local, dist, barrier, lib, ste
     step_ms = [one_step() for _ in range(steps)]
     wall1 = time.perf_counter()
     launches = int(c.pb200_xlinear_launches(h))
+    sampler.pause()
     barrier()
-    clocks = sampler.stop() if (rank == 0 and with_clocks) else None
     total_ms = _max_over_ranks(dist, sum(step_ms))
     ms_per_step = total_ms / steps
     value = Q_total / (ms_per_step * 1e-3)
@@ -817,13 +825,17 @@ def measure_xlinear(args, workload, rank, n_gpus, local, dist, barrier, lib, ste
     for _ in range(max(3, warmup)):
         e2e_step()
     barrier()
+    sampler.resume()
     e2e_times = []
     for _ in range(steps):
         c.pb200_l2_flush()
         t0 = time.perf_counter()
         out = e2e_step()
         e2e_times.append(time.perf_counter() - t0)
+    sampler.pause()
     barrier()
+    # clocks / throttle reasons were sampled over BOTH timed regions (device-resident steps and end-to-end calls)
+    clocks = sampler.stop() if (rank == 0 and with_clocks) else None
     e2e_total = _max_over_ranks(dist, sum(e2e_times))
     e2e_value = Q_total * steps / e2e_total
     h2d = int(ip.array.nbytes + X.nnz * 8)
