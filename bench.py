@@ -355,7 +355,7 @@ def workload_config(name, cfg, X, extra=None):
 
 
 SCORE_KERNELS = ["xl_chunk_scores_kernel<stream>", "xl_chunk_scores_kernel", "xl_chunk_scores_kernel<dense>", "xl_query_warp_scores_kernel",
-                 "xl_cm_scores_kernel"]
+                 "xl_cm_scores_kernel", "xl_cmg_scores_kernel"]
 TOPK_KERNELS = ["xl_topk_kernel", "xl_topk_warp_kernel", "xl_topk_filter_kernel"]
 
 HNSW_WORKLOADS = {
@@ -778,10 +778,10 @@ def measure_xlinear(args, workload, rank, n_gpus, local, dist, barrier, lib, ste
     peak, peak_src = measured_peak_gbs()
     # per feature of a (query, chunk) pair: the chunk-major kernel (id 4) reads the query once per pair (8 B); the query-major
     # lookup kernels read one 32-byte sector of the chunk's feature map per feature on top of the query (8 B, once per query)
-    probe = np.array([8.0 if kid[2 * d] == 4 else 32.0 for d in range(depth)])
+    probe = np.array([{4: 8.0, 5: 40.0}.get(kid[2 * d], 32.0) for d in range(depth)])  # 5: query once per pair + one map sector per lookup
     pairs_per_query = st[:, 0] / np.maximum(st[:, 5] / np.maximum(X.nnz / max(Q, 1), 1e-9), 1.0)  # st5 = sum nnz over queries with a beam
     impl_scores = (32 * st[:, 0] + probe * st[:, 5] * np.maximum(pairs_per_query, 1.0) + 8 * st[:, 2] + 8 * st[:, 3] + 4 * st[:, 4]
-                   + np.where(probe > 8, 8 * st[:, 5], 0.0))
+                   + np.where(probe == 32.0, 8 * st[:, 5], 0.0))
     kernels = []
     for d in range(depth):
         kernels.append({"kernel": f"{SCORE_KERNELS[kid[2 * d]]}[layer {d}]", "ms": pm[d, 0], "algorithmic_bytes": float(impl_scores[d]),

@@ -1100,6 +1100,7 @@ XLinearEngine::XLinearEngine(std::unique_ptr<XLinearHostModel> host, int device)
     PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
     PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
     PB200_CUDA(cudaFuncSetAttribute(xl_cm_scores_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
+    PB200_CUDA(cudaFuncSetAttribute(xl_cmg_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCmSmemBudget)));
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     PB200_CUDA(cudaFuncSetAttribute(xl_query_warp_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     stats_dev_.reserve(8 * layers_.size());
@@ -1133,6 +1134,9 @@ void XLinearEngine::set_kernel_mode(int mode) {
     no_topk_filter_ = (mode == 4);
     chunk_major_ = on && (mode != 6);
     cm_force_ = (mode == 5);
+    cmg_ = (mode != 9);      // 9: as 1 without the image-less lane-per-pair kernel
+    cmg_all_ = (mode == 8 || mode == 10);  // 8: image-less lane-per-pair kernel also in place of the query-warp kernel
+    cm_image_ = (mode != 10);              // 10: as 8, and in place of the staged-image kernel too (tests: every layer on it)
 }
 
 bool XLinearEngine::has_feature_maps() const {
@@ -1250,11 +1254,29 @@ int XLinearEngine::score_layer_(size_t d, const QueryDev& q, uint32_t b_prev, in
     // and the chunks are visited by enough pairs to amortise the staging; otherwise the query-major kernels below.
     // (the statistics pass always runs the query-major kernels: their counters are the canonical ones)
     const bool cm_offsets_fit = static_cast<uint64_t>(rows) * std::max<uint32_t>(q.max_row_nnz, 1u) < (1ull << 32);  // 32-bit feature offsets
-    const CmPlan cm = (chunk_major_ && lookup && !collect_stats && cm_offsets_fit && cm_slot_pos_.capacity() && layers_[d].cm_images.capacity())
+    const CmPlan cm = (chunk_major_ && cm_image_ && lookup && !collect_stats && cm_offsets_fit && cm_slot_pos_.capacity() && layers_[d].cm_images.capacity())
                           ? cm_plan(layers_[d].cm_shape, L.n_chunks, static_cast<uint64_t>(rows) * b_prev, n_sm_, cm_force_)
                           : CmPlan{};
     const bool chunk_major = cm.eligible;
-    if (chunk_major) {
+    // the same lane-per-pair walk without a staged image (xl_cmg_scores_kernel) where the image variant does not apply: layers
+    // of large feature spaces / chunks visited by few pairs.  By default in place of the feature-map chunk kernel; kernel mode 8
+    // also in place of the query-warp kernel (A/B).
+    const CmgPlan cmg = (chunk_major_ && cmg_ && lookup && !collect_stats && !chunk_major && cm_offsets_fit && cm_slot_pos_.capacity() &&
+                         (cmg_all_ || !query_warp))
+                            ? cmg_plan(L.c_max, layers_[d].e_max, L.n_chunks, static_cast<uint64_t>(rows) * b_prev, n_sm_, cm_force_ || cmg_all_)
+                            : CmgPlan{};
+    const bool chunk_major_global = cmg.eligible;
+    if (chunk_major_global) {
+        CmWork w{cm_slot_pos_.get(), cm_count_.get(), cm_bucket_ptr_.get(), cm_item_ptr_.get(), cm_pair_q_.get(), cm_pair_pos_.get(),
+                 cmg.warps * 32u};
+        PB200_CUDA(cudaMemsetAsync(w.count, 0, (static_cast<uint64_t>(L.n_chunks) + 1) * 4, stream_));
+        const uint32_t warp_grid = (rows * 32u + 127u) / 128u;
+        xl_cm_count_kernel<<<warp_grid, 128, 0, stream_>>>(L, q, bid_(cur), bcnt_(cur), beam_stride_, rows, w, nullptr);
+        xl_cm_scan_kernel<<<1, 1024, 0, stream_>>>(L.n_chunks, w);
+        xl_cm_scatter_kernel<<<warp_grid, 128, 0, stream_>>>(L, bid_(cur), bcnt_(cur), beam_stride_, rows, w, nullptr);
+        xl_cmg_scores_kernel<<<cmg.grid, cmg.warps * 32, cmg.smem, stream_>>>(L, q, w, cand_at_(cand_stride_q), cand_stride_q, L.c_max);
+        launches_ += 3;
+    } else if (chunk_major) {
         const CmShape& shape = layers_[d].cm_shape;
         const uint32_t n_vc = shape.n_vc;
         CmWork w{cm_slot_pos_.get(), cm_count_.get(), cm_bucket_ptr_.get(), cm_item_ptr_.get(), cm_pair_q_.get(), cm_pair_pos_.get(),
@@ -1293,7 +1315,7 @@ int XLinearEngine::score_layer_(size_t d, const QueryDev& q, uint32_t b_prev, in
     }
     PB200_CUDA(cudaGetLastError());
     ++launches_;
-    layer_profile_[d].scores_kernel = chunk_major ? 4 : query_warp ? 3 : dense ? 2 : lookup ? 1 : 0;
+    layer_profile_[d].scores_kernel = chunk_major_global ? 5 : chunk_major ? 4 : query_warp ? 3 : dense ? 2 : lookup ? 1 : 0;
     return layer_profile_[d].scores_kernel;
 }
 

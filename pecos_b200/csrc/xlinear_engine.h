@@ -75,7 +75,7 @@ struct XLinearLayerProfile {
     double scores_ms = 0.0;  // score kernel of the layer
     double topk_ms = 0.0;    // top-k kernel of the layer
     uint64_t launches = 0;
-    int scores_kernel = 0;   // last launch: 0 row-list streaming, 1 feature-map lookup, 2 dense, 3 query-warp, 4 chunk-major
+    int scores_kernel = 0;   // last launch: 0 row-list streaming, 1 feature-map lookup, 2 dense, 3 query-warp, 4 chunk-major, 5 chunk-major without image
     int topk_kernel = 0;     // last launch: 0 block-wide sort, 1 warp arg-max, 2 estimate filter
 };
 
@@ -253,6 +253,9 @@ private:
     bool no_topk_filter_ = false;
     bool chunk_major_ = true;   // chunk-major scoring wherever cm_plan() finds it eligible (kernel mode 6 switches it off)
     bool cm_force_ = false;     // kernel mode 5
+    bool cmg_ = true;           // image-less lane-per-pair kernel (kernel mode 9 switches it off)
+    bool cmg_all_ = false;      // kernel modes 8, 10
+    bool cm_image_ = true;      // staged-image chunk-major kernel (kernel mode 10 switches it off)
     uint32_t n_sm_ = 148;
     DeviceBuffer<uint32_t> cm_slot_pos_, cm_count_, cm_bucket_ptr_, cm_item_ptr_, cm_pair_q_, cm_pair_pos_;
     bool force_block_topk_ = false;  // A/B switch: first-generation kernels (row-list streaming + block-wide sort)

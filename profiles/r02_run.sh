@@ -46,6 +46,10 @@ pipe) for p in 0 2 3 8; do PB200_XL_PIPELINE=$p python bench.py --steps 20 --war
    PB200_XL_KERNEL_MODE=6 PB200_XL_PIPELINE=8 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-secondary > $o/${tag}_bench_eurlex4k_mode6_pipe8.json 2> /dev/null; summ $o/${tag}_bench_eurlex4k_mode6_pipe8.json | head -1;;
 ncu_sleaf) ncu --set full --clock-control none --import-source on -k regex:xl_chunk_scores_kernel -s 11 -c 1 -o $o/${tag}_ncu_chunk_synthetic3m_leaf python bench.py --workload synthetic-3m --steps 1 --warmup 3 --no-cpu-baseline --no-secondary > /dev/null 2> $o/${tag}_ncu_sleaf.err;;
 ncu_h) ncu --set full --clock-control none -k regex:hnsw_search -s 2 -c 1 -o $o/${tag}_ncu_hnsw1m python bench.py --workload hnsw-1m --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2> $o/${tag}_ncu_h.err;;
+s8) PB200_XL_KERNEL_MODE=8 python bench.py --workload synthetic-3m --steps 5 --warmup 3 --no-cpu-baseline > $o/${tag}_bench_synthetic3m_mode8.json 2> $o/${tag}_bench_synthetic3m_mode8.err
+   summ $o/${tag}_bench_synthetic3m_mode8.json;;
+cmtests) python -m pytest tests/test_chunk_major_gpu.py tests/test_xlinear_gpu.py -x -q -m gpu > $o/${tag}_gpu_tests_cm.log 2>&1; tail -4 $o/${tag}_gpu_tests_cm.log;;
+ncu_cmg) ncu --set full --clock-control none --import-source on -k regex:xl_cmg_scores -s 5 -c 1 -o $o/${tag}_ncu_cmg_synthetic3m python bench.py --workload synthetic-3m --steps 1 --warmup 3 --no-cpu-baseline --no-secondary > /dev/null 2> $o/${tag}_ncu_cmg.err;;
 ref) python bench.py --impl reference --steps 5 --warmup 2 > $o/${tag}_bench_reference_arm.json 2> $o/${tag}_bench_reference_arm.err; cut -c1-600 $o/${tag}_bench_reference_arm.json;;
 ncu_e) ncu --set full --clock-control none --import-source on -k regex:xl_cm_scores_kernel -s ${NCU_SKIP_E:-9} -c 1 -o $o/${tag}_ncu_cm_eurlex4k python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary > /dev/null 2> $o/${tag}_ncu_e.err;;
 ncu_s) ncu --set full --clock-control none --import-source on -k regex:xl_cm_scores_kernel -s ${NCU_SKIP_S:-13} -c 1 -o $o/${tag}_ncu_cm_synthetic3m python bench.py --workload synthetic-3m --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2> $o/${tag}_ncu_s.err;;
