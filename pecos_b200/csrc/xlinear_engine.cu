@@ -1134,7 +1134,7 @@ void XLinearEngine::set_kernel_mode(int mode) {
     no_topk_filter_ = (mode == 4);
     chunk_major_ = on && (mode != 6);
     cm_force_ = (mode == 5);
-    cmg_ = (mode != 9);      // 9: as 1 without the image-less lane-per-pair kernel
+    cmg_ = (mode == 8 || mode == 9 || mode == 10);  // 9: as 1 plus the image-less lane-per-pair kernel on lookup layers without an image
     cmg_all_ = (mode == 8 || mode == 10);  // 8: image-less lane-per-pair kernel also in place of the query-warp kernel
     cm_image_ = (mode != 10);              // 10: as 8, and in place of the staged-image kernel too (tests: every layer on it)
 }
@@ -1259,8 +1259,10 @@ int XLinearEngine::score_layer_(size_t d, const QueryDev& q, uint32_t b_prev, in
                           : CmPlan{};
     const bool chunk_major = cm.eligible;
     // the same lane-per-pair walk without a staged image (xl_cmg_scores_kernel) where the image variant does not apply: layers
-    // of large feature spaces / chunks visited by few pairs.  By default in place of the feature-map chunk kernel; kernel mode 8
-    // also in place of the query-warp kernel (A/B).
+    // of large feature spaces / chunks visited by few pairs.  OPT-IN (kernel modes 8-10): bit-exact but measured slower than the
+    // query-major kernels on the 3M-label model (leaf 16.4 vs 5.4 ms: 92 registers + 224 KB keep 12 warps per SM, every lookup a
+    // dependent global load; profiles/r02_l_ncu_cmg.txt).  Mode 9: in place of the feature-map chunk kernel; 8: also of the
+    // query-warp kernel.
     const CmgPlan cmg = (chunk_major_ && cmg_ && lookup && !collect_stats && !chunk_major && cm_offsets_fit && cm_slot_pos_.capacity() &&
                          (cmg_all_ || !query_warp))
                             ? cmg_plan(L.c_max, layers_[d].e_max, L.n_chunks, static_cast<uint64_t>(rows) * b_prev, n_sm_, cm_force_ || cmg_all_)

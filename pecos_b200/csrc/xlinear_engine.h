@@ -253,7 +253,7 @@ private:
     bool no_topk_filter_ = false;
     bool chunk_major_ = true;   // chunk-major scoring wherever cm_plan() finds it eligible (kernel mode 6 switches it off)
     bool cm_force_ = false;     // kernel mode 5
-    bool cmg_ = true;           // image-less lane-per-pair kernel (kernel mode 9 switches it off)
+    bool cmg_ = false;          // image-less lane-per-pair kernel: opt-in (kernel modes 8, 9, 10); measured slower, DESIGN.md 3.3
     bool cmg_all_ = false;      // kernel modes 8, 10
     bool cm_image_ = true;      // staged-image chunk-major kernel (kernel mode 10 switches it off)
     uint32_t n_sm_ = 148;

@@ -93,8 +93,8 @@ def test_chunk_major_tiles_and_small_batches(tmp_path, gpu_clib, have_ref):
 
 @pytest.mark.parametrize("permute,prune,sizes,bias", [(False, 0.0, [4, 24, 1500], 1.0), (True, 0.2, [8, 64, 512], 1.0), (True, 0.1, [6, 300], -1.0)])
 def test_imageless_lane_per_pair_kernel_equals_query_major_kernels_and_oracles(tmp_path, gpu_clib, have_ref, permute, prune, sizes, bias):
-    """xl_cmg_scores_kernel (lane per pair, lookups / extents / entries read from global memory in chunk order; by default the
-    scorer of the lookup layers that cannot stage an image, e.g. the 3M-label leaf): kernel mode 10 puts EVERY layer on it --
+    """xl_cmg_scores_kernel (lane per pair, lookups / extents / entries read from global memory in chunk order; opt-in:
+    measured slower than the query-major kernels on the 3M-label model, kept as a validated A/B arm): kernel mode 10 puts EVERY layer on it --
     same bits as the query-major kernels (mode 6), ids bit-exact / scores 1e-5 vs both oracles."""
     from pecos_b200.xlinear import XLinearModel
 
