@@ -364,7 +364,45 @@ HNSW_WORKLOADS = {
     "hnsw-100k": dict(N=100_000, d=768, M=32, efC=100, Q=10_000, efS=200, topk=10, metric="ip"),
     "hnsw-1m": dict(N=1_000_000, d=768, M=32, efC=100, Q=50_000, efS=200, topk=10, metric="ip"),
     "hnsw-10m": dict(N=10_000_000, d=768, M=32, efC=200, Q=100_000, efS=200, topk=10, metric="ip"),
+    # SPARSE (csr) indices, SURVEY 8(f)-4.  hnsw-rcv1 has the shape of the one HNSW result the reference publishes (BASELINE.md:
+    # RCV1, 781,265 x 47,236 sparse ip, 23,149 queries, M=32, efC=100, efS=100, top-10) on synthetic tf-idf-like rows (topic
+    # mixture over a Zipf vocabulary, ~76 stored entries per row); the index is built by the reference's HNSW.train on the host.
+    "hnsw-rcv1": dict(N=781_265, d=47_236, nnz=76, M=32, efC=100, Q=23_149, efS=100, topk=10, metric="ip", sparse=True),
+    "hnsw-sparse-100k": dict(N=100_000, d=47_236, nnz=76, M=32, efC=100, Q=10_000, efS=100, topk=10, metric="ip", sparse=True),
 }
+
+
+def make_sparse_rows(seed, n, D, nnz, topics=2000):
+    """tf-idf-like csr rows: every row draws half of its features from its topic's own popularity ranking of the vocabulary and
+    half from a global Zipf law (duplicates dropped: ~nnz distinct per row), values |N(0,1)| row-L2-normalised, indices ascending."""
+    import scipy.sparse as smat
+
+    rng = np.random.default_rng(seed)
+    draws = int(nnz * 1.04)
+    cdf = np.cumsum(1.0 / (np.arange(D) + 10.0))
+    cdf /= cdf[-1]
+    z = np.searchsorted(cdf, rng.random((n, draws))).astype(np.int64)
+    topic = rng.integers(0, topics, size=n)
+    trng = np.random.default_rng(12345)  # the topics are the same for the base rows and the queries
+    mult = (2 * trng.integers(1000, D, size=topics) + 1).astype(np.int64)
+    while True:
+        bad = np.gcd(mult, D) != 1
+        if not bad.any():
+            break
+        mult[bad] += 2
+    shift = trng.integers(0, D, size=topics).astype(np.int64)
+    half = draws // 2
+    z[:, :half] = (z[:, :half] * mult[topic][:, None] + shift[topic][:, None]) % D
+    z.sort(axis=1)
+    keep = np.ones(z.shape, dtype=bool)
+    keep[:, 1:] = z[:, 1:] != z[:, :-1]
+    vals = (np.abs(rng.standard_normal(z.shape)) + 0.05).astype(np.float32) * keep
+    vals /= np.maximum(np.linalg.norm(vals, axis=1, keepdims=True), 1e-12)
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(keep.sum(axis=1), out=indptr[1:])
+    X = smat.csr_matrix((vals[keep].astype(np.float32), z[keep].astype(np.int32), indptr), shape=(n, D), dtype=np.float32)
+    X.has_sorted_indices = True
+    return X
 
 
 def hnsw_prepare(args, rank, barrier, local=0):
@@ -374,6 +412,36 @@ def hnsw_prepare(args, rank, barrier, local=0):
     reference's own (CPU, minutes to hours) HNSW.train instead."""
     cfg = dict(HNSW_WORKLOADS[args.workload])
     folder = os.path.join(args.cache_dir, args.workload)
+    if cfg.get("sparse"):
+        import scipy.sparse as smat
+
+        if rank == 0 and not os.path.exists(os.path.join(folder, "c_model", "index.mmap_store")):
+            import oracle
+            from oracle import ref
+
+            os.makedirs(folder, exist_ok=True)
+            oracle.build()
+            X = make_sparse_rows(30, cfg["N"], cfg["d"], cfg["nnz"])
+            t0 = time.perf_counter()
+            r = ref.RefHNSW.train(X, M=cfg["M"], efC=cfg["efC"], metric=cfg["metric"], threads=-1)
+            build_s = time.perf_counter() - t0
+            r.save(os.path.join(folder, "c_model"))
+            del r
+            smat.save_npz(os.path.join(folder, "X.npz"), X, compressed=False)
+            with open(os.path.join(folder, "param.json"), "w") as f:
+                json.dump({"model": "HNSW", "data_type": "csr", "metric_type": cfg["metric"], "num_item": cfg["N"],
+                           "feat_dim": cfg["d"], "pred_kwargs": {"efS": cfg["efS"], "topk": cfg["topk"], "threads": 1}}, f)
+            with open(os.path.join(folder, "build.json"), "w") as f:
+                json.dump({"builder": "reference HNSW.train (csr, all host threads)", "build_seconds": build_s,
+                           "stored_entries_per_row": X.nnz / X.shape[0]}, f)
+            del X
+        barrier()
+        Q = make_sparse_rows(31 + 1000 * rank, cfg["Q"], cfg["d"], cfg["nnz"])
+        try:
+            cfg["index_build"] = json.load(open(os.path.join(folder, "build.json")))
+        except Exception:
+            cfg["index_build"] = None
+        return folder, Q, cfg
     if rank == 0 and not os.path.exists(os.path.join(folder, "c_model", "index.mmap_store")):
         os.makedirs(folder, exist_ok=True)
         rng = np.random.default_rng(30)
@@ -415,6 +483,7 @@ def hnsw_prepare(args, rank, barrier, local=0):
 def hnsw_config(name, cfg, extra=None):
     c = {"workload": name, "base_vectors": cfg["N"], "dim": cfg["d"], "M": cfg["M"], "efC": cfg["efC"], "efS": cfg["efS"],
          "topk": cfg["topk"], "metric": cfg["metric"], "queries_per_step_per_gpu": cfg["Q"],
+         "rows": ("csr, ~%d stored entries per row" % cfg["nnz"]) if cfg.get("sparse") else "dense",
          "parallelism": "query-sharded replicas (no collective)", "index_build": cfg.get("index_build")}
     if extra:
         c.update(extra)
@@ -425,7 +494,7 @@ def hnsw_time_reference(folder, Q, cfg, steps, warmup, budget_s=60.0):
     from oracle import ref
 
     n_cores = os.cpu_count() or 1
-    m = ref.RefHNSW.load(os.path.join(folder, "c_model"), cfg["metric"])
+    m = ref.RefHNSW.load(os.path.join(folder, "c_model"), cfg["metric"], data_type="csr" if cfg.get("sparse") else "drm")
     sample = Q
     t0 = time.perf_counter()
     m.predict(sample[:2048], cfg["efS"], cfg["topk"], threads=n_cores)
@@ -447,7 +516,7 @@ def hnsw_time_reference(folder, Q, cfg, steps, warmup, budget_s=60.0):
 def main_hnsw(args):
     rank, world, local = dist_env()
     n_gpus = max(world, 1)
-    metric_name, unit = "HNSW top-10 queries/sec (efS=200)", UNIT
+    metric_name, unit = "HNSW top-10 queries/sec (efS=%d)" % HNSW_WORKLOADS[args.workload]["efS"], UNIT
     if args.impl == "reference":
         if rank != 0:
             return 0
@@ -465,7 +534,7 @@ def main_hnsw(args):
     from ctypes import POINTER, byref, c_float, c_uint32, c_uint64
 
     from pecos_b200 import core
-    from pecos_b200.core import ScipyDrmF32
+    from pecos_b200.core import ScipyCsrF32, ScipyDrmF32
     from pecos_b200.hnsw import HNSW
 
     dist = None
@@ -490,8 +559,13 @@ def main_hnsw(args):
     model = HNSW.load(folder)
     h = model.model_ptr
     nq, d, efS, topk = Q.shape[0], Q.shape[1], cfg["efS"], cfg["topk"]
-    qv = ScipyDrmF32.init_from(Q)
-    c.pb200_hnsw_resident_upload(h, byref(qv))
+    sparse = bool(cfg.get("sparse"))
+    if sparse:
+        qv = ScipyCsrF32.init_from(Q)
+        c.pb200_hnsw_resident_upload_csr(h, byref(qv))
+    else:
+        qv = ScipyDrmF32.init_from(Q)
+        c.pb200_hnsw_resident_upload(h, byref(qv))
 
     def one_step():
         c.pb200_l2_flush()
@@ -507,6 +581,11 @@ def main_hnsw(args):
     maxM, maxM0 = int(info[2]), int(info[3])
     # n_dist * 4d + n_expand * 4(1+maxM0) + hops * 4(1+maxM) + 4d + 8k per query
     bytes_per_step = n_dist * 4.0 * d + n_expand * 4.0 * (1 + maxM0) + n_hops * 4.0 * (1 + maxM) + nq * (4.0 * d + 8.0 * topk)
+    n_entries = 0
+    if sparse:  # a distance reads the row's two offsets + its stored {index, value} entries; the query row is read once
+        n_entries = int(c.pb200_hnsw_sparse_entries(h))
+        bytes_per_step = (n_entries * 8.0 + n_dist * 16.0 + n_expand * 4.0 * (1 + maxM0) + n_hops * 4.0 * (1 + maxM) +
+                          Q.nnz * 8.0 + nq * (16.0 + 8.0 * topk))
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -541,6 +620,8 @@ def main_hnsw(args):
                 "kernel": "hnsw_search_kernel", "kernel_ms": ms_per_step, "algorithmic_bytes_per_launch": bytes_per_step,
                 "peak_source": peak_src, "per_query": {"distance_evals": n_dist / nq, "expansions": n_expand / nq,
                                                        "upper_level_reads": n_hops / nq, "bytes": bytes_per_step / nq}}
+    if sparse:
+        roofline["per_query"]["stored_entries_read"] = n_entries / nq
 
     # parity gate: the first queries of the timed batch, searched by the reference library ON THE SAME index file
     gi = np.zeros((nq, topk), dtype=np.uint32)
@@ -553,11 +634,12 @@ def main_hnsw(args):
         from oracle import ref, restatement
 
         n_chk = min(512, nq)
-        ri, rd = ref.RefHNSW.load(os.path.join(folder, "c_model"), cfg["metric"]).predict(Q[:n_chk], efS, topk, threads=os.cpu_count() or 1)
+        ri, rd = ref.RefHNSW.load(os.path.join(folder, "c_model"), cfg["metric"], data_type="csr" if sparse else "drm").predict(
+            Q[:n_chk], efS, topk, threads=os.cpu_count() or 1)
         if not np.array_equal(ri, gi[:n_chk]):
             raise RuntimeError("parity gate (hnsw): neighbour ids / ranks differ from the reference library on the same index file")
         bits = bool(np.array_equal(rd.view(np.uint32), gd[:n_chk].view(np.uint32)))
-        if not bits and (restatement.host_isa() == 0 or not np.allclose(rd, gd[:n_chk], rtol=1e-5, atol=1e-7)):
+        if not bits and (sparse or restatement.host_isa() == 0 or not np.allclose(rd, gd[:n_chk], rtol=1e-5, atol=1e-7)):
             raise RuntimeError("parity gate (hnsw): distances differ from the reference library")
         parity = {"checked_queries": n_chk, "checker": "reference library (oracle/_ref), same index file", "ids_bit_equal": True,
                   "distance_bits_equal": bits}
@@ -570,6 +652,17 @@ def main_hnsw(args):
         from oracle import restatement as _rs
 
         n_rc = min(256, nq)
+        if sparse:
+            import scipy.sparse as smat
+
+            n_rc = min(128, nq)
+            Xb = smat.load_npz(os.path.join(folder, "X.npz"))
+            sc = np.asarray((Q[:n_rc] @ Xb.T).todense(), dtype=np.float32)
+            dist_np = (1.0 - sc) if cfg["metric"] == "ip" else (-2.0 * sc)  # the reference's sparse "l2" (feat_vectors.hpp:186-192)
+            exact = np.argpartition(dist_np, topk, axis=1)[:, :topk]
+            recall = float(np.mean([len(set(gi[i].tolist()) & set(exact[i].tolist())) / topk for i in range(n_rc)]))
+            del Xb, sc, dist_np
+            raise StopIteration
         base = torch.from_numpy(_rs.OracleHNSW(folder, isa=0).vectors()).to(f"cuda:{local}")
         qs = torch.from_numpy(Q[:n_rc]).to(base.device)
         sc = qs @ base.T
@@ -578,17 +671,28 @@ def main_hnsw(args):
         recall = float(np.mean([len(set(gi[i].tolist()) & set(exact[i].tolist())) / topk for i in range(n_rc)]))
         del base, sc, dist_all
         torch.cuda.empty_cache()
+    except StopIteration:
+        pass
     except Exception as e:  # noqa: BLE001
         print(f"bench.py: recall check skipped: {e}", file=sys.stderr)
     parity["recall_at_topk_vs_brute_force"] = recall
 
     # end to end through the C ABI with pinned host buffers
-    qp = lib.pinned_empty(Q.size, np.float32)
-    qp.array[:] = Q.ravel()
-    qpin = qp.array.reshape(Q.shape)
     ip = lib.pinned_empty(nq * topk, np.uint32)
     dp = lib.pinned_empty(nq * topk, np.float32)
-    qv_p = ScipyDrmF32.init_from(qpin)
+    if sparse:
+        p_ptr, p_idx, p_val = lib.pinned_empty(nq + 1, np.uint64), lib.pinned_empty(max(Q.nnz, 1), np.uint32), lib.pinned_empty(max(Q.nnz, 1), np.float32)
+        p_ptr.array[:] = Q.indptr
+        p_idx.array[:Q.nnz] = Q.indices
+        p_val.array[:Q.nnz] = Q.data
+        qv_p = ScipyCsrF32.init_from_arrays(nq, d, p_ptr.array, p_idx.array, p_val.array)
+        h2d_bytes = int(8 * (nq + 1) + 8 * Q.nnz)
+    else:
+        qp = lib.pinned_empty(Q.size, np.float32)
+        qp.array[:] = Q.ravel()
+        qpin = qp.array.reshape(Q.shape)
+        qv_p = ScipyDrmF32.init_from(qpin)
+        h2d_bytes = int(Q.nbytes)
     predict = model.fn_dict["predict"]
 
     def e2e_step():
@@ -630,9 +734,9 @@ def main_hnsw(args):
             "timing": "CUDA events around the search kernel per step, summed, max over ranks",
             "parity": parity,
             "clocks": clocks,
-            "e2e": {"value": n_gpus * nq * args.steps / e2e_total, "unit": unit, "h2d_bytes_per_step": int(Q.nbytes),
+            "e2e": {"value": n_gpus * nq * args.steps / e2e_total, "unit": unit, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": int(nq * topk * 8), "ms_per_step": 1e3 * e2e_total / args.steps,
-                    "api": "c_ann_hnsw_predict_drm_ip_f32 (pinned host queries in, host id/distance arrays out)"},
+                    "api": "c_ann_hnsw_predict_%s_%s_f32 (pinned host queries in, host id/distance arrays out)" % ("csr" if sparse else "drm", cfg["metric"])},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}))
     if dist is not None:
         dist.barrier()

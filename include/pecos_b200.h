@@ -155,6 +155,23 @@ void c_ann_hnsw_predict_drm_ip_f32(void* model_ptr, const ScipyDrmF32* pX, uint3
                                    uint32_t efS, uint32_t topk, int32_t threads, void* searchers_ptr);
 void c_ann_hnsw_predict_drm_l2_f32(void* model_ptr, const ScipyDrmF32* pX, uint32_t* ret_idx, float* ret_val,
                                    uint32_t efS, uint32_t topk, int32_t threads, void* searchers_ptr);
+/* Sparse (csr) indices: HNSW<float, FeatVecSparse{IP,L2}Simd<uint32_t, float>> (libpecos.cpp:449-450, :479-480, :497-498,
+ * :508-513, :522-523, :563-564; distances pecos/core/ann/feat_vectors.hpp:186-210 + distance_impl/common.hpp:15-86).  Rows of the
+ * index and of the queries carry strictly ascending column indices (what scipy's sort_indices()/sum_duplicates() give and
+ * the reference's block intersection assumes).  The reference's sparse "l2" evaluates to -2<x,y> (feat_vectors.hpp:186-192: the
+ * squared norms are taken as do_l2_distance_simd(x, x) = 0); this library returns the same values. */
+void* c_ann_hnsw_load_csr_ip_f32(const char* model_dir, const bool lazy_load);
+void* c_ann_hnsw_load_csr_l2_f32(const char* model_dir, const bool lazy_load);
+void c_ann_hnsw_destruct_csr_ip_f32(void* model_ptr);
+void c_ann_hnsw_destruct_csr_l2_f32(void* model_ptr);
+void* c_ann_hnsw_searchers_create_csr_ip_f32(void* model_ptr, uint32_t num_searcher);
+void* c_ann_hnsw_searchers_create_csr_l2_f32(void* model_ptr, uint32_t num_searcher);
+void c_ann_hnsw_searchers_destruct_csr_ip_f32(void* searchers_ptr);
+void c_ann_hnsw_searchers_destruct_csr_l2_f32(void* searchers_ptr);
+void c_ann_hnsw_predict_csr_ip_f32(void* model_ptr, const ScipyCsrF32* pX, uint32_t* ret_idx, float* ret_val,
+                                   uint32_t efS, uint32_t topk, int32_t threads, void* searchers_ptr);
+void c_ann_hnsw_predict_csr_l2_f32(void* model_ptr, const ScipyCsrF32* pX, uint32_t* ret_idx, float* ret_val,
+                                   uint32_t efS, uint32_t topk, int32_t threads, void* searchers_ptr);
 
 /* ============================================ pecos_b200 additions ============================================== */
 
@@ -236,16 +253,21 @@ void pb200_hnsw_resident_upload(void* model_ptr, const ScipyDrmF32* pX);
 double pb200_hnsw_resident_predict(void* model_ptr, uint32_t efS, uint32_t topk);
 void pb200_hnsw_resident_fetch(void* model_ptr, uint32_t* ret_idx, float* ret_val);
 void pb200_hnsw_get_counters(void* model_ptr, uint64_t* out);
+/* sparse (csr) indices: resident csr batch; stored entries (8 bytes each) of the base rows evaluated by the last search */
+void pb200_hnsw_resident_upload_csr(void* model_ptr, const ScipyCsrF32* pX);
+uint64_t pb200_hnsw_sparse_entries(void* model_ptr);
 /* libpecos.cpp:482-490  c_ann_hnsw_save_drm_{ip,l2}_f32(model_ptr, model_dir): for an index loaded by THIS library the saved
  * form is what it was loaded from (config.json + index.mmap_store are copied to model_dir).
  *
  * Handles are library-specific: an index TRAINED by the reference (c_ann_hnsw_train_* is not served here) is a reference
  * handle, but after the overlay the reference's Python passes it to this library's destruct / searchers / predict / save.
- * pb200_hnsw_set_foreign registers the reference's own functions for one metric (0 = ip, 1 = l2); handles and searcher tokens
+ * pb200_hnsw_set_foreign registers the reference's own functions for one index type (0 = drm ip, 1 = drm l2, 2 = csr ip, 3 = csr l2); handles and searcher tokens
  * that were not created here are forwarded to them (pecos_b200.integration.overlay does this).  Without the registration a
  * foreign handle is a fatal error with a clear message. */
 void c_ann_hnsw_save_drm_ip_f32(void* model_ptr, const char* model_dir);
 void c_ann_hnsw_save_drm_l2_f32(void* model_ptr, const char* model_dir);
+void c_ann_hnsw_save_csr_ip_f32(void* model_ptr, const char* model_dir);
+void c_ann_hnsw_save_csr_l2_f32(void* model_ptr, const char* model_dir);
 void pb200_hnsw_set_foreign(int metric, void* destruct, void* searchers_create, void* searchers_destruct, void* predict, void* save);
 
 /* base-vector rows kept in flight per warp by the bulk-copy (TMA) ring: 0 = direct loads, 4 (default) or 8; returns the

@@ -17,6 +17,14 @@
  *                                    multiply-add as compiled by GCC 13 for that clone -- checked by disassembly),
  *                            isa 1 = avx (8 partial sums), isa 2 = sse (4 partial sums), isa 3 = plain scalar loop.
  *   level-0 node record .... GraphL0 [deg][maxM0 ids][len][d floats]   hnsw.hpp:92-178
+ *   SPARSE indices (csr) ... FeatVecSparse record [deg][maxM0 ids][len][len floats][len u32 indices] at byte offset
+ *                            mem_start_of_node[node]                      feat_vectors.hpp:97-131, hnsw.hpp:122-176
+ *   hno_sparse_dot ......... do_dot_product_sparse_block<4>               distance_impl/common.hpp:15-86   (the `avx` clone,
+ *                            x86.hpp:305-428, intersects the same 4x4 blocks with SSE compares and adds the matched
+ *                            products of a block in ascending position: the same sum for strictly ascending indices)
+ *   hno_sparse_distance .... FeatVecSparse{IP,L2}Simd::distance           feat_vectors.hpp:186-210.  NOTE the reference's
+ *                            sparse L2 calls do_l2_distance_simd(x, x, len) for the squared norms (feat_vectors.hpp:189-190),
+ *                            i.e. the distance of x to itself = 0: its "l2" is -2 * <x, y>.  Restated literally.
  *   upper levels ........... GraphL1                                     hnsw.hpp:180-220
  */
 #include <math.h>
@@ -37,6 +45,8 @@ typedef struct {
     const uint32_t* l1_buffer;
     int metric; /* 0 = ip, 1 = l2 */
     int isa;    /* see header */
+    int sparse; /* 1: FeatVecSparse records located by mem_start (variable size) */
+    const uint64_t* mem_start; /* [num_node + 1] byte offsets into l0_buffer (sparse only) */
 } hno_index_t;
 
 static float hno_dot_or_l2(const float* x, const float* y, size_t len, int metric, int isa) {
@@ -144,11 +154,74 @@ static void heap_pop(hno_pair_t* h, long* n, hno_comp_t comp) {
     *n -= 1;
 }
 
-static const uint32_t* l0_neighborhood(const hno_index_t* ix, uint32_t node) {
-    return (const uint32_t*)(ix->l0_buffer + (size_t)node * ix->l0_node_mem_size);
+static const uint8_t* l0_record(const hno_index_t* ix, uint32_t node) {
+    return ix->l0_buffer + (ix->sparse ? (size_t)ix->mem_start[node] : (size_t)node * ix->l0_node_mem_size);
 }
+static const uint32_t* l0_neighborhood(const hno_index_t* ix, uint32_t node) { return (const uint32_t*)l0_record(ix, node); }
 static const float* l0_vector(const hno_index_t* ix, uint32_t node) {
-    return (const float*)(ix->l0_buffer + (size_t)node * ix->l0_node_mem_size + (size_t)(1 + ix->l0_max_degree) * 4 + 4);
+    return (const float*)(l0_record(ix, node) + (size_t)(1 + ix->l0_max_degree) * 4 + 4);
+}
+
+/* do_dot_product_sparse_block<4> (distance_impl/common.hpp:15-86) */
+float hno_sparse_dot(size_t s_a, const float* x, const uint32_t* A, size_t s_b, const float* y, const uint32_t* B) {
+    size_t i_a = 0, i_b = 0;
+    volatile float ret = 0.0f;
+    const size_t st_a = (s_a / 4) * 4, st_b = (s_b / 4) * 4;
+    if (i_a < st_a && i_b < st_b) {
+        for (;;) {
+            for (int i = 0; i < 4; ++i) {
+                for (int j = 0; j < 4; ++j) {
+                    if (A[i_a + i] == B[i_b + j]) {
+                        volatile float p = x[i_a + i] * y[i_b + j];
+                        ret = ret + p;
+                        break;
+                    }
+                }
+            }
+            const uint32_t a_last = A[i_a + 3], b_last = B[i_b + 3];
+            if (a_last <= b_last) { i_a += 4; if (i_a == st_a) break; }
+            if (a_last >= b_last) { i_b += 4; if (i_b == st_b) break; }
+        }
+    }
+    if (i_a < s_a && i_b < s_b) {
+        for (;;) {
+            while (A[i_a] < B[i_b]) { if (++i_a == s_a) return ret; }
+            while (B[i_b] < A[i_a]) { if (++i_b == s_b) return ret; }
+            if (A[i_a] == B[i_b]) {
+                volatile float p = x[i_a] * y[i_b];
+                ret = ret + p;
+                if (++i_a == s_a || ++i_b == s_b) return ret;
+            }
+        }
+    }
+    return ret;
+}
+
+/* FeatVecSparse{IP,L2}Simd::distance (feat_vectors.hpp:186-210) */
+float hno_sparse_distance(size_t s_a, const float* x, const uint32_t* A, size_t s_b, const float* y, const uint32_t* B, int metric,
+                          int isa) {
+    const float dot = hno_sparse_dot(s_a, x, A, s_b, y, B);
+    if (metric == 0) return (float)(1.0 - dot);
+    volatile float x_sq = hno_dot_or_l2(x, x, s_a, 1, isa); /* do_l2_distance_simd(x, x, s_a): zero for finite values */
+    volatile float y_sq = hno_dot_or_l2(y, y, s_b, 1, isa);
+    volatile float sq = x_sq + y_sq;
+    return (float)(sq - 2.0 * dot);
+}
+
+typedef struct {
+    const float* dense;      /* dense query row, or */
+    uint32_t nnz;            /* sparse query row */
+    const float* val;
+    const uint32_t* idx;
+} hno_query_t;
+
+static float query_distance(const hno_index_t* ix, const hno_query_t* q, uint32_t node) {
+    if (!ix->sparse) return hno_distance(q->dense, l0_vector(ix, node), ix->feat_dim, ix->metric, ix->isa);
+    const uint8_t* fv = l0_record(ix, node) + (size_t)(1 + ix->l0_max_degree) * 4;
+    const uint32_t len = *(const uint32_t*)fv;
+    const float* val = (const float*)(fv + 4);
+    const uint32_t* idx = (const uint32_t*)(fv + 4 + (size_t)len * 4);
+    return hno_sparse_distance(q->nnz, q->val, q->idx, len, val, idx, ix->metric, ix->isa);
 }
 static const uint32_t* l1_neighborhood(const hno_index_t* ix, uint32_t node, uint32_t level) {
     return ix->l1_buffer + (size_t)node * ix->l1_node_mem_size + (size_t)(level - 1) * ix->l1_level_mem_size;
@@ -157,8 +230,8 @@ static const uint32_t* l1_neighborhood(const hno_index_t* ix, uint32_t node, uin
 /* Search the index for every query row; out arrays are Q x topk and must be zero-initialised by the caller
  * (libpecos.cpp:554-558 only writes the entries that exist).  counters (may be NULL): per query
  * {distance evaluations, level-0 expansions, upper-level hops (neighbourhood reads on levels >= 1)}. */
-int hno_search(const hno_index_t* ix, const float* Q, uint32_t nq, uint32_t efS, uint32_t topk, uint32_t* out_idx,
-               float* out_val, uint64_t* counters) {
+static int search_core(const hno_index_t* ix, const float* Q, const uint64_t* q_indptr, const uint32_t* q_idx, const float* q_val,
+                       uint32_t nq, uint32_t efS, uint32_t topk, uint32_t* out_idx, float* out_val, uint64_t* counters) {
     const uint32_t d = ix->feat_dim;
     const uint32_t ef = efS > topk ? efS : topk;
     uint8_t* visited = (uint8_t*)calloc(ix->num_node ? ix->num_node : 1, 1);
@@ -168,10 +241,18 @@ int hno_search(const hno_index_t* ix, const float* Q, uint32_t nq, uint32_t efS,
     if (!visited || !topq || !candq || !touched) return 1;
 
     for (uint32_t qi = 0; qi < nq; ++qi) {
-        const float* q = Q + (size_t)qi * d;
+        hno_query_t qrow = {0, 0, 0, 0};
+        if (ix->sparse) {
+            qrow.nnz = (uint32_t)(q_indptr[qi + 1] - q_indptr[qi]);
+            qrow.val = q_val + q_indptr[qi];
+            qrow.idx = q_idx + q_indptr[qi];
+        } else {
+            qrow.dense = Q + (size_t)qi * d;
+        }
+        const hno_query_t* q = &qrow;
         uint64_t n_dist = 0, n_expand = 0, n_hops = 0;
         uint32_t curr = ix->init_node;
-        float curr_dist = hno_distance(q, l0_vector(ix, curr), d, ix->metric, ix->isa);
+        float curr_dist = query_distance(ix, q, curr);
         ++n_dist;
         for (uint32_t level = ix->max_level; level >= 1; --level) {
             int changed = 1;
@@ -182,14 +263,14 @@ int hno_search(const hno_index_t* ix, const float* Q, uint32_t nq, uint32_t efS,
                 ++n_hops;
                 for (uint32_t j = 0; j < deg; ++j) {
                     const uint32_t next = nb[1 + j];
-                    const float nd = hno_distance(q, l0_vector(ix, next), d, ix->metric, ix->isa);
+                    const float nd = query_distance(ix, q, next);
                     ++n_dist;
                     if (nd < curr_dist) { curr_dist = nd; curr = next; changed = 1; }
                 }
             }
         }
         long ntop = 0, ncand = 0, ntouched = 0;
-        float ub = hno_distance(q, l0_vector(ix, curr), d, ix->metric, ix->isa);
+        float ub = query_distance(ix, q, curr);
         ++n_dist;
         hno_pair_t p0 = {ub, curr};
         heap_push(topq, &ntop, p0, comp_less);
@@ -206,7 +287,7 @@ int hno_search(const hno_index_t* ix, const float* Q, uint32_t nq, uint32_t efS,
                 const uint32_t next = nb[1 + j];
                 if (visited[next]) continue;
                 visited[next] = 1; touched[ntouched++] = next;
-                const float nd = hno_distance(q, l0_vector(ix, next), d, ix->metric, ix->isa);
+                const float nd = query_distance(ix, q, next);
                 ++n_dist;
                 if ((uint32_t)ntop < ef || nd < ub) {
                     hno_pair_t pn = {nd, next};
@@ -235,4 +316,17 @@ int hno_search(const hno_index_t* ix, const float* Q, uint32_t nq, uint32_t efS,
     }
     free(visited); free(topq); free(candq); free(touched);
     return 0;
+}
+
+int hno_search(const hno_index_t* ix, const float* Q, uint32_t nq, uint32_t efS, uint32_t topk, uint32_t* out_idx,
+               float* out_val, uint64_t* counters) {
+    if (ix->sparse) return 2;
+    return search_core(ix, Q, 0, 0, 0, nq, efS, topk, out_idx, out_val, counters);
+}
+
+/* sparse (csr) queries against a sparse index: rows are [q_indptr[i], q_indptr[i+1]) of q_idx / q_val, indices ascending */
+int hno_search_csr(const hno_index_t* ix, const uint64_t* q_indptr, const uint32_t* q_idx, const float* q_val, uint32_t nq,
+                   uint32_t efS, uint32_t topk, uint32_t* out_idx, float* out_val, uint64_t* counters) {
+    if (!ix->sparse) return 2;
+    return search_core(ix, 0, q_indptr, q_idx, q_val, nq, efS, topk, out_idx, out_val, counters);
 }

@@ -71,11 +71,14 @@ def bind(L):
     L.c_mlmodel_predict_on_selected_outputs_csr_f32.argtypes = [c_void_p, POINTER(ScipyCsrF32)] + mls
     L.c_mlmodel_predict_on_selected_outputs_drm_f32.restype = None
     L.c_mlmodel_predict_on_selected_outputs_drm_f32.argtypes = [c_void_p, POINTER(ScipyDrmF32)] + mls
-    for metric in ("ip", "l2"):
-        sfx = f"drm_{metric}_f32"
+    for data_type, metric in (("drm", "ip"), ("drm", "l2"), ("csr", "ip"), ("csr", "l2")):
+        sfx = f"{data_type}_{metric}_f32"
+        mat_t = ScipyDrmF32 if data_type == "drm" else ScipyCsrF32
+        if not hasattr(L, "c_ann_hnsw_load_" + sfx):
+            continue
         f = getattr(L, "c_ann_hnsw_train_" + sfx)
         f.restype = c_void_p
-        f.argtypes = [POINTER(ScipyDrmF32), c_uint32, c_uint32, c_int, c_int]
+        f.argtypes = [POINTER(mat_t), c_uint32, c_uint32, c_int, c_int]
         f = getattr(L, "c_ann_hnsw_load_" + sfx)
         f.restype = c_void_p
         f.argtypes = [c_char_p, c_bool]
@@ -93,7 +96,7 @@ def bind(L):
         f.argtypes = [c_void_p]
         f = getattr(L, "c_ann_hnsw_predict_" + sfx)
         f.restype = None
-        f.argtypes = [c_void_p, POINTER(ScipyDrmF32), POINTER(c_uint32), POINTER(c_float), c_uint32, c_uint32,
+        f.argtypes = [c_void_p, POINTER(mat_t), POINTER(c_uint32), POINTER(c_float), c_uint32, c_uint32,
                       c_int32, c_void_p]
     return L
 
@@ -235,45 +238,55 @@ def compile_mmap_model(npz_ranker_folder, mmap_folder):
 
 
 class RefHNSW(object):
-    """Reference HNSW index handle (dense float32, ip or l2)."""
+    """Reference HNSW index handle (float32; dense ``drm`` or sparse ``csr`` rows; ip or l2)."""
 
-    def __init__(self, handle, metric):
-        self.h, self.metric = handle, metric
+    def __init__(self, handle, metric, data_type="drm"):
+        self.h, self.metric, self.data_type = handle, metric, data_type
+
+    @staticmethod
+    def _mat(X, data_type):
+        """-> (ctypes matrix, keep-alive).  csr rows get sorted indices like pecos/ann/hnsw/model.py does."""
+        if data_type == "drm":
+            X = np.ascontiguousarray(X, dtype=np.float32)
+            return ScipyDrmF32.init_from(X), X
+        X = smat.csr_matrix(X, dtype=np.float32)
+        X.sort_indices()
+        return ScipyCsrF32.init_from(X), X
 
     @classmethod
     def train(cls, X, M=32, efC=100, metric="ip", threads=-1, max_level_upper_bound=-1):
         L = lib()
-        X = np.ascontiguousarray(X, dtype=np.float32)
-        cx = ScipyDrmF32.init_from(X)
-        h = getattr(L, f"c_ann_hnsw_train_drm_{metric}_f32")(byref(cx), M, efC, threads, max_level_upper_bound)
-        return cls(c_void_p(h), metric)
+        data_type = "csr" if smat.issparse(X) else "drm"
+        cx, keep = cls._mat(X, data_type)
+        h = getattr(L, f"c_ann_hnsw_train_{data_type}_{metric}_f32")(byref(cx), M, efC, threads, max_level_upper_bound)
+        return cls(c_void_p(h), metric, data_type)
 
     @classmethod
-    def load(cls, c_model_dir, metric="ip", lazy_load=False):
-        h = getattr(lib(), f"c_ann_hnsw_load_drm_{metric}_f32")(c_model_dir.encode(), lazy_load)
-        return cls(c_void_p(h), metric)
+    def load(cls, c_model_dir, metric="ip", lazy_load=False, data_type="drm"):
+        h = getattr(lib(), f"c_ann_hnsw_load_{data_type}_{metric}_f32")(c_model_dir.encode(), lazy_load)
+        return cls(c_void_p(h), metric, data_type)
+
+    def _fn(self, slot):
+        return getattr(lib(), f"c_ann_hnsw_{slot}_{self.data_type}_{self.metric}_f32")
 
     def save(self, c_model_dir):
         os.makedirs(c_model_dir, exist_ok=True)
-        getattr(lib(), f"c_ann_hnsw_save_drm_{self.metric}_f32")(self.h, c_model_dir.encode())
+        self._fn("save")(self.h, c_model_dir.encode())
 
     def predict(self, X, efS, topk, threads=1):
-        L = lib()
-        X = np.ascontiguousarray(X, dtype=np.float32)
-        cx = ScipyDrmF32.init_from(X)
+        cx, keep = self._mat(X, self.data_type)
         idx = np.zeros((X.shape[0], topk), dtype=np.uint32)
         val = np.zeros((X.shape[0], topk), dtype=np.float32)
-        searchers = c_void_p(getattr(L, f"c_ann_hnsw_searchers_create_drm_{self.metric}_f32")(self.h, max(1, threads)))
-        getattr(L, f"c_ann_hnsw_predict_drm_{self.metric}_f32")(
-            self.h, byref(cx), idx.ctypes.data_as(POINTER(c_uint32)), val.ctypes.data_as(POINTER(c_float)), efS, topk,
-            threads, searchers)
-        getattr(L, f"c_ann_hnsw_searchers_destruct_drm_{self.metric}_f32")(searchers)
+        searchers = c_void_p(self._fn("searchers_create")(self.h, max(1, threads)))
+        self._fn("predict")(self.h, byref(cx), idx.ctypes.data_as(POINTER(c_uint32)), val.ctypes.data_as(POINTER(c_float)), efS,
+                            topk, threads, searchers)
+        self._fn("searchers_destruct")(searchers)
         return idx, val
 
     def __del__(self):
         try:
             if self.h:
-                getattr(lib(), f"c_ann_hnsw_destruct_drm_{self.metric}_f32")(self.h)
+                self._fn("destruct")(self.h)
                 self.h = None
         except Exception:
             pass

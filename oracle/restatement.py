@@ -199,7 +199,7 @@ class _HnswIndex(Structure):
                 ("l0_buffer", ctypes.c_void_p),
                 ("l1_max_level", c_uint32), ("l1_max_degree", c_uint32), ("l1_node_mem_size", c_uint32),
                 ("l1_level_mem_size", c_uint32), ("l1_buffer", ctypes.c_void_p),
-                ("metric", c_int), ("isa", c_int)]
+                ("metric", c_int), ("isa", c_int), ("sparse", c_int), ("mem_start", ctypes.c_void_p)]
 
 
 def _hnsw_lib():
@@ -208,6 +208,12 @@ def _hnsw_lib():
         L.hno_search.restype = c_int
         L.hno_search.argtypes = [POINTER(_HnswIndex), POINTER(c_float), c_uint32, c_uint32, c_uint32, POINTER(c_uint32),
                                  POINTER(c_float), POINTER(c_uint64)]
+        L.hno_search_csr.restype = c_int
+        L.hno_search_csr.argtypes = [POINTER(_HnswIndex), POINTER(c_uint64), POINTER(c_uint32), POINTER(c_float), c_uint32, c_uint32,
+                                     c_uint32, POINTER(c_uint32), POINTER(c_float), POINTER(c_uint64)]
+        L.hno_sparse_distance.restype = c_float
+        L.hno_sparse_distance.argtypes = [ctypes.c_size_t, POINTER(c_float), POINTER(c_uint32), ctypes.c_size_t, POINTER(c_float),
+                                          POINTER(c_uint32), c_int, c_int]
         L.hno_distance.restype = c_float
         L.hno_distance.argtypes = [POINTER(c_float), POINTER(c_float), c_uint32, c_int, c_int]
         L._hnsw_ready = True
@@ -245,14 +251,15 @@ class OracleHNSW(object):
 
     def __init__(self, model_dir, isa=0):
         param = json.load(open(os.path.join(model_dir, "param.json")))
-        assert param["data_type"] == "drm", "only dense indices are restated"
+        self.sparse = param["data_type"] == "csr"
         self.metric = {"ip": 0, "l2": 1}[param["metric_type"]]
         blocks = read_mmap_store(os.path.join(model_dir, "c_model", "index.mmap_store"))
         u32 = lambda b: int(b.view(np.uint32)[0])  # noqa: E731
         it = iter(blocks)
         self.num_node, self.maxM, self.maxM0, self.efC, self.max_level, self.init_node = [u32(next(it)) for _ in range(6)]
         l0_num, self.feat_dim, self.l0_max_degree, self.l0_node_mem = [u32(next(it)) for _ in range(4)]
-        next(it); next(it)  # mem_start_of_node: size + data
+        next(it)            # mem_start_of_node: size,
+        self.mem_start = np.ascontiguousarray(next(it)).view(np.uint64)  # data (num_node + 1 byte offsets)
         next(it)            # buffer size
         self.l0 = np.ascontiguousarray(next(it))
         l1_num, self.l1_max_level, self.l1_max_degree, self.l1_node_mem, self.l1_level_mem = [u32(next(it)) for _ in range(5)]
@@ -261,7 +268,10 @@ class OracleHNSW(object):
         if self.l1.size == 0:
             self.l1 = np.zeros(4, dtype=np.uint8)
         self.isa = isa
-        assert self.l0_node_mem == (1 + self.l0_max_degree) * 4 + 4 + 4 * self.feat_dim
+        if self.sparse:
+            assert self.mem_start.size == self.num_node + 1 and int(self.mem_start[-1]) == self.l0.size
+        else:
+            assert self.l0_node_mem == (1 + self.l0_max_degree) * 4 + 4 + 4 * self.feat_dim
 
     def _struct(self):
         s = _HnswIndex()
@@ -273,22 +283,48 @@ class OracleHNSW(object):
                                                                                       self.l1_node_mem, self.l1_level_mem)
         s.l1_buffer = self.l1.ctypes.data
         s.metric, s.isa = self.metric, self.isa
+        s.sparse = 1 if self.sparse else 0
+        s.mem_start = self.mem_start.ctypes.data if self.sparse else None
         return s
 
     def vectors(self):
+        if self.sparse:  # -> scipy csr of the stored rows
+            import scipy.sparse as smat
+            off = (1 + self.l0_max_degree) * 4
+            indptr, idx, val = [0], [], []
+            for i in range(self.num_node):
+                b = int(self.mem_start[i]) + off
+                n = int(self.l0[b:b + 4].view(np.uint32)[0])
+                val.append(self.l0[b + 4:b + 4 + 4 * n].view(np.float32))
+                idx.append(self.l0[b + 4 + 4 * n:b + 4 + 8 * n].view(np.uint32))
+                indptr.append(indptr[-1] + n)
+            return smat.csr_matrix((np.concatenate(val), np.concatenate(idx), indptr), shape=(self.num_node, self.feat_dim))
         rec = self.l0.reshape(self.num_node, self.l0_node_mem)
         off = (1 + self.l0_max_degree) * 4 + 4
         return np.ascontiguousarray(rec[:, off:]).view(np.float32).reshape(self.num_node, self.feat_dim)
 
     def predict(self, X, efS, topk, return_counters=False):
         L = _hnsw_lib()
-        X = np.ascontiguousarray(X, dtype=np.float32)
-        assert X.shape[1] == self.feat_dim
         nq = X.shape[0]
         idx = np.zeros((nq, topk), dtype=np.uint32)
         val = np.zeros((nq, topk), dtype=np.float32)
         cnt = np.zeros((nq, 3), dtype=np.uint64)
         s = self._struct()
+        if self.sparse:
+            import scipy.sparse as smat
+            X = smat.csr_matrix(X, dtype=np.float32)
+            X.sort_indices()
+            assert X.shape[1] == self.feat_dim
+            indptr = np.ascontiguousarray(X.indptr, dtype=np.uint64)
+            indices = np.ascontiguousarray(X.indices, dtype=np.uint32)
+            data = np.ascontiguousarray(X.data, dtype=np.float32)
+            rc = L.hno_search_csr(byref(s), indptr.ctypes.data_as(POINTER(c_uint64)), indices.ctypes.data_as(POINTER(c_uint32)),
+                                  data.ctypes.data_as(POINTER(c_float)), nq, efS, topk, idx.ctypes.data_as(POINTER(c_uint32)),
+                                  val.ctypes.data_as(POINTER(c_float)), cnt.ctypes.data_as(POINTER(c_uint64)))
+            assert rc == 0
+            return (idx, val, cnt) if return_counters else (idx, val)
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        assert X.shape[1] == self.feat_dim
         rc = L.hno_search(byref(s), X.ctypes.data_as(POINTER(c_float)), nq, efS, topk, idx.ctypes.data_as(POINTER(c_uint32)),
                           val.ctypes.data_as(POINTER(c_float)), cnt.ctypes.data_as(POINTER(c_uint64)))
         assert rc == 0

@@ -347,9 +347,10 @@ class B200CoreLib(object):
         c = self.clib_float32
         fp = B200CoreLib.fillprototype
         self.ann_hnsw_fn_dict = {}
-        for metric in ("ip", "l2"):
-            key = ("drm", metric)
-            suffix = "drm_{}_f32".format(metric)
+        for data_type, metric in (("drm", "ip"), ("drm", "l2"), ("csr", "ip"), ("csr", "l2")):
+            key = (data_type, metric)
+            suffix = "{}_{}_f32".format(data_type, metric)
+            mat_t = ScipyDrmF32 if data_type == "drm" else ScipyCsrF32
             if not hasattr(c, "c_ann_hnsw_load_" + suffix):
                 continue
             load = getattr(c, "c_ann_hnsw_load_" + suffix)
@@ -361,9 +362,12 @@ class B200CoreLib(object):
             s_destruct = getattr(c, "c_ann_hnsw_searchers_destruct_" + suffix)
             fp(s_destruct, None, [c_void_p])
             predict = getattr(c, "c_ann_hnsw_predict_" + suffix)
-            fp(predict, None, [c_void_p, POINTER(ScipyDrmF32), POINTER(c_uint32), POINTER(c_float), c_uint32,
+            fp(predict, None, [c_void_p, POINTER(mat_t), POINTER(c_uint32), POINTER(c_float), c_uint32,
                                c_uint32, c_int32, c_void_p])
+            save = getattr(c, "c_ann_hnsw_save_" + suffix)
+            fp(save, None, [c_void_p, c_char_p])
             self.ann_hnsw_fn_dict[key] = {
+                "save": save,
                 "load": load,
                 "destruct": destruct,
                 "searchers_create": s_create,
@@ -413,6 +417,8 @@ class B200CoreLib(object):
         fp(c.pb200_hnsw_replicas, c_uint32, [c_void_p])
         fp(c.pb200_hnsw_vcap_retries, c_uint32, [c_void_p])
         fp(c.pb200_hnsw_resident_upload, None, [c_void_p, POINTER(ScipyDrmF32)])
+        fp(c.pb200_hnsw_resident_upload_csr, None, [c_void_p, POINTER(ScipyCsrF32)])
+        fp(c.pb200_hnsw_sparse_entries, c_uint64, [c_void_p])
         fp(c.pb200_hnsw_resident_predict, c_double, [c_void_p, c_uint32, c_uint32])
         fp(c.pb200_hnsw_resident_fetch, None, [c_void_p, POINTER(c_uint32), POINTER(c_float)])
         fp(c.pb200_hnsw_get_counters, None, [c_void_p, POINTER(c_uint64)])

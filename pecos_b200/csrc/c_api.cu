@@ -845,7 +845,7 @@ pb200::HnswEngine& hnsw_of(void* ptr) {
     return *static_cast<HnswHandle*>(ptr)->engines.at(0);
 }
 
-void* hnsw_load(const char* model_dir, bool lazy_load, int metric) {
+void* hnsw_load(const char* model_dir, bool lazy_load, int metric, bool sparse) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0)
         throw std::runtime_error("no CUDA device visible: pecos_b200 has no CPU fallback");
@@ -854,7 +854,7 @@ void* hnsw_load(const char* model_dir, bool lazy_load, int metric) {
     h->engines.resize(devs.size());
     // the host index is a view of the memory-mapped file: every replica maps it again (shared page cache)
     std::vector<std::unique_ptr<pb200::HnswHostIndex>> views(devs.size());
-    for (size_t i = 0; i < devs.size(); ++i) views[i] = pb200::load_hnsw_index(model_dir, metric, lazy_load);
+    for (size_t i = 0; i < devs.size(); ++i) views[i] = pb200::load_hnsw_index(model_dir, metric, lazy_load, sparse);
     fan_out(devs.size(), [&](size_t i) { h->engines[i] = std::make_unique<pb200::HnswEngine>(std::move(views[i]), devs[i]); });
     h->model_dir = model_dir;
     return h.release();
@@ -875,6 +875,22 @@ void hnsw_predict(void* model_ptr, const ScipyDrmF32* pX, uint32_t* ret_idx, flo
     });
 }
 
+// sparse index, csr queries: the same row fan-out; every engine gets its rows of the caller's csr arrays
+void hnsw_predict(void* model_ptr, const ScipyCsrF32* pX, uint32_t* ret_idx, float* ret_val, uint32_t efS, uint32_t topk,
+                  int metric) {
+    PB200_LOCK_HNSW(model_ptr)
+    auto& H = *static_cast<HnswHandle*>(model_ptr);
+    if (hnsw_of(model_ptr).metric() != metric) throw std::runtime_error("HNSW handle was loaded with a different metric");
+    size_t n = H.engines.size();
+    if (static_cast<uint64_t>(pX->rows) < static_cast<uint64_t>(kFanOutMinRows) * n) n = 1;
+    fan_out(n, [&](size_t i) {
+        const uint32_t r0 = static_cast<uint32_t>(static_cast<uint64_t>(pX->rows) * i / n);
+        const uint32_t r1 = static_cast<uint32_t>(static_cast<uint64_t>(pX->rows) * (i + 1) / n);
+        H.engines[i]->predict_csr(pX->row_ptr + r0, pX->col_idx, pX->val, r1 - r0, pX->cols, efS, topk,
+                                  ret_idx + static_cast<uint64_t>(r0) * topk, ret_val + static_cast<uint64_t>(r0) * topk);
+    });
+}
+
 }  // namespace
 
 extern "C" {
@@ -886,7 +902,7 @@ extern "C" {
 // instead of undefined behaviour).
 typedef void (*hnsw_destruct_fn)(void*);
 typedef void* (*hnsw_searchers_create_fn)(void*, uint32_t);
-typedef void (*hnsw_predict_fn)(void*, const ScipyDrmF32*, uint32_t*, float*, uint32_t, uint32_t, int32_t, void*);
+typedef void (*hnsw_predict_fn)(void*, const void*, uint32_t*, float*, uint32_t, uint32_t, int32_t, void*);
 typedef void (*hnsw_save_fn)(void*, const char*);
 struct HnswForeign {
     hnsw_destruct_fn destruct = nullptr;
@@ -901,7 +917,7 @@ namespace {
 std::mutex g_hnsw_reg_mutex;
 std::unordered_set<void*>& g_hnsw_models = *new std::unordered_set<void*>();
 std::unordered_set<void*>& g_hnsw_tokens = *new std::unordered_set<void*>();
-HnswForeign g_hnsw_foreign[2];
+HnswForeign g_hnsw_foreign[4];  // [metric + 2 * sparse]
 
 bool hnsw_is_ours(void* p, bool token = false) {
     std::lock_guard<std::mutex> lock(g_hnsw_reg_mutex);
@@ -937,7 +953,7 @@ void hnsw_save_copy(void* model_ptr, const char* model_dir) {
 extern "C" {
 
 void pb200_hnsw_set_foreign(int metric, void* destruct, void* searchers_create, void* searchers_destruct, void* predict, void* save) {
-    if (metric < 0 || metric > 1) return;
+    if (metric < 0 || metric > 3) return;  // 0 / 1: dense ip / l2; 2 / 3: sparse (csr) ip / l2
     HnswForeign& f = g_hnsw_foreign[metric];
     f.destruct = reinterpret_cast<hnsw_destruct_fn>(destruct);
     f.searchers_create = reinterpret_cast<hnsw_searchers_create_fn>(searchers_create);
@@ -946,10 +962,10 @@ void pb200_hnsw_set_foreign(int metric, void* destruct, void* searchers_create, 
     f.save = reinterpret_cast<hnsw_save_fn>(save);
 }
 
-#define PB200_HNSW_API(SUFFIX, METRIC)                                                                                  \
+#define PB200_HNSW_API(SUFFIX, METRIC, MAT_T, SPARSE)                                                                              \
     void* c_ann_hnsw_load##SUFFIX(const char* model_dir, const bool lazy_load) {                                        \
         PB200_API_BEGIN                                                                                                 \
-        void* h = hnsw_load(model_dir, lazy_load, METRIC);                                                              \
+        void* h = hnsw_load(model_dir, lazy_load, METRIC, SPARSE);                                                              \
         hnsw_register(h, false, true);                                                                                  \
         return h;                                                                                                       \
         PB200_API_END("c_ann_hnsw_load" #SUFFIX)                                                                        \
@@ -958,8 +974,8 @@ void pb200_hnsw_set_foreign(int metric, void* destruct, void* searchers_create, 
         PB200_API_BEGIN                                                                                                 \
         if (!model_ptr) return;                                                                                         \
         if (!hnsw_is_ours(model_ptr)) {                                                                                 \
-            if (!g_hnsw_foreign[METRIC].destruct) hnsw_foreign_missing("c_ann_hnsw_destruct" #SUFFIX);                  \
-            g_hnsw_foreign[METRIC].destruct(model_ptr);                                                                 \
+            if (!g_hnsw_foreign[METRIC + 2 * SPARSE].destruct) hnsw_foreign_missing("c_ann_hnsw_destruct" #SUFFIX);                  \
+            g_hnsw_foreign[METRIC + 2 * SPARSE].destruct(model_ptr);                                                                 \
             return;                                                                                                     \
         }                                                                                                               \
         hnsw_register(model_ptr, false, false);                                                                         \
@@ -969,8 +985,8 @@ void pb200_hnsw_set_foreign(int metric, void* destruct, void* searchers_create, 
     void* c_ann_hnsw_searchers_create##SUFFIX(void* model_ptr, uint32_t num_searcher) {                                 \
         PB200_API_BEGIN                                                                                                 \
         if (!hnsw_is_ours(model_ptr)) {                                                                                 \
-            if (!g_hnsw_foreign[METRIC].searchers_create) hnsw_foreign_missing("c_ann_hnsw_searchers_create" #SUFFIX);  \
-            return g_hnsw_foreign[METRIC].searchers_create(model_ptr, num_searcher);                                    \
+            if (!g_hnsw_foreign[METRIC + 2 * SPARSE].searchers_create) hnsw_foreign_missing("c_ann_hnsw_searchers_create" #SUFFIX);  \
+            return g_hnsw_foreign[METRIC + 2 * SPARSE].searchers_create(model_ptr, num_searcher);                                    \
         }                                                                                                               \
         void* t = new HnswSearchers{static_cast<HnswHandle*>(model_ptr), num_searcher};                                 \
         hnsw_register(t, true, true);                                                                                   \
@@ -981,20 +997,20 @@ void pb200_hnsw_set_foreign(int metric, void* destruct, void* searchers_create, 
         PB200_API_BEGIN                                                                                                 \
         if (!searchers_ptr) return;                                                                                     \
         if (!hnsw_is_ours(searchers_ptr, true)) {                                                                       \
-            if (!g_hnsw_foreign[METRIC].searchers_destruct) hnsw_foreign_missing("c_ann_hnsw_searchers_destruct" #SUFFIX); \
-            g_hnsw_foreign[METRIC].searchers_destruct(searchers_ptr);                                                   \
+            if (!g_hnsw_foreign[METRIC + 2 * SPARSE].searchers_destruct) hnsw_foreign_missing("c_ann_hnsw_searchers_destruct" #SUFFIX); \
+            g_hnsw_foreign[METRIC + 2 * SPARSE].searchers_destruct(searchers_ptr);                                                   \
             return;                                                                                                     \
         }                                                                                                               \
         hnsw_register(searchers_ptr, true, false);                                                                      \
         delete static_cast<HnswSearchers*>(searchers_ptr);                                                              \
         PB200_API_END("c_ann_hnsw_searchers_destruct" #SUFFIX)                                                          \
     }                                                                                                                   \
-    void c_ann_hnsw_predict##SUFFIX(void* model_ptr, const ScipyDrmF32* pX, uint32_t* ret_idx, float* ret_val,          \
+    void c_ann_hnsw_predict##SUFFIX(void* model_ptr, const MAT_T* pX, uint32_t* ret_idx, float* ret_val,                \
                                     uint32_t efS, uint32_t topk, int32_t threads, void* searchers_ptr) {                \
         PB200_API_BEGIN                                                                                                 \
         if (!hnsw_is_ours(model_ptr)) {                                                                                 \
-            if (!g_hnsw_foreign[METRIC].predict) hnsw_foreign_missing("c_ann_hnsw_predict" #SUFFIX);                    \
-            g_hnsw_foreign[METRIC].predict(model_ptr, pX, ret_idx, ret_val, efS, topk, threads, searchers_ptr);         \
+            if (!g_hnsw_foreign[METRIC + 2 * SPARSE].predict) hnsw_foreign_missing("c_ann_hnsw_predict" #SUFFIX);                    \
+            g_hnsw_foreign[METRIC + 2 * SPARSE].predict(model_ptr, pX, ret_idx, ret_val, efS, topk, threads, searchers_ptr);         \
             return;                                                                                                     \
         }                                                                                                               \
         hnsw_predict(model_ptr, pX, ret_idx, ret_val, efS, topk, METRIC);                                               \
@@ -1003,16 +1019,25 @@ void pb200_hnsw_set_foreign(int metric, void* destruct, void* searchers_create, 
     void c_ann_hnsw_save##SUFFIX(void* model_ptr, const char* model_dir) {                                              \
         PB200_API_BEGIN                                                                                                 \
         if (!hnsw_is_ours(model_ptr)) {                                                                                 \
-            if (!g_hnsw_foreign[METRIC].save) hnsw_foreign_missing("c_ann_hnsw_save" #SUFFIX);                          \
-            g_hnsw_foreign[METRIC].save(model_ptr, model_dir);                                                          \
+            if (!g_hnsw_foreign[METRIC + 2 * SPARSE].save) hnsw_foreign_missing("c_ann_hnsw_save" #SUFFIX);                          \
+            g_hnsw_foreign[METRIC + 2 * SPARSE].save(model_ptr, model_dir);                                                          \
             return;                                                                                                     \
         }                                                                                                               \
         hnsw_save_copy(model_ptr, model_dir);                                                                           \
         PB200_API_END("c_ann_hnsw_save" #SUFFIX)                                                                        \
     }
 
-PB200_HNSW_API(_drm_ip_f32, pb200::HNSW_IP)
-PB200_HNSW_API(_drm_l2_f32, pb200::HNSW_L2)
+PB200_HNSW_API(_drm_ip_f32, pb200::HNSW_IP, ScipyDrmF32, 0)
+PB200_HNSW_API(_drm_l2_f32, pb200::HNSW_L2, ScipyDrmF32, 0)
+PB200_HNSW_API(_csr_ip_f32, pb200::HNSW_IP, ScipyCsrF32, 1)
+PB200_HNSW_API(_csr_l2_f32, pb200::HNSW_L2, ScipyCsrF32, 1)
+
+void pb200_hnsw_resident_upload_csr(void* model_ptr, const ScipyCsrF32* pX) {
+    PB200_API_BEGIN
+    PB200_LOCK_HNSW(model_ptr)
+    hnsw_of(model_ptr).resident_upload_csr(pX->row_ptr, pX->col_idx, pX->val, pX->rows, pX->cols);
+    PB200_API_END("pb200_hnsw_resident_upload_csr")
+}
 
 void pb200_hnsw_resident_upload(void* model_ptr, const ScipyDrmF32* pX) {
     PB200_API_BEGIN
@@ -1049,6 +1074,13 @@ void pb200_hnsw_get_counters(void* model_ptr, uint64_t* out) {
     auto c = hnsw_of(model_ptr).counters();
     out[0] = c.n_dist; out[1] = c.n_expand; out[2] = c.n_hops; out[3] = c.n_queries;
     PB200_API_END("pb200_hnsw_get_counters")
+}
+
+uint64_t pb200_hnsw_sparse_entries(void* model_ptr) {
+    PB200_API_BEGIN
+    PB200_LOCK_HNSW(model_ptr)
+    return hnsw_of(model_ptr).counters().n_entries;
+    PB200_API_END("pb200_hnsw_sparse_entries")
 }
 
 uint32_t pb200_hnsw_vcap_retries(void* ptr) {

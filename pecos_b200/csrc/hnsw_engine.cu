@@ -12,6 +12,12 @@
 // The reference evaluates the distance of every unvisited neighbour before touching the queues (hnsw.hpp:897-914), which
 // is what makes step B independent of step C.
 //
+// Sparse (csr) indices (FeatVecSparse{IP,L2}Simd, feat_vectors.hpp:186-210) use the same walk; only step B differs: a half-warp
+// streams the neighbour's {index, value} entries (16 per step, 128 contiguous bytes), every lane looks its entry up in the query
+// row staged in shared memory (a 8,192-bit filter first, binary search on a filter hit) and the matched products are added in
+// ascending index order -- the order of the reference's block intersection (distance_impl/common.hpp:15-86) for rows with strictly
+// ascending indices.  The reference's sparse "l2" is -2<x,y> (its squared norms are do_l2_distance_simd(x, x) = 0): restated as is.
+//
 // HBM traffic per query: n_dist * 4d + n_expand * 4(1+maxM0) + hops * 4(1+maxM) + 4d + 8k.
 #include "hnsw_engine.h"
 
@@ -158,6 +164,95 @@ __device__ __forceinline__ void batch_distances(const HnswDev& ix, const float* 
     __syncwarp();
 }
 
+// ---- sparse rows: ordered intersection ---------------------------------------------------------------------------------
+constexpr uint32_t kSpFilterWords = 256;  // 8,192-bit membership filter of the query row's indices, per warp
+constexpr uint32_t kSpQcapMax = 4096;     // query entries staged per warp at most (longer rows are searched in global memory)
+
+__device__ __forceinline__ uint32_t sp_hash(uint32_t idx) { return (idx * 2654435761u) >> 19; }  // 13 bits
+
+struct SparseQuery {  // one query row: generic pointers (shared-memory copy, or the global arrays for very long rows)
+    const uint32_t* idx;
+    const float* val;
+    uint32_t n;
+    const uint32_t* filter;
+};
+
+__device__ __forceinline__ uint2 ld_stream_u2(const uint2* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+
+// one 16-entry step of a half-warp: look the lane's entry up, then add the matched products of this step in entry order
+__device__ __forceinline__ float sparse_step(const SparseQuery& q, bool has, uint2 ent, float ret, int lane) {
+    bool hit = false;
+    float prod = 0.0f;
+    if (has) {
+        const uint32_t h = sp_hash(ent.x);
+        if ((q.filter[h >> 5] >> (h & 31u)) & 1u) {
+            uint32_t lo = 0, hi = q.n;  // std::lower_bound
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (q.idx[mid] < ent.x) lo = mid + 1; else hi = mid;
+            }
+            if (lo < q.n && q.idx[lo] == ent.x) { hit = true; prod = __fmul_rn(q.val[lo], __uint_as_float(ent.y)); }
+        }
+    }
+    const unsigned m = __ballot_sync(kFull, hit);
+    if (m == 0u) return ret;
+    const int half = lane >> 4;
+    unsigned mh = (m >> (16 * half)) & 0xFFFFu;
+    const int n_it = max(__popc(m & 0xFFFFu), __popc(m >> 16));
+    for (int it = 0; it < n_it; ++it) {
+        const int src = mh ? (__ffs(mh) - 1 + 16 * half) : lane;
+        const float pv = __shfl_sync(kFull, prod, src);
+        if (mh) { ret = __fadd_rn(ret, pv); mh &= mh - 1u; }
+    }
+    return ret;
+}
+
+// distances of ids[0..n) -> dist[0..n) for a sparse index, two rows at a time (one per half-warp)
+template <int METRIC>
+__device__ __forceinline__ void batch_distances_sparse(const HnswDev& ix, const SparseQuery& q, const uint32_t* ids, float* dist,
+                                                       uint32_t n, int lane, unsigned long long& n_entries) {
+    const int half = lane >> 4, hl = lane & 15;
+    for (uint32_t b = 0; b < n; b += 2) {
+        const uint32_t slot = b + half;
+        const bool valid = slot < n;
+        unsigned long long r0 = 0, r1 = 0;
+        if (valid) {
+            const uint32_t node = ids[slot];
+            r0 = ix.sp_ptr[node];
+            r1 = ix.sp_ptr[node + 1];
+        }
+        const uint32_t len = static_cast<uint32_t>(r1 - r0);
+        const uint32_t len_max = max(len, __shfl_xor_sync(kFull, len, 16));
+        if (hl == 0) n_entries += len;
+        const uint2* row = ix.sp_ent + r0;
+        float ret = 0.0f;
+        for (uint32_t j0 = 0; j0 < len_max; j0 += 64) {  // four independent 128-byte loads per half-warp in flight
+            uint2 e[4];
+            bool has[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t j = j0 + 16u * u + hl;
+                has[u] = (j < len) && q.n != 0u;
+                e[u] = has[u] ? ld_stream_u2(row + j) : make_uint2(0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (j0 + 16u * u < len_max) ret = sparse_step(q, has[u], e[u], ret, lane);
+            }
+        }
+        if (hl == 0 && valid) {
+            // FeatVecSparseIPSimd: 1.0 - dot ; FeatVecSparseL2Simd: x_sq + y_sq - 2.0 * dot with x_sq = y_sq = 0 (see the header)
+            dist[slot] = (METRIC == HNSW_IP) ? static_cast<float>(1.0 - static_cast<double>(ret))
+                                             : static_cast<float>(static_cast<double>(0.0f) - 2.0 * static_cast<double>(ret));
+        }
+    }
+    __syncwarp();
+}
+
 // ---- libstdc++ heap algorithms (std::push_heap / std::pop_heap), entries {dist bits, node}; MAXH: std::less ---------
 template <bool MAXH>
 __device__ __forceinline__ bool heap_comp(uint2 a, float value_dist) {
@@ -222,9 +317,9 @@ __device__ __forceinline__ uint32_t permuted_pos_dev(const HnswDev& ix, uint32_t
     return ix.main_pad + (i - m);
 }
 
-template <int METRIC, int STAGES>
+template <int METRIC, int STAGES, bool SPARSE>
 __global__ void __launch_bounds__(256)
-hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const uint32_t nq, const uint32_t efS, const uint32_t topk,
+hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const HnswSparseQueries SQ, const uint32_t nq, const uint32_t efS, const uint32_t topk,
                    const uint32_t ef, uint32_t* __restrict__ out_idx, float* __restrict__ out_val, uint32_t* bitmap_all,
                    const uint32_t bitmap_words, uint32_t* vlist_all, uint2* cand_all, const uint32_t vcap, uint2* topk_all,
                    const uint32_t nbmax, const uint32_t per_warp_bytes, unsigned long long* ctrl) {
@@ -234,15 +329,19 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const uint32_t
     const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;
     unsigned char* base = smem_raw + static_cast<size_t>(warp) * per_warp_bytes;
     // per-warp slice: [query | STAGES ring slots | STAGES mbarriers | neighbour ids | distances | result heap]
+    // (sparse: [query indices qcap | query values qcap | filter | neighbour ids | distances | result heap])
     float* qs = reinterpret_cast<float*>(base);
     float* ring = qs + ix.vstride;
     unsigned long long* mbars = reinterpret_cast<unsigned long long*>(ring + static_cast<size_t>(STAGES) * ix.vstride);
-    uint32_t* nb_ids = reinterpret_cast<uint32_t*>(mbars + STAGES);
+    uint32_t* sq_idx = reinterpret_cast<uint32_t*>(base);
+    float* sq_val = reinterpret_cast<float*>(sq_idx + SQ.qcap);
+    uint32_t* sq_filter = reinterpret_cast<uint32_t*>(sq_val + SQ.qcap);
+    uint32_t* nb_ids = SPARSE ? sq_filter + kSpFilterWords : reinterpret_cast<uint32_t*>(mbars + STAGES);
     float* nb_dist = reinterpret_cast<float*>(nb_ids + nbmax);
     uint2* topq = topk_all ? topk_all + static_cast<uint64_t>(gw) * (ef + 1) : reinterpret_cast<uint2*>(nb_dist + nbmax);
     const uint32_t mbar0 = smem_addr(mbars);
     uint32_t phase_bits = 0;
-    if (STAGES > 0) {
+    if (STAGES > 0 && !SPARSE) {
         if (lane == 0) {
             for (int s = 0; s < STAGES; ++s) mbar_init(mbar0 + 8u * s, 1u);
             fence_proxy_async_smem();
@@ -260,20 +359,44 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const uint32_t
         qq = __shfl_sync(kFull, qq, 0);
         if (qq >= nq) break;
         const uint32_t q = static_cast<uint32_t>(qq);
-        unsigned long long n_dist = 0, n_expand = 0, n_hops = 0;
+        unsigned long long n_dist = 0, n_expand = 0, n_hops = 0, n_entries = 0;
 
-        // stage the query in the permuted layout (padding = 0)
-        for (uint32_t i = lane; i < ix.vstride; i += 32) qs[i] = 0.0f;
-        __syncwarp();
-        const float* qrow = Q + static_cast<uint64_t>(q) * d;
-        for (uint32_t i = lane; i < d; i += 32) qs[permuted_pos_dev(ix, i)] = qrow[i];
-        __syncwarp();
+        SparseQuery sq{nullptr, nullptr, 0u, nullptr};
+        if (SPARSE) {
+            // stage the query row (indices, values) and the membership filter of its indices
+            const unsigned long long q0 = SQ.ptr[q];
+            sq.n = static_cast<uint32_t>(SQ.ptr[q + 1] - q0);
+            for (uint32_t w = lane; w < kSpFilterWords; w += 32) sq_filter[w] = 0u;
+            __syncwarp();
+            const bool staged = sq.n <= SQ.qcap;
+            for (uint32_t i = lane; i < sq.n; i += 32) {
+                const uint32_t c = SQ.idx[q0 + i];
+                if (staged) { sq_idx[i] = c; sq_val[i] = SQ.val[q0 + i]; }
+                const uint32_t h = sp_hash(c);
+                atomicOr(&sq_filter[h >> 5], 1u << (h & 31u));
+            }
+            sq.idx = staged ? sq_idx : SQ.idx + q0;
+            sq.val = staged ? sq_val : SQ.val + q0;
+            sq.filter = sq_filter;
+            __syncwarp();
+        } else {
+            // stage the query in the permuted layout (padding = 0)
+            for (uint32_t i = lane; i < ix.vstride; i += 32) qs[i] = 0.0f;
+            __syncwarp();
+            const float* qrow = Q + static_cast<uint64_t>(q) * d;
+            for (uint32_t i = lane; i < d; i += 32) qs[permuted_pos_dev(ix, i)] = qrow[i];
+            __syncwarp();
+        }
+        auto distances = [&](uint32_t n) {
+            if (SPARSE) batch_distances_sparse<METRIC>(ix, sq, nb_ids, nb_dist, n, lane, n_entries);
+            else batch_distances<METRIC, STAGES>(ix, qs, nb_ids, nb_dist, n, lane, ring, mbar0, phase_bits);
+        };
 
         // ---- entry point + greedy descent on levels max_level..1 (hnsw.hpp:928-959)
         uint32_t curr = ix.init_node;
         if (lane == 0) nb_ids[0] = curr;
         __syncwarp();
-        batch_distances<METRIC, STAGES>(ix, qs, nb_ids, nb_dist, 1, lane, ring, mbar0, phase_bits);
+        distances(1);
         float curr_dist = nb_dist[0];
         n_dist += 1;
         __syncwarp();
@@ -286,7 +409,7 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const uint32_t
                 n_hops += 1;
                 for (uint32_t j = lane; j < deg; j += 32) nb_ids[j] = nb[1 + j];
                 __syncwarp();
-                if (deg) batch_distances<METRIC, STAGES>(ix, qs, nb_ids, nb_dist, deg, lane, ring, mbar0, phase_bits);
+                if (deg) distances(deg);
                 n_dist += deg;
                 if (lane == 0) {
                     for (uint32_t j = 0; j < deg; ++j) {
@@ -350,7 +473,7 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const uint32_t
             }
             nvis += nu;
             // B. all distances
-            if (nu) batch_distances<METRIC, STAGES>(ix, qs, nb_ids, nb_dist, nu, lane, ring, mbar0, phase_bits);
+            if (nu) distances(nu);
             n_dist += nu;
             // C. sequential replay of the queue updates (hnsw.hpp:904-914)
             if (lane == 0) {
@@ -405,6 +528,10 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const uint32_t
             atomicAdd(&ctrl[4], n_hops);
             atomicAdd(&ctrl[5], 1ull);
         }
+        if (SPARSE) {  // per half-warp partial sums of the stored entries read
+            n_entries += __shfl_xor_sync(kFull, n_entries, 16);
+            if (lane == 0) atomicAdd(&ctrl[6], n_entries);
+        }
     }
 }
 
@@ -417,7 +544,50 @@ HnswEngine::HnswEngine(std::unique_ptr<HnswHostIndex> host, int device) : host_(
     for (auto& e : ev_) PB200_CUDA(cudaEventCreate(&e));
     const HnswHostIndex& H = *host_;
     const uint64_t N = H.num_node;
-    const uint32_t vs = H.vstride(), n0 = H.n0stride(), d = H.feat_dim;
+    const uint32_t vs = H.sparse ? 0u : H.vstride(), n0 = H.n0stride(), d = H.feat_dim;
+    uint64_t sparse_bytes = 0;
+    if (H.sparse) {
+        // entry offsets + interleaved {index, value} entries + neighbour lists, re-laid-out on the host
+        std::vector<unsigned long long> ptr(N + 1, 0ull);
+        for (uint64_t i = 0; i < N; ++i) {
+            const float* v; const uint32_t* c;
+            ptr[i + 1] = ptr[i] + H.l0_sparse_row(static_cast<uint32_t>(i), &v, &c);
+        }
+        const uint64_t nnz = ptr[N];
+        sp_ptr_.upload(ptr.data(), N + 1, stream_);
+        sp_ent_.reserve(std::max<uint64_t>(nnz, 1));
+        nbr0_.reserve(N * n0);
+        const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(N, 1u << 16));
+        PinnedBuffer<uint2> se;
+        PinnedBuffer<uint32_t> sn;
+        sn.reserve(chunk * n0);
+        for (uint64_t c0 = 0; c0 < N; c0 += chunk) {
+            const uint64_t cn = std::min(chunk, N - c0);
+            const uint64_t e0 = ptr[c0], en = ptr[c0 + cn] - e0;
+            se.reserve(std::max<uint64_t>(en, 1));
+            std::memset(sn.get(), 0, cn * n0 * 4);
+            parallel_for_chunks(cn, [&](uint64_t r) {
+                const uint32_t node = static_cast<uint32_t>(c0 + r);
+                const float* v; const uint32_t* c;
+                const uint32_t len = H.l0_sparse_row(node, &v, &c);
+                uint2* dst = se.get() + (ptr[node] - e0);
+                for (uint32_t j = 0; j < len; ++j) {
+                    uint32_t bits;
+                    std::memcpy(&bits, v + j, 4);
+                    dst[j] = make_uint2(c[j], bits);
+                }
+                const uint32_t* nb = H.l0_neighborhood(node);
+                uint32_t* nd = sn.get() + r * n0;
+                const uint32_t deg = std::min(nb[0], H.l0_max_degree);
+                nd[0] = deg;
+                for (uint32_t j = 0; j < deg; ++j) nd[1 + j] = nb[1 + j];
+            });
+            if (en) PB200_CUDA(cudaMemcpyAsync(sp_ent_.get() + e0, se.get(), en * sizeof(uint2), cudaMemcpyHostToDevice, stream_));
+            PB200_CUDA(cudaMemcpyAsync(nbr0_.get() + c0 * n0, sn.get(), cn * n0 * 4, cudaMemcpyHostToDevice, stream_));
+            PB200_CUDA(cudaStreamSynchronize(stream_));
+        }
+        sparse_bytes = (N + 1) * 8 + nnz * 8;
+    } else {
     vec_.reserve(N * vs);
     nbr0_.reserve(N * n0);
     // re-layout in chunks through a pinned staging buffer
@@ -447,13 +617,16 @@ HnswEngine::HnswEngine(std::unique_ptr<HnswHostIndex> host, int device) : host_(
         PB200_CUDA(cudaMemcpyAsync(nbr0_.get() + c0 * n0, sn.get(), cn * n0 * 4, cudaMemcpyHostToDevice, stream_));
         PB200_CUDA(cudaStreamSynchronize(stream_));
     }
+    }
     uint64_t l1_len = 0;
     if (H.max_level > 0) {
         l1_len = static_cast<uint64_t>(N) * H.l1_node_mem_size;
         l1_.upload(H.l1_buffer, l1_len, stream_);
         PB200_CUDA(cudaStreamSynchronize(stream_));
     }
-    index_bytes_ = N * vs * 4 + N * n0 * 4 + l1_len * 4;
+    index_bytes_ = N * vs * 4 + N * n0 * 4 + l1_len * 4 + sparse_bytes;
+    view_.sp_ptr = sp_ptr_.get();
+    view_.sp_ent = sp_ent_.get();
     view_.vec = vec_.get();
     view_.nbr0 = nbr0_.get();
     view_.l1 = l1_.get();
@@ -462,8 +635,8 @@ HnswEngine::HnswEngine(std::unique_ptr<HnswHostIndex> host, int device) : host_(
     view_.init_node = H.init_node;
     view_.feat_dim = d;
     view_.vstride = vs;
-    view_.main_pad = H.main_pad();
-    view_.tail_len = H.tail_len();
+    view_.main_pad = H.sparse ? 0u : H.main_pad();
+    view_.tail_len = H.sparse ? 0u : H.tail_len();
     view_.n0stride = n0;
     view_.l0_max_degree = H.l0_max_degree;
     view_.l1_node_mem = H.l1_node_mem_size;
@@ -474,12 +647,14 @@ HnswEngine::HnswEngine(std::unique_ptr<HnswHostIndex> host, int device) : host_(
     PB200_CUDA(cudaMemsetAsync(ctrl_.get(), 0, 8 * sizeof(unsigned long long), stream_));
     PB200_CUDA(cudaStreamSynchronize(stream_));
     const int max_smem = 200 * 1024;
-    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_IP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_L2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_IP, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_L2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_IP, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_L2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_IP, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_L2, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_IP, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_L2, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_IP, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_L2, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_IP, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PB200_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<HNSW_L2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     stages_ = 4;  // rows in flight per warp through the bulk-copy ring; 0 = direct loads (first-generation kernel)
     if (const char* env = std::getenv("PB200_HNSW_STAGES")) {
         const int v = std::atoi(env);
@@ -487,6 +662,7 @@ HnswEngine::HnswEngine(std::unique_ptr<HnswHostIndex> host, int device) : host_(
     }
     // the mapped file is no longer needed once the arrays live in HBM
     host_->l0_buffer = nullptr;
+    host_->l0_mem_start = nullptr;
     host_->l1_buffer = nullptr;
     host_->store.reset();
 }
@@ -503,6 +679,8 @@ uint32_t HnswEngine::per_warp_smem_(uint32_t ef, uint32_t* nbmax_out) const {
     const uint32_t nbmax = ((std::max(H.l0_max_degree, H.l1_max_degree) + 31u) / 32u) * 32u;
     const bool top_in_smem = ef <= kEfSmemMax;
     if (nbmax_out) *nbmax_out = nbmax;
+    if (H.sparse)  // [query indices | query values | filter | ids | distances | result heap]
+        return (qcap_ * 8u + kSpFilterWords * 4u + nbmax * 8 + (top_in_smem ? (ef + 1) * 8 : 0) + 15u) & ~15u;
     // [query | stages_ ring slots | stages_ mbarriers | ids | distances | result heap]
     return (H.vstride() * 4 * (1u + static_cast<uint32_t>(stages_)) + static_cast<uint32_t>(stages_) * 8u + nbmax * 8 +
             (top_in_smem ? (ef + 1) * 8 : 0) + 15u) & ~15u;
@@ -523,7 +701,7 @@ void HnswEngine::ensure_scratch_(uint32_t ef) {
         throw std::runtime_error("pecos_b200: HNSW query dimension too large for the shared-memory staging area");
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_);
-    const uint32_t ctas_per_sm = std::max<uint32_t>(1, std::min<uint32_t>(16u / warps, static_cast<uint32_t>((220u * 1024u) / (static_cast<uint64_t>(warps) * per_warp))));
+    const uint32_t ctas_per_sm = std::max<uint32_t>(1, std::min<uint32_t>((H.sparse ? 32u : 16u) / warps, static_cast<uint32_t>((220u * 1024u) / (static_cast<uint64_t>(warps) * per_warp))));
     uint32_t n_ctas = static_cast<uint32_t>(sms) * ctas_per_sm;
     // bound the scratch footprint (bitmap N/8 bytes per warp)
     const uint64_t words = (static_cast<uint64_t>(H.num_node) + 31) / 32;
@@ -558,16 +736,18 @@ double HnswEngine::launch_once_(const float* q_dev, uint32_t nq, uint32_t efS, u
     PB200_CUDA(cudaMemsetAsync(out_val_.get(), 0, static_cast<uint64_t>(nq) * topk * 4, stream_));
     const uint32_t ctas = std::max<uint32_t>(1, std::min<uint32_t>(n_ctas_, (nq + warps_per_cta_ - 1) / warps_per_cta_));
     const size_t smem = static_cast<size_t>(warps_per_cta_) * per_warp;
+    const HnswSparseQueries sq{q_ptr_.get(), q_idx_.get(), q_dev, qcap_};  // csr batch (sparse indices; q_dev = its values)
     PB200_CUDA(cudaEventRecord(ev_[0], stream_));
     auto launch = [&](auto kernel) {
-        kernel<<<ctas, warps_per_cta_ * 32, smem, stream_>>>(view_, q_dev, nq, efS, topk, ef, out_idx_.get(), out_val_.get(),
+        kernel<<<ctas, warps_per_cta_ * 32, smem, stream_>>>(view_, q_dev, sq, nq, efS, topk, ef, out_idx_.get(), out_val_.get(),
                                                              bitmap_.get(), words, vlist_.get(), cand_.get(), vcap_,
                                                              top_in_smem ? nullptr : topk_heap_.get(), nbmax, per_warp, ctrl_.get());
     };
     const bool ip = H.metric == HNSW_IP;
-    if (stages_ == 0) { if (ip) launch(hnsw_search_kernel<HNSW_IP, 0>); else launch(hnsw_search_kernel<HNSW_L2, 0>); }
-    else if (stages_ == 4) { if (ip) launch(hnsw_search_kernel<HNSW_IP, 4>); else launch(hnsw_search_kernel<HNSW_L2, 4>); }
-    else { if (ip) launch(hnsw_search_kernel<HNSW_IP, 8>); else launch(hnsw_search_kernel<HNSW_L2, 8>); }
+    if (H.sparse) { if (ip) launch(hnsw_search_kernel<HNSW_IP, 0, true>); else launch(hnsw_search_kernel<HNSW_L2, 0, true>); }
+    else if (stages_ == 0) { if (ip) launch(hnsw_search_kernel<HNSW_IP, 0, false>); else launch(hnsw_search_kernel<HNSW_L2, 0, false>); }
+    else if (stages_ == 4) { if (ip) launch(hnsw_search_kernel<HNSW_IP, 4, false>); else launch(hnsw_search_kernel<HNSW_L2, 4, false>); }
+    else { if (ip) launch(hnsw_search_kernel<HNSW_IP, 8, false>); else launch(hnsw_search_kernel<HNSW_L2, 8, false>); }
     PB200_CUDA(cudaGetLastError());
     PB200_CUDA(cudaEventRecord(ev_[1], stream_));
     ++launches_;
@@ -599,6 +779,7 @@ double HnswEngine::launch_(const float* q_dev, uint32_t nq, uint32_t efS, uint32
 
 void HnswEngine::predict(const float* X, uint32_t nq, uint32_t d, uint32_t efS, uint32_t topk, uint32_t* ret_idx, float* ret_val) {
     PB200_CUDA(cudaSetDevice(device_));
+    if (host_->sparse) throw std::runtime_error("pecos_b200: dense queries against a sparse (csr) HNSW index");
     if (d != host_->feat_dim) throw std::runtime_error("pecos_b200: query dimension != index dimension");
     if (nq == 0 || topk == 0) return;
     q_dev_.upload(X, static_cast<uint64_t>(nq) * d, stream_);
@@ -611,8 +792,54 @@ void HnswEngine::predict(const float* X, uint32_t nq, uint32_t d, uint32_t efS, 
     PB200_CUDA(cudaStreamSynchronize(stream_));
 }
 
+// csr query batch -> device (row offsets rebased to the batch), and the per-warp staging capacity for its longest row
+void HnswEngine::upload_csr_(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, uint32_t nq) {
+    const uint64_t e0 = row_ptr[0], nnz = row_ptr[nq] - e0;
+    std::vector<unsigned long long> ptr(static_cast<size_t>(nq) + 1);
+    uint64_t longest = 0;
+    for (uint32_t i = 0; i <= nq; ++i) {
+        ptr[i] = row_ptr[i] - e0;
+        if (i) longest = std::max<uint64_t>(longest, row_ptr[i] - row_ptr[i - 1]);
+    }
+    q_ptr_.upload(ptr.data(), static_cast<uint64_t>(nq) + 1, stream_);
+    q_idx_.reserve(std::max<uint64_t>(nnz, 1));
+    q_dev_.reserve(std::max<uint64_t>(nnz, 1));
+    if (nnz) {
+        PB200_CUDA(cudaMemcpyAsync(q_idx_.get(), col_idx + e0, nnz * 4, cudaMemcpyHostToDevice, stream_));
+        PB200_CUDA(cudaMemcpyAsync(q_dev_.get(), val + e0, nnz * 4, cudaMemcpyHostToDevice, stream_));
+    }
+    PB200_CUDA(cudaStreamSynchronize(stream_));  // `ptr` is a local
+    const uint32_t qcap = static_cast<uint32_t>(std::min<uint64_t>(kSpQcapMax, (std::max<uint64_t>(longest, 1) + 31) / 32 * 32));
+    if (qcap != qcap_) { qcap_ = qcap; n_warps_ = 0; }  // launch geometry depends on the staging capacity
+}
+
+void HnswEngine::predict_csr(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, uint32_t nq, uint32_t cols,
+                             uint32_t efS, uint32_t topk, uint32_t* ret_idx, float* ret_val) {
+    PB200_CUDA(cudaSetDevice(device_));
+    if (!host_->sparse) throw std::runtime_error("pecos_b200: csr queries against a dense HNSW index");
+    if (cols != host_->feat_dim) throw std::runtime_error("pecos_b200: query dimension != index dimension");
+    if (nq == 0 || topk == 0) return;
+    upload_csr_(row_ptr, col_idx, val, nq);
+    out_idx_.reserve(static_cast<uint64_t>(nq) * topk);
+    out_val_.reserve(static_cast<uint64_t>(nq) * topk);
+    launch_(q_dev_.get(), nq, efS, topk);
+    PB200_CUDA(cudaMemcpyAsync(ret_idx, out_idx_.get(), static_cast<uint64_t>(nq) * topk * 4, cudaMemcpyDeviceToHost, stream_));
+    PB200_CUDA(cudaMemcpyAsync(ret_val, out_val_.get(), static_cast<uint64_t>(nq) * topk * 4, cudaMemcpyDeviceToHost, stream_));
+    PB200_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void HnswEngine::resident_upload_csr(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, uint32_t nq, uint32_t cols) {
+    PB200_CUDA(cudaSetDevice(device_));
+    if (!host_->sparse) throw std::runtime_error("pecos_b200: csr queries against a dense HNSW index");
+    if (cols != host_->feat_dim) throw std::runtime_error("pecos_b200: query dimension != index dimension");
+    upload_csr_(row_ptr, col_idx, val, nq);
+    res_nq_ = nq;
+    res_d_ = cols;
+}
+
 void HnswEngine::resident_upload(const float* X, uint32_t nq, uint32_t d) {
     PB200_CUDA(cudaSetDevice(device_));
+    if (host_->sparse) throw std::runtime_error("pecos_b200: dense queries against a sparse (csr) HNSW index");
     if (d != host_->feat_dim) throw std::runtime_error("pecos_b200: query dimension != index dimension");
     q_dev_.upload(X, static_cast<uint64_t>(nq) * d, stream_);
     PB200_CUDA(cudaStreamSynchronize(stream_));
@@ -640,7 +867,7 @@ HnswCounters HnswEngine::counters() {
     unsigned long long h[8];
     PB200_CUDA(cudaMemcpy(h, ctrl_.get(), sizeof(h), cudaMemcpyDeviceToHost));
     HnswCounters c;
-    c.n_dist = h[2]; c.n_expand = h[3]; c.n_hops = h[4]; c.n_queries = h[5];
+    c.n_dist = h[2]; c.n_expand = h[3]; c.n_hops = h[4]; c.n_queries = h[5]; c.n_entries = h[6];
     return c;
 }
 

@@ -24,6 +24,16 @@ struct HnswDev {
     uint32_t vstride, main_pad, tail_len, n0stride, l0_max_degree;
     uint32_t l1_node_mem, l1_level_mem, l1_max_degree;
     int metric;
+    // sparse (csr) indices: row r = entries [sp_ptr[r], sp_ptr[r+1]) of sp_ent, {index, value bits}, indices ascending
+    const unsigned long long* sp_ptr;
+    const uint2* sp_ent;
+};
+
+struct HnswSparseQueries {  // device CSR of the query batch (sparse indices)
+    const unsigned long long* ptr;
+    const uint32_t* idx;
+    const float* val;
+    uint32_t qcap;  // query entries staged per warp in shared memory (longer rows are searched in global memory)
 };
 
 struct HnswCounters {  // algorithmic-byte counters of SURVEY.md 8(d), totals over the last search call
@@ -31,6 +41,7 @@ struct HnswCounters {  // algorithmic-byte counters of SURVEY.md 8(d), totals ov
     unsigned long long n_expand = 0;  // level-0 expansions (one neighbour-list read each)
     unsigned long long n_hops = 0;    // upper-level neighbourhood reads
     unsigned long long n_queries = 0;
+    unsigned long long n_entries = 0;  // sparse indices: stored entries of the evaluated base rows (8 bytes each)
 };
 
 class HnswEngine {
@@ -43,6 +54,12 @@ public:
 
     // Host-buffer entry point: X row-major nq x d; ret arrays nq x topk (caller-zeroed, like the reference).
     void predict(const float* X, uint32_t nq, uint32_t d, uint32_t efS, uint32_t topk, uint32_t* ret_idx, float* ret_val);
+
+    // Sparse index, csr queries (column indices ascending within a row): the same walk, distances by ordered sparse intersection.
+    void predict_csr(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, uint32_t nq, uint32_t cols, uint32_t efS,
+                     uint32_t topk, uint32_t* ret_idx, float* ret_val);
+    void resident_upload_csr(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, uint32_t nq, uint32_t cols);
+    bool sparse() const { return host_->sparse; }
 
     // Device-resident queries (bench "value" leg).
     void resident_upload(const float* X, uint32_t nq, uint32_t d);
@@ -85,6 +102,12 @@ private:
     DeviceBuffer<uint2> topk_heap_;
     DeviceBuffer<unsigned long long> ctrl_;  // [0] query counter, [1] error flag, [2..5] counters
 
+    DeviceBuffer<unsigned long long> sp_ptr_;
+    DeviceBuffer<uint2> sp_ent_;
+    DeviceBuffer<unsigned long long> q_ptr_;  // csr query batch
+    DeviceBuffer<uint32_t> q_idx_;
+    uint32_t qcap_ = 0;
+    void upload_csr_(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, uint32_t nq);
     DeviceBuffer<float> q_dev_;
     DeviceBuffer<uint32_t> out_idx_;
     DeviceBuffer<float> out_val_;

@@ -12,8 +12,10 @@ ret_csr=True)``                                ``(indices, distances)`` arrays
 ``HNSW.searchers_create(n)`` / ``Searchers``   opaque scratch token (the per-warp scratch lives with the engine)
 =============================================  =======================================================
 
-Index construction and ``save`` stay on the reference CPU library.  Served index kinds: dense ``drm`` float32 with the
-``ip`` or ``l2`` metric.  There is no CPU fallback: loading without a visible CUDA device raises ``RuntimeError``.
+Index construction stays on the reference CPU library (dense indices can also be built on the GPU:
+``pecos_b200.hnsw_build``).  Served index kinds: dense ``drm`` and sparse ``csr`` float32 with the ``ip`` or ``l2`` metric
+(csr rows: column indices strictly ascending -- queries are canonicalised with ``sum_duplicates()`` / ``sort_indices()``
+when needed).  There is no CPU fallback: loading without a visible CUDA device raises ``RuntimeError``.
 """
 import dataclasses as dc
 import json
@@ -23,7 +25,7 @@ from ctypes import POINTER, byref, c_bool, c_char_p, c_float, c_uint32, c_void_p
 import numpy as np
 import scipy.sparse as smat
 
-from .core import ScipyDrmF32, get_clib
+from .core import ScipyCsrF32, ScipyDrmF32, get_clib
 
 _REQUIRED_KEYS = ("model", "data_type", "metric_type", "num_item", "feat_dim")
 
@@ -115,13 +117,19 @@ class HNSW(object):
     # ------------------------------------------------------------------ search
     @staticmethod
     def create_pymat(X):
-        """Query matrix -> (ctypes view, kind).  Dense float32 row-major queries only."""
+        """Query matrix -> (ctypes view, kind): dense float32 row-major, or csr float32 with ascending column indices."""
         if isinstance(X, ScipyDrmF32):
             return X, "drm"
+        if isinstance(X, ScipyCsrF32):
+            return X, "csr"
         if isinstance(X, np.ndarray):
             return ScipyDrmF32.init_from(np.ascontiguousarray(X, dtype=np.float32)), "drm"
         if smat.issparse(X):
-            return None, "csr"
+            X = smat.csr_matrix(X, dtype=np.float32)
+            if not X.has_canonical_format:  # the intersection kernels walk strictly ascending indices
+                X = X.copy()
+                X.sum_duplicates()
+            return ScipyCsrF32.init_from(X), "csr"
         raise ValueError(f"queries of type {type(X)} are not supported")
 
     def predict(self, X, pred_params=None, searchers=None, ret_csr=True):

@@ -1,6 +1,6 @@
 """Overlay the B200 hot-path symbols onto a live ``pecos.core.clib``.
 
-``overlay(clib)`` re-points the XR-Linear predict-only and dense-HNSW function pointers of the reference's
+``overlay(clib)`` re-points the XR-Linear predict-only and HNSW (dense and sparse) search function pointers of the reference's
 ``corelib`` instance (pecos/core/base.py:481-539, :1951-1964) at ``libpecos_b200_float32.so``; every other symbol keeps
 using the reference CPU library.  The reference package itself is not imported here: pass its ``clib`` object in.
 """
@@ -52,18 +52,18 @@ def overlay(clib, lib_path=LIB_PATH, require_gpu=True):
     fn_dict = getattr(clib, "ann_hnsw_fn_dict", {})
     b200.pb200_hnsw_set_foreign.restype = None
     b200.pb200_hnsw_set_foreign.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 5
-    for metric_id, metric in enumerate(("ip", "l2")):
-        key = ("drm", metric)
+    for type_id, key in enumerate((("drm", "ip"), ("drm", "l2"), ("csr", "ip"), ("csr", "l2"))):
+        data_type, metric = key
         if key not in fn_dict:
             continue
         # Indices trained by the reference are REFERENCE handles: hand the reference's own functions to the library, which
         # forwards every handle / searcher token it did not create itself (train stays on the reference).
         ref_fns = [fn_dict[key].get(slot) for slot in ("destruct", "searchers_create", "searchers_destruct", "predict", "save")]
-        b200.pb200_hnsw_set_foreign(metric_id, *[ctypes.cast(f, ctypes.c_void_p) if f is not None else None for f in ref_fns])
+        b200.pb200_hnsw_set_foreign(type_id, *[ctypes.cast(f, ctypes.c_void_p) if f is not None else None for f in ref_fns])
         for slot in HNSW_SLOTS:
             if slot not in fn_dict[key]:
                 continue
-            name = "c_ann_hnsw_{}_drm_{}_f32".format(slot, metric)
+            name = "c_ann_hnsw_{}_{}_{}_f32".format(slot, data_type, metric)
             ref = fn_dict[key][slot]
             fn = getattr(b200, name)
             fn.restype, fn.argtypes = ref.restype, ref.argtypes

@@ -54,5 +54,11 @@ ref) python bench.py --impl reference --steps 5 --warmup 2 > $o/${tag}_bench_ref
 ncu_e) ncu --set full --clock-control none --import-source on -k regex:xl_cm_scores_kernel -s ${NCU_SKIP_E:-9} -c 1 -o $o/${tag}_ncu_cm_eurlex4k python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary > /dev/null 2> $o/${tag}_ncu_e.err;;
 ncu_s) ncu --set full --clock-control none --import-source on -k regex:xl_cm_scores_kernel -s ${NCU_SKIP_S:-13} -c 1 -o $o/${tag}_ncu_cm_synthetic3m python bench.py --workload synthetic-3m --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2> $o/${tag}_ncu_s.err;;
 launches) ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/${tag}_launches_eurlex4k.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary > /dev/null 2>&1;;
+sptests) python -m pytest tests/test_hnsw_sparse_gpu.py tests/test_hnsw_gpu.py -x -q -m gpu > $o/${tag}_gpu_tests_hnsw.log 2>&1; tail -6 $o/${tag}_gpu_tests_hnsw.log;;
+hsp100k) python bench.py --workload hnsw-sparse-100k --steps 5 --warmup 3 > $o/${tag}_bench_hnsw_sparse100k.json 2> $o/${tag}_bench_hnsw_sparse100k.err || tail -5 $o/${tag}_bench_hnsw_sparse100k.err
+   summ $o/${tag}_bench_hnsw_sparse100k.json;;
+hrcv1) python bench.py --workload hnsw-rcv1 --steps 5 --warmup 3 > $o/${tag}_bench_hnsw_rcv1.json 2> $o/${tag}_bench_hnsw_rcv1.err || tail -5 $o/${tag}_bench_hnsw_rcv1.err
+   summ $o/${tag}_bench_hnsw_rcv1.json;;
+ncu_hsp) ncu --set full --clock-control none --import-source on -k regex:hnsw_search -s 2 -c 1 -o $o/${tag}_ncu_hnsw_sparse python bench.py --workload ${NCU_HSP_WORKLOAD:-hnsw-sparse-100k} --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2> $o/${tag}_ncu_hsp.err;;
 esac
 done

@@ -75,10 +75,10 @@ print("RESULT" + json.dumps(out))
     assert all(p.endswith("libpecos_b200_float32.so") for p in out["xlinear"].values()), out["xlinear"]
     for key, path in out["hnsw"].items():
         slot = key.split("_", 2)[2]
-        if key.startswith("drm_") and slot in ("load", "destruct", "searchers_create", "searchers_destruct", "predict", "save"):
-            assert path.endswith("libpecos_b200_float32.so"), (key, path)
-        else:  # train and the sparse (csr) variants stay on the reference library
+        if slot in ("load", "destruct", "searchers_create", "searchers_destruct", "predict", "save"):
+            assert path.endswith("libpecos_b200_float32.so"), (key, path)  # dense (drm) and sparse (csr) indices
+        else:  # train stays on the reference library
             assert path.endswith("libpecos_float32.so"), (key, path)
     assert all(p.endswith("libpecos_float32.so") for p in out["other"].values()), out["other"]
     assert out["argtypes_kept"] and out["matmul_ok"]
-    assert len(out["swapped"]) == len(set(out["swapped"])) >= 19 + 10
+    assert len(out["swapped"]) == len(set(out["swapped"])) >= 19 + 24
