@@ -12,11 +12,11 @@
 // The reference evaluates the distance of every unvisited neighbour before touching the queues (hnsw.hpp:897-914), which
 // is what makes step B independent of step C.
 //
-// Sparse (csr) indices (FeatVecSparse{IP,L2}Simd, feat_vectors.hpp:186-210) use the same walk; only step B differs: a half-warp
-// streams the neighbour's {index, value} entries (16 per step, 128 contiguous bytes), every lane looks its entry up in the query
-// row staged in shared memory (a 8,192-bit filter first, binary search on a filter hit) and the matched products are added in
-// ascending index order -- the order of the reference's block intersection (distance_impl/common.hpp:15-86) for rows with strictly
-// ascending indices.  The reference's sparse "l2" is -2<x,y> (its squared norms are do_l2_distance_simd(x, x) = 0): restated as is.
+// Sparse (csr) indices (FeatVecSparse{IP,L2}Simd, feat_vectors.hpp:186-210) use the same walk; only step B differs: the warp
+// streams the concatenated {index, value} entries of ALL unvisited neighbours of the expansion (32 per step, 256 contiguous bytes
+// within a row), every lane looks its entry up in the query row staged in shared memory (8,192-bit filter, then a hash table) and
+// the matched products are added row by row in ascending index order -- the order of the reference's block intersection
+// (distance_impl/common.hpp:15-86) for rows with strictly ascending indices.  The reference's sparse "l2" is -2<x,y> (its squared norms are do_l2_distance_simd(x, x) = 0): restated as is.
 //
 // HBM traffic per query: n_dist * 4d + n_expand * 4(1+maxM0) + hops * 4(1+maxM) + 4d + 8k.
 #include "hnsw_engine.h"
@@ -165,23 +165,23 @@ __device__ __forceinline__ void batch_distances(const HnswDev& ix, const float* 
 }
 
 // ---- sparse rows: ordered intersection ---------------------------------------------------------------------------------
-// The query row lives in a per-warp open-addressing table in shared memory ({index, value bits}, linear probing, load factor
-// <= 1/2): a lookup is one 8-byte shared-memory load in the common case.  Rows longer than kSpTableMaxRow entries are not staged:
-// their lookups go through an 8,192-bit membership filter (aliasing the table area) + a binary search in the global arrays.
+// Per query row: an 8,192-bit membership filter of its column indices (rejects ~99 % of the foreign entries with one 4-byte
+// shared-memory load) + an open-addressing table {index, value bits} (linear probing, load factor <= 1/2) for the entries that
+// pass.  Rows longer than kSpTableMaxRow entries are not staged: a filter hit is resolved by a binary search in global memory.
 constexpr uint32_t kSpFilterWords = 256;
-constexpr uint32_t kSpTableMinSlots = 256;   // >= 2 KB: the filter of the long-row path fits into the table area
+constexpr uint32_t kSpTableMinSlots = 256;
 constexpr uint32_t kSpTableMaxRow = 1024;    // longest query row served by the table (2,048 slots = 16 KB per warp)
 constexpr uint32_t kSpEmpty = 0xFFFFFFFFu;   // not a column index: cols is a uint32, so indices are <= 2^32 - 2
 
 __device__ __forceinline__ uint32_t sp_hash(uint32_t idx) { return idx * 2654435761u; }
 
 struct SparseQuery {  // one query row
-    const uint2* table;   // shared memory, or nullptr on the long-row path
-    uint32_t mask;        // slots - 1
-    const uint32_t* idx;  // long-row path: the row in global memory + the filter in shared memory
+    const uint32_t* filter;  // shared memory
+    const uint2* table;      // shared memory, or nullptr on the long-row path
+    uint32_t mask;           // slots - 1
+    const uint32_t* idx;     // the row in global memory
     const float* val;
     uint32_t n;
-    const uint32_t* filter;
 };
 
 __device__ __forceinline__ uint2 ld_stream_u2(const uint2* p) {
@@ -192,8 +192,11 @@ __device__ __forceinline__ uint2 ld_stream_u2(const uint2* p) {
 
 // query value stored under column `key`, if any
 __device__ __forceinline__ bool sparse_lookup(const SparseQuery& q, uint32_t key, float* qv) {
+    const uint32_t hh = sp_hash(key);
+    const uint32_t h = hh >> 19;
+    if (!((q.filter[h >> 5] >> (h & 31u)) & 1u)) return false;
     if (q.table) {
-        uint32_t s = (sp_hash(key) >> 8) & q.mask;
+        uint32_t s = (hh >> 6) & q.mask;
         uint2 t = q.table[s];
         while (t.x != key && t.x != kSpEmpty) {
             s = (s + 1u) & q.mask;
@@ -202,8 +205,6 @@ __device__ __forceinline__ bool sparse_lookup(const SparseQuery& q, uint32_t key
         *qv = __uint_as_float(t.y);
         return t.x == key;
     }
-    const uint32_t h = sp_hash(key) >> 19;
-    if (!((q.filter[h >> 5] >> (h & 31u)) & 1u)) return false;
     uint32_t lo = 0, hi = q.n;  // std::lower_bound
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
@@ -213,63 +214,87 @@ __device__ __forceinline__ bool sparse_lookup(const SparseQuery& q, uint32_t key
     return false;
 }
 
-// distances of ids[0..n) -> dist[0..n) for a sparse index, two rows at a time (one per half-warp): 16 entries per step and
-// half-warp, four steps' loads and lookups issued together, matched products added in entry (= ascending index) order
+// Distances of ids[0..n) -> dist[0..n) for a sparse index: ENTRY-parallel over the concatenated rows of all n neighbours.  The
+// lanes first fetch the n row extents together (one round trip), then the warp streams the concatenated {index, value} entries
+// 32 per step (four steps' loads in flight), every lane looks its entry up in the query row, and the matched products are added
+// row by row in entry (= ascending index) order -- the order of the reference's intersection (distance_impl/common.hpp:15-86).
 template <int METRIC>
 __device__ __forceinline__ void batch_distances_sparse(const HnswDev& ix, const SparseQuery& q, const uint32_t* ids, float* dist,
-                                                       uint32_t n, int lane, unsigned long long& n_entries) {
-    const int half = lane >> 4, hl = lane & 15;
-    for (uint32_t b = 0; b < n; b += 2) {
-        const uint32_t slot = b + half;
-        const bool valid = slot < n;
-        unsigned long long r0 = 0, r1 = 0;
-        if (valid) {
-            const uint32_t node = ids[slot];
+                                                       uint32_t n, int lane, uint32_t* row_start, unsigned long long* row_base,
+                                                       unsigned long long& n_entries) {
+    // 1. row extents + exclusive prefix of the row lengths
+    uint32_t carry = 0;
+    for (uint32_t b = 0; b < n; b += 32) {
+        const uint32_t i = b + lane;
+        uint32_t len = 0;
+        unsigned long long r0 = 0;
+        if (i < n) {
+            const uint32_t node = ids[i];
             r0 = ix.sp_ptr[node];
-            r1 = ix.sp_ptr[node + 1];
+            len = q.n ? static_cast<uint32_t>(ix.sp_ptr[node + 1] - r0) : 0u;  // an empty query row matches nothing
         }
-        const uint32_t len = q.n ? static_cast<uint32_t>(r1 - r0) : 0u;  // an empty query row matches nothing
-        const uint32_t len_max = max(len, __shfl_xor_sync(kFull, len, 16));
-        if (hl == 0) n_entries += len;
-        const uint2* row = ix.sp_ent + r0;
-        float ret = 0.0f;
-        for (uint32_t j0 = 0; j0 < len_max; j0 += 64) {
-            uint2 e[4];
+        uint32_t x = len;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t j = j0 + 16u * u + hl;
-                e[u] = (j < len) ? ld_stream_u2(row + j) : make_uint2(kSpEmpty, 0u);
-            }
-            float prod[4];
-            unsigned m[4];
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(kFull, x, o);
+            if (lane >= o) x += y;
+        }
+        if (i < n) { row_start[i] = carry + x - len; row_base[i] = r0; dist[i] = 0.0f; }
+        carry += __shfl_sync(kFull, x, 31);
+    }
+    if (lane == 0) { row_start[n] = carry; n_entries += carry; }
+    __syncwarp();
+    const uint32_t total = carry;
+    // 2. stream the entries; r = row of this lane's current entry (non-decreasing), [rs, rn) its extent in the concatenation
+    uint32_t r = 0, rs = 0, rn = row_start[1];
+    unsigned long long rb = row_base[0];
+    uint32_t cur_row = 0;  // warp-uniform: row whose matched products are being summed
+    float cur_ret = 0.0f;
+    for (uint32_t g0 = 0; g0 < total; g0 += 128) {
+        uint2 e[4];
+        uint32_t er[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                prod[u] = 0.0f;
-                m[u] = 0u;
-                if (j0 + 16u * u >= len_max) continue;  // warp-uniform
-                float qv = 0.0f;
-                const bool hit = (e[u].x != kSpEmpty) && sparse_lookup(q, e[u].x, &qv);
-                prod[u] = __fmul_rn(qv, __uint_as_float(e[u].y));
-                m[u] = __ballot_sync(kFull, hit);
-            }
-            if ((m[0] | m[1] | m[2] | m[3]) == 0u) continue;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (m[u] == 0u) continue;
-                unsigned mh = (m[u] >> (16 * half)) & 0xFFFFu;
-                const int n_it = max(__popc(m[u] & 0xFFFFu), __popc(m[u] >> 16));
-                for (int it = 0; it < n_it; ++it) {
-                    const int src = mh ? (__ffs(mh) - 1 + 16 * half) : lane;
-                    const float pv = __shfl_sync(kFull, prod[u], src);
-                    if (mh) { ret = __fadd_rn(ret, pv); mh &= mh - 1u; }
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t g = g0 + 32u * u + lane;
+            e[u] = make_uint2(kSpEmpty, 0u);
+            er[u] = 0u;
+            if (g < total) {
+                if (g >= rn) {
+                    do { ++r; rs = rn; rn = row_start[r + 1]; } while (g >= rn);
+                    rb = row_base[r];
                 }
+                e[u] = ld_stream_u2(ix.sp_ent + rb + (g - rs));
+                er[u] = r;
             }
         }
-        if (hl == 0 && valid) {
-            // FeatVecSparseIPSimd: 1.0 - dot ; FeatVecSparseL2Simd: x_sq + y_sq - 2.0 * dot with x_sq = y_sq = 0 (see the header)
-            dist[slot] = (METRIC == HNSW_IP) ? static_cast<float>(1.0 - static_cast<double>(ret))
-                                             : static_cast<float>(static_cast<double>(0.0f) - 2.0 * static_cast<double>(ret));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (g0 + 32u * u >= total) continue;  // warp-uniform
+            float qv = 0.0f;
+            const bool hit = (e[u].x != kSpEmpty) && sparse_lookup(q, e[u].x, &qv);
+            const float prod = __fmul_rn(qv, __uint_as_float(e[u].y));
+            unsigned m = __ballot_sync(kFull, hit);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1u;
+                const float pv = __shfl_sync(kFull, prod, src);
+                const uint32_t rr = __shfl_sync(kFull, er[u], src);
+                if (rr != cur_row) {  // rows are contiguous in the stream: the previous row is complete
+                    if (lane == 0) dist[cur_row] = cur_ret;
+                    cur_row = rr;
+                    cur_ret = 0.0f;
+                }
+                cur_ret = __fadd_rn(cur_ret, pv);
+            }
         }
+    }
+    if (lane == 0 && n) dist[cur_row] = cur_ret;
+    __syncwarp();
+    // 3. FeatVecSparseIPSimd: 1.0 - dot ; FeatVecSparseL2Simd: x_sq + y_sq - 2.0 * dot with x_sq = y_sq = 0 (see the header)
+    for (uint32_t i = lane; i < n; i += 32) {
+        const float ret = dist[i];
+        dist[i] = (METRIC == HNSW_IP) ? static_cast<float>(1.0 - static_cast<double>(ret))
+                                      : static_cast<float>(static_cast<double>(0.0f) - 2.0 * static_cast<double>(ret));
     }
     __syncwarp();
 }
@@ -350,13 +375,15 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const HnswSpar
     const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;
     unsigned char* base = smem_raw + static_cast<size_t>(warp) * per_warp_bytes;
     // per-warp slice: [query | STAGES ring slots | STAGES mbarriers | neighbour ids | distances | result heap]
-    // (sparse: [query table, SQ.qcap slots | neighbour ids | distances | result heap])
+    // (sparse: [query table, SQ.qcap slots | filter | row bases | row starts | neighbour ids | distances | result heap])
     float* qs = reinterpret_cast<float*>(base);
     float* ring = qs + ix.vstride;
     unsigned long long* mbars = reinterpret_cast<unsigned long long*>(ring + static_cast<size_t>(STAGES) * ix.vstride);
     uint2* sq_table = reinterpret_cast<uint2*>(base);
-    uint32_t* sq_filter = reinterpret_cast<uint32_t*>(base);  // long-row path only (aliases the table)
-    uint32_t* nb_ids = SPARSE ? reinterpret_cast<uint32_t*>(sq_table + SQ.qcap) : reinterpret_cast<uint32_t*>(mbars + STAGES);
+    uint32_t* sq_filter = reinterpret_cast<uint32_t*>(sq_table + SQ.qcap);
+    unsigned long long* sp_row_base = reinterpret_cast<unsigned long long*>(sq_filter + kSpFilterWords);
+    uint32_t* sp_row_start = reinterpret_cast<uint32_t*>(sp_row_base + nbmax);  // nbmax + 1 used, nbmax + 4 reserved
+    uint32_t* nb_ids = SPARSE ? sp_row_start + nbmax + 4 : reinterpret_cast<uint32_t*>(mbars + STAGES);
     float* nb_dist = reinterpret_cast<float*>(nb_ids + nbmax);
     uint2* topq = topk_all ? topk_all + static_cast<uint64_t>(gw) * (ef + 1) : reinterpret_cast<uint2*>(nb_dist + nbmax);
     const uint32_t mbar0 = smem_addr(mbars);
@@ -381,21 +408,25 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const HnswSpar
         const uint32_t q = static_cast<uint32_t>(qq);
         unsigned long long n_dist = 0, n_expand = 0, n_hops = 0, n_entries = 0;
 
-        SparseQuery sq{nullptr, 0u, nullptr, nullptr, 0u, nullptr};
+        SparseQuery sq{nullptr, nullptr, 0u, nullptr, nullptr, 0u};
         if (SPARSE) {
             const unsigned long long q0 = SQ.ptr[q];
             sq.n = static_cast<uint32_t>(SQ.ptr[q + 1] - q0);
             sq.idx = SQ.idx + q0;
             sq.val = SQ.val + q0;
-            if (2u * sq.n <= SQ.qcap) {
-                // the row's {index, value} pairs into the open-addressing table (linear probing; first occurrence wins)
-                for (uint32_t w = lane; w < SQ.qcap; w += 32) sq_table[w] = make_uint2(kSpEmpty, 0u);
-                __syncwarp();
-                const uint32_t mask = SQ.qcap - 1u;
-                for (uint32_t i = lane; i < sq.n; i += 32) {
-                    const uint32_t c = sq.idx[i];
+            sq.filter = sq_filter;
+            const bool staged = 2u * sq.n <= SQ.qcap;
+            for (uint32_t w = lane; w < kSpFilterWords; w += 32) sq_filter[w] = 0u;
+            if (staged) for (uint32_t w = lane; w < SQ.qcap; w += 32) sq_table[w] = make_uint2(kSpEmpty, 0u);
+            __syncwarp();
+            const uint32_t mask = SQ.qcap - 1u;
+            for (uint32_t i = lane; i < sq.n; i += 32) {
+                const uint32_t c = sq.idx[i];
+                const uint32_t hh = sp_hash(c);
+                atomicOr(&sq_filter[hh >> 24], 1u << ((hh >> 19) & 31u));
+                if (staged) {  // {index, value} into the open-addressing table (linear probing; first writer of an index wins)
                     const uint32_t vbits = __float_as_uint(sq.val[i]);
-                    uint32_t s = (sp_hash(c) >> 8) & mask;
+                    uint32_t s = (hh >> 6) & mask;
                     for (;;) {
                         const uint32_t old = atomicCAS(&sq_table[s].x, kSpEmpty, c);
                         if (old == kSpEmpty) { sq_table[s].y = vbits; break; }
@@ -403,17 +434,8 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const HnswSpar
                         s = (s + 1u) & mask;
                     }
                 }
-                sq.table = sq_table;
-                sq.mask = mask;
-            } else {
-                for (uint32_t w = lane; w < kSpFilterWords; w += 32) sq_filter[w] = 0u;
-                __syncwarp();
-                for (uint32_t i = lane; i < sq.n; i += 32) {
-                    const uint32_t h = sp_hash(sq.idx[i]) >> 19;
-                    atomicOr(&sq_filter[h >> 5], 1u << (h & 31u));
-                }
-                sq.filter = sq_filter;
             }
+            if (staged) { sq.table = sq_table; sq.mask = mask; }
             __syncwarp();
         } else {
             // stage the query in the permuted layout (padding = 0)
@@ -424,7 +446,7 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const HnswSpar
             __syncwarp();
         }
         auto distances = [&](uint32_t n) {
-            if (SPARSE) batch_distances_sparse<METRIC>(ix, sq, nb_ids, nb_dist, n, lane, n_entries);
+            if (SPARSE) batch_distances_sparse<METRIC>(ix, sq, nb_ids, nb_dist, n, lane, sp_row_start, sp_row_base, n_entries);
             else batch_distances<METRIC, STAGES>(ix, qs, nb_ids, nb_dist, n, lane, ring, mbar0, phase_bits);
         };
 
@@ -564,10 +586,7 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const HnswSpar
             atomicAdd(&ctrl[4], n_hops);
             atomicAdd(&ctrl[5], 1ull);
         }
-        if (SPARSE) {  // per half-warp partial sums of the stored entries read
-            n_entries += __shfl_xor_sync(kFull, n_entries, 16);
-            if (lane == 0) atomicAdd(&ctrl[6], n_entries);
-        }
+        if (SPARSE && lane == 0) atomicAdd(&ctrl[6], n_entries);
     }
 }
 
@@ -715,8 +734,8 @@ uint32_t HnswEngine::per_warp_smem_(uint32_t ef, uint32_t* nbmax_out) const {
     const uint32_t nbmax = ((std::max(H.l0_max_degree, H.l1_max_degree) + 31u) / 32u) * 32u;
     const bool top_in_smem = ef <= kEfSmemMax;
     if (nbmax_out) *nbmax_out = nbmax;
-    if (H.sparse)  // [query table (qcap_ slots of 8 bytes) | ids | distances | result heap]
-        return (qcap_ * 8u + nbmax * 8 + (top_in_smem ? (ef + 1) * 8 : 0) + 15u) & ~15u;
+    if (H.sparse)  // [query table (qcap_ slots of 8 bytes) | filter | row bases | row starts | ids | distances | result heap]
+        return (qcap_ * 8u + kSpFilterWords * 4u + nbmax * 8u + (nbmax + 4u) * 4u + nbmax * 8 + (top_in_smem ? (ef + 1) * 8 : 0) + 15u) & ~15u;
     // [query | stages_ ring slots | stages_ mbarriers | ids | distances | result heap]
     return (H.vstride() * 4 * (1u + static_cast<uint32_t>(stages_)) + static_cast<uint32_t>(stages_) * 8u + nbmax * 8 +
             (top_in_smem ? (ef + 1) * 8 : 0) + 15u) & ~15u;
