@@ -132,6 +132,17 @@ void c_xlinear_single_layer_predict_csr_f32(const ScipyCsrF32* input_x, const Sc
 void c_xlinear_single_layer_predict_drm_f32(const ScipyDrmF32* input_x, const ScipyCsrF32* csr_codes, ScipyCscF32* W,
                                             ScipyCscF32* C, const char* post_processor_str, const uint32_t only_topk,
                                             const int num_threads, const float bias, py_sparse_allocator_t pred_alloc);
+/* libpecos.cpp:238-273  the same single layer, scores of exactly the (query, label) pairs of selected_outputs_csr
+ * (MLModel::predict_on_selected_outputs, inference.hpp:2129-2224; pecos/xmc/base.py:1003 = predict_on_selected_outputs of
+ * is_predict_only=False models).  Result: the pattern of selected_outputs_csr, values = transformed (+ combined) scores. */
+void c_xlinear_single_layer_predict_on_selected_outputs_csr_f32(const ScipyCsrF32* input_x, const ScipyCsrF32* selected_outputs_csr,
+                                                                const ScipyCsrF32* csr_codes, ScipyCscF32* W, ScipyCscF32* C,
+                                                                const char* post_processor_str, const int num_threads,
+                                                                const float bias, py_sparse_allocator_t pred_alloc);
+void c_xlinear_single_layer_predict_on_selected_outputs_drm_f32(const ScipyDrmF32* input_x, const ScipyCsrF32* selected_outputs_csr,
+                                                                const ScipyCsrF32* csr_codes, ScipyCscF32* W, ScipyCscF32* C,
+                                                                const char* post_processor_str, const int num_threads,
+                                                                const float bias, py_sparse_allocator_t pred_alloc);
 /* drops every cached single-layer engine; returns how many were held */
 uint32_t pb200_layer_cache_clear(void);
 /* out[0] = entries held, out[1] = hits, out[2] = misses (builds) since load */

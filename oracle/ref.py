@@ -52,6 +52,12 @@ def bind(L):
     L.c_xlinear_single_layer_predict_csr_f32.argtypes = [POINTER(ScipyCsrF32)] + single
     L.c_xlinear_single_layer_predict_drm_f32.restype = None
     L.c_xlinear_single_layer_predict_drm_f32.argtypes = [POINTER(ScipyDrmF32)] + single
+    single_sel = [POINTER(ScipyCsrF32), POINTER(ScipyCsrF32), POINTER(ScipyCscF32), POINTER(ScipyCscF32), c_char_p, c_int, c_float,
+                  ScipyCompressedSparseAllocator.CFUNCTYPE]  # pecos/core/base.py:936-976
+    L.c_xlinear_single_layer_predict_on_selected_outputs_csr_f32.restype = None
+    L.c_xlinear_single_layer_predict_on_selected_outputs_csr_f32.argtypes = [POINTER(ScipyCsrF32)] + single_sel
+    L.c_xlinear_single_layer_predict_on_selected_outputs_drm_f32.restype = None
+    L.c_xlinear_single_layer_predict_on_selected_outputs_drm_f32.argtypes = [POINTER(ScipyDrmF32)] + single_sel
     # single-layer mmap handles (pecos/core/base.py:541-606)
     L.c_mlmodel_compile_mmap_model.restype = None
     L.c_mlmodel_compile_mmap_model.argtypes = [c_char_p, c_char_p]
@@ -181,6 +187,30 @@ def single_layer_predict(X, csr_codes, W, C, post_processor, only_topk, bias, th
         cx = ScipyDrmF32.init_from(np.ascontiguousarray(X, dtype=np.float32))
         fn = L.c_xlinear_single_layer_predict_drm_f32
     fn(byref(cx), codes, byref(cw), byref(cc), post_processor.encode(), only_topk, threads, bias, alloc.cfunc)
+    return alloc.get()
+
+
+def single_layer_predict_on_selected_outputs(X, selected_outputs_csr, csr_codes, W, C, post_processor, bias, threads=-1, clib=None):
+    """c_xlinear_single_layer_predict_on_selected_outputs_{csr,drm}_f32 (pecos/core/libpecos.cpp:238-273) of the reference library,
+    or of `clib` (a ctypes library with the same prototypes, e.g. the CUDA library)."""
+    L = clib if clib is not None else lib()
+    alloc = ScipyCompressedSparseAllocator()
+    cw = ScipyCscF32.init_from(smat.csc_matrix(W, dtype=np.float32))
+    cc = ScipyCscF32.init_from(smat.csc_matrix(C, dtype=np.float32))
+    sel = smat.csr_matrix(selected_outputs_csr, dtype=np.float32)
+    sel.sort_indices()
+    cs = ScipyCsrF32.init_from(sel)
+    codes = None
+    if csr_codes is not None:
+        codes = byref(ScipyCsrF32.init_from(smat.csr_matrix(csr_codes, dtype=np.float32)))
+    if isinstance(X, smat.csr_matrix):
+        assert X.has_sorted_indices
+        cx = ScipyCsrF32.init_from(X)
+        fn = L.c_xlinear_single_layer_predict_on_selected_outputs_csr_f32
+    else:
+        cx = ScipyDrmF32.init_from(np.ascontiguousarray(X, dtype=np.float32))
+        fn = L.c_xlinear_single_layer_predict_on_selected_outputs_drm_f32
+    fn(byref(cx), byref(cs), codes, byref(cw), byref(cc), post_processor.encode(), threads, bias, alloc.cfunc)
     return alloc.get()
 
 

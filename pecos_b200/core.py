@@ -223,6 +223,10 @@ class B200CoreLib(object):
                   ScipyCompressedSparseAllocator.CFUNCTYPE]  # pecos/core/base.py:880-933
         fp(c.c_xlinear_single_layer_predict_csr_f32, None, [POINTER(ScipyCsrF32)] + single)
         fp(c.c_xlinear_single_layer_predict_drm_f32, None, [POINTER(ScipyDrmF32)] + single)
+        single_sel = [POINTER(ScipyCsrF32), POINTER(ScipyCsrF32), POINTER(ScipyCscF32), POINTER(ScipyCscF32), c_char_p, c_int, c_float,
+                      ScipyCompressedSparseAllocator.CFUNCTYPE]  # pecos/core/base.py:936-976
+        fp(c.c_xlinear_single_layer_predict_on_selected_outputs_csr_f32, None, [POINTER(ScipyCsrF32)] + single_sel)
+        fp(c.c_xlinear_single_layer_predict_on_selected_outputs_drm_f32, None, [POINTER(ScipyDrmF32)] + single_sel)
         fp(c.pb200_xlinear_host_from_csc, c_void_p, [POINTER(ScipyCscF32), POINTER(ScipyCscF32), c_float])
         fp(c.pb200_layer_cache_clear, c_uint32, [])
         fp(c.pb200_layer_cache_info, None, [POINTER(c_uint64)])

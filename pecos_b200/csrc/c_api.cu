@@ -279,17 +279,7 @@ void c_xlinear_predict_drm_f32(void* ptr, const ScipyDrmF32* X, const uint32_t o
 
 namespace {
 
-void predict_selected(void* ptr, const ScipyCsrF32* Xs, const ScipyDrmF32* Xd, const ScipyCsrF32* sel, const char* pp,
-                      py_sparse_allocator_t pred_alloc) {
-    PB200_LOCK_XL(ptr)
-    auto& eng = engine_of(ptr);
-    const uint32_t rows = Xs ? Xs->rows : Xd->rows;
-    const uint32_t cols = Xs ? Xs->cols : Xd->cols;
-    if (!sel) throw std::runtime_error("selected_outputs_csr is required");
-    if (sel->rows != rows) throw std::runtime_error("Instance dimension of query and selected output matrix do not match");
-    if (Xd && cols != eng.host().nr_features()) throw std::runtime_error("dense query width != nr_features");
-    auto r = eng.predict_selected(Xs ? Xs->row_ptr : nullptr, Xs ? Xs->col_idx : nullptr, Xs ? Xs->val : nullptr,
-                                  Xd ? Xd->val : nullptr, rows, cols, sel->row_ptr, sel->col_idx, sel->cols, pp);
+void emit_selected(const pb200::XLinearEngine::SelectedResult& r, py_sparse_allocator_t pred_alloc) {
     uint32_t* indices = nullptr;
     uint64_t* indptr = nullptr;
     float* data = nullptr;
@@ -301,6 +291,20 @@ void predict_selected(void* ptr, const ScipyCsrF32* Xs, const ScipyDrmF32* Xd, c
         std::memcpy(indices, r.indices.data(), nnz * sizeof(uint32_t));
         std::memcpy(data, r.data.data(), nnz * sizeof(float));
     }
+}
+
+void predict_selected(void* ptr, const ScipyCsrF32* Xs, const ScipyDrmF32* Xd, const ScipyCsrF32* sel, const char* pp,
+                      py_sparse_allocator_t pred_alloc) {
+    PB200_LOCK_XL(ptr)
+    auto& eng = engine_of(ptr);
+    const uint32_t rows = Xs ? Xs->rows : Xd->rows;
+    const uint32_t cols = Xs ? Xs->cols : Xd->cols;
+    if (!sel) throw std::runtime_error("selected_outputs_csr is required");
+    if (sel->rows != rows) throw std::runtime_error("Instance dimension of query and selected output matrix do not match");
+    if (Xd && cols != eng.host().nr_features()) throw std::runtime_error("dense query width != nr_features");
+    auto r = eng.predict_selected(Xs ? Xs->row_ptr : nullptr, Xs ? Xs->col_idx : nullptr, Xs ? Xs->val : nullptr,
+                                  Xd ? Xd->val : nullptr, rows, cols, sel->row_ptr, sel->col_idx, sel->cols, pp);
+    emit_selected(r, pred_alloc);
 }
 
 }  // namespace
@@ -438,9 +442,51 @@ void single_layer_predict(const ScipyCsrF32* Xs, const ScipyDrmF32* Xd, const Sc
     emit_result(r, pred_alloc);
 }
 
+// c_xlinear_single_layer_predict_on_selected_outputs_* (libpecos.cpp:238-273): one layer handed over by the caller, scores of
+// exactly the given (query, label) pairs; prev_layer_pred = csr_codes or all ones (MLModel::predict_on_selected_outputs,
+// inference.hpp:2129-2224)
+void single_layer_predict_selected(const ScipyCsrF32* Xs, const ScipyDrmF32* Xd, const ScipyCsrF32* sel, const ScipyCsrF32* codes,
+                                   ScipyCscF32* W, ScipyCscF32* C, const char* pp, float bias, py_sparse_allocator_t pred_alloc) {
+    if (!pp) throw std::runtime_error("single layer: post_processor_str is required");
+    if (!sel) throw std::runtime_error("selected_outputs_csr is required");
+    const uint32_t rows = Xs ? Xs->rows : Xd->rows;
+    const uint32_t cols = Xs ? Xs->cols : Xd->cols;
+    auto h = layer_engine(W, C, bias);
+    std::lock_guard<std::mutex> lock(h->mu);
+    auto& eng = *h->engines[0];
+    if (sel->rows != rows) throw std::runtime_error("Instance dimension of query and selected output matrix do not match");
+    if (codes && codes->rows != rows) throw std::runtime_error("Instance dimension of query and prev_layer_pred matrix do not match");
+    if (codes && codes->cols != C->cols) throw std::runtime_error("Label dimension of prev_layer_pred and C matrix do not match");
+    if (Xd && cols != eng.host().nr_features()) throw std::runtime_error("dense query width != nr_features");
+    auto r = eng.predict_selected(Xs ? Xs->row_ptr : nullptr, Xs ? Xs->col_idx : nullptr, Xs ? Xs->val : nullptr,
+                                  Xd ? Xd->val : nullptr, rows, cols, sel->row_ptr, sel->col_idx, sel->cols, pp,
+                                  codes ? codes->row_ptr : nullptr, codes ? codes->col_idx : nullptr, codes ? codes->val : nullptr);
+    emit_selected(r, pred_alloc);
+}
+
 }  // namespace
 
 extern "C" {
+
+void c_xlinear_single_layer_predict_on_selected_outputs_csr_f32(const ScipyCsrF32* input_x, const ScipyCsrF32* selected_outputs_csr,
+                                                                const ScipyCsrF32* csr_codes, ScipyCscF32* W, ScipyCscF32* C,
+                                                                const char* post_processor_str, const int num_threads,
+                                                                const float bias, py_sparse_allocator_t pred_alloc) {
+    (void)num_threads;
+    PB200_API_BEGIN
+    single_layer_predict_selected(input_x, nullptr, selected_outputs_csr, csr_codes, W, C, post_processor_str, bias, pred_alloc);
+    PB200_API_END("c_xlinear_single_layer_predict_on_selected_outputs_csr_f32")
+}
+
+void c_xlinear_single_layer_predict_on_selected_outputs_drm_f32(const ScipyDrmF32* input_x, const ScipyCsrF32* selected_outputs_csr,
+                                                                const ScipyCsrF32* csr_codes, ScipyCscF32* W, ScipyCscF32* C,
+                                                                const char* post_processor_str, const int num_threads,
+                                                                const float bias, py_sparse_allocator_t pred_alloc) {
+    (void)num_threads;
+    PB200_API_BEGIN
+    single_layer_predict_selected(nullptr, input_x, selected_outputs_csr, csr_codes, W, C, post_processor_str, bias, pred_alloc);
+    PB200_API_END("c_xlinear_single_layer_predict_on_selected_outputs_drm_f32")
+}
 
 void c_xlinear_single_layer_predict_csr_f32(const ScipyCsrF32* input_x, const ScipyCsrF32* csr_codes, ScipyCscF32* W,
                                             ScipyCscF32* C, const char* post_processor_str, const uint32_t only_topk,
@@ -539,17 +585,7 @@ void mlmodel_predict_selected(void* ptr, const ScipyCsrF32* Xs, const ScipyDrmF3
     auto r = eng.predict_selected(Xs ? Xs->row_ptr : nullptr, Xs ? Xs->col_idx : nullptr, Xs ? Xs->val : nullptr,
                                   Xd ? Xd->val : nullptr, rows, cols, sel->row_ptr, sel->col_idx, sel->cols, pp,
                                   codes ? codes->row_ptr : nullptr, codes ? codes->col_idx : nullptr, codes ? codes->val : nullptr);
-    uint32_t* indices = nullptr;
-    uint64_t* indptr = nullptr;
-    float* data = nullptr;
-    const uint64_t nnz = r.indptr.empty() ? 0 : r.indptr.back();
-    pred_alloc(false, r.rows, r.cols, nnz, &indices, &indptr, &data);
-    if (!indptr || (nnz && (!indices || !data))) throw std::runtime_error("result allocator returned null buffers");
-    std::memcpy(indptr, r.indptr.data(), r.indptr.size() * sizeof(uint64_t));
-    if (nnz) {
-        std::memcpy(indices, r.indices.data(), nnz * sizeof(uint32_t));
-        std::memcpy(data, r.data.data(), nnz * sizeof(float));
-    }
+    emit_selected(r, pred_alloc);
 }
 
 }  // namespace

@@ -12,11 +12,11 @@
 // The reference evaluates the distance of every unvisited neighbour before touching the queues (hnsw.hpp:897-914), which
 // is what makes step B independent of step C.
 //
-// Sparse (csr) indices (FeatVecSparse{IP,L2}Simd, feat_vectors.hpp:186-210) use the same walk; only step B differs: the warp
-// streams the concatenated {index, value} entries of ALL unvisited neighbours of the expansion (32 per step, 256 contiguous bytes
-// within a row), every lane looks its entry up in the query row staged in shared memory (8,192-bit filter, then a hash table) and
-// the matched products are added row by row in ascending index order -- the order of the reference's block intersection
-// (distance_impl/common.hpp:15-86) for rows with strictly ascending indices.  The reference's sparse "l2" is -2<x,y> (its squared norms are do_l2_distance_simd(x, x) = 0): restated as is.
+// Sparse (csr) indices (FeatVecSparse{IP,L2}Simd, feat_vectors.hpp:186-210) use the same walk; only step B differs: the row
+// extents of all unvisited neighbours are fetched together, then a half-warp streams a neighbour's {index, value} entries (16 per
+// step, 128 contiguous bytes, four steps in flight), every lane looks its entry up in the query row staged in shared memory
+// (8,192-bit filter, then a hash table) and the matched products are added in ascending index order -- the order of the
+// reference's block intersection (distance_impl/common.hpp:15-86) for rows with strictly ascending indices.  The reference's sparse "l2" is -2<x,y> (its squared norms are do_l2_distance_simd(x, x) = 0): restated as is.
 //
 // HBM traffic per query: n_dist * 4d + n_expand * 4(1+maxM0) + hops * 4(1+maxM) + 4d + 8k.
 #include "hnsw_engine.h"
@@ -214,87 +214,62 @@ __device__ __forceinline__ bool sparse_lookup(const SparseQuery& q, uint32_t key
     return false;
 }
 
-// Distances of ids[0..n) -> dist[0..n) for a sparse index: ENTRY-parallel over the concatenated rows of all n neighbours.  The
-// lanes first fetch the n row extents together (one round trip), then the warp streams the concatenated {index, value} entries
-// 32 per step (four steps' loads in flight), every lane looks its entry up in the query row, and the matched products are added
-// row by row in entry (= ascending index) order -- the order of the reference's intersection (distance_impl/common.hpp:15-86).
+// Distances of ids[0..n) -> dist[0..n) for a sparse index.  The lanes first fetch the n row extents together (one round trip,
+// kept in shared memory); then two rows at a time, one per half-warp: 16 entries per step, four steps' loads in flight, every
+// lane looks its entry up in the query row, and the matched products are added in entry (= ascending index) order -- the order of
+// the reference's intersection (distance_impl/common.hpp:15-86).
 template <int METRIC>
 __device__ __forceinline__ void batch_distances_sparse(const HnswDev& ix, const SparseQuery& q, const uint32_t* ids, float* dist,
-                                                       uint32_t n, int lane, uint32_t* row_start, unsigned long long* row_base,
+                                                       uint32_t n, int lane, uint32_t* row_len, unsigned long long* row_base,
                                                        unsigned long long& n_entries) {
-    // 1. row extents + exclusive prefix of the row lengths
-    uint32_t carry = 0;
-    for (uint32_t b = 0; b < n; b += 32) {
-        const uint32_t i = b + lane;
-        uint32_t len = 0;
-        unsigned long long r0 = 0;
-        if (i < n) {
-            const uint32_t node = ids[i];
-            r0 = ix.sp_ptr[node];
-            len = q.n ? static_cast<uint32_t>(ix.sp_ptr[node + 1] - r0) : 0u;  // an empty query row matches nothing
-        }
-        uint32_t x = len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(kFull, x, o);
-            if (lane >= o) x += y;
-        }
-        if (i < n) { row_start[i] = carry + x - len; row_base[i] = r0; dist[i] = 0.0f; }
-        carry += __shfl_sync(kFull, x, 31);
-    }
-    if (lane == 0) { row_start[n] = carry; n_entries += carry; }
-    __syncwarp();
-    const uint32_t total = carry;
-    // 2. stream the entries; r = row of this lane's current entry (non-decreasing), [rs, rn) its extent in the concatenation
-    uint32_t r = 0, rs = 0, rn = row_start[1];
-    unsigned long long rb = row_base[0];
-    uint32_t cur_row = 0;  // warp-uniform: row whose matched products are being summed
-    float cur_ret = 0.0f;
-    for (uint32_t g0 = 0; g0 < total; g0 += 128) {
-        uint2 e[4];
-        uint32_t er[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint32_t g = g0 + 32u * u + lane;
-            e[u] = make_uint2(kSpEmpty, 0u);
-            er[u] = 0u;
-            if (g < total) {
-                if (g >= rn) {
-                    do { ++r; rs = rn; rn = row_start[r + 1]; } while (g >= rn);
-                    rb = row_base[r];
-                }
-                e[u] = ld_stream_u2(ix.sp_ent + rb + (g - rs));
-                er[u] = r;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (g0 + 32u * u >= total) continue;  // warp-uniform
-            float qv = 0.0f;
-            const bool hit = (e[u].x != kSpEmpty) && sparse_lookup(q, e[u].x, &qv);
-            const float prod = __fmul_rn(qv, __uint_as_float(e[u].y));
-            unsigned m = __ballot_sync(kFull, hit);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1u;
-                const float pv = __shfl_sync(kFull, prod, src);
-                const uint32_t rr = __shfl_sync(kFull, er[u], src);
-                if (rr != cur_row) {  // rows are contiguous in the stream: the previous row is complete
-                    if (lane == 0) dist[cur_row] = cur_ret;
-                    cur_row = rr;
-                    cur_ret = 0.0f;
-                }
-                cur_ret = __fadd_rn(cur_ret, pv);
-            }
-        }
-    }
-    if (lane == 0 && n) dist[cur_row] = cur_ret;
-    __syncwarp();
-    // 3. FeatVecSparseIPSimd: 1.0 - dot ; FeatVecSparseL2Simd: x_sq + y_sq - 2.0 * dot with x_sq = y_sq = 0 (see the header)
+    uint32_t sum = 0;
     for (uint32_t i = lane; i < n; i += 32) {
-        const float ret = dist[i];
-        dist[i] = (METRIC == HNSW_IP) ? static_cast<float>(1.0 - static_cast<double>(ret))
-                                      : static_cast<float>(static_cast<double>(0.0f) - 2.0 * static_cast<double>(ret));
+        const uint32_t node = ids[i];
+        const unsigned long long r0 = ix.sp_ptr[node];
+        const uint32_t len = q.n ? static_cast<uint32_t>(ix.sp_ptr[node + 1] - r0) : 0u;  // an empty query row matches nothing
+        row_base[i] = r0;
+        row_len[i] = len;
+        sum += len;
+    }
+    n_entries += sum;  // per-lane partial sums (added up once per query)
+    __syncwarp();
+    const int half = lane >> 4, hl = lane & 15;
+    for (uint32_t b = 0; b < n; b += 2) {
+        const uint32_t slot = b + half;
+        const bool valid = slot < n;
+        const uint32_t len = valid ? row_len[slot] : 0u;
+        const uint2* row = ix.sp_ent + (valid ? row_base[slot] : 0ull);
+        const uint32_t len_max = max(len, __shfl_xor_sync(kFull, len, 16));
+        float ret = 0.0f;
+        for (uint32_t j0 = 0; j0 < len_max; j0 += 64) {
+            uint2 e[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t j = j0 + 16u * u + hl;
+                e[u] = (j < len) ? ld_stream_u2(row + j) : make_uint2(kSpEmpty, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (j0 + 16u * u >= len_max) continue;  // warp-uniform
+                float qv = 0.0f;
+                const bool hit = (e[u].x != kSpEmpty) && sparse_lookup(q, e[u].x, &qv);
+                const float prod = __fmul_rn(qv, __uint_as_float(e[u].y));
+                const unsigned m = __ballot_sync(kFull, hit);
+                if (m == 0u) continue;
+                unsigned mh = (m >> (16 * half)) & 0xFFFFu;
+                const int n_it = max(__popc(m & 0xFFFFu), __popc(m >> 16));
+                for (int it = 0; it < n_it; ++it) {
+                    const int src = mh ? (__ffs(mh) - 1 + 16 * half) : lane;
+                    const float pv = __shfl_sync(kFull, prod, src);
+                    if (mh) { ret = __fadd_rn(ret, pv); mh &= mh - 1u; }
+                }
+            }
+        }
+        if (hl == 0 && valid) {
+            // FeatVecSparseIPSimd: 1.0 - dot ; FeatVecSparseL2Simd: x_sq + y_sq - 2.0 * dot with x_sq = y_sq = 0 (see the header)
+            dist[slot] = (METRIC == HNSW_IP) ? static_cast<float>(1.0 - static_cast<double>(ret))
+                                             : static_cast<float>(static_cast<double>(0.0f) - 2.0 * static_cast<double>(ret));
+        }
     }
     __syncwarp();
 }
@@ -586,7 +561,10 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const HnswSpar
             atomicAdd(&ctrl[4], n_hops);
             atomicAdd(&ctrl[5], 1ull);
         }
-        if (SPARSE && lane == 0) atomicAdd(&ctrl[6], n_entries);
+        if (SPARSE) {  // per-lane partial sums of the stored entries read
+            for (int o = 16; o > 0; o >>= 1) n_entries += __shfl_xor_sync(kFull, n_entries, o);
+            if (lane == 0) atomicAdd(&ctrl[6], n_entries);
+        }
     }
 }
 

@@ -24,6 +24,8 @@ XLINEAR_SYMBOLS = (
     # python prediction chain (is_predict_only=False models): one layer per call, W / C handed over by the caller
     "c_xlinear_single_layer_predict_csr_f32",
     "c_xlinear_single_layer_predict_drm_f32",
+    "c_xlinear_single_layer_predict_on_selected_outputs_csr_f32",
+    "c_xlinear_single_layer_predict_on_selected_outputs_drm_f32",
     # single-layer mmap handles (load / attrs / predict / destruct swapped together: handles are library-specific)
     "c_mlmodel_load_mmap_model",
     "c_mlmodel_destruct_model",

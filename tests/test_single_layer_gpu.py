@@ -114,3 +114,35 @@ def test_layer_cache_and_edge_cases(gpu_clib, have_ref):
     none = m.predict(X[:0, :], only_topk=5, post_processor="l3-hinge")
     assert none.shape == (0, 40) and none.nnz == 0
     assert c.pb200_layer_cache_clear() == 2
+
+
+@pytest.mark.parametrize("permute,prune", [(False, 0.0), (True, 0.2)])
+def test_single_layer_selected_outputs_equal_the_reference_library(gpu_clib, have_ref, permute, prune):
+    """c_xlinear_single_layer_predict_on_selected_outputs_{csr,drm}_f32 (libpecos.cpp:238-273; the per-layer call of
+    predict_on_selected_outputs for is_predict_only=False models, pecos/xmc/base.py:1003): the pattern of the selection, values =
+    transformed (+ combined) scores -- ids bit-exact, scores 1e-5 vs the reference library on the same W / C / codes."""
+    if not have_ref:
+        pytest.fail("oracle/_ref/libpecos_float32.so did not travel to this box")
+    from oracle import ref
+
+    layers = random_tree(411, [5, 40, 500], 300, 20, bias=1.0, permute=permute, prune=prune)
+    X = synth.make_queries(412, 300, 300, 30)
+    rng = np.random.default_rng(413)
+    g = gpu_clib.clib_float32
+    for d in (1, 2):
+        W, C = layers[d]
+        Cr = smat.csr_matrix(C)
+        n_labels, n_codes = C.shape
+        has_parent = np.asarray(Cr.sum(axis=1)).ravel() > 0  # a parentless label is outside the reference's contract (it reads out of bounds)
+        sel = smat.csr_matrix(((rng.random((300, n_labels)) < 0.04) & has_parent[None, :]).astype(np.float32))
+        pattern = ((sel @ Cr) + smat.csr_matrix((rng.random((300, n_codes)) < 0.1).astype(np.float32))).tocsr()
+        pattern.sort_indices()
+        codes = smat.csr_matrix((0.05 + rng.random(pattern.nnz).astype(np.float32), pattern.indices, pattern.indptr), shape=pattern.shape)
+        for pp in ("l3-hinge", "sigmoid", "log-l2-hinge", "noop"):
+            for cc in ((codes, None) if d == 1 else (codes,)):
+                for Xq in (X, np.ascontiguousarray(X.toarray()[:40])):
+                    c2 = cc if cc is None or Xq is X else cc[:40]
+                    s2 = sel if Xq is X else sel[:40]
+                    want = ref.single_layer_predict_on_selected_outputs(Xq, s2, c2, W, C, pp, 1.0)
+                    got = ref.single_layer_predict_on_selected_outputs(Xq, s2, c2, W, C, pp, 1.0, clib=g)
+                    assert_csr_parity(got, want, what=f"single-layer selected d={d} {pp} codes={cc is not None}")
