@@ -12,11 +12,11 @@
 // The reference evaluates the distance of every unvisited neighbour before touching the queues (hnsw.hpp:897-914), which
 // is what makes step B independent of step C.
 //
-// Sparse (csr) indices (FeatVecSparse{IP,L2}Simd, feat_vectors.hpp:186-210) use the same walk; only step B differs: the row
-// extents of all unvisited neighbours are fetched together, then a half-warp streams a neighbour's {index, value} entries (16 per
-// step, 128 contiguous bytes, four steps in flight), every lane looks its entry up in the query row staged in shared memory
-// (8,192-bit filter, then a hash table) and the matched products are added in ascending index order -- the order of the
-// reference's block intersection (distance_impl/common.hpp:15-86) for rows with strictly ascending indices.  The reference's sparse "l2" is -2<x,y> (its squared norms are do_l2_distance_simd(x, x) = 0): restated as is.
+// Sparse (csr) indices (FeatVecSparse{IP,L2}Simd, feat_vectors.hpp:186-210) use the same walk; only step B differs: a half-warp
+// streams the neighbour's {index, value} entries (16 per step, 128 contiguous bytes), every lane looks its entry up in the query
+// row staged in shared memory (a 8,192-bit filter first, binary search on a filter hit) and the matched products are added in
+// ascending index order -- the order of the reference's block intersection (distance_impl/common.hpp:15-86) for rows with strictly
+// ascending indices.  The reference's sparse "l2" is -2<x,y> (its squared norms are do_l2_distance_simd(x, x) = 0): restated as is.
 //
 // HBM traffic per query: n_dist * 4d + n_expand * 4(1+maxM0) + hops * 4(1+maxM) + 4d + 8k.
 #include "hnsw_engine.h"
@@ -165,23 +165,16 @@ __device__ __forceinline__ void batch_distances(const HnswDev& ix, const float* 
 }
 
 // ---- sparse rows: ordered intersection ---------------------------------------------------------------------------------
-// Per query row: an 8,192-bit membership filter of its column indices (rejects ~99 % of the foreign entries with one 4-byte
-// shared-memory load) + an open-addressing table {index, value bits} (linear probing, load factor <= 1/2) for the entries that
-// pass.  Rows longer than kSpTableMaxRow entries are not staged: a filter hit is resolved by a binary search in global memory.
-constexpr uint32_t kSpFilterWords = 256;
-constexpr uint32_t kSpTableMinSlots = 256;
-constexpr uint32_t kSpTableMaxRow = 1024;    // longest query row served by the table (2,048 slots = 16 KB per warp)
-constexpr uint32_t kSpEmpty = 0xFFFFFFFFu;   // not a column index: cols is a uint32, so indices are <= 2^32 - 2
+constexpr uint32_t kSpFilterWords = 256;  // 8,192-bit membership filter of the query row's indices, per warp
+constexpr uint32_t kSpQcapMax = 4096;     // query entries staged per warp at most (longer rows are searched in global memory)
 
-__device__ __forceinline__ uint32_t sp_hash(uint32_t idx) { return idx * 2654435761u; }
+__device__ __forceinline__ uint32_t sp_hash(uint32_t idx) { return (idx * 2654435761u) >> 19; }  // 13 bits
 
-struct SparseQuery {  // one query row
-    const uint32_t* filter;  // shared memory
-    const uint2* table;      // shared memory, or nullptr on the long-row path
-    uint32_t mask;           // slots - 1
-    const uint32_t* idx;     // the row in global memory
+struct SparseQuery {  // one query row: generic pointers (shared-memory copy, or the global arrays for very long rows)
+    const uint32_t* idx;
     const float* val;
     uint32_t n;
+    const uint32_t* filter;
 };
 
 __device__ __forceinline__ uint2 ld_stream_u2(const uint2* p) {
@@ -190,79 +183,65 @@ __device__ __forceinline__ uint2 ld_stream_u2(const uint2* p) {
     return r;
 }
 
-// query value stored under column `key`, if any
-__device__ __forceinline__ bool sparse_lookup(const SparseQuery& q, uint32_t key, float* qv) {
-    const uint32_t hh = sp_hash(key);
-    const uint32_t h = hh >> 19;
-    if (!((q.filter[h >> 5] >> (h & 31u)) & 1u)) return false;
-    if (q.table) {
-        uint32_t s = (hh >> 6) & q.mask;
-        uint2 t = q.table[s];
-        while (t.x != key && t.x != kSpEmpty) {
-            s = (s + 1u) & q.mask;
-            t = q.table[s];
+// one 16-entry step of a half-warp: look the lane's entry up, then add the matched products of this step in entry order
+__device__ __forceinline__ float sparse_step(const SparseQuery& q, bool has, uint2 ent, float ret, int lane) {
+    bool hit = false;
+    float prod = 0.0f;
+    if (has) {
+        const uint32_t h = sp_hash(ent.x);
+        if ((q.filter[h >> 5] >> (h & 31u)) & 1u) {
+            uint32_t lo = 0, hi = q.n;  // std::lower_bound
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (q.idx[mid] < ent.x) lo = mid + 1; else hi = mid;
+            }
+            if (lo < q.n && q.idx[lo] == ent.x) { hit = true; prod = __fmul_rn(q.val[lo], __uint_as_float(ent.y)); }
         }
-        *qv = __uint_as_float(t.y);
-        return t.x == key;
     }
-    uint32_t lo = 0, hi = q.n;  // std::lower_bound
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (q.idx[mid] < key) lo = mid + 1; else hi = mid;
+    const unsigned m = __ballot_sync(kFull, hit);
+    if (m == 0u) return ret;
+    const int half = lane >> 4;
+    unsigned mh = (m >> (16 * half)) & 0xFFFFu;
+    const int n_it = max(__popc(m & 0xFFFFu), __popc(m >> 16));
+    for (int it = 0; it < n_it; ++it) {
+        const int src = mh ? (__ffs(mh) - 1 + 16 * half) : lane;
+        const float pv = __shfl_sync(kFull, prod, src);
+        if (mh) { ret = __fadd_rn(ret, pv); mh &= mh - 1u; }
     }
-    if (lo < q.n && q.idx[lo] == key) { *qv = q.val[lo]; return true; }
-    return false;
+    return ret;
 }
 
-// Distances of ids[0..n) -> dist[0..n) for a sparse index.  The lanes first fetch the n row extents together (one round trip,
-// kept in shared memory); then two rows at a time, one per half-warp: 16 entries per step, four steps' loads in flight, every
-// lane looks its entry up in the query row, and the matched products are added in entry (= ascending index) order -- the order of
-// the reference's intersection (distance_impl/common.hpp:15-86).
+// distances of ids[0..n) -> dist[0..n) for a sparse index, two rows at a time (one per half-warp)
 template <int METRIC>
 __device__ __forceinline__ void batch_distances_sparse(const HnswDev& ix, const SparseQuery& q, const uint32_t* ids, float* dist,
-                                                       uint32_t n, int lane, uint32_t* row_len, unsigned long long* row_base,
-                                                       unsigned long long& n_entries) {
-    uint32_t sum = 0;
-    for (uint32_t i = lane; i < n; i += 32) {
-        const uint32_t node = ids[i];
-        const unsigned long long r0 = ix.sp_ptr[node];
-        const uint32_t len = q.n ? static_cast<uint32_t>(ix.sp_ptr[node + 1] - r0) : 0u;  // an empty query row matches nothing
-        row_base[i] = r0;
-        row_len[i] = len;
-        sum += len;
-    }
-    n_entries += sum;  // per-lane partial sums (added up once per query)
-    __syncwarp();
+                                                       uint32_t n, int lane, unsigned long long& n_entries) {
     const int half = lane >> 4, hl = lane & 15;
     for (uint32_t b = 0; b < n; b += 2) {
         const uint32_t slot = b + half;
         const bool valid = slot < n;
-        const uint32_t len = valid ? row_len[slot] : 0u;
-        const uint2* row = ix.sp_ent + (valid ? row_base[slot] : 0ull);
+        unsigned long long r0 = 0, r1 = 0;
+        if (valid) {
+            const uint32_t node = ids[slot];
+            r0 = ix.sp_ptr[node];
+            r1 = ix.sp_ptr[node + 1];
+        }
+        const uint32_t len = static_cast<uint32_t>(r1 - r0);
         const uint32_t len_max = max(len, __shfl_xor_sync(kFull, len, 16));
+        if (hl == 0) n_entries += len;
+        const uint2* row = ix.sp_ent + r0;
         float ret = 0.0f;
-        for (uint32_t j0 = 0; j0 < len_max; j0 += 64) {
+        for (uint32_t j0 = 0; j0 < len_max; j0 += 64) {  // four independent 128-byte loads per half-warp in flight
             uint2 e[4];
+            bool has[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const uint32_t j = j0 + 16u * u + hl;
-                e[u] = (j < len) ? ld_stream_u2(row + j) : make_uint2(kSpEmpty, 0u);
+                has[u] = (j < len) && q.n != 0u;
+                e[u] = has[u] ? ld_stream_u2(row + j) : make_uint2(0u, 0u);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (j0 + 16u * u >= len_max) continue;  // warp-uniform
-                float qv = 0.0f;
-                const bool hit = (e[u].x != kSpEmpty) && sparse_lookup(q, e[u].x, &qv);
-                const float prod = __fmul_rn(qv, __uint_as_float(e[u].y));
-                const unsigned m = __ballot_sync(kFull, hit);
-                if (m == 0u) continue;
-                unsigned mh = (m >> (16 * half)) & 0xFFFFu;
-                const int n_it = max(__popc(m & 0xFFFFu), __popc(m >> 16));
-                for (int it = 0; it < n_it; ++it) {
-                    const int src = mh ? (__ffs(mh) - 1 + 16 * half) : lane;
-                    const float pv = __shfl_sync(kFull, prod, src);
-                    if (mh) { ret = __fadd_rn(ret, pv); mh &= mh - 1u; }
-                }
+                if (j0 + 16u * u < len_max) ret = sparse_step(q, has[u], e[u], ret, lane);
             }
         }
         if (hl == 0 && valid) {
@@ -350,15 +329,14 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const HnswSpar
     const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;
     unsigned char* base = smem_raw + static_cast<size_t>(warp) * per_warp_bytes;
     // per-warp slice: [query | STAGES ring slots | STAGES mbarriers | neighbour ids | distances | result heap]
-    // (sparse: [query table, SQ.qcap slots | filter | row bases | row starts | neighbour ids | distances | result heap])
+    // (sparse: [query indices qcap | query values qcap | filter | neighbour ids | distances | result heap])
     float* qs = reinterpret_cast<float*>(base);
     float* ring = qs + ix.vstride;
     unsigned long long* mbars = reinterpret_cast<unsigned long long*>(ring + static_cast<size_t>(STAGES) * ix.vstride);
-    uint2* sq_table = reinterpret_cast<uint2*>(base);
-    uint32_t* sq_filter = reinterpret_cast<uint32_t*>(sq_table + SQ.qcap);
-    unsigned long long* sp_row_base = reinterpret_cast<unsigned long long*>(sq_filter + kSpFilterWords);
-    uint32_t* sp_row_start = reinterpret_cast<uint32_t*>(sp_row_base + nbmax);  // nbmax + 1 used, nbmax + 4 reserved
-    uint32_t* nb_ids = SPARSE ? sp_row_start + nbmax + 4 : reinterpret_cast<uint32_t*>(mbars + STAGES);
+    uint32_t* sq_idx = reinterpret_cast<uint32_t*>(base);
+    float* sq_val = reinterpret_cast<float*>(sq_idx + SQ.qcap);
+    uint32_t* sq_filter = reinterpret_cast<uint32_t*>(sq_val + SQ.qcap);
+    uint32_t* nb_ids = SPARSE ? sq_filter + kSpFilterWords : reinterpret_cast<uint32_t*>(mbars + STAGES);
     float* nb_dist = reinterpret_cast<float*>(nb_ids + nbmax);
     uint2* topq = topk_all ? topk_all + static_cast<uint64_t>(gw) * (ef + 1) : reinterpret_cast<uint2*>(nb_dist + nbmax);
     const uint32_t mbar0 = smem_addr(mbars);
@@ -383,34 +361,23 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const HnswSpar
         const uint32_t q = static_cast<uint32_t>(qq);
         unsigned long long n_dist = 0, n_expand = 0, n_hops = 0, n_entries = 0;
 
-        SparseQuery sq{nullptr, nullptr, 0u, nullptr, nullptr, 0u};
+        SparseQuery sq{nullptr, nullptr, 0u, nullptr};
         if (SPARSE) {
+            // stage the query row (indices, values) and the membership filter of its indices
             const unsigned long long q0 = SQ.ptr[q];
             sq.n = static_cast<uint32_t>(SQ.ptr[q + 1] - q0);
-            sq.idx = SQ.idx + q0;
-            sq.val = SQ.val + q0;
-            sq.filter = sq_filter;
-            const bool staged = 2u * sq.n <= SQ.qcap;
             for (uint32_t w = lane; w < kSpFilterWords; w += 32) sq_filter[w] = 0u;
-            if (staged) for (uint32_t w = lane; w < SQ.qcap; w += 32) sq_table[w] = make_uint2(kSpEmpty, 0u);
             __syncwarp();
-            const uint32_t mask = SQ.qcap - 1u;
+            const bool staged = sq.n <= SQ.qcap;
             for (uint32_t i = lane; i < sq.n; i += 32) {
-                const uint32_t c = sq.idx[i];
-                const uint32_t hh = sp_hash(c);
-                atomicOr(&sq_filter[hh >> 24], 1u << ((hh >> 19) & 31u));
-                if (staged) {  // {index, value} into the open-addressing table (linear probing; first writer of an index wins)
-                    const uint32_t vbits = __float_as_uint(sq.val[i]);
-                    uint32_t s = (hh >> 6) & mask;
-                    for (;;) {
-                        const uint32_t old = atomicCAS(&sq_table[s].x, kSpEmpty, c);
-                        if (old == kSpEmpty) { sq_table[s].y = vbits; break; }
-                        if (old == c) break;
-                        s = (s + 1u) & mask;
-                    }
-                }
+                const uint32_t c = SQ.idx[q0 + i];
+                if (staged) { sq_idx[i] = c; sq_val[i] = SQ.val[q0 + i]; }
+                const uint32_t h = sp_hash(c);
+                atomicOr(&sq_filter[h >> 5], 1u << (h & 31u));
             }
-            if (staged) { sq.table = sq_table; sq.mask = mask; }
+            sq.idx = staged ? sq_idx : SQ.idx + q0;
+            sq.val = staged ? sq_val : SQ.val + q0;
+            sq.filter = sq_filter;
             __syncwarp();
         } else {
             // stage the query in the permuted layout (padding = 0)
@@ -421,7 +388,7 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const HnswSpar
             __syncwarp();
         }
         auto distances = [&](uint32_t n) {
-            if (SPARSE) batch_distances_sparse<METRIC>(ix, sq, nb_ids, nb_dist, n, lane, sp_row_start, sp_row_base, n_entries);
+            if (SPARSE) batch_distances_sparse<METRIC>(ix, sq, nb_ids, nb_dist, n, lane, n_entries);
             else batch_distances<METRIC, STAGES>(ix, qs, nb_ids, nb_dist, n, lane, ring, mbar0, phase_bits);
         };
 
@@ -561,8 +528,8 @@ hnsw_search_kernel(const HnswDev ix, const float* __restrict__ Q, const HnswSpar
             atomicAdd(&ctrl[4], n_hops);
             atomicAdd(&ctrl[5], 1ull);
         }
-        if (SPARSE) {  // per-lane partial sums of the stored entries read
-            for (int o = 16; o > 0; o >>= 1) n_entries += __shfl_xor_sync(kFull, n_entries, o);
+        if (SPARSE) {  // per half-warp partial sums of the stored entries read
+            n_entries += __shfl_xor_sync(kFull, n_entries, 16);
             if (lane == 0) atomicAdd(&ctrl[6], n_entries);
         }
     }
@@ -712,8 +679,8 @@ uint32_t HnswEngine::per_warp_smem_(uint32_t ef, uint32_t* nbmax_out) const {
     const uint32_t nbmax = ((std::max(H.l0_max_degree, H.l1_max_degree) + 31u) / 32u) * 32u;
     const bool top_in_smem = ef <= kEfSmemMax;
     if (nbmax_out) *nbmax_out = nbmax;
-    if (H.sparse)  // [query table (qcap_ slots of 8 bytes) | filter | row bases | row starts | ids | distances | result heap]
-        return (qcap_ * 8u + kSpFilterWords * 4u + nbmax * 8u + (nbmax + 4u) * 4u + nbmax * 8 + (top_in_smem ? (ef + 1) * 8 : 0) + 15u) & ~15u;
+    if (H.sparse)  // [query indices | query values | filter | ids | distances | result heap]
+        return (qcap_ * 8u + kSpFilterWords * 4u + nbmax * 8 + (top_in_smem ? (ef + 1) * 8 : 0) + 15u) & ~15u;
     // [query | stages_ ring slots | stages_ mbarriers | ids | distances | result heap]
     return (H.vstride() * 4 * (1u + static_cast<uint32_t>(stages_)) + static_cast<uint32_t>(stages_) * 8u + nbmax * 8 +
             (top_in_smem ? (ef + 1) * 8 : 0) + 15u) & ~15u;
@@ -829,13 +796,10 @@ void HnswEngine::predict(const float* X, uint32_t nq, uint32_t d, uint32_t efS, 
 void HnswEngine::upload_csr_(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, uint32_t nq) {
     const uint64_t e0 = row_ptr[0], nnz = row_ptr[nq] - e0;
     std::vector<unsigned long long> ptr(static_cast<size_t>(nq) + 1);
-    uint64_t longest = 0;  // longest row the shared-memory table serves
+    uint64_t longest = 0;
     for (uint32_t i = 0; i <= nq; ++i) {
         ptr[i] = row_ptr[i] - e0;
-        if (i) {
-            const uint64_t len = row_ptr[i] - row_ptr[i - 1];
-            if (len <= kSpTableMaxRow) longest = std::max(longest, len);
-        }
+        if (i) longest = std::max<uint64_t>(longest, row_ptr[i] - row_ptr[i - 1]);
     }
     q_ptr_.upload(ptr.data(), static_cast<uint64_t>(nq) + 1, stream_);
     q_idx_.reserve(std::max<uint64_t>(nnz, 1));
@@ -845,9 +809,8 @@ void HnswEngine::upload_csr_(const uint64_t* row_ptr, const uint32_t* col_idx, c
         PB200_CUDA(cudaMemcpyAsync(q_dev_.get(), val + e0, nnz * 4, cudaMemcpyHostToDevice, stream_));
     }
     PB200_CUDA(cudaStreamSynchronize(stream_));  // `ptr` is a local
-    uint32_t qcap = kSpTableMinSlots;  // table slots per warp: a power of two >= twice the longest served row
-    while (qcap < 2 * longest) qcap <<= 1;
-    if (qcap != qcap_) { qcap_ = qcap; n_warps_ = 0; }  // launch geometry depends on the table size
+    const uint32_t qcap = static_cast<uint32_t>(std::min<uint64_t>(kSpQcapMax, (std::max<uint64_t>(longest, 1) + 31) / 32 * 32));
+    if (qcap != qcap_) { qcap_ = qcap; n_warps_ = 0; }  // launch geometry depends on the staging capacity
 }
 
 void HnswEngine::predict_csr(const uint64_t* row_ptr, const uint32_t* col_idx, const float* val, uint32_t nq, uint32_t cols,

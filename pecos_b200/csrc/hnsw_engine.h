@@ -33,7 +33,7 @@ struct HnswSparseQueries {  // device CSR of the query batch (sparse indices)
     const unsigned long long* ptr;
     const uint32_t* idx;
     const float* val;
-    uint32_t qcap;  // slots of the per-warp query table in shared memory (rows with 2 * nnz > qcap are searched in global memory)
+    uint32_t qcap;  // query entries staged per warp in shared memory (longer rows are searched in global memory)
 };
 
 struct HnswCounters {  // algorithmic-byte counters of SURVEY.md 8(d), totals over the last search call
