@@ -513,43 +513,20 @@ def hnsw_time_reference(folder, Q, cfg, steps, warmup, budget_s=60.0):
             "sample": f"{sample.shape[0]} of {Q.shape[0]} queries per step, {steps} steps, {n_cores} searchers (all host threads)"}
 
 
-def main_hnsw(args):
-    rank, world, local = dist_env()
-    n_gpus = max(world, 1)
-    metric_name, unit = "HNSW top-10 queries/sec (efS=%d)" % HNSW_WORKLOADS[args.workload]["efS"], UNIT
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        folder, Q, cfg = hnsw_prepare(args, 0, lambda: None)
-        r = hnsw_time_reference(folder, Q, cfg, args.steps, args.warmup)
-        print(json.dumps({"impl": "reference", "metric": metric_name, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": hnsw_config(args.workload, cfg),
-                          "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
-                          "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "gpu_launches": 0}))
-        return 0
-
+def measure_hnsw(args, workload, rank, n_gpus, local, dist, barrier, steps, warmup, with_cpu=True):
+    """One HNSW workload on this rank's GPU (replicas: every rank its own query batch, same index file); returns the JSON line as
+    a dict on rank 0 (None elsewhere)."""
     from ctypes import POINTER, byref, c_float, c_uint32, c_uint64
 
     from pecos_b200 import core
     from pecos_b200.core import ScipyCsrF32, ScipyDrmF32
     from pecos_b200.hnsw import HNSW
 
-    dist = None
-    if n_gpus > 1:
-        import torch
-        import torch.distributed as dist_mod
-
-        torch.cuda.set_device(local)
-        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist = dist_mod
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
+    wargs = argparse.Namespace(**vars(args))
+    wargs.workload, wargs.steps, wargs.warmup = workload, steps, warmup
+    wargs.no_cpu_baseline = args.no_cpu_baseline or not with_cpu
+    args = wargs
+    metric_name, unit = "HNSW top-10 queries/sec (efS=%d)" % HNSW_WORKLOADS[args.workload]["efS"], UNIT
     barrier()
     lib = core.get_clib()
     lib.require_gpu()
@@ -724,8 +701,9 @@ def main_hnsw(args):
         if oracle.have_ref():
             r = hnsw_time_reference(folder, Q, cfg, steps=3, warmup=1, budget_s=30.0)
             cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+    line = None
     if rank == 0:
-        print(json.dumps({
+        line = {
             "metric": metric_name, "value": value, "unit": unit, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
@@ -737,11 +715,57 @@ def main_hnsw(args):
             "e2e": {"value": n_gpus * nq * args.steps / e2e_total, "unit": unit, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": int(nq * topk * 8), "ms_per_step": 1e3 * e2e_total / args.steps,
                     "api": "c_ann_hnsw_predict_%s_%s_f32 (pinned host queries in, host id/distance arrays out)" % ("csr" if sparse else "drm", cfg["metric"])},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}))
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+    return line
+
+
+def main_hnsw(args):
+    rank, world, local = dist_env()
+    n_gpus = max(world, 1)
+    metric_name, unit = "HNSW top-10 queries/sec (efS=%d)" % HNSW_WORKLOADS[args.workload]["efS"], UNIT
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        folder, Q, cfg = hnsw_prepare(args, 0, lambda: None)
+        r = hnsw_time_reference(folder, Q, cfg, args.steps, args.warmup)
+        print(json.dumps({"impl": "reference", "metric": metric_name, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": hnsw_config(args.workload, cfg),
+                          "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+                          "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return 0
+
+    from ctypes import POINTER, byref, c_float, c_uint32, c_uint64
+
+    from pecos_b200 import core
+    from pecos_b200.core import ScipyCsrF32, ScipyDrmF32
+    from pecos_b200.hnsw import HNSW
+
+    dist = None
+    if n_gpus > 1:
+        import torch
+        import torch.distributed as dist_mod
+
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    barrier()
+    line = measure_hnsw(args, args.workload, rank, n_gpus, local, dist, barrier, args.steps, args.warmup)
+    if rank == 0:
+        print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
 
 
 def parity_gate_xlinear(got, folder, X, cfg, rows=1024, what="resident batch"):
@@ -1092,6 +1116,16 @@ def main():
         except Exception as e:  # noqa: BLE001
             secondary["error"] = f"{type(e).__name__}: {e}"
             print(f"bench.py: secondary workloads failed: {e}", file=sys.stderr)
+        if n_gpus == 1:
+            # the HNSW path (BASELINE configs[3] shape at a size whose index builds in seconds, dense + sparse), same gates
+            for w in ("hnsw-100k", "hnsw-sparse-100k"):
+                try:
+                    h_line = measure_hnsw(args, w, rank, n_gpus, local, dist, barrier, steps=3, warmup=3, with_cpu=False)
+                    secondary[w] = {k: h_line[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "config", "parity",
+                                                           "e2e", "gpu_launches", "roofline")}
+                except Exception as e:  # noqa: BLE001
+                    secondary[w] = {"error": f"{type(e).__name__}: {e}"}
+                    print(f"bench.py: secondary workload {w} failed: {e}", file=sys.stderr)
         secondary["wall_s"] = time.perf_counter() - t_sec
     if rank == 0:
         if secondary:
