@@ -33,7 +33,7 @@ h100k) python bench.py --workload hnsw-100k --steps 5 --warmup 3 > $o/${tag}_ben
    summ $o/${tag}_bench_hnsw100k.json;;
 h1m) python bench.py --workload hnsw-1m --steps 3 --warmup 3 > $o/${tag}_bench_hnsw1m.json 2> $o/${tag}_bench_hnsw1m.err || tail -5 $o/${tag}_bench_hnsw1m.err
    summ $o/${tag}_bench_hnsw1m.json;;
-full) python bench.py --steps 20 --warmup 5 > $o/${tag}_bench_default.json 2> $o/${tag}_bench_default.err || tail -5 $o/${tag}_bench_default.err
+full) python __graft_entry__.py --smoke 2>&1 | tail -1; python bench.py --steps 20 --warmup 5 > $o/${tag}_bench_default.json 2> $o/${tag}_bench_default.err || tail -5 $o/${tag}_bench_default.err
    summ $o/${tag}_bench_default.json
    python - <<PY
 import json
