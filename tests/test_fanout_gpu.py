@@ -70,6 +70,26 @@ def test_hnsw_fanout_equals_single_engine(gpu_clib, devices_env):
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32))
 
 
+def test_sparse_hnsw_fanout_equals_single_engine(gpu_clib, devices_env):
+    """csr queries: every replica gets its rows of the caller's csr arrays (row offsets rebased per slice)."""
+    import scipy.sparse as smat
+
+    from pecos_b200.hnsw import HNSW
+
+    folder = os.path.join(os.path.dirname(MID), "hnsw_sparse", "ip_tfidf")
+    Q = smat.load_npz(os.path.join(folder, "Q.npz"))
+    Qbig = smat.vstack([Q] * 11 + [Q[:37]]).tocsr().astype(np.float32)
+    Qbig.sort_indices()
+    os.environ.pop("PB200_DEVICES", None)
+    single = HNSW.load(folder)
+    want = single.predict(Qbig, pred_params=HNSW.PredParams(efS=100, topk=10, threads=1), ret_csr=False)
+    os.environ["PB200_DEVICES"] = "0,0,0"
+    m = HNSW.load(folder)
+    assert gpu_clib.clib_float32.pb200_hnsw_replicas(m.model_ptr) == 3
+    got = m.predict(Qbig, pred_params=HNSW.PredParams(efS=100, topk=10, threads=1), ret_csr=False)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32))
+
+
 def test_bad_device_list_is_rejected(tmp_path, gpu_clib, devices_env):
     import subprocess
     import sys
