@@ -78,7 +78,7 @@ def test_sparse_hnsw_fanout_equals_single_engine(gpu_clib, devices_env):
 
     folder = os.path.join(os.path.dirname(MID), "hnsw_sparse", "ip_tfidf")
     Q = smat.load_npz(os.path.join(folder, "Q.npz"))
-    Qbig = smat.vstack([Q] * 11 + [Q[:37]]).tocsr().astype(np.float32)
+    Qbig = smat.vstack([Q] * 13 + [Q[:37]]).tocsr().astype(np.float32)
     Qbig.sort_indices()
     os.environ.pop("PB200_DEVICES", None)
     single = HNSW.load(folder)
