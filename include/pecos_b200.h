@@ -285,6 +285,11 @@ void pb200_hnsw_set_foreign(int metric, void* destruct, void* searchers_create, 
  * value in effect.  Results are identical for every setting. */
 int pb200_hnsw_set_stages(void* model_ptr, int stages);
 void pb200_hnsw_get_info(void* model_ptr, uint64_t* out);
+/* Host-only ingest check of an HNSW index folder (<model>/c_model), no GPU needed: the loader's validation of config.json
+ * (hnsw_t string of the requested metric / data type, version) and of index.mmap_store (record sizes; sparse: record offsets,
+ * strictly ascending in-range indices).  metric 0 = ip, 1 = l2; sparse 0 = drm, 1 = csr.  Returns 0 and
+ * out[8] = {num_node, feat_dim, maxM, maxM0, max_level, init_node, stored vector entries, level-0 degree sum}, or 1 (reason on stderr). */
+int pb200_hnsw_host_info(const char* model_dir, int metric, int sparse, uint64_t* out);
 /* A query whose candidate queue outgrows the per-warp scratch (PB200_HNSW_VCAP entries, default 32768) makes the engine re-run
  * the batch with twice the capacity (up to num_node + 1, which cannot overflow) -- this counts those re-runs. */
 uint32_t pb200_hnsw_vcap_retries(void* model_ptr);

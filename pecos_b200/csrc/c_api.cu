@@ -1132,6 +1132,34 @@ uint32_t pb200_hnsw_replicas(void* ptr) {
     PB200_API_END("pb200_hnsw_replicas")
 }
 
+// host-only ingest of an HNSW index (no CUDA calls): validates config.json + index.mmap_store exactly like the loader does and
+// reports what it found.  Returns 0, or 1 with the reason on stderr (wrong index type, version, truncated records ...).
+int pb200_hnsw_host_info(const char* model_dir, int metric, int sparse, uint64_t* out) {
+    try {
+        auto ix = pb200::load_hnsw_index(model_dir, metric, false, sparse != 0);
+        uint64_t entries = 0, degree_sum = 0;
+        for (uint32_t i = 0; i < ix->num_node; ++i) {
+            degree_sum += std::min(ix->l0_neighborhood(i)[0], ix->l0_max_degree);
+            if (ix->sparse) {
+                const float* v; const uint32_t* c;
+                const uint32_t len = ix->l0_sparse_row(i, &v, &c);
+                for (uint32_t j = 1; j < len; ++j)
+                    if (c[j] <= c[j - 1]) throw std::runtime_error("hnsw index: a stored row does not have strictly ascending indices");
+                if (len && c[len - 1] >= ix->feat_dim) throw std::runtime_error("hnsw index: a stored index is out of range");
+                entries += len;
+            } else {
+                entries += ix->feat_dim;
+            }
+        }
+        out[0] = ix->num_node; out[1] = ix->feat_dim; out[2] = ix->maxM; out[3] = ix->maxM0; out[4] = ix->max_level;
+        out[5] = ix->init_node; out[6] = entries; out[7] = degree_sum;
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "pb200_hnsw_host_info: %s\n", e.what());
+        return 1;
+    }
+}
+
 void pb200_hnsw_get_info(void* model_ptr, uint64_t* out) {
     PB200_API_BEGIN
     auto& e = hnsw_of(model_ptr);

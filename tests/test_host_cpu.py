@@ -226,3 +226,27 @@ def test_mmap_writer_output_loads_in_the_reference_library(tmp_path, clib, have_
     for lb, lc in zip(b, c):
         for key in lb:
             assert np.array_equal(np.asarray(lb[key]), np.asarray(lc[key])), key
+
+
+def test_hnsw_host_ingest_of_dense_and_sparse_indices(clib):
+    """The C++ loader (pecos_b200/csrc/hnsw_host.h) on the committed reference-built indices, without a GPU: header fields, record
+    walk and totals agree with the independent numpy parse of the oracle; a folder of the wrong index type is rejected."""
+    from ctypes import c_uint64
+
+    from oracle import restatement
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    c = clib.clib_float32
+    cases = [("hnsw_toy/model_ip", 0, 0), ("hnsw_mid/l2_d128", 1, 0), ("hnsw_mid/ip_d70", 0, 0), ("hnsw_sparse/fixture_ip", 0, 1),
+             ("hnsw_sparse/ip_tfidf", 0, 1), ("hnsw_sparse/l2_tfidf", 1, 1), ("hnsw_sparse/ip_short", 0, 1)]
+    for rel, metric, sparse in cases:
+        folder = os.path.join(gold, rel)
+        out = (c_uint64 * 8)()
+        assert c.pb200_hnsw_host_info(os.path.join(folder, "c_model").encode(), metric, sparse, out) == 0, rel
+        o = restatement.OracleHNSW(folder, isa=0)
+        assert [int(x) for x in out[:6]] == [o.num_node, o.feat_dim, o.maxM, o.maxM0, o.max_level, o.init_node], rel
+        V = o.vectors()
+        assert int(out[6]) == (V.nnz if sparse else V.size), rel
+        # wrong metric / wrong data type: the hnsw_t string of config.json does not match (hnsw.hpp:541-546)
+        assert c.pb200_hnsw_host_info(os.path.join(folder, "c_model").encode(), 1 - metric, sparse, out) == 1
+        assert c.pb200_hnsw_host_info(os.path.join(folder, "c_model").encode(), metric, 1 - sparse, out) == 1
