@@ -96,12 +96,15 @@ void c_xlinear_predict_on_selected_outputs_drm_f32(void* ptr, const ScipyDrmF32*
                                                    const char* overridden_post_processor_str, const int threads,
                                                    py_sparse_allocator_t pred_alloc);
 
+/* libpecos.cpp:32-36  one npz layer folder (param.json + W.npz [+ C.npz]) -> the single-layer mmap format read by
+ * c_mlmodel_load_mmap_model (MLModel<csc_t>::save_mmap, inference.hpp:2274-2289).  Host-only, needs no GPU. */
+void c_mlmodel_compile_mmap_model(const char* model_path, const char* mmap_model_path);
 /* libpecos.cpp:37-113  Single-layer handles over ONE mmap-format MLModel folder (MLModel<csc_t>::save_mmap,
  * pecos/core/xmc/inference.hpp:2274-2289: param.json with is_mmap = true + W.mmap_store + C.mmap_store in csc_t's mmap
  * format, pecos/core/utils/matrix.hpp:386-407).  c_mlmodel_get_int_attr: nr_labels | nr_codes | nr_features.
  * c_mlmodel_predict_*: csr_codes = previous layer's prediction or NULL (= ones(rows x nr_codes), no combine);
  * overridden_post_processor NULL / overridden_only_topk 0 = the values stored with the layer.
- * c_mlmodel_compile_mmap_model (the writer) stays on the reference library. */
+ * Folders written by this library's or by the reference's c_mlmodel_compile_mmap_model are interchangeable. */
 void* c_mlmodel_load_mmap_model(const char* model_path, const bool lazy_load);
 void c_mlmodel_destruct_model(void* ptr);
 uint32_t c_mlmodel_get_int_attr(void* ptr, const char* attr);

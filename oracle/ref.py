@@ -258,9 +258,9 @@ class MLModelHandle(object):
         return alloc.get()
 
 
-def compile_mlmodel_mmap(npz_layer_folder, mmap_folder):
+def compile_mlmodel_mmap(npz_layer_folder, mmap_folder, clib=None):
     """c_mlmodel_compile_mmap_model: one `<d>.model` folder (npz) -> single-layer mmap folder."""
-    lib().c_mlmodel_compile_mmap_model(npz_layer_folder.encode(), mmap_folder.encode())
+    (clib if clib is not None else lib()).c_mlmodel_compile_mmap_model(npz_layer_folder.encode(), mmap_folder.encode())
 
 
 def compile_mmap_model(npz_ranker_folder, mmap_folder):

@@ -212,6 +212,7 @@ class B200CoreLib(object):
         fp(c.c_mlmodel_load_mmap_model, c_void_p, [c_char_p, c_bool])
         fp(c.c_mlmodel_destruct_model, None, [c_void_p])
         fp(c.c_mlmodel_get_int_attr, c_uint32, [c_void_p, c_char_p])
+        fp(c.c_mlmodel_compile_mmap_model, None, [c_char_p, c_char_p])
         ml_args = [POINTER(ScipyCsrF32), c_char_p, c_uint32, c_int, ScipyCompressedSparseAllocator.CFUNCTYPE]
         fp(c.c_mlmodel_predict_csr_f32, None, [c_void_p, POINTER(ScipyCsrF32)] + ml_args)
         fp(c.c_mlmodel_predict_drm_f32, None, [c_void_p, POINTER(ScipyDrmF32)] + ml_args)

@@ -209,6 +209,13 @@ void c_xlinear_compile_mmap_model(const char* model_path, const char* mmap_model
     PB200_API_END("c_xlinear_compile_mmap_model")
 }
 
+void c_mlmodel_compile_mmap_model(const char* model_path, const char* mmap_model_path) {
+    // host-only (no CUDA calls): one npz layer folder -> the reference's single-layer mmap format (libpecos.cpp:32-36)
+    PB200_API_BEGIN
+    pb200::compile_mlmodel_mmap(model_path, mmap_model_path);
+    PB200_API_END("c_mlmodel_compile_mmap_model")
+}
+
 void c_xlinear_destruct_model(void* ptr) {
     PB200_API_BEGIN
     delete static_cast<XLinearHandle*>(ptr);

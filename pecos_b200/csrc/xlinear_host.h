@@ -684,6 +684,38 @@ inline void write_xlinear_mmap_model(const XLinearHostModel& m, const std::strin
     }
 }
 
+// c_mlmodel_compile_mmap_model (pecos/core/libpecos.cpp:32-36; MLModel<csc_t>::save_mmap inference.hpp:2274-2289, LayerData<csc_t>
+// :1676-1680, csc_t::save_to_mmap_store matrix.hpp:386-396): ONE npz layer folder (param.json + W.npz + C.npz; the root layer may
+// lack C.npz = one parent holding every label, inference.hpp:1580-1583) -> param.json (is_mmap = true) + W.mmap_store + C.mmap_store,
+// both in csc_t's layout [rows u32][cols u32][nnz u64][col_ptr u64 x (cols + 1)][row_idx u32 x nnz][val f32 x nnz].  Host-only.
+inline void write_csc_mmap(const CscHost& A, const std::string& path) {
+    MmapStoreWriter w(path);
+    w.put_one<uint32_t>(A.rows);
+    w.put_one<uint32_t>(A.cols);
+    w.put_one<uint64_t>(A.nnz());
+    w.put_multiple<uint64_t>(A.col_ptr.data(), static_cast<uint64_t>(A.cols) + 1);
+    w.put_multiple<uint32_t>(A.row_idx.data(), A.nnz());
+    w.put_multiple<float>(A.val.data(), A.nnz());
+    w.close();
+}
+
+inline void compile_mlmodel_mmap(const std::string& npz_folder, const std::string& mmap_folder) {
+    const LayerMeta meta = load_layer_meta(npz_folder + "/param.json");
+    if (meta.is_mmap) throw std::runtime_error("This folder contains mmap model. Cannot load in npz format.");
+    const CscHost W = load_csc_npz(npz_folder + "/W.npz");
+    const std::string c_path = npz_folder + "/C.npz";
+    const CscHost C = file_exists(c_path) ? load_csc_npz(c_path) : csc_ones_column(W.cols);
+    if (system(("mkdir -p '" + mmap_folder + "'").c_str()) != 0) throw std::runtime_error("Cannot create folder: " + mmap_folder);
+    char bias_txt[64];
+    std::snprintf(bias_txt, sizeof(bias_txt), "%.9g", static_cast<double>(meta.bias));
+    write_json_text(mmap_folder + "/param.json",
+                    std::string("{\n\"model\": \"MLModel\",\n\"bias\": ") + bias_txt + ",\n\"pred_kwargs\": {\n\t\"only_topk\": " +
+                        std::to_string(meta.only_topk) + ",\n\t\"post_processor\": \"" + meta.post_processor +
+                        "\"\n\t},\n\"is_mmap\": true\n}\n");
+    write_csc_mmap(W, mmap_folder + "/W.mmap_store");
+    write_csc_mmap(C, mmap_folder + "/C.mmap_store");
+}
+
 struct HierMeta { int depth = 0; bool is_mmap = false; };
 
 inline HierMeta load_hier_meta(const std::string& path) {

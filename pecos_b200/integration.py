@@ -27,6 +27,7 @@ XLINEAR_SYMBOLS = (
     "c_xlinear_single_layer_predict_on_selected_outputs_csr_f32",
     "c_xlinear_single_layer_predict_on_selected_outputs_drm_f32",
     # single-layer mmap handles (load / attrs / predict / destruct swapped together: handles are library-specific)
+    "c_mlmodel_compile_mmap_model",  # host-only writer
     "c_mlmodel_load_mmap_model",
     "c_mlmodel_destruct_model",
     "c_mlmodel_get_int_attr",

@@ -250,3 +250,36 @@ def test_hnsw_host_ingest_of_dense_and_sparse_indices(clib):
         # wrong metric / wrong data type: the hnsw_t string of config.json does not match (hnsw.hpp:541-546)
         assert c.pb200_hnsw_host_info(os.path.join(folder, "c_model").encode(), 1 - metric, sparse, out) == 1
         assert c.pb200_hnsw_host_info(os.path.join(folder, "c_model").encode(), metric, 1 - sparse, out) == 1
+
+
+@pytest.mark.parametrize("permute,prune", [(False, 0.0), (True, 0.25)])
+def test_mlmodel_mmap_writer_is_interchangeable_with_the_reference(tmp_path, clib, have_ref, permute, prune):
+    """c_mlmodel_compile_mmap_model of THIS library (host-only; pecos_b200/csrc/xlinear_host.h compile_mlmodel_mmap): every layer
+    folder it writes holds the same blocks (W.mmap_store, C.mmap_store) as the reference's output, loads in the reference library and
+    predicts what the reference predicts from its own copy -- incl. the root layer, whose C.npz may be absent."""
+    from .util import assert_csr_parity, random_tree
+
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from oracle import ref
+
+    folder = str(tmp_path / "m")
+    layers = random_tree(91, [4, 24, 300], 200, 18, bias=1.0, permute=permute, prune=prune)
+    synth.save_xlinear_model(folder, layers, bias=1.0, only_topk=6, post_processor="l3-hinge")
+    X = synth.make_queries(92, 40, 200, 20)
+    for d in range(3):
+        src = os.path.join(folder, "ranker", f"{d}.model")
+        if d == 0 and os.path.exists(os.path.join(src, "C.npz")):
+            os.remove(os.path.join(src, "C.npz"))  # the root layer's C is optional (inference.hpp:1580-1583)
+        ours, theirs = str(tmp_path / f"ours{d}"), str(tmp_path / f"theirs{d}")
+        ref.compile_mlmodel_mmap(src, ours, clib=clib.clib_float32)
+        ref.compile_mlmodel_mmap(src, theirs)
+        from oracle import restatement
+
+        for f in ("W.mmap_store", "C.mmap_store"):  # block by block (the padding between blocks is not initialised by the reference)
+            ba, bb = restatement.read_mmap_store(os.path.join(ours, f)), restatement.read_mmap_store(os.path.join(theirs, f))
+            assert len(ba) == len(bb) == 6 and all(np.array_equal(x, y) for x, y in zip(ba, bb)), (d, f)
+        a, b = ref.MLModelHandle(ours), ref.MLModelHandle(theirs)
+        assert [a.attr(k) for k in ("nr_labels", "nr_codes", "nr_features")] == [b.attr(k) for k in ("nr_labels", "nr_codes", "nr_features")]
+        assert_csr_parity(a.predict(X, None, None, 0), b.predict(X, None, None, 0), rtol=0.0, what=f"layer {d}: reference on our folder")
+        assert_csr_parity(a.predict(X, None, "sigmoid", 3), b.predict(X, None, "sigmoid", 3), rtol=0.0, what=f"layer {d}: overrides")
