@@ -60,7 +60,7 @@ def where(fn):
     i = I(); dl.dladdr(ctypes.cast(fn, ctypes.c_void_p).value, ctypes.byref(i)); return i.f.decode()
 out["xlinear"] = {n: where(getattr(clib.clib_float32, n)) for n in integration.XLINEAR_SYMBOLS}
 out["hnsw"] = {"%%s_%%s_%%s" %% (k[0], k[1], s): where(f) for k, d in clib.ann_hnsw_fn_dict.items() for s, f in d.items() if hasattr(f, "argtypes")}
-out["other"] = {n: where(getattr(clib.clib_float32, n)) for n in ("c_sparse_matmul_csc_f32", "c_mlmodel_compile_mmap_model", "c_xlinear_single_layer_train_csc_f32" if hasattr(clib.clib_float32, "c_xlinear_single_layer_train_csc_f32") else "c_sparse_matmul_csr_f32")}
+out["other"] = {n: where(getattr(clib.clib_float32, n)) for n in ("c_sparse_matmul_csc_f32", "c_xlinear_single_layer_train_csr_f32", "c_xlinear_single_layer_train_csc_f32" if hasattr(clib.clib_float32, "c_xlinear_single_layer_train_csc_f32") else "c_sparse_matmul_csr_f32")}
 out["argtypes_kept"] = all(getattr(clib.clib_float32, n).argtypes is not None for n in integration.XLINEAR_SYMBOLS)
 A = smat.random(20, 30, 0.2, format="csr", dtype=np.float32, random_state=1); B = smat.random(30, 10, 0.3, format="csc", dtype=np.float32, random_state=2)
 C = clib.sparse_matmul(A, B)
