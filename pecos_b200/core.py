@@ -271,6 +271,50 @@ class B200CoreLib(object):
             pred_alloc.cfunc,
         )
 
+    def xlinear_single_layer_predict_on_selected_outputs(self, X, selected_outputs_csr, csr_codes, W, C, post_processor_str,
+                                                         num_threads, bias, pred_alloc):
+        """Same contract as corelib.xlinear_single_layer_predict_on_selected_outputs (pecos/core/base.py:1227-1300): one layer,
+        scores of exactly the (instance, label) pairs of ``selected_outputs_csr``."""
+        self.require_gpu()
+        clib = self.clib_float32
+        if isinstance(X, smat.csr_matrix):
+            if not X.has_sorted_indices:
+                raise ValueError("Query matrix does not have sorted indices!")
+            X = ScipyCsrF32.init_from(X)
+        elif isinstance(X, np.ndarray):
+            X = ScipyDrmF32.init_from(X)
+        if isinstance(X, ScipyCsrF32):
+            c_predict = clib.c_xlinear_single_layer_predict_on_selected_outputs_csr_f32
+        elif isinstance(X, ScipyDrmF32):
+            c_predict = clib.c_xlinear_single_layer_predict_on_selected_outputs_drm_f32
+        else:
+            raise NotImplementedError("type(X) = {} not implemented".format(type(X)))
+        if isinstance(selected_outputs_csr, smat.csr_matrix):
+            selected_outputs_csr = ScipyCsrF32.init_from(selected_outputs_csr.astype(np.float32))
+        if not isinstance(selected_outputs_csr, ScipyCsrF32):
+            raise NotImplementedError("selected_outputs_csr must be a csr_matrix / ScipyCsrF32")
+        if isinstance(W, smat.csc_matrix):
+            W = ScipyCscF32.init_from(W)
+        if isinstance(C, smat.csc_matrix):
+            C = ScipyCscF32.init_from(C)
+        if not isinstance(W, ScipyCscF32) or not isinstance(C, ScipyCscF32):
+            raise NotImplementedError("W and C must be csc_matrix / ScipyCscF32")
+        if csr_codes is not None and isinstance(csr_codes, smat.csr_matrix):
+            csr_codes = ScipyCsrF32.init_from(csr_codes)
+        if csr_codes is not None and not isinstance(csr_codes, ScipyCsrF32):
+            raise NotImplementedError("type(csr_codes) = {} not implemented".format(type(csr_codes)))
+        c_predict(
+            byref(X),
+            byref(selected_outputs_csr),
+            byref(csr_codes) if csr_codes is not None else None,
+            byref(W),
+            byref(C),
+            post_processor_str.encode("utf-8"),
+            num_threads,
+            bias,
+            pred_alloc.cfunc,
+        )
+
     def require_gpu(self):
         if self.clib_float32.pb200_device_count() <= 0:
             raise RuntimeError("pecos_b200: no CUDA device visible and there is no CPU fallback")

@@ -9,8 +9,9 @@ Same names, argument meaning and error behaviour as the reference for the predic
 
 * ``MLModel.load / predict`` (one layer of the python chain, ``is_predict_only=False``) .. pecos/xmc/base.py:832-878, :890-949
 
-Training, pruning and ``predict_on_selected_outputs`` stay on the reference CPU library; they are outside this engine's
-scope and raise ``NotImplementedError`` here.
+``predict_on_selected_outputs`` is served for predict-only handles and for the python chain (one
+``c_xlinear_single_layer_predict_on_selected_outputs_*`` call per layer).  Training and pruning stay on the reference CPU library;
+they are outside this engine's scope and raise ``NotImplementedError`` here.
 """
 import copy
 import dataclasses as dc
@@ -139,6 +140,27 @@ class MLModel(object):
         return pred_alloc.get()
 
 
+    def predict_on_selected_outputs(self, X, selected_outputs_csr, csr_codes=None, pred_params=None, **kwargs):
+        """Scores of exactly the (instance, label) pairs of ``selected_outputs_csr`` for this layer (pecos/xmc/base.py:950-1012);
+        ``csr_codes`` = the previous layer's selected-outputs result (must hold the parents of the selected labels)."""
+        if X.shape[1] != self.nr_features:
+            raise ValueError("Feature dimension of query matrix does not match weight matrix")
+        if X.shape[0] != selected_outputs_csr.shape[0]:
+            raise ValueError("Instance dimension of query and selected output matrix do not match")
+        if selected_outputs_csr.shape[1] != self.nr_labels:
+            raise ValueError("Label dimension of selected output matrix does not match")
+        pred_params = self.get_pred_params() if pred_params is None else copy.deepcopy(pred_params)
+        if kwargs.get("post_processor", None):
+            pred_params.post_processor = kwargs["post_processor"]
+        if isinstance(X, smat.csr_matrix) and not X.has_sorted_indices:
+            raise ValueError("Query matrix does not have sorted indices!")
+        pred_alloc = ScipyCompressedSparseAllocator()
+        self._clib.xlinear_single_layer_predict_on_selected_outputs(
+            X, selected_outputs_csr, csr_codes, self.W, self.C, pred_params.post_processor, kwargs.get("threads", -1), self.bias,
+            pred_alloc)
+        return pred_alloc.get()
+
+
 class _PythonChain(object):
     """``HierarchicalMLModel`` with ``is_predict_only=False``: a list of ``MLModel`` (pecos/xmc/base.py:1669-1679)."""
 
@@ -167,6 +189,30 @@ class _PythonChain(object):
         for d in range(self.depth):
             pred_csr = self.model_chain[d].predict(X, csr_codes=pred_csr, pred_params=pred_params.model_chain[d],
                                                    threads=kwargs.get("threads", -1))
+        return pred_csr
+
+    def predict_on_selected_outputs(self, X, selected_outputs_csr, csr_codes=None, pred_params=None, **kwargs):
+        """Layer by layer (pecos/xmc/base.py:1772-1793): the selected set of layer d is the set of parents of layer d + 1's
+        selection (pattern of ``selection @ C``); every layer scores exactly its selection with the previous result as codes."""
+        assert X.dtype == np.float32
+        if not isinstance(selected_outputs_csr, smat.csr_matrix):
+            raise ValueError("type(selected_outputs_csr) = {} is not supported".format(type(selected_outputs_csr)))
+        if selected_outputs_csr.shape[1] != self.nr_labels:
+            raise ValueError("Label dimension of selected output matrix does not match")
+        if X.shape[0] != selected_outputs_csr.shape[0]:
+            raise ValueError("Instance dimension of query and selected output matrix do not match")
+        pred_params = self.get_pred_params() if pred_params is None else copy.deepcopy(pred_params)
+        pred_params.override_with_kwargs(kwargs)
+        selections = [selected_outputs_csr.astype(np.float32)]
+        for d in range(self.depth - 1, 0, -1):
+            parents = (selections[0] @ self.model_chain[d].C).tocsr().astype(np.float32)
+            parents.sort_indices()
+            selections.insert(0, parents)
+        pred_csr = csr_codes
+        for d in range(self.depth):
+            pred_csr = self.model_chain[d].predict_on_selected_outputs(X, selections[d], csr_codes=pred_csr,
+                                                                       pred_params=pred_params.model_chain[d],
+                                                                       threads=kwargs.get("threads", -1))
         return pred_csr
 
 
@@ -365,8 +411,6 @@ class XLinearModel(object):
     def predict(self, X, pred_params=None, selected_outputs_csr=None, **kwargs):
         if (pred_params is not None) and (not isinstance(pred_params, self.PredParams)):
             raise TypeError("type(pred_kwargs) is not supported")
-        if selected_outputs_csr is not None and not hasattr(self.model, "predict_on_selected_outputs"):
-            raise NotImplementedError("predict_on_selected_outputs needs a predict-only model (is_predict_only=True)")
         max_pred_chunk = kwargs.get("max_pred_chunk", 10**7)
         if max_pred_chunk is not None and not isinstance(max_pred_chunk, int):
             raise TypeError("type(max_pred_chunk) is not supported.")

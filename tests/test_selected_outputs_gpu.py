@@ -110,3 +110,34 @@ def test_selected_outputs_argument_checks(tmp_path, gpu_clib):
         m.predict(X, selected_outputs_csr=np.zeros((10, 30), dtype=np.float32))
     empty = m.predict(X, selected_outputs_csr=smat.csr_matrix((10, 30), dtype=np.float32))
     assert empty.nnz == 0 and empty.shape == (10, 30)
+
+
+@pytest.mark.parametrize("permute,prune", [(False, 0.0), (True, 0.2)])
+def test_python_chain_selected_outputs_equal_predict_only_and_reference(tmp_path, gpu_clib, have_ref, permute, prune):
+    """is_predict_only=False models (list of MLModel, one c_xlinear_single_layer_predict_on_selected_outputs_* call per layer,
+    pecos/xmc/base.py:1772-1793) score a selection exactly like the predict-only handle and like the reference library."""
+    from pecos_b200.xlinear import XLinearModel
+
+    from .util import reachable_labels
+
+    folder = str(tmp_path / "m")
+    layers = random_tree(511, [6, 40, 400], 250, 22, bias=1.0, permute=permute, prune=prune)
+    synth.save_xlinear_model(folder, layers, bias=1.0, only_topk=6, post_processor="l3-hinge")
+    X = synth.make_queries(512, 300, 250, 28)
+    rng = np.random.default_rng(513)
+    ok = np.zeros(layers[-1][0].shape[1], dtype=bool)
+    ok[reachable_labels(layers)] = True
+    sel = smat.csr_matrix(((rng.random((300, ok.size)) < 0.03) & ok[None, :]).astype(np.float32))
+    chain = XLinearModel.load(folder, is_predict_only=False)
+    handle = XLinearModel.load(folder, is_predict_only=True, weight_matrix_type="CSC")
+    for pp in (None, "sigmoid", "log-l2-hinge"):
+        kw = {} if pp is None else {"post_processor": pp}
+        for Xq, s in ((X, sel), (np.ascontiguousarray(X.toarray()[:50]), sel[:50])):
+            got = chain.predict(Xq, selected_outputs_csr=s, **kw)
+            want = handle.predict(Xq, selected_outputs_csr=s, **kw)
+            assert_csr_parity(got, want, what=f"python chain vs predict-only handle ({pp})")
+            if have_ref:
+                from oracle import ref
+
+                r = ref.RefXLinear(os.path.join(folder, "ranker"), weight_matrix_type="CSC")
+                assert_csr_parity(got, ref.predict_on_selected_outputs(r, Xq, s, pp), what=f"python chain vs reference library ({pp})")
