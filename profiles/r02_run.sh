@@ -22,13 +22,8 @@ e) python bench.py --steps 20 --warmup 5 --no-secondary > $o/${tag}_bench_eurlex
    summ $o/${tag}_bench_eurlex4k.json $o/${tag}_bench_eurlex4k_mode6.json;;
 s) python bench.py --workload synthetic-3m --steps 5 --warmup 3 --no-cpu-baseline > $o/${tag}_bench_synthetic3m.json 2> $o/${tag}_bench_synthetic3m.err || tail -5 $o/${tag}_bench_synthetic3m.err
    summ $o/${tag}_bench_synthetic3m.json;;
-eflat) PB200_CM_FLAT=1 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $o/${tag}_bench_eurlex4k_flat.json 2> $o/${tag}_bench_eurlex4k_flat.err
-   summ $o/${tag}_bench_eurlex4k_flat.json;;
-sflat) PB200_CM_FLAT=1 python bench.py --workload synthetic-3m --steps 5 --warmup 3 --no-cpu-baseline > $o/${tag}_bench_synthetic3m_flat.json 2> $o/${tag}_bench_synthetic3m_flat.err
-   summ $o/${tag}_bench_synthetic3m_flat.json;;
 s7) PB200_XL_KERNEL_MODE=6 python bench.py --workload synthetic-3m --steps 5 --warmup 3 --no-cpu-baseline > $o/${tag}_bench_synthetic3m_mode6.json 2> $o/${tag}_bench_synthetic3m_mode6.err
    summ $o/${tag}_bench_synthetic3m_mode6.json;;
-ncu_pw) ncu --set full --clock-control none --import-source on -k regex:xl_pair_scores -s 3 -c 1 -o $o/${tag}_ncu_pw_synthetic3m python bench.py --workload synthetic-3m --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2> $o/${tag}_ncu_pw.err;;
 h100k) python bench.py --workload hnsw-100k --steps 5 --warmup 3 > $o/${tag}_bench_hnsw100k.json 2> $o/${tag}_bench_hnsw100k.err || tail -5 $o/${tag}_bench_hnsw100k.err
    summ $o/${tag}_bench_hnsw100k.json;;
 h1m) python bench.py --workload hnsw-1m --steps 3 --warmup 3 > $o/${tag}_bench_hnsw1m.json 2> $o/${tag}_bench_hnsw1m.err || tail -5 $o/${tag}_bench_hnsw1m.err
