@@ -485,6 +485,11 @@ def hnsw_config(name, cfg, extra=None):
          "topk": cfg["topk"], "metric": cfg["metric"], "queries_per_step_per_gpu": cfg["Q"],
          "rows": ("csr, ~%d stored entries per row" % cfg["nnz"]) if cfg.get("sparse") else "dense",
          "parallelism": "query-sharded replicas (no collective)", "index_build": cfg.get("index_build")}
+    if name == "hnsw-rcv1":
+        # informational only: `vs_baseline` stays null because the published number is for the REAL RCV1 vectors, one searcher thread
+        c["published_by_the_reference"] = {"value": 1478.6, "unit": "queries/s", "recall_at_10": 0.9020,
+                                           "setup": "RCV1-47236 sparse ip, N=781,265, 23,149 queries, M=32, efC=100, efS=100, top-10, 1 searcher thread, "
+                                                    "AWS r5dn.24xlarge", "source": "BASELINE.md (tutorials/kdd22 Session 3 notebook)"}
     if extra:
         c.update(extra)
     return c
